@@ -1,0 +1,185 @@
+"""Generates tests/golden/*.npz by running the UNMODIFIED reference (/root/reference) on seeded inputs.
+
+Run in the build container only (the reference does not travel to the GPU box):
+
+    python tests/golden/make_golden.py
+
+Harness shims, both test-side only:
+  * torch.Tensor.cuda -> identity, because YoloLayer.forward hard-codes .cuda() (yololayer.py:98-100)
+    and this container has no GPU;
+  * torch.Tensor.sort -> stable=True, because torch.sort(descending=True) is unstable on ties and the
+    parity contract fixes the tie-break to score-descending, candidate-order-ascending.
+"""
+import os
+import sys
+
+import numpy as np
+import torch
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(os.path.dirname(HERE))
+sys.path.insert(0, "/root/reference")
+sys.path.insert(0, ROOT)
+
+torch.Tensor.cuda = lambda self, *a, **k: self
+_orig_sort = torch.Tensor.sort
+
+
+def _stable_sort(self, *a, **k):
+    k.setdefault("stable", True)
+    return _orig_sort(self, *a, **k)
+
+
+torch.Tensor.sort = _stable_sort
+
+import darknet            # noqa: E402  (reference)
+import utils as ref_utils  # noqa: E402  (reference)
+import yololayer          # noqa: E402  (reference)
+
+from yolo_v3_b200 import synth  # noqa: E402
+
+ANCHORS = [(10, 13), (16, 30), (33, 23), (30, 61), (62, 45), (59, 119), (116, 90), (156, 198), (373, 326)]
+MASKS = ([6, 7, 8], [3, 4, 5], [0, 1, 2])
+
+
+def pack_results(res, prefix, out):
+    """list-of-tensors -> flat arrays (npz cannot hold ragged lists)."""
+    out[prefix + "_is_empty_list"] = np.array(isinstance(res, list) and len(res) == 0)
+    counts, rows = [], []
+    for r in res:
+        r = r.numpy() if r.numel() else np.zeros((0, 7), np.float32)
+        counts.append(len(r))
+        rows.append(r.reshape(-1, 7))
+    out[prefix + "_counts"] = np.array(counts, np.int64)
+    out[prefix + "_rows"] = np.concatenate(rows, 0).astype(np.float32) if rows else np.zeros((0, 7), np.float32)
+
+
+def make_decode():
+    out = {}
+    for tag, (hw, nc, b) in {"a": ((64, 64), 80, 2), "b": ((96, 160), 20, 1)}.items():
+        h, w = hw
+        rs = np.random.RandomState(11)
+        out[f"{tag}_img_hw"] = np.array([h, w])
+        out[f"{tag}_num_classes"] = np.array(nc)
+        for i, s in enumerate((32, 16, 8)):
+            x = torch.from_numpy((rs.standard_normal((b, 3 * (5 + nc), h // s, w // s)) * 1.5).astype(np.float32))
+            layer = yololayer.YoloLayer(ANCHORS, MASKS[i], (w, h), nc)
+            with torch.no_grad():
+                y = layer(x, (w, h), None)
+            out[f"{tag}_logits{i}"] = x.numpy()
+            out[f"{tag}_det{i}"] = y.numpy()
+    np.savez_compressed(os.path.join(HERE, "decode_golden.npz"), **out)
+
+
+def synth_det(rs, b, n, nc, frac_hot=0.25):
+    """Decoded-looking rows: clustered boxes so NMS suppresses, a few exact score ties, a zero-area box."""
+    d = np.zeros((b, n, 5 + nc), np.float32)
+    centers = rs.uniform(40, 360, (b, 12, 2))
+    which = rs.randint(0, 12, (b, n))
+    for i in range(b):
+        d[i, :, 0:2] = centers[i, which[i]] + rs.standard_normal((n, 2)) * 9
+    d[..., 2:4] = rs.uniform(20, 120, (b, n, 2))
+    d[..., 4] = np.where(rs.rand(b, n) < frac_hot, rs.uniform(0.3, 1.0, (b, n)), rs.uniform(0, 0.05, (b, n)))
+    d[..., 5:] = rs.uniform(0, 0.2, (b, n, nc))
+    hot = rs.randint(0, min(nc, 6), (b, n))
+    for i in range(b):
+        d[i, np.arange(n), 5 + hot[i]] = rs.uniform(0.5, 1.0, n)
+    # exact ties: copy score-defining entries between a few rows of the same class
+    d[0, 10] = d[0, 3]
+    d[0, 10, 0] += 200.0
+    d[0, 17] = d[0, 3]
+    d[0, 17, 1] += 150.0
+    # zero-area box with a top score (NaN self-IOU: never kept, never suppresses)
+    d[0, 5, 2] = 0.0
+    d[0, 5, 4] = 0.99
+    d[0, 5, 5:] = 0.0
+    d[0, 5, 5] = 0.99
+    return d
+
+
+def make_postprocess():
+    out = {}
+    rs = np.random.RandomState(5)
+    cases = {
+        "c80": (synth_det(rs, 2, 300, 80), 80),
+        "c20": (synth_det(rs, 3, 200, 20), 20),
+    }
+    # an image with no candidates in a batch that has some
+    cases["c20"][0][1, :, 4] = 0.0
+    for tag, (det, nc) in cases.items():
+        out[f"{tag}_det"] = det
+        out[f"{tag}_num_classes"] = np.array(nc)
+        t = torch.from_numpy(det)
+        modes = {
+            "nms": dict(obj_conf_thr=0.5, nms_thr=0.4),
+            "nms_low": dict(obj_conf_thr=0.05, nms_thr=0.45),
+            "eval": dict(obj_conf_thr=0.05, nms_thr=0.45, is_eval=True),
+            "raw": dict(obj_conf_thr=0.3, nms_thr=0.4, use_nms=False),
+            "raw_eval": dict(obj_conf_thr=0.1, nms_thr=0.4, is_eval=True, use_nms=False),
+            "none": dict(obj_conf_thr=2.0, nms_thr=0.4),
+            "none_eval": dict(obj_conf_thr=2.0, nms_thr=0.4, is_eval=True),
+        }
+        for m, kw in modes.items():
+            res = ref_utils.postprocessing(t.clone(), nc, **kw)
+            pack_results(res, f"{tag}_{m}", out)
+            out[f"{tag}_{m}_kw"] = np.array([kw.get("obj_conf_thr"), kw.get("nms_thr"),
+                                             float(kw.get("is_eval", False)), float(kw.get("use_nms", True))])
+    np.savez_compressed(os.path.join(HERE, "postprocess_golden.npz"), **out)
+
+
+def make_net():
+    out = {}
+    sd = synth.make_state_dict(seed=1234, recipe="analytic")
+    net = darknet.YoloNet((64, 96)).eval()
+    net.load_state_dict(sd)
+    x = synth.make_images(2, 64, 96, seed=3)
+    feats = {}
+    net.pre_det1.mlist[6].register_forward_hook(lambda m, i, o: feats.__setitem__("l0", o.detach().numpy()))
+    net.pre_det2.mlist[6].register_forward_hook(lambda m, i, o: feats.__setitem__("l1", o.detach().numpy()))
+    net.pre_det3.mlist[6].register_forward_hook(lambda m, i, o: feats.__setitem__("l2", o.detach().numpy()))
+    net.feature.register_forward_hook(lambda m, i, o: feats.__setitem__("backbone", o.detach().numpy()))
+    with torch.no_grad():
+        dets = net(x, None)
+    out["img_hw"] = np.array([64, 96])
+    out["seed"] = np.array(1234)
+    out["img_seed"] = np.array(3)
+    for i, d in enumerate(dets):
+        out[f"det{i}"] = d.numpy()
+        out[f"logits{i}"] = feats[f"l{i}"]
+    out["backbone"] = feats["backbone"]
+    res = ref_utils.postprocessing(torch.cat(dets, 1).clone(), 80, obj_conf_thr=0.05, nms_thr=0.4)
+    pack_results(res, "post", out)
+    # weight-stream order (WeightManager, darknet.py:249-303): write a synthetic darknet file from the
+    # state_dict in our claimed order, load it with the reference loader, and record what it consumed.
+    from oracle import yolo_oracle as O
+    blob = O.darknet_blob_from_state_dict(sd)
+    path = "/tmp/_golden_synth.weights"
+    with open(path, "wb") as fp:
+        np.array([0, 2, 0, 32013312, 0], np.int32).tofile(fp)
+        blob.tofile(fp)
+    net2 = darknet.YoloNet((64, 96)).eval()
+    wm = darknet.WeightManager(net2)
+    consumed = wm.loadWeight(path)
+    os.remove(path)
+    sd2 = net2.state_dict()
+    same = all(torch.equal(sd[k], sd2[k]) for k in sd if not k.endswith("num_batches_tracked"))
+    out["darknet_consumed"] = np.array(consumed)
+    out["darknet_total"] = np.array(len(blob))
+    out["darknet_roundtrip_equal"] = np.array(same)
+    out["darknet_seen"] = np.array(int(wm.seen))
+    # order-sensitive digest of the float stream, cheap to recompute anywhere
+    w = np.arange(1, 1 + 4096, dtype=np.float64)
+    out["darknet_blob_probe"] = np.array([float(blob[:4096].astype(np.float64) @ w),
+                                          float(blob[-4096:].astype(np.float64) @ w),
+                                          float(blob[20_000_000:20_004_096].astype(np.float64) @ w)])
+    np.savez_compressed(os.path.join(HERE, "net_golden.npz"), **out)
+    print("darknet consumed", consumed, "of", len(blob), "roundtrip equal", same)
+
+
+if __name__ == "__main__":
+    make_decode()
+    make_postprocess()
+    make_net()
+    for f in sorted(os.listdir(HERE)):
+        if f.endswith(".npz"):
+            print(f, os.path.getsize(os.path.join(HERE, f)))
