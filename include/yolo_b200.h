@@ -1,0 +1,158 @@
+/* yolo_b200.h -- C ABI of the B200-native YOLOv3 inference path (libyolo_b200.so).
+ *
+ * The reference (ydixon/yolo_v3) is pure Python; it has no FFI for this path.  The entry points
+ * below are what a ctypes binding for the path binds (yolo_v3_b200/_lib.py is that binding; the
+ * stub a reference maintainer would add is in INTEGRATION.md).  Each one names the reference
+ * interface it stands in for.  Plain pointers and sizes only -- no torch types.
+ *
+ * Conventions
+ *   - every function returns YB_OK (0) or a negative yb_status; yb_last_error() has the text;
+ *     nothing throws across the ABI;
+ *   - "dev" pointers are CUDA device pointers owned by the caller; the library owns packed
+ *     weights, TMA descriptors and the activation arena (grown lazily per (B,H,W), freed in
+ *     yb_destroy).  Nothing is allocated on the steady-state path;
+ *   - all work is enqueued on the `stream` argument (a cudaStream_t passed as void*, so this
+ *     header needs no CUDA include) and is asynchronous unless stated otherwise;
+ *   - one yb_ctx per (device, host thread); calls on one ctx are serialised by the caller;
+ *   - tensors: images NCHW fp32 in [0,1] exactly as the reference feeds them (test.py:32);
+ *     detections [B, N, 5+C] fp32, N = 3*(H/32*W/32 + H/16*W/16 + H/8*W/8), rows ordered
+ *     stride-32 head, stride-16 head, stride-8 head (= torch.cat((det1,det2,det3),1), test.py:36).
+ */
+#ifndef YOLO_B200_H_
+#define YOLO_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct yb_ctx yb_ctx;
+
+typedef enum {
+    YB_OK = 0,
+    YB_E_ARG = -1,        /* bad argument / shape (H or W not a multiple of 32, B <= 0, ...) */
+    YB_E_KEY = -2,        /* unknown state_dict key or wrong element count */
+    YB_E_STATE = -3,      /* call order (forward before finalize, ...) */
+    YB_E_CUDA = -4,       /* CUDA runtime / driver error (text in yb_last_error) */
+    YB_E_NCCL = -5,       /* NCCL error or libnccl not loadable */
+    YB_E_CAP = -6,        /* output capacity too small */
+    YB_E_NOMEM = -7,
+    YB_E_UNSUPPORTED = -8 /* e.g. fp16 tensor-core mode on a non-sm_100 device */
+} yb_status;
+
+/* precision_mode for yb_finalize */
+#define YB_MODE_FP32 0  /* fp32 activations + fp32 CUDA-core implicit GEMM: fp32-grade parity with the reference */
+#define YB_MODE_FP16 1  /* fp16 activations/weights, fp32 accumulate in TMEM on tcgen05 tensor cores (perf path) */
+
+/* ---- lifetime -------------------------------------------------------------------------------- */
+
+/* Replaces YoloNet.__init__(img_dim, anchors, numClass) (darknet.py:167-195).  anchors: 9 (w,h)
+ * pairs in pixels, may be NULL for the reference default. */
+int yb_create(yb_ctx** out, int device, int num_classes, const float anchors[18]);
+void yb_destroy(yb_ctx* ctx);
+/* ctx may be NULL: returns the text of the last error raised by a call that had no ctx. */
+const char* yb_last_error(const yb_ctx* ctx);
+int yb_num_tensors(const yb_ctx* ctx);
+/* i-th state_dict key in registration order and its element count (438 keys for 80 classes). */
+const char* yb_tensor_key(const yb_ctx* ctx, int i, size_t* numel);
+
+/* ---- weights --------------------------------------------------------------------------------- */
+
+/* Replaces nn.Module.load_state_dict(...) entry by entry (darknet.py:240-243, train.py:26).  Keys
+ * are the reference's own ("feature.mlist.2.conv1.conv.weight", "pre_det3.mlist.6.bias", ...);
+ * values fp32, conv weights [Cout,Cin,k,k].  "*.num_batches_tracked" is accepted and ignored. */
+int yb_set_tensor(yb_ctx* ctx, const char* key, const float* data, size_t n, int on_host);
+int yb_get_tensor(const yb_ctx* ctx, const char* key, float* host_out, size_t n);
+
+/* Replaces WeightManager.loadWeight (darknet.py:249-303): `host` is the float stream that follows
+ * the 5-int32 header of a darknet .weights file; per BN conv: bn.bias, bn.weight, running_mean,
+ * running_var, conv.weight; per plain conv: bias, weight; modules in cfg order.  backbone_only=1
+ * is Darknet.loadWeight (darknet.py:102-104, darknet53.conv.74).  *consumed <- floats used. */
+int yb_load_darknet_blob(yb_ctx* ctx, const float* host, size_t nfloats, int backbone_only, size_t* consumed);
+/* Inverse of the above (the reference leaves saveWeight(format='darknet') unimplemented,
+ * darknet.py:237-238).  Pass host_out=NULL to query the float count. */
+int yb_save_darknet_blob(const yb_ctx* ctx, float* host_out, size_t capacity, int backbone_only, size_t* written);
+
+/* Folds BN (eval, eps 1e-5) into per-channel fp32 scale/bias, packs the weights for the chosen
+ * mode and uploads them.  Must be called after the weights change and before forward.  Synchronous. */
+int yb_finalize(yb_ctx* ctx, int precision_mode);
+
+/* ---- the hot path ---------------------------------------------------------------------------- */
+
+/* Replaces YoloNet.forward(x, target=None) + torch.cat((det1,det2,det3),1) (darknet.py:198-231,
+ * test.py:35-36).  x_nchw: dev [B,3,H,W] fp32.  det_cat: dev [B,N,5+C] fp32; det1/det2/det3 are
+ * the row ranges [0,n1), [n1,n1+n2), [n1+n2,N) of it. */
+int yb_forward(yb_ctx* ctx, const float* x_nchw, int B, int H, int W, float* det_cat, void* stream);
+
+/* Same convolution stack, but returns the three raw head maps (what pre_detN.mlist[6] outputs,
+ * darknet.py:118) as dev NCHW fp32 [B,3*(5+C),H/32,W/32], [.., H/16, W/16], [.., H/8, W/8].
+ * Parity / debugging aid for the conv kernels. */
+int yb_forward_logits(yb_ctx* ctx, const float* x_nchw, int B, int H, int W,
+                      float* logits32, float* logits16, float* logits8, void* stream);
+
+/* Replaces Darknet.forward (darknet.py:83-88): backbone only.  feat_nchw: dev [B,1024,H/32,W/32] fp32. */
+int yb_backbone(yb_ctx* ctx, const float* x_nchw, int B, int H, int W, float* feat_nchw, void* stream);
+
+/* Replaces the three YoloLayer.forward(x, img_dim, None) calls (yololayer.py:31-59,97-105) on raw
+ * head maps given in the reference layout (dev NCHW fp32), writing the concatenated det tensor. */
+int yb_decode(yb_ctx* ctx, const float* logits32, const float* logits16, const float* logits8,
+              int B, int H, int W, float* det_cat, void* stream);
+
+/* Replaces utils.postprocessing(detections, num_classes, obj_conf_thr, nms_thr, is_eval, use_nms)
+ * (utils.py:226-258 incl. get_nms_detections :148-202, iou_vectorized :98-119, get_raw_detections
+ * :204-224, boundingbox.bbox_cxcywh_to_x1y1x2y2 :25-29).  det_cat: dev [B,N,5+C] (not modified).
+ * Outputs (dev): rows7 [B,cap,7] = x1,y1,x2,y2,obj,score,cls, class-ascending / score-descending
+ * per image (candidate order when use_nms=0); counts [B] = rows produced per image (if > cap the
+ * image was truncated to cap rows: caller should retry with a larger cap); src_index [B,cap] =
+ * flat box index of each row (may be NULL); cand_counts [B] = boxes (box,class pairs when is_eval)
+ * that passed the threshold (may be NULL; all zero <=> the reference returns []).
+ * Tie-break is fixed: score descending, then candidate order ascending. */
+int yb_postprocess(yb_ctx* ctx, const float* det_cat, int B, int N, float obj_conf_thr, float nms_thr,
+                   int is_eval, int use_nms, float* rows7, int* counts, int* src_index, int* cand_counts,
+                   int cap, void* stream);
+
+/* forward + postprocess with no intermediate host round trip (what test.py:35-36 does per batch). */
+int yb_detect(yb_ctx* ctx, const float* x_nchw, int B, int H, int W, float obj_conf_thr, float nms_thr,
+              int is_eval, int use_nms, float* rows7, int* counts, int* src_index, int* cand_counts,
+              int cap, void* stream);
+
+/* ---- multi-GPU (absent in the reference; batch sharding) ------------------------- */
+
+/* 128-byte NCCL unique id, created on rank 0 and shipped to the other ranks by the host plumbing
+ * (torch.distributed / gloo object broadcast). */
+int yb_comm_unique_id(uint8_t id_out[128]);
+int yb_comm_init(yb_ctx* ctx, const uint8_t id[128], int rank, int world);
+/* ncclBroadcast of the finalized (packed) weight blob from `root`; every rank must have called
+ * yb_finalize with the same mode (so the buffers exist) -- non-root contents are overwritten. */
+int yb_bcast_weights(yb_ctx* ctx, int root, void* stream);
+/* ncclAllGather of fixed-capacity detection rows + counts: all_rows [world*B_local,cap,7],
+ * all_counts [world*B_local], rank-major. */
+int yb_allgather_dets(yb_ctx* ctx, const float* rows7, const int* counts, int B_local, int cap,
+                      float* all_rows, int* all_counts, void* stream);
+
+/* ---- introspection for bench.py / tests -------------------------------------------------------- */
+
+/* Number of kernels this library launched on behalf of ctx since creation. */
+long long yb_launch_count(const yb_ctx* ctx);
+/* Average device time (ms) of the convolution stack / decode / post-process sections of the last
+ * yb_forward/yb_detect call with profiling enabled; see yb_set_profiling. */
+int yb_set_profiling(yb_ctx* ctx, int enabled);
+int yb_get_section_ms(yb_ctx* ctx, float* conv_ms, float* decode_ms, float* post_ms);
+/* Per-layer timing of the last profiled call: ms[i] for the i-th convolution (75), returns count. */
+int yb_get_layer_ms(yb_ctx* ctx, float* ms, int capacity);
+/* Watchdog words of the tensor-core kernel (host-mapped, survive a device trap): [0]=1 if a
+ * pipeline wait timed out, [1]=block, [2]=role (0 producer,1 mma,2 epilogue), [3]=barrier, [4]=parity.
+ * Returns the number of words copied. */
+int yb_debug_words(const yb_ctx* ctx, int* out, int n);
+/* Standalone single-convolution entry used by the kernel unit tests: runs layer `layer_index`
+ * (0..74, cfg order) in the finalized mode on a dev NHWC tensor of the mode's element type
+ * (fp32 or fp16), in [B,H,W,Cin] -> out [B,Ho,Wo,Cout(+pad)], with optional residual (same shape as out). */
+int yb_run_layer(yb_ctx* ctx, int layer_index, const void* in_nhwc, int B, int H, int W,
+                 const void* residual_nhwc, void* out_nhwc, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* YOLO_B200_H_ */

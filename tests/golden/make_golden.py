@@ -141,6 +141,9 @@ def make_net():
     with torch.no_grad():
         dets = net(x, None)
     out["img_hw"] = np.array([64, 96])
+    ref_sd = net.state_dict()
+    out["state_dict_keys"] = np.array(list(ref_sd.keys()))
+    out["state_dict_shapes"] = np.array([",".join(str(int(d)) for d in v.shape) for v in ref_sd.values()])
     out["seed"] = np.array(1234)
     out["img_seed"] = np.array(3)
     for i, d in enumerate(dets):

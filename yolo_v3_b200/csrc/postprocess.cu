@@ -1,0 +1,394 @@
+// K3-K5: the post-process -- utils.postprocessing (reference utils.py:226-258) on the GPU.
+//
+//   pp_score    box convert cx,cy,w,h -> x1,y1,x2,y2 (boundingbox.py:25-29), score_c = cls_c*obj
+//               (utils.py:233), per-row max / threshold (utils.py:242-246) or per-(row,class)
+//               threshold in eval mode (utils.py:236-238).  One warp per 85-float row, coalesced.
+//   pp_scan     per-image exclusive scan -> candidate slots in the reference's nonzero() order.
+//   pp_scatter  ordered compaction of the candidates + 64-bit sort keys.
+//   pp_sort     per-image bitonic sort by (class asc, score desc, candidate order asc)
+//               (utils.py:161 unique() ascending, :171 sort(descending) + the fixed tie-break),
+//               gather of the boxes in sorted order, per-class segment table.
+//   pp_nms      greedy suppression per (image, class) segment (utils.py:175-193) in 64-wide chunks:
+//               bit-mask inside the chunk, serial resolve by one thread, parallel suppression of the
+//               tail.  IOU as iou_vectorized (utils.py:98-119): every fp32 op rounded separately
+//               (__f*_rn intrinsics, no FMA contraction), IEEE divide, strict '>' and the NaN
+//               self-IOU rule (a zero-area box is never kept and never suppresses).
+//   pp_emit     ordered compaction of the survivors into rows7 / src_index / counts.
+//
+// HBM-bound part is pp_score (reads the whole [B,N,5+C] tensor once: 7.73 MB / image at 608);
+// everything after touches 32 B per candidate.
+#include "yb_internal.h"
+
+namespace yb {
+namespace {
+
+constexpr int kSlotBits = 22;     // candidates per image < 4M
+constexpr int kClsShift = 54;     // classes < 1024
+constexpr unsigned long long kSlotMask = (1ull << kSlotBits) - 1;
+constexpr int kSortSmemKeys = 16384;   // 128 KB of shared memory
+constexpr int kNmsSmemBoxes = 4096;    // 64 KB + flags
+
+__device__ __forceinline__ float iou_rn(const float4 a, const float4 b) {
+    const float ltx = fmaxf(a.x, b.x), lty = fmaxf(a.y, b.y);
+    const float rbx = fminf(a.z, b.z), rby = fminf(a.w, b.w);
+    const float iw = fmaxf(__fsub_rn(rbx, ltx), 0.f), ih = fmaxf(__fsub_rn(rby, lty), 0.f);
+    const float inter = __fmul_rn(iw, ih);
+    const float area_a = __fmul_rn(__fsub_rn(a.z, a.x), __fsub_rn(a.w, a.y));
+    const float area_b = __fmul_rn(__fsub_rn(b.z, b.x), __fsub_rn(b.w, b.y));
+    const float uni = __fsub_rn(__fadd_rn(area_b, area_a), inter);
+    return __fdiv_rn(inter, uni);
+}
+
+__device__ __forceinline__ unsigned ord_desc(float s) {
+    unsigned u = __float_as_uint(s);
+    u = (u & 0x80000000u) ? ~u : (u | 0x80000000u);   // ascending total order
+    return ~u;                                        // descending
+}
+
+__device__ __forceinline__ unsigned long long make_key(int cls, float score, int slot) {
+    return ((unsigned long long)cls << kClsShift) | ((unsigned long long)ord_desc(score) << kSlotBits) | (unsigned)slot;
+}
+
+// ---- K3a ---------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) pp_score_kernel(const float* __restrict__ det, long rows, int N, int C,
+                                                       float thr, int is_eval, int* __restrict__ rowcount,
+                                                       float* __restrict__ rowcand) {
+    const int lane = threadIdx.x & 31;
+    const long row = (long)blockIdx.x * 8 + (threadIdx.x >> 5);
+    if (row >= rows) return;
+    const int A = 5 + C;
+    const float* r = det + row * A;
+    const float v0 = lane < A ? __ldg(r + lane) : 0.f;
+    const float obj = __shfl_sync(0xffffffffu, v0, 4);
+    float best = -INFINITY;
+    int bidx = 0x7fffffff;
+    int cnt = 0;
+    for (int e0 = 0; e0 < A; e0 += 32) {
+        const int e = e0 + lane;
+        const float v = e0 == 0 ? v0 : (e < A ? __ldg(r + e) : 0.f);
+        const bool isc = e >= 5 && e < A;
+        const float s = __fmul_rn(v, obj);
+        if (is_eval) {
+            cnt += __popc(__ballot_sync(0xffffffffu, isc && s > thr));
+        } else if (isc && s > best) {
+            best = s;
+            bidx = e - 5;
+        }
+    }
+    if (is_eval) {
+        if (lane == 0) rowcount[row] = cnt;
+        return;
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        const float ob = __shfl_xor_sync(0xffffffffu, best, o);
+        const int oi = __shfl_xor_sync(0xffffffffu, bidx, o);
+        if (ob > best || (ob == best && oi < bidx)) { best = ob; bidx = oi; }
+    }
+    const bool pass = best > thr;
+    if (lane == 0) rowcount[row] = pass ? 1 : 0;
+    if (pass) {
+        const float cx = __shfl_sync(0xffffffffu, v0, 0), cy = __shfl_sync(0xffffffffu, v0, 1);
+        const float w = __shfl_sync(0xffffffffu, v0, 2), h = __shfl_sync(0xffffffffu, v0, 3);
+        const float hw = __fdiv_rn(w, 2.f), hh = __fdiv_rn(h, 2.f);
+        float o = 0.f;
+        switch (lane) {
+            case 0: o = __fsub_rn(cx, hw); break;
+            case 1: o = __fsub_rn(cy, hh); break;
+            case 2: o = __fadd_rn(cx, hw); break;
+            case 3: o = __fadd_rn(cy, hh); break;
+            case 4: o = obj; break;
+            case 5: o = best; break;
+            case 6: o = (float)bidx; break;
+            case 7: o = __int_as_float((int)(row % N)); break;
+            default: break;
+        }
+        if (lane < 8) rowcand[row * 8 + lane] = o;
+    }
+}
+
+// ---- K3b ---------------------------------------------------------------------------------------
+__device__ __forceinline__ int block_incl_scan(int v, int* warp_tot, int& block_total) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
+    int x = v;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const int y = __shfl_up_sync(0xffffffffu, x, o);
+        if (lane >= o) x += y;
+    }
+    if (lane == 31) warp_tot[warp] = x;
+    __syncthreads();
+    if (warp == 0) {
+        int t = lane < nw ? warp_tot[lane] : 0;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const int y = __shfl_up_sync(0xffffffffu, t, o);
+            if (lane >= o) t += y;
+        }
+        warp_tot[lane] = t;   // inclusive totals
+    }
+    __syncthreads();
+    const int before = warp > 0 ? warp_tot[warp - 1] : 0;
+    block_total = warp_tot[nw - 1];
+    __syncthreads();
+    return x + before;
+}
+
+__global__ void __launch_bounds__(1024) pp_scan_kernel(const int* __restrict__ rowcount, int N, int* __restrict__ rowoff,
+                                                       int* __restrict__ cand_total) {
+    __shared__ int wt[32];
+    const int b = blockIdx.x;
+    int running = 0;
+    for (int base = 0; base < N; base += blockDim.x) {
+        const int i = base + threadIdx.x;
+        const int v = i < N ? rowcount[(long)b * N + i] : 0;
+        int tot;
+        const int incl = block_incl_scan(v, wt, tot);
+        if (i < N) rowoff[(long)b * N + i] = running + incl - v;
+        running += tot;
+    }
+    if (threadIdx.x == 0) cand_total[b] = running;
+}
+
+// ---- K3c ---------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) pp_scatter_kernel(const float* __restrict__ det, int N, int C, float thr, int is_eval,
+                                                         long rows, const int* __restrict__ rowcount,
+                                                         const int* __restrict__ rowoff, const float* __restrict__ rowcand,
+                                                         float* __restrict__ cand, unsigned long long* __restrict__ keys,
+                                                         int cand_cap, int sort_cap) {
+    if (!is_eval) {
+        const long row = (long)blockIdx.x * blockDim.x + threadIdx.x;
+        if (row >= rows || rowcount[row] == 0) return;
+        const int b = (int)(row / N);
+        const int off = rowoff[row];
+        if (off >= cand_cap) return;
+        const float4 lo = *reinterpret_cast<const float4*>(rowcand + row * 8);
+        const float4 hi = *reinterpret_cast<const float4*>(rowcand + row * 8 + 4);
+        float* o = cand + ((long)b * cand_cap + off) * 8;
+        *reinterpret_cast<float4*>(o) = lo;
+        *reinterpret_cast<float4*>(o + 4) = hi;
+        keys[(long)b * sort_cap + off] = make_key((int)hi.z, hi.y, off);
+        return;
+    }
+    const int lane = threadIdx.x & 31;
+    const long row = (long)blockIdx.x * 8 + (threadIdx.x >> 5);
+    if (row >= rows || rowcount[row] == 0) return;
+    const int b = (int)(row / N), n = (int)(row % N);
+    const int A = 5 + C;
+    const float* r = det + row * A;
+    const float v0 = lane < A ? __ldg(r + lane) : 0.f;
+    const float obj = __shfl_sync(0xffffffffu, v0, 4);
+    const float cx = __shfl_sync(0xffffffffu, v0, 0), cy = __shfl_sync(0xffffffffu, v0, 1);
+    const float w = __shfl_sync(0xffffffffu, v0, 2), h = __shfl_sync(0xffffffffu, v0, 3);
+    const float hw = __fdiv_rn(w, 2.f), hh = __fdiv_rn(h, 2.f);
+    int running = rowoff[row];
+    for (int e0 = 0; e0 < A; e0 += 32) {
+        const int e = e0 + lane;
+        const float v = e0 == 0 ? v0 : (e < A ? __ldg(r + e) : 0.f);
+        const float s = __fmul_rn(v, obj);
+        const bool pass = e >= 5 && e < A && s > thr;
+        const unsigned bal = __ballot_sync(0xffffffffu, pass);
+        if (pass) {
+            const int off = running + __popc(bal & ((1u << lane) - 1));
+            if (off < cand_cap) {
+                float* o = cand + ((long)b * cand_cap + off) * 8;
+                *reinterpret_cast<float4*>(o) = make_float4(__fsub_rn(cx, hw), __fsub_rn(cy, hh), __fadd_rn(cx, hw), __fadd_rn(cy, hh));
+                *reinterpret_cast<float4*>(o + 4) = make_float4(obj, s, (float)(e - 5), __int_as_float(n));
+                keys[(long)b * sort_cap + off] = make_key(e - 5, s, off);
+            }
+        }
+        running += __popc(bal);
+    }
+}
+
+// ---- K4 ----------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(1024) pp_sort_kernel(unsigned long long* __restrict__ keys_g, const float* __restrict__ cand,
+                                                       const int* __restrict__ cand_total, int cand_cap, int sort_cap, int C,
+                                                       float4* __restrict__ sbox, int* __restrict__ seg) {
+    extern __shared__ unsigned long long skeys[];
+    const int b = blockIdx.x, tid = threadIdx.x, nt = blockDim.x;
+    int* sg = seg + (long)b * C * 2;
+    for (int i = tid; i < 2 * C; i += nt) sg[i] = 0;
+    const int n = min(cand_total[b], cand_cap);
+    if (n == 0) return;
+    int P = 2;
+    while (P < n) P <<= 1;
+    unsigned long long* kg = keys_g + (long)b * sort_cap;
+    const bool in_smem = P <= kSortSmemKeys;
+    unsigned long long* k = in_smem ? skeys : kg;
+    for (int i = tid; i < P; i += nt) {
+        const unsigned long long v = i < n ? kg[i] : ~0ull;
+        if (in_smem) skeys[i] = v; else if (i >= n) kg[i] = v;
+    }
+    __syncthreads();
+    for (int kk = 2; kk <= P; kk <<= 1) {
+        for (int j = kk >> 1; j > 0; j >>= 1) {
+            for (int i = tid; i < P; i += nt) {
+                const int ixj = i ^ j;
+                if (ixj > i) {
+                    const unsigned long long a = k[i], c = k[ixj];
+                    const bool asc = (i & kk) == 0;
+                    if ((a > c) == asc) { k[i] = c; k[ixj] = a; }
+                }
+            }
+            __syncthreads();
+        }
+    }
+    const float* cb = cand + (long)b * cand_cap * 8;
+    for (int pos = tid; pos < n; pos += nt) {
+        const unsigned long long key = k[pos];
+        if (in_smem) kg[pos] = key;
+        const int slot = (int)(key & kSlotMask);
+        sbox[(long)b * cand_cap + pos] = *reinterpret_cast<const float4*>(cb + (long)slot * 8);
+        const int cls = (int)(key >> kClsShift);
+        const int prev = pos > 0 ? (int)(k[pos - 1] >> kClsShift) : -1;
+        const int next = pos + 1 < n ? (int)(k[pos + 1] >> kClsShift) : -1;
+        if (cls != prev) sg[cls * 2] = pos;
+        if (cls != next) sg[cls * 2 + 1] = pos + 1;
+    }
+}
+
+// ---- K5a ---------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) pp_nms_kernel(const float4* __restrict__ sbox, const int* __restrict__ seg,
+                                                     unsigned char* __restrict__ keep, int cand_cap, int C, float thr) {
+    extern __shared__ __align__(16) unsigned char nms_smem[];
+    __shared__ unsigned long long mparts[4][64];
+    __shared__ unsigned long long kept_s;
+    const int c = blockIdx.x, b = blockIdx.y, tid = threadIdx.x;
+    const int s0 = seg[((long)b * C + c) * 2], s1 = seg[((long)b * C + c) * 2 + 1];
+    const int m = s1 - s0;
+    if (m <= 0) return;
+    const float4* gb = sbox + (long)b * cand_cap + s0;
+    unsigned char* gk = keep + (long)b * cand_cap + s0;
+    const bool in_smem = m <= kNmsSmemBoxes;
+    float4* sb = reinterpret_cast<float4*>(nms_smem);
+    unsigned char* sa = nms_smem + (size_t)kNmsSmemBoxes * sizeof(float4);
+    if (in_smem)
+        for (int i = tid; i < m; i += blockDim.x) sb[i] = gb[i];
+    const float4* bx = in_smem ? sb : gb;
+    unsigned char* al = in_smem ? sa : gk;
+    if (in_smem) __syncthreads();
+    for (int i = tid; i < m; i += blockDim.x) {
+        const float4 v = bx[i];
+        al[i] = iou_rn(v, v) > thr ? 1 : 0;          // diagonal (utils.py:182); NaN -> 0
+    }
+    __syncthreads();
+    for (int s = 0; s < m; s += 64) {
+        const int cn = min(64, m - s);
+        {
+            const int i = tid & 63, part = tid >> 6;
+            unsigned long long bits = 0;
+            if (i < cn && al[s + i]) {
+                const float4 bi = bx[s + i];
+                const int j0 = max(part * 16, i + 1), j1 = min(part * 16 + 16, cn);
+                for (int j = j0; j < j1; ++j)
+                    if (iou_rn(bi, bx[s + j]) > thr) bits |= 1ull << j;
+            }
+            mparts[part][i] = bits;
+        }
+        __syncthreads();
+        if (tid == 0) {
+            unsigned long long removed = 0, kept = 0;
+            for (int i = 0; i < cn; ++i) {
+                if (al[s + i] && !((removed >> i) & 1ull)) {
+                    kept |= 1ull << i;
+                    removed |= mparts[0][i] | mparts[1][i] | mparts[2][i] | mparts[3][i];
+                }
+            }
+            kept_s = kept;
+        }
+        __syncthreads();
+        const unsigned long long kept = kept_s;
+        if (tid < cn) al[s + tid] = (unsigned char)((kept >> tid) & 1ull);
+        if (kept) {
+            for (int j = s + 64 + tid; j < m; j += blockDim.x) {
+                if (!al[j]) continue;
+                const float4 bj = bx[j];
+                unsigned long long kk = kept;
+                while (kk) {
+                    const int i = __ffsll((long long)kk) - 1;
+                    kk &= kk - 1;
+                    if (iou_rn(bx[s + i], bj) > thr) { al[j] = 0; break; }
+                }
+            }
+        }
+        __syncthreads();
+    }
+    if (in_smem)
+        for (int i = tid; i < m; i += blockDim.x) gk[i] = sa[i];
+}
+
+// ---- K5b ---------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(1024) pp_emit_kernel(const unsigned long long* __restrict__ keys, const float* __restrict__ cand,
+                                                       const unsigned char* __restrict__ keep, const int* __restrict__ cand_total,
+                                                       int cand_cap, int sort_cap, int use_nms, int cap,
+                                                       float* __restrict__ rows7, int* __restrict__ counts,
+                                                       int* __restrict__ src_index, int* __restrict__ cand_counts) {
+    __shared__ int wt[32];
+    const int b = blockIdx.x;
+    const int total = cand_total[b];
+    const int n = min(total, cand_cap);
+    const float* cb = cand + (long)b * cand_cap * 8;
+    int running = 0;
+    for (int base = 0; base < n; base += blockDim.x) {
+        const int pos = base + threadIdx.x;
+        int v = 0, slot = 0;
+        if (pos < n) {
+            if (use_nms) {
+                v = keep[(long)b * cand_cap + pos];
+                slot = (int)(keys[(long)b * sort_cap + pos] & kSlotMask);
+            } else {
+                v = 1;
+                slot = pos;
+            }
+        }
+        int tot;
+        const int incl = block_incl_scan(v, wt, tot);
+        const int o = running + incl - v;
+        if (v && o < cap) {
+            const float* src = cb + (long)slot * 8;
+            float* dst = rows7 + ((long)b * cap + o) * 7;
+#pragma unroll
+            for (int i = 0; i < 7; ++i) dst[i] = src[i];
+            if (src_index) src_index[(long)b * cap + o] = __float_as_int(src[7]);
+        }
+        running += tot;
+    }
+    if (threadIdx.x == 0) {
+        counts[b] = running;
+        if (cand_counts) cand_counts[b] = total;
+    }
+}
+
+}  // namespace
+
+cudaError_t launch_postprocess(const PostArgs& a, PostBuffers& buf, long long* launches, cudaStream_t s) {
+    const long rows = (long)a.B * a.N;
+    const int cand_cap = buf.cand_cap, sort_cap = buf.sort_cap;
+    static bool attrs_set = false;
+    if (!attrs_set) {
+        cudaFuncSetAttribute(pp_sort_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSortSmemKeys * 8);
+        cudaFuncSetAttribute(pp_nms_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kNmsSmemBoxes * 17);
+        attrs_set = true;
+    }
+    pp_score_kernel<<<(unsigned)((rows + 7) / 8), 256, 0, s>>>(a.det, rows, a.N, a.C, a.conf_thr, a.is_eval, buf.rowcount, buf.rowcand);
+    pp_scan_kernel<<<a.B, 1024, 0, s>>>(buf.rowcount, a.N, buf.rowoff, buf.cand_total);
+    if (a.is_eval)
+        pp_scatter_kernel<<<(unsigned)((rows + 7) / 8), 256, 0, s>>>(a.det, a.N, a.C, a.conf_thr, 1, rows, buf.rowcount, buf.rowoff,
+                                                                    buf.rowcand, buf.cand, buf.keys, cand_cap, sort_cap);
+    else
+        pp_scatter_kernel<<<(unsigned)((rows + 255) / 256), 256, 0, s>>>(a.det, a.N, a.C, a.conf_thr, 0, rows, buf.rowcount, buf.rowoff,
+                                                                        buf.rowcand, buf.cand, buf.keys, cand_cap, sort_cap);
+    *launches += 3;
+    if (a.use_nms) {
+        pp_sort_kernel<<<a.B, 1024, kSortSmemKeys * 8, s>>>(buf.keys, buf.cand, buf.cand_total, cand_cap, sort_cap, a.C, buf.sbox, buf.seg);
+        pp_nms_kernel<<<dim3(a.C, a.B), 256, kNmsSmemBoxes * 17, s>>>(buf.sbox, buf.seg, buf.keep, cand_cap, a.C, a.nms_thr);
+        *launches += 2;
+    }
+    pp_emit_kernel<<<a.B, 1024, 0, s>>>(buf.keys, buf.cand, buf.keep, buf.cand_total, cand_cap, sort_cap, a.use_nms, a.cap,
+                                        a.rows7, a.counts, a.src_index, a.cand_counts);
+    *launches += 1;
+    return cudaGetLastError();
+}
+
+}  // namespace yb

@@ -1,0 +1,118 @@
+// Internal declarations shared by the translation units of libyolo_b200.so.
+// Public C ABI: include/yolo_b200.h.
+#pragma once
+
+#include <cuda.h>
+#include <cuda_fp16.h>
+#include <cuda_runtime.h>
+
+#include <cstdint>
+#include <cstdio>
+#include <map>
+#include <string>
+#include <vector>
+
+#include "../../include/yolo_b200.h"
+
+namespace yb {
+
+constexpr float kBnEps = 1e-5f;   // nn.BatchNorm2d default (reference darknet.py:39)
+constexpr float kLeaky = 0.1f;    // reference darknet.py:41
+
+// One convolution of the network, in darknet-cfg order (reference darknet.py:72-79,107-118,153-157).
+struct Layer {
+    std::string key;      // state_dict prefix
+    int cin = 0, cout = 0, ks = 1, stride = 1;
+    bool bn = true;
+    int cout_pad = 0;     // cout rounded up to 16 (heads: 255 -> 256)
+    // host master copies (fp32, reference layouts)
+    std::vector<float> w;                     // [cout][cin][ks][ks]
+    std::vector<float> g, b, mean, var;       // bn.weight, bn.bias, running_mean, running_var  (bn)
+    std::vector<float> bias;                  // conv bias (plain head conv)
+    // device, filled by finalize()
+    float* d_scale = nullptr;                 // [cout_pad]  gamma/sqrt(var+eps)  (1 for heads)
+    float* d_bias = nullptr;                  // [cout_pad]  beta-mean*scale      (conv bias for heads)
+    float* d_w32 = nullptr;                   // [ks*ks][cin][cout_pad] fp32      (YB_MODE_FP32)
+    __half* d_w16 = nullptr;                  // [cout_pad][ks*ks*cin] fp16, K-major (YB_MODE_FP16)
+};
+
+// NHWC activation view: `p` already includes the channel offset of a concat slice.
+struct TView {
+    void* p = nullptr;
+    int B = 0, H = 0, W = 0, C = 0;
+    long ld = 0;          // elements between consecutive pixels
+};
+
+// Arguments common to both convolution kernels.
+struct ConvArgs {
+    const void* in; long in_ld;
+    void* out; long out_ld;
+    const void* res; long res_ld;     // nullable residual, added after the activation
+    const float* scale; const float* bias;
+    int B, H, W, Cin;
+    int Ho, Wo, Cout;                 // Cout = channels actually stored (cout_pad for fp32 head maps)
+    int ks, stride, pad;
+    int leaky;                        // LeakyReLU(0.1) after scale/bias
+    int upsample;                     // nearest x2: every output pixel is written to a 2x2 block of a [B,2Ho,2Wo] tensor
+    int out_f32;                      // output element is fp32 regardless of the activation type (head maps)
+};
+
+// conv_simt.cu
+template <typename T>
+cudaError_t launch_conv_simt(const ConvArgs& a, const float* w32, int cout_pad, cudaStream_t s);
+template <typename T>
+cudaError_t launch_stem(const float* x_nchw, T* out_nhwc, const float* w32, const float* scale, const float* bias,
+                        int B, int H, int W, cudaStream_t s);
+template <typename T>
+cudaError_t launch_nhwc_to_nchw_f32(const T* in, long in_ld, int C, int B, int HW, float* out, cudaStream_t s);
+cudaError_t launch_f32_to_f16(const float* in, __half* out, size_t n, cudaStream_t s);
+
+// conv_tc.cu  (tcgen05 + TMA implicit GEMM)
+struct TcPlan {
+    CUtensorMap tmA, tmB;
+    int swz = 128;        // 128: 64-channel k-blocks, 64: 32-channel k-blocks (Cin == 32)
+    int BN = 0, n_tiles = 0, m_tiles = 0, stages = 0, tmem_cols = 0;
+    int num_kblocks = 0, cin_blocks = 0;
+    int grid = 0;
+    size_t smem = 0;
+    long M = 0;
+};
+// Builds TMA descriptors + tile configuration for one layer invocation. Returns "" or an error text.
+std::string tc_make_plan(TcPlan& p, const ConvArgs& a, const __half* w16, int cout_pad, int K, int num_sms);
+cudaError_t tc_launch(const TcPlan& p, const ConvArgs& a, int* dbg, cudaStream_t s);
+bool tc_supported(const ConvArgs& a);
+
+// decode.cu
+struct DecodeScale {
+    const float* logits;  // NHWC [B,h,w,ld] (internal) or NCHW [B,3*(5+C),h,w] (API)
+    long ld;              // NHWC pixel pitch in floats (ignored for NCHW)
+    int h, w;
+    int row_off;          // first row of this scale in det_cat
+    float stride;         // pixels per cell
+    float aw[3], ah[3];   // anchors / stride, fp32 (reference yololayer.py:37-38)
+};
+cudaError_t launch_decode(const DecodeScale sc[3], int nchw, int B, int attrs, int n_total, float* det, cudaStream_t s);
+
+// postprocess.cu
+struct PostBuffers {
+    int B = 0, N = 0, cand_cap = 0, sort_cap = 0, C = 0;
+    int* rowcount = nullptr;    // [B][N]
+    int* rowoff = nullptr;      // [B][N]
+    int* cand_total = nullptr;  // [B]
+    float* rowcand = nullptr;   // [B][N][8]   (non-eval: candidate of the row, written only when it passes)
+    float* cand = nullptr;      // [B][cand_cap][8]  x1,y1,x2,y2,obj,score,cls,boxidx(bits)
+    unsigned long long* keys = nullptr;  // [B][sort_cap]
+    float4* sbox = nullptr;     // [B][cand_cap] boxes in sorted order
+    unsigned char* keep = nullptr;  // [B][cand_cap]
+    int* seg = nullptr;         // [B][C][2] start,end
+    size_t bytes = 0;
+};
+struct PostArgs {
+    const float* det; int B, N, C;
+    float conf_thr, nms_thr;
+    int is_eval, use_nms;
+    float* rows7; int* counts; int* src_index; int* cand_counts; int cap;
+};
+cudaError_t launch_postprocess(const PostArgs& a, PostBuffers& buf, long long* launches, cudaStream_t s);
+
+}  // namespace yb

@@ -24,37 +24,7 @@ from typing import Dict, List
 import numpy as np
 import torch
 
-BLOCKS = [1, 2, 8, 8, 4]
-
-
-def layer_specs(num_classes: int = 80) -> List[dict]:
-    """The 75 convolutions in darknet-cfg order: key, cin, cout, ks, stride, bn, res2 (second conv
-    of a residual block)."""
-    t: List[dict] = []
-
-    def add(key, cin, cout, ks, s=1, bn=True, res2=False):
-        t.append(dict(key=key, cin=cin, cout=cout, ks=ks, stride=s, bn=bn, res2=res2))
-
-    add("feature.mlist.0", 3, 32, 3)
-    idx, ch = 1, 32
-    for nb in BLOCKS:
-        add(f"feature.mlist.{idx}", ch, 2 * ch, 3, 2)
-        idx, ch = idx + 1, 2 * ch
-        for _ in range(nb):
-            add(f"feature.mlist.{idx}.conv1", ch, ch // 2, 1)
-            add(f"feature.mlist.{idx}.conv2", ch // 2, ch, 3, res2=True)
-            idx += 1
-    for name, nin, nout in (("pre_det1", 1024, 512), ("up1", 512, 256), ("pre_det2", 768, 256),
-                            ("up2", 256, 128), ("pre_det3", 384, 128)):
-        if name.startswith("up"):
-            add(f"{name}.conv", nin, nout, 1)
-            continue
-        for i in range(3):
-            add(f"{name}.mlist.{2 * i}", nin, nout, 1)
-            add(f"{name}.mlist.{2 * i + 1}", nout, 2 * nout, 3)
-            nin = 2 * nout
-        add(f"{name}.mlist.6", nin, (num_classes + 5) * 3, 1, bn=False)
-    return t
+from .topology import BLOCKS, layer_specs
 
 
 def make_state_dict(seed: int = 1234, num_classes: int = 80, recipe: str = "calibrated",
