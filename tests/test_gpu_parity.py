@@ -5,8 +5,10 @@ Tolerances (stated where used):
   * post-process: bit-exact rows and identical survivor indices (integer/index work);
   * decode given identical fp32 logits: allclose(atol=1e-4, rtol=1e-6)  (1 fp32 ulp at
     608 px is 6.1e-5; exp(tw)*anchor reaches thousands of px, hence the rtol term);
-  * fp32 convolution stack: head logits within 1e-4 * max|logit|; boxes/scores atol 1e-4 + rtol 1e-4
-    end to end (75 layers of fp32 re-association against oneDNN);
+  * fp32 convolution stack: head logits within 1e-4 * max|logit| (75 layers of fp32 re-association
+    against oneDNN; measured 2e-5 relative).  End to end that gives xy / conf / cls within 1e-4 absolute,
+    and w/h -- exp(t)*anchor, so the absolute logit error becomes a RELATIVE box error -- within 1e-3
+    relative (measured 1.7e-4): the checks use atol 1e-4 + rtol 1e-3;
   * fp16 tensor-core stack: every layer against a torch conv on the same fp16-rounded operands
     (atol 3e-3*max|y| + rtol 2e-3 = fp16 output rounding); end-to-end deviation vs the fp32 oracle is
     REPORTED and only sanity-bounded, as BASELINE/SURVEY state (it cannot meet 1e-4).
@@ -269,7 +271,7 @@ def test_fp32_net_vs_reference_golden(golden, sd_analytic):
         np.testing.assert_allclose(l.cpu().numpy(), ref, rtol=0, atol=1e-4 * np.abs(ref).max())
     dets = net(x.cuda(), None)
     for i, d in enumerate(dets):
-        np.testing.assert_allclose(d.cpu().numpy(), g[f"det{i}"], rtol=1e-4, atol=1e-4)
+        np.testing.assert_allclose(d.cpu().numpy(), g[f"det{i}"], rtol=1e-3, atol=1e-4)
     bb = net.backbone(x.cuda())
     np.testing.assert_allclose(bb.cpu().numpy(), g["backbone"], rtol=0, atol=1e-4 * np.abs(g["backbone"]).max())
 
@@ -283,7 +285,9 @@ def test_fp32_net_416_plumbing_config(oracle, sd_calibrated):
     assert d1.shape == (1, 507, 85) and d2.shape == (1, 2028, 85) and d3.shape == (1, 8112, 85)   # yolo_detect.ipynb:643
     det = torch.cat((d1, d2, d3), 1)
     ref = torch.cat(oracle.forward(sd_calibrated, x), 1)
-    np.testing.assert_allclose(det.cpu().numpy(), ref.numpy(), rtol=1e-4, atol=1e-4)
+    np.testing.assert_allclose(det.cpu().numpy(), ref.numpy(), rtol=1e-3, atol=1e-4)
+    np.testing.assert_allclose(det[..., :2].cpu().numpy(), ref[..., :2].numpy(), rtol=0, atol=1e-4 + 608 * 2e-7)
+    np.testing.assert_allclose(det[..., 4:].cpu().numpy(), ref[..., 4:].numpy(), rtol=0, atol=1e-4)
     # identical candidates -> identical survivors: run both post-processes on the SAME tensor
     res, idx = postprocessing(det, 80, 0.1, 0.4, return_index=True)
     ref_res, ref_idx = oracle.postprocessing_c(det.cpu(), 80, 0.1, 0.4)
@@ -299,7 +303,9 @@ def test_fp32_net_608_batch(oracle, sd_calibrated):
     det = torch.cat(net(x.cuda(), None), 1)
     assert det.shape == (2, 22743, 85)
     ref = torch.cat(oracle.forward(sd_calibrated, x), 1)
-    np.testing.assert_allclose(det.cpu().numpy(), ref.numpy(), rtol=1e-4, atol=1e-4)
+    np.testing.assert_allclose(det.cpu().numpy(), ref.numpy(), rtol=1e-3, atol=1e-4)
+    np.testing.assert_allclose(det[..., :2].cpu().numpy(), ref[..., :2].numpy(), rtol=0, atol=1e-4 + 608 * 2e-7)
+    np.testing.assert_allclose(det[..., 4:].cpu().numpy(), ref[..., 4:].numpy(), rtol=0, atol=1e-4)
 
 
 # ---------------------------------------------------------------------------------------------
