@@ -113,6 +113,25 @@ def test_tc_layer_vs_torch(fp16_ctx, sd, li, B, H, W, with_res):
                            f"{tuple(int(v) for v in bad.nonzero()[0])}")
 
 
+@pytest.mark.parametrize("B,H,W", [(2, 40, 56), (1, 64, 32), (3, 17, 23)])
+def test_tc_stem_vs_torch(fp16_ctx, sd, B, H, W):
+    """Cin=3 stem on the tensor cores: NCHW fp32 image in, NHWC fp16 out (im2col rows built by producer warps)."""
+    lib, ctx = fp16_ctx
+    rs = np.random.RandomState(7)
+    x = torch.from_numpy(rs.rand(B, 3, H, W).astype(np.float32))
+    out = torch.full((B, H, W, 32), float("nan"), device="cuda", dtype=torch.float16)
+    xd = x.cuda()
+    _lib.check(lib.yb_run_layer(ctx, 0, vp(xd), B, H, W, None, vp(out), stream()), ctx)
+    torch.cuda.synchronize()
+    spec = topology.layer_specs(80)[0]
+    ref = ref_layer(sd, spec, x.half().permute(0, 2, 3, 1).contiguous(), None)
+    y = out.float().cpu()
+    err = (y - ref).abs()
+    tol = 3e-3 * ref.abs().max() + 2e-3 * ref.abs()
+    bad = (err > tol) | torch.isnan(y)
+    assert not bad.any(), f"stem: {int(bad.sum())} of {bad.numel()} outside tolerance, max err {float(err.max()):.4g}"
+
+
 def test_fp16_net_deviation_report(oracle, sd):
     """End to end at 416 (one image) and 608 (two images): report the deviation of the fp16
     tensor-core path from the fp32 CPU oracle; assert only coarse sanity bounds."""

@@ -6,9 +6,11 @@ Tolerances (stated where used):
   * decode given identical fp32 logits: allclose(atol=1e-4, rtol=1e-6)  (1 fp32 ulp at
     608 px is 6.1e-5; exp(tw)*anchor reaches thousands of px, hence the rtol term);
   * fp32 convolution stack: head logits within 1e-4 * max|logit| (75 layers of fp32 re-association
-    against oneDNN; measured 2e-5 relative).  End to end that gives xy / conf / cls within 1e-4 absolute,
-    and w/h -- exp(t)*anchor, so the absolute logit error becomes a RELATIVE box error -- within 1e-3
-    relative (measured 1.7e-4): the checks use atol 1e-4 + rtol 1e-3;
+    against oneDNN; measured 2e-5 of max|logit|, i.e. ~1.7e-4 absolute).  The decode turns that logit
+    error d into: conf/cls 0.25*d (< 1e-4 absolute), xy 0.25*stride*d (<= 8*d: measured 5e-4 px, bound
+    2e-3 px), w/h a RELATIVE error d (measured 1.7e-4, bound 1e-3).  So end to end the checks are
+    conf/cls atol 1e-4, xy atol 2e-3 px, w/h rtol 1e-3 -- the fp32 noise floor of two different
+    75-layer fp32 convolution stacks, not a loosened kernel tolerance (decode alone holds 1e-4, above);
   * fp16 tensor-core stack: every layer against a torch conv on the same fp16-rounded operands
     (atol 3e-3*max|y| + rtol 2e-3 = fp16 output rounding); end-to-end deviation vs the fp32 oracle is
     REPORTED and only sanity-bounded, as BASELINE/SURVEY state (it cannot meet 1e-4).
@@ -286,7 +288,7 @@ def test_fp32_net_416_plumbing_config(oracle, sd_calibrated):
     det = torch.cat((d1, d2, d3), 1)
     ref = torch.cat(oracle.forward(sd_calibrated, x), 1)
     np.testing.assert_allclose(det.cpu().numpy(), ref.numpy(), rtol=1e-3, atol=1e-4)
-    np.testing.assert_allclose(det[..., :2].cpu().numpy(), ref[..., :2].numpy(), rtol=0, atol=1e-4 + 608 * 2e-7)
+    np.testing.assert_allclose(det[..., :2].cpu().numpy(), ref[..., :2].numpy(), rtol=0, atol=2e-3)
     np.testing.assert_allclose(det[..., 4:].cpu().numpy(), ref[..., 4:].numpy(), rtol=0, atol=1e-4)
     # identical candidates -> identical survivors: run both post-processes on the SAME tensor
     res, idx = postprocessing(det, 80, 0.1, 0.4, return_index=True)
@@ -304,7 +306,7 @@ def test_fp32_net_608_batch(oracle, sd_calibrated):
     assert det.shape == (2, 22743, 85)
     ref = torch.cat(oracle.forward(sd_calibrated, x), 1)
     np.testing.assert_allclose(det.cpu().numpy(), ref.numpy(), rtol=1e-3, atol=1e-4)
-    np.testing.assert_allclose(det[..., :2].cpu().numpy(), ref[..., :2].numpy(), rtol=0, atol=1e-4 + 608 * 2e-7)
+    np.testing.assert_allclose(det[..., :2].cpu().numpy(), ref[..., :2].numpy(), rtol=0, atol=2e-3)
     np.testing.assert_allclose(det[..., 4:].cpu().numpy(), ref[..., 4:].numpy(), rtol=0, atol=1e-4)
 
 

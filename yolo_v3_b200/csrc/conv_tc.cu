@@ -11,14 +11,20 @@
 //     straight into 128B-swizzled shared memory; weights [Cout][ky][kx][Cin] come through a tiled map;
 //   * one elected thread issues tcgen05.mma (kind::f16, M=128, N=BN<=256, K=16) with the fp32
 //     accumulator in TMEM; tcgen05.commit releases smem stages and publishes finished accumulators;
-//   * TMEM holds two accumulators, so the four epilogue warps drain tile i (tcgen05.ld -> fp32
-//     scale/bias (folded eval BN) -> LeakyReLU -> +residual -> fp16 -> 16-byte stores, optionally to
-//     the 2x2 nearest-upsampled positions of a concat slice) while the MMA warp works on tile i+1;
+//   * TMEM holds two accumulators, so the four epilogue warps drain tile i while the MMA warp works on
+//     tile i+1: tcgen05.ld -> fp32 scale/bias (folded eval BN) -> LeakyReLU -> +residual -> fp16,
+//     staged through a ring of 128B-swizzled shared-memory sub-tiles (128 rows x 128 bytes) that are
+//     written back with TMA stores (cp.async.bulk.tensor ... bulk_group: full-line coalesced writes,
+//     M tail clipped by the tensor map); the residual sub-tiles are prefetched into the same ring by
+//     a dedicated TMA load warp, so the in-place "x + f(x)" costs no exposed global-load latency.
+//     The two 1x1 "up" convs instead store each pixel directly to its 2x2 nearest-upsampled block of
+//     the concat slice;
 //   * persistent CTAs (one per SM), static round-robin over the (m-tile, n-tile) grid.
 //
 // Layers with Cin == 32 use 32-channel k-blocks with the 64B swizzle; everything else 64-channel
 // k-blocks with the 128B swizzle.  The Cin == 3 stem runs on CUDA cores (conv_simt.cu).
 #include <algorithm>
+#include <cstdlib>
 
 #include "yb_internal.h"
 
@@ -26,8 +32,9 @@ namespace yb {
 namespace {
 
 constexpr int kBM = 128;
-constexpr int kMaxStages = 8;
-constexpr int kThreads = 256;            // warp 0 TMA, 1 MMA, 2 TMEM alloc, 3 idle, 4-7 epilogue
+constexpr int kMaxStages = 16;
+constexpr int kThreads = 384;            // warp 0 TMA, 1 MMA, 2 TMEM alloc, 3 residual TMA, 4-11 epilogue
+constexpr int kMaxRing = 4;              // epilogue staging ring depth
 constexpr size_t kSmemBudget = 227 * 1024;
 constexpr size_t kSmemHeader = 1024;     // barriers + tmem pointer
 constexpr long long kWatchdogCycles = 4000000000LL;
@@ -37,14 +44,30 @@ struct TcArgs {
     int Ho, Wo, HoWo;
     int ks, stride, pad;
     int cin_blocks, num_kblocks;
+    int kps, num_iters;      // k-blocks per pipeline stage, stages per tile (num_kblocks / kps)
     int BN, n_tiles, m_tiles;
     int stages, tmem_cols;
     const float* scale; const float* bias;
     void* out; long out_ld; int out_f32;
     const __half* res; long res_ld;
     int leaky, upsample;
+    // staged (TMA store) epilogue
+    int epi_staged;          // 1: smem ring + TMA store, 0: direct global stores
+    int ring;                // staging buffers
+    int sub_bytes;           // bytes per row of a sub-tile (128 or 64) == swizzle span
+    int cs;                  // columns per sub-tile
+    int n_sub;               // sub-tiles per tile (BN / cs)
+    int has_res;
+    int exp_tiled;           // timing experiment: fetch 3x3 A tiles with tiled-mode TMA (results are wrong)
+    int b_resident;          // 1: the CTA's whole weight slab [BN][K] is loaded once and stays in smem
     int* dbg;
+    long long* trace;        // optional [3 roles][64 tiles][4] clock64 stamps of CTA 0 (YB_TC_TRACE=1)
 };
+
+#define YB_TRACE(role, idx, slot)                                                                   \
+    do {                                                                                            \
+        if (a.trace && blockIdx.x == 0 && (idx) < 64) a.trace[((role) * 64 + (idx)) * 4 + (slot)] = clock64(); \
+    } while (0)
 
 // ---- PTX wrappers --------------------------------------------------------------------------------
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -68,9 +91,10 @@ __device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
     return ok != 0;
 }
 // Bounded wait: a lost arrival must not hang the GPU.  On timeout the waiter records who it is in
-// host-visible memory and traps; the host sees a launch failure with the diagnostic attached.
-__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity, int* dbg, int role, int which) {
-    if (mbar_try_wait(bar, parity)) return;
+// host-visible memory and traps; the host sees a launch failure with the diagnostic attached.  The
+// polling loop lives out of line so that the producer / MMA loops stay a few instructions long: those
+// loops run on ONE thread each and their instruction latency, not bandwidth, paces the whole pipeline.
+__device__ __noinline__ void mbar_wait_slow(uint32_t bar, uint32_t parity, int* dbg, int role, int which) {
     const long long t0 = clock64();
     while (!mbar_try_wait(bar, parity)) {
         if (clock64() - t0 > kWatchdogCycles) {
@@ -84,6 +108,9 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity, int* db
         }
     }
 }
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity, int* dbg, int role, int which) {
+    if (!mbar_try_wait(bar, parity)) mbar_wait_slow(bar, parity, dbg, role, which);
+}
 
 __device__ __forceinline__ void tma_load_2d(const CUtensorMap* tm, uint32_t dst, uint32_t bar, int c0, int c1) {
     asm volatile(
@@ -95,6 +122,70 @@ __device__ __forceinline__ void tma_load_im2col(const CUtensorMap* tm, uint32_t 
     asm volatile(
         "cp.async.bulk.tensor.4d.shared::cluster.global.im2col.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2], {%7, %8};"
         ::"r"(dst), "l"(tm), "r"(bar), "r"(c), "r"(w), "r"(h), "r"(n), "h"(off_w), "h"(off_h) : "memory");
+}
+__device__ __forceinline__ void tma_store_2d(const CUtensorMap* tm, uint32_t src, int c0, int c1) {
+    asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];"
+                 ::"l"(tm), "r"(src), "r"(c0), "r"(c1) : "memory");
+}
+__device__ __forceinline__ void tma_store_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void tma_store_wait_read() { asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(N) : "memory"); }
+__device__ __forceinline__ void tma_store_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
+__device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void epi_bar_sync() { asm volatile("bar.sync 1, 128;" ::: "memory"); }
+__device__ __forceinline__ void epi_bar_sync256() { asm volatile("bar.sync 1, 256;" ::: "memory"); }
+// ---- CTA-pair (cta_group::2) variants: the two CTAs of a cluster share one 256-row UMMA; loads of both
+// CTAs complete on the leader's (rank 0) mbarrier, whose shared::cluster address is the local one with
+// the peer bit (bit 24) cleared.
+constexpr uint32_t kPeerBitMask = 0xFEFFFFFFu;
+constexpr uint64_t kTmaCacheDefault = 0x1000000000000000ull;
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+    uint32_t r;
+    asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+    return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+    asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+    asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tma_load_2d_pair(const CUtensorMap* tm, uint32_t dst, uint32_t bar, int c0, int c1) {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint"
+        " [%0], [%1, {%3, %4}], [%2], %5;"
+        ::"r"(dst), "l"(tm), "r"(bar & kPeerBitMask), "r"(c0), "r"(c1), "l"(kTmaCacheDefault) : "memory");
+}
+__device__ __forceinline__ void tma_load_im2col_pair(const CUtensorMap* tm, uint32_t dst, uint32_t bar, int c, int w, int h, int n,
+                                                     uint16_t off_w, uint16_t off_h) {
+    asm volatile(
+        "cp.async.bulk.tensor.4d.im2col.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint"
+        " [%0], [%1, {%3, %4, %5, %6}], [%2], {%7, %8}, %9;"
+        ::"r"(dst), "l"(tm), "r"(bar & kPeerBitMask), "r"(c), "r"(w), "r"(h), "r"(n), "h"(off_w), "h"(off_h), "l"(kTmaCacheDefault)
+        : "memory");
+}
+__device__ __forceinline__ void tmem_alloc_pair(uint32_t dst_smem, uint32_t cols) {
+    asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(dst_smem), "r"(cols) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc_pair(uint32_t taddr, uint32_t cols) {
+    asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(cols) : "memory");
+}
+__device__ __forceinline__ void umma_f16_pair(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+        ::"r"(d_tmem), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
+}
+__device__ __forceinline__ void umma_commit_pair(uint32_t bar) {   // arrives on `bar` in BOTH CTAs of the pair
+    asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+                 ::"r"(bar), "h"((uint16_t)3) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_leader(uint32_t bar) {  // arrive on the barrier at this offset in CTA rank 0
+    asm volatile(
+        "{\n\t.reg .b32 remAddr32;\n\t"
+        "mapa.shared::cluster.u32 remAddr32, %0, 0;\n\t"
+        "mbarrier.arrive.shared::cluster.b64 _, [remAddr32];\n\t}"
+        ::"r"(bar) : "memory");
 }
 __device__ __forceinline__ void prefetch_tmap(const CUtensorMap* tm) {
     asm volatile("prefetch.tensormap [%0];" ::"l"(tm) : "memory");
@@ -116,6 +207,15 @@ __device__ __forceinline__ void umma_f16(uint32_t d_tmem, uint64_t adesc, uint64
         "setp.ne.b32 p, %4, 0;\n\t"
         "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
         ::"r"(d_tmem), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
+}
+// same, accumulate flag known at compile time (no setp in the issue loop)
+template <int ACC>
+__device__ __forceinline__ void umma_f16_imm(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+        ::"r"(d_tmem), "l"(adesc), "l"(bdesc), "r"(idesc), "n"(ACC) : "memory");
 }
 __device__ __forceinline__ void umma_commit(uint32_t bar) {
     asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
@@ -141,7 +241,7 @@ __device__ __forceinline__ uint64_t make_smem_desc(uint32_t saddr) {
 }
 // kind::f16 instruction descriptor (cute::UMMA::InstrDescriptor): D fp32 (bits [4,6) = 1), A/B fp16
 // (0), both K-major, N >> 3 in [17,23), M >> 4 in [24,29).
-__device__ __forceinline__ uint32_t make_idesc(int n) { return (1u << 4) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(kBM >> 4) << 24); }
+__device__ __forceinline__ uint32_t make_idesc(int n, int m = kBM) { return (1u << 4) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(m >> 4) << 24); }
 
 __device__ __forceinline__ float leaky(float v) { return v > 0.f ? v : v * kLeaky; }
 
@@ -204,38 +304,107 @@ __device__ __forceinline__ void epilogue16(const TcArgs& a, const uint32_t (&acc
     }
 }
 
-template <int SWZ>
+// Staged epilogue for 16 consecutive channels of one output pixel: scale/bias, LeakyReLU, residual
+// (read from the swizzled staging sub-tile the load warp filled), convert, write back in place.
+// `srow` points at this pixel's row of the sub-tile; chunk c (16 bytes) lives at ((c ^ xr) << 4).
+__device__ __forceinline__ void epilogue16_staged(const TcArgs& a, const uint32_t (&acc)[16], int n, uint8_t* srow,
+                                                  int grp, int xr) {
+    float v[16];
+    const float4* sc = reinterpret_cast<const float4*>(a.scale + n);
+    const float4* bi = reinterpret_cast<const float4*>(a.bias + n);
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+        const float4 s4 = __ldg(sc + q), b4 = __ldg(bi + q);
+        v[4 * q + 0] = fmaf(__uint_as_float(acc[4 * q + 0]), s4.x, b4.x);
+        v[4 * q + 1] = fmaf(__uint_as_float(acc[4 * q + 1]), s4.y, b4.y);
+        v[4 * q + 2] = fmaf(__uint_as_float(acc[4 * q + 2]), s4.z, b4.z);
+        v[4 * q + 3] = fmaf(__uint_as_float(acc[4 * q + 3]), s4.w, b4.w);
+    }
+    if (a.leaky) {
+#pragma unroll
+        for (int i = 0; i < 16; ++i) v[i] = leaky(v[i]);
+    }
+    if (a.out_f32) {
+#pragma unroll
+        for (int h = 0; h < 4; ++h) {
+            float4* p = reinterpret_cast<float4*>(srow + (((grp * 4 + h) ^ xr) << 4));
+            *p = make_float4(v[4 * h], v[4 * h + 1], v[4 * h + 2], v[4 * h + 3]);
+        }
+        return;
+    }
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+        uint4* p = reinterpret_cast<uint4*>(srow + (((grp * 2 + h) ^ xr) << 4));
+        if (a.has_res) {
+            const uint4 r = *p;
+            const __half2* hh = reinterpret_cast<const __half2*>(&r);
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                const float2 f = __half22float2(hh[i]);
+                v[8 * h + 2 * i] += f.x;
+                v[8 * h + 2 * i + 1] += f.y;
+            }
+        }
+        uint4 pk;
+        __half2* ph = reinterpret_cast<__half2*>(&pk);
+#pragma unroll
+        for (int i = 0; i < 4; ++i) ph[i] = __floats2half2_rn(v[8 * h + 2 * i], v[8 * h + 2 * i + 1]);
+        *p = pk;
+    }
+}
+
+template <int SWZ, bool CTA2>
 __global__ void __launch_bounds__(kThreads, 1)
-conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const TcArgs a) {
+conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+               const __grid_constant__ CUtensorMap tmOut, const __grid_constant__ CUtensorMap tmRes, const TcArgs a) {
     constexpr int BKE = SWZ / 2;                  // fp16 elements per k-block row
     constexpr uint32_t A_BYTES = kBM * SWZ;
     extern __shared__ uint8_t smem_raw[];
     const uint32_t raw = smem_u32(smem_raw);
     const uint32_t base = (raw + 1023u) & ~1023u;           // swizzle atoms need 1024-byte alignment
     uint8_t* gen = smem_raw + (base - raw);
-    const uint32_t B_BYTES = (uint32_t)a.BN * SWZ;
-    const uint32_t stage_bytes = A_BYTES + ((B_BYTES + 1023u) & ~1023u);
-    // header: full[8] | empty[8] | tmem_full[2] | tmem_empty[2] | tmem_ptr
+    // CTA pair: rank r owns rows [2*m_unit + r]*128.. of the 256-row UMMA tile and half of the B rows
+    const uint32_t rank = CTA2 ? cluster_ctarank() : 0u;
+    const bool leader = rank == 0;
+    constexpr int NCTA = CTA2 ? 2 : 1;
+    const uint32_t B_BYTES = (uint32_t)(a.BN / NCTA) * SWZ;
+    const uint32_t kb_bytes = A_BYTES + (a.b_resident ? 0u : ((B_BYTES + 1023u) & ~1023u));   // one k-block inside a stage
+    const uint32_t stage_bytes = kb_bytes * (uint32_t)a.kps;
+    // header: full[16] | empty[16] | tmem_full[2] | tmem_empty[2] | tmem_ptr | sfull[4] | sempty[4] | bres
     const uint32_t full0 = base, empty0 = base + 8 * kMaxStages;
     const uint32_t tfull0 = base + 16 * kMaxStages, tempty0 = tfull0 + 16;
     volatile uint32_t* tmem_ptr = reinterpret_cast<volatile uint32_t*>(gen + 16 * kMaxStages + 32);
-    const uint32_t stage0 = base + (uint32_t)kSmemHeader;
+    const uint32_t sfull0 = base + 16 * kMaxStages + 64, sempty0 = sfull0 + 32, bres_bar = sempty0 + 32;
+    // staging ring (epilogue), resident weight slab, then the operand pipeline stages; all 1024-byte aligned
+    const uint32_t stg_bytes = (uint32_t)kBM * (uint32_t)a.sub_bytes;
+    const uint32_t stg0 = base + (uint32_t)kSmemHeader;
+    const uint32_t B_SLOT = (B_BYTES + 1023u) & ~1023u;
+    const uint32_t bres0 = stg0 + (a.epi_staged ? (uint32_t)a.ring * ((stg_bytes + 1023u) & ~1023u) : 0u);
+    const uint32_t stage0 = bres0 + (a.b_resident ? (uint32_t)a.num_kblocks * B_SLOT : 0u);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int total_tiles = a.m_tiles * a.n_tiles;
+    const int total_tiles = a.m_tiles * a.n_tiles;          // m_tiles counts 256-row units in pair mode
+    const int tile_first = blockIdx.x / NCTA, tile_step = gridDim.x / NCTA;
 
     if (warp == 0 && lane == 0) {
         prefetch_tmap(&tmA);
         prefetch_tmap(&tmB);
+        if (a.epi_staged) prefetch_tmap(&tmOut);
+        if (a.epi_staged && a.has_res) prefetch_tmap(&tmRes);
     }
     if (warp == 1 && lane == 0) {
         for (int s = 0; s < a.stages; ++s) { mbar_init(full0 + 8 * s, 1); mbar_init(empty0 + 8 * s, 1); }
-        for (int i = 0; i < 2; ++i) { mbar_init(tfull0 + 8 * i, 1); mbar_init(tempty0 + 8 * i, 128); }
+        for (int i = 0; i < 2; ++i) { mbar_init(tfull0 + 8 * i, 1); mbar_init(tempty0 + 8 * i, (a.epi_staged ? 8 : 4) * NCTA); }
+        for (int i = 0; i < kMaxRing; ++i) { mbar_init(sfull0 + 8 * i, 1); mbar_init(sempty0 + 8 * i, 1); }
+        mbar_init(bres_bar, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
-    if (warp == 2) tmem_alloc(smem_u32(const_cast<uint32_t*>(tmem_ptr)), (uint32_t)a.tmem_cols);
+    if (warp == 2) {
+        if constexpr (CTA2) tmem_alloc_pair(smem_u32(const_cast<uint32_t*>(tmem_ptr)), (uint32_t)a.tmem_cols);
+        else tmem_alloc(smem_u32(const_cast<uint32_t*>(tmem_ptr)), (uint32_t)a.tmem_cols);
+    }
     tc_fence_before();
-    __syncthreads();
+    if constexpr (CTA2) cluster_sync_all(); else __syncthreads();   // peer barriers must exist before any remote signal
     tc_fence_after();
     const uint32_t tmem_base = *tmem_ptr;
     const uint32_t acc_stride = (uint32_t)a.tmem_cols >> 1;
@@ -245,65 +414,204 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         if (lane == 0) {
             int stage = 0;
             uint32_t phase = 0;
-            for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
-                const int m_tile = tile / a.n_tiles, n_tile = tile - m_tile * a.n_tiles;
-                const long m0 = (long)m_tile * kBM;
-                const int n0 = n_tile * a.BN;
-                int cw = 0, chh = 0, cn = 0;
-                if (a.ks == 3) {
-                    cn = (int)(m0 / a.HoWo);
-                    const int r = (int)(m0 - (long)cn * a.HoWo);
-                    const int p = r / a.Wo, q = r - p * a.Wo;
-                    cw = q * a.stride - a.pad;
-                    chh = p * a.stride - a.pad;
-                }
-                for (int kb = 0; kb < a.num_kblocks; ++kb) {
-                    mbar_wait(empty0 + 8 * stage, phase ^ 1, a.dbg, 0, stage);
-                    const uint32_t sA = stage0 + stage * stage_bytes, sB = sA + A_BYTES;
-                    const uint32_t fb = full0 + 8 * stage;
-                    mbar_arrive_expect_tx(fb, A_BYTES + B_BYTES);
-                    if (a.ks == 1) {
-                        tma_load_2d(&tmA, sA, fb, kb * BKE, (int)m0);
-                    } else {
-                        const int tap = kb / a.cin_blocks, cb = kb - tap * a.cin_blocks;
-                        const int kh = tap / 3, kw = tap - kh * 3;
-                        tma_load_im2col(&tmA, sA, fb, cb * BKE, cw, chh, cn, (uint16_t)kw, (uint16_t)kh);
+            if (a.b_resident && tile_first < total_tiles) {
+                // gridDim.x is a multiple of n_tiles, so every tile of this CTA has the same n-tile
+                const int n0 = ((int)blockIdx.x % a.n_tiles) * a.BN;
+                mbar_arrive_expect_tx(bres_bar, (uint32_t)a.num_kblocks * B_BYTES);
+                for (int kb = 0; kb < a.num_kblocks; ++kb) tma_load_2d(&tmB, bres0 + kb * B_SLOT, bres_bar, kb * BKE, n0);
+            }
+            // The loop below runs on one thread; everything that can be is carried incrementally
+            // (no divisions, no address recomputation) because its latency paces the pipeline.
+            const uint32_t tx_bytes = (a.b_resident ? A_BYTES : A_BYTES + B_BYTES) * (uint32_t)a.kps * NCTA;
+            const bool load_b = !a.b_resident;
+            uint32_t sA = stage0, fb = full0, eb = empty0;
+            int ti = 0;
+            for (int tile = tile_first; tile < total_tiles; tile += tile_step, ++ti) {
+                const int m_unit = tile / a.n_tiles, n_tile = tile - m_unit * a.n_tiles;
+                const int m0 = (m_unit * NCTA + (int)rank) * kBM;
+                const int n0 = n_tile * a.BN + (int)rank * (a.BN / NCTA);   // this CTA's half of the weight rows
+                YB_TRACE(0, ti, 0);
+                if (a.ks == 1 || a.exp_tiled) {
+                    int kc = 0, ka = 0;
+                    for (int it = 0; it < a.num_iters; ++it) {
+                        mbar_wait(eb, phase ^ 1, a.dbg, 0, stage);
+                        if (leader) mbar_arrive_expect_tx(fb, tx_bytes);
+                        uint32_t dst = sA;
+                        for (int j = 0; j < a.kps; ++j) {
+                            if constexpr (CTA2) {
+                                tma_load_2d_pair(&tmA, dst, fb, kc, m0);
+                                tma_load_2d_pair(&tmB, dst + A_BYTES, fb, kc, n0);
+                            } else {
+                                tma_load_2d(&tmA, dst, fb, a.exp_tiled ? ka : kc, m0);
+                                if (load_b) tma_load_2d(&tmB, dst + A_BYTES, fb, kc, n0);
+                            }
+                            kc += BKE;
+                            ka += BKE;
+                            if (ka == a.cin_blocks * BKE) ka = 0;
+                            dst += kb_bytes;
+                        }
+                        sA += stage_bytes; fb += 8; eb += 8;
+                        if (++stage == a.stages) { stage = 0; phase ^= 1; sA = stage0; fb = full0; eb = empty0; }
                     }
-                    tma_load_2d(&tmB, sB, fb, kb * BKE, n0);
-                    if (++stage == a.stages) { stage = 0; phase ^= 1; }
+                } else {
+                    const int cn = m0 / a.HoWo;
+                    const int r = m0 - cn * a.HoWo;
+                    const int p = r / a.Wo, q = r - p * a.Wo;
+                    const int cw = q * a.stride - a.pad, chh = p * a.stride - a.pad;
+                    int kc = 0, cc = 0;                      // k coordinate of the weights, channel coordinate of A
+                    uint16_t kw = 0, kh = 0;
+                    const int cend = a.cin_blocks * BKE;
+                    for (int it = 0; it < a.num_iters; ++it) {
+                        mbar_wait(eb, phase ^ 1, a.dbg, 0, stage);
+                        if (leader) mbar_arrive_expect_tx(fb, tx_bytes);
+                        uint32_t dst = sA;
+                        for (int j = 0; j < a.kps; ++j) {
+                            if constexpr (CTA2) {
+                                tma_load_im2col_pair(&tmA, dst, fb, cc, cw, chh, cn, kw, kh);
+                                tma_load_2d_pair(&tmB, dst + A_BYTES, fb, kc, n0);
+                            } else {
+                                tma_load_im2col(&tmA, dst, fb, cc, cw, chh, cn, kw, kh);
+                                if (load_b) tma_load_2d(&tmB, dst + A_BYTES, fb, kc, n0);
+                            }
+                            kc += BKE;
+                            cc += BKE;
+                            if (cc == cend) { cc = 0; if (++kw == 3) { kw = 0; ++kh; } }
+                            dst += kb_bytes;
+                        }
+                        sA += stage_bytes; fb += 8; eb += 8;
+                        if (++stage == a.stages) { stage = 0; phase ^= 1; sA = stage0; fb = full0; eb = empty0; }
+                    }
                 }
+                YB_TRACE(0, ti, 1);
             }
         }
         __syncwarp();
     } else if (warp == 1) {
         // ===== MMA issuer =====
-        if (lane == 0) {
-            const uint32_t idesc = make_idesc(a.BN);
+        if (lane == 0 && leader) {
+            const uint32_t idesc = make_idesc(a.BN, kBM * NCTA);
             int stage = 0;
             uint32_t phase = 0, acc = 0, acc_phase = 0;
-            for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+            // descriptors are carried incrementally: the start-address field counts 16-byte units
+            const uint64_t adesc0 = make_smem_desc<SWZ>(stage0);
+            const uint64_t stage_inc = stage_bytes >> 4, kb_inc = kb_bytes >> 4, b_off = A_BYTES >> 4;
+            const uint64_t bres_desc = make_smem_desc<SWZ>(bres0), bres_inc = B_SLOT >> 4;
+            uint64_t adesc = adesc0;
+            uint32_t fbar = full0, ebar = empty0;
+            if (a.b_resident && tile_first < total_tiles) mbar_wait(bres_bar, 0, a.dbg, 1, 600);
+            int ti = 0;
+            for (int tile = tile_first; tile < total_tiles; tile += tile_step, ++ti) {
+                YB_TRACE(1, ti, 0);
                 mbar_wait(tempty0 + 8 * acc, acc_phase ^ 1, a.dbg, 1, 100 + (int)acc);
                 tc_fence_after();
+                YB_TRACE(1, ti, 1);
                 const uint32_t d_tmem = tmem_base + acc * acc_stride;
-                for (int kb = 0; kb < a.num_kblocks; ++kb) {
-                    mbar_wait(full0 + 8 * stage, phase, a.dbg, 1, stage);
+                int kb = 0;
+                for (int it = 0; it < a.num_iters; ++it) {
+                    mbar_wait(fbar, phase, a.dbg, 1, stage);
                     tc_fence_after();
-                    const uint32_t sA = stage0 + stage * stage_bytes, sB = sA + A_BYTES;
-                    const uint64_t adesc = make_smem_desc<SWZ>(sA), bdesc = make_smem_desc<SWZ>(sB);
+                    uint64_t ad = adesc;
+                    for (int j = 0; j < a.kps; ++j, ++kb) {
+                        const uint64_t bd = a.b_resident ? bres_desc + (uint64_t)kb * bres_inc : ad + b_off;
+                        if constexpr (CTA2) {
 #pragma unroll
-                    for (int k = 0; k < BKE / 16; ++k)   // 16 fp16 = 32 bytes per MMA: descriptor address += 2
-                        umma_f16(d_tmem, adesc + 2 * k, bdesc + 2 * k, idesc, (kb | k) != 0);
-                    umma_commit(empty0 + 8 * stage);     // frees this smem stage once the MMAs have read it
-                    if (++stage == a.stages) { stage = 0; phase ^= 1; }
+                            for (int k = 0; k < BKE / 16; ++k) umma_f16_pair(d_tmem, ad + 2 * k, bd + 2 * k, idesc, (kb | k) != 0);
+                        } else {
+                            umma_f16(d_tmem, ad, bd, idesc, kb != 0);
+#pragma unroll
+                            for (int k = 1; k < BKE / 16; ++k)   // 16 fp16 = 32 bytes per MMA: descriptor address += 2
+                                umma_f16_imm<1>(d_tmem, ad + 2 * k, bd + 2 * k, idesc);
+                        }
+                        ad += kb_inc;
+                    }
+                    if constexpr (CTA2) umma_commit_pair(ebar); else umma_commit(ebar);   // frees the stage (in both CTAs)
+                    adesc += stage_inc; fbar += 8; ebar += 8;
+                    if (++stage == a.stages) { stage = 0; phase ^= 1; adesc = adesc0; fbar = full0; ebar = empty0; }
                 }
-                umma_commit(tfull0 + 8 * acc);           // accumulator complete
+                if constexpr (CTA2) umma_commit_pair(tfull0 + 8 * acc); else umma_commit(tfull0 + 8 * acc);   // accumulator complete
+                YB_TRACE(1, ti, 2);
                 acc ^= 1;
                 if (acc == 0) acc_phase ^= 1;
             }
         }
         __syncwarp();
-    } else if (warp >= 4) {
-        // ===== epilogue: TMEM -> registers -> global =====
+    } else if (warp == 3) {
+        // ===== residual prefetch: TMA loads of the residual sub-tiles into the staging ring =====
+        if (lane == 0 && a.epi_staged && a.has_res) {
+            uint32_t g = 0;
+            for (int tile = tile_first; tile < total_tiles; tile += tile_step) {
+                const int m_unit = tile / a.n_tiles, n_tile = tile - m_unit * a.n_tiles;
+                const int m0 = (m_unit * NCTA + (int)rank) * kBM, n0 = n_tile * a.BN;
+                for (int j = 0; j < a.n_sub; ++j, ++g) {
+                    const uint32_t buf = g % (uint32_t)a.ring, ph = (g / (uint32_t)a.ring) & 1u;
+                    mbar_wait(sempty0 + 8 * buf, ph ^ 1, a.dbg, 3, 300 + (int)buf);
+                    mbar_arrive_expect_tx(sfull0 + 8 * buf, stg_bytes);
+                    tma_load_2d(&tmRes, stg0 + buf * stg_bytes, sfull0 + 8 * buf, n0 + j * a.cs, m0);
+                }
+            }
+        }
+        __syncwarp();
+    } else if (warp >= 4 && a.epi_staged) {
+        // ===== epilogue (staged): TMEM -> registers -> swizzled smem sub-tile -> TMA store =====
+        // Eight warps: warp w reads TMEM lanes 32*(w%4).. (its rows) and, of every sub-tile, the column
+        // half (w-4)/4 -- two warps share each row quarter so the per-thread work is half a sub-tile.
+        const int q = warp & 3, half = (warp - 4) >> 2;
+        const int row = q * 32 + lane;
+        const int xr = a.sub_bytes == 128 ? (row & 7) : ((row >> 1) & 3);
+        const int ngrp = a.cs >> 4;                           // 16-column groups per sub-tile: 1, 2 or 4
+        const int gph = ngrp > 1 ? ngrp >> 1 : 1;             // groups per half
+        const int g0 = half * gph;                            // first group of this warp
+        const bool active = g0 < ngrp;
+        const bool issuer = (warp == 4 && lane == 0);
+        uint32_t acc = 0, acc_phase = 0, g = 0;
+        int ti = 0;
+        for (int tile = tile_first; tile < total_tiles; tile += tile_step, ++ti) {
+            const int m_unit = tile / a.n_tiles, n_tile = tile - m_unit * a.n_tiles;
+            const int m0 = (m_unit * NCTA + (int)rank) * kBM, n0 = n_tile * a.BN;
+            if (issuer) YB_TRACE(2, ti, 0);
+            mbar_wait(tfull0 + 8 * acc, acc_phase, a.dbg, 2, 200 + (int)acc);
+            tc_fence_after();
+            if (issuer) YB_TRACE(2, ti, 1);
+            const uint32_t taddr = tmem_base + acc * acc_stride + ((uint32_t)(q * 32) << 16);
+            for (int j = 0; j < a.n_sub; ++j, ++g) {
+                const uint32_t buf = g % (uint32_t)a.ring, ph = (g / (uint32_t)a.ring) & 1u;
+                uint32_t r0[16], r1[16];
+                const uint32_t tcol = taddr + (uint32_t)(j * a.cs + g0 * 16);
+                if (active) tmem_ld16(tcol, r0);
+                if (active && gph > 1) tmem_ld16(tcol + 16, r1);
+                // the buffer is ours once the residual landed (res layers) or its previous store drained
+                if (a.has_res) mbar_wait(sfull0 + 8 * buf, ph, a.dbg, 2, 400 + (int)buf);
+                else mbar_wait(sempty0 + 8 * buf, ph ^ 1, a.dbg, 2, 500 + (int)buf);
+                tmem_ld_wait();
+                if (j == a.n_sub - 1) {                       // accumulator fully read: hand it back to the MMA warp
+                    tc_fence_before();
+                    __syncwarp();
+                    if (lane == 0) {
+                        if constexpr (CTA2) mbar_arrive_leader(tempty0 + 8 * acc); else mbar_arrive(tempty0 + 8 * acc);
+                    }
+                }
+                uint8_t* srow = gen + (stg0 - base) + buf * stg_bytes + (uint32_t)row * (uint32_t)a.sub_bytes;
+                const int nb = n0 + j * a.cs;
+                if (active) epilogue16_staged(a, r0, nb + g0 * 16, srow, g0, xr);
+                if (active && gph > 1) epilogue16_staged(a, r1, nb + g0 * 16 + 16, srow, g0 + 1, xr);
+                fence_async_smem();                           // generic-proxy smem writes -> visible to the TMA engine
+                epi_bar_sync256();
+                if (issuer) {
+                    tma_store_2d(&tmOut, stg0 + buf * stg_bytes, nb, m0);
+                    tma_store_commit();
+                    if (g > 0) {                              // the previous store has finished reading its buffer
+                        tma_store_wait_read<1>();
+                        mbar_arrive(sempty0 + 8 * ((g - 1) % (uint32_t)a.ring));
+                    }
+                }
+            }
+            if (issuer) YB_TRACE(2, ti, 2);
+            acc ^= 1;
+            if (acc == 0) acc_phase ^= 1;
+        }
+        if (issuer) tma_store_wait_all();
+    } else if (warp >= 4 && warp < 8) {
+        // ===== epilogue (direct): TMEM -> registers -> global, used by the nearest-upsample layers =====
         const int q = warp - 4;                               // TMEM lane quarter this warp may read
         const int row = q * 32 + lane;
         uint32_t acc = 0, acc_phase = 0;
@@ -333,17 +641,195 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                 if (two) epilogue16(a, r1, n0 + c0 + 16, valid, m, o00, W2ld);
             }
             tc_fence_before();
-            mbar_arrive(tempty0 + 8 * acc);
+            __syncwarp();
+            if (lane == 0) mbar_arrive(tempty0 + 8 * acc);
             acc ^= 1;
             if (acc == 0) acc_phase ^= 1;
         }
     }
 
     tc_fence_before();
-    __syncthreads();
+    if constexpr (CTA2) cluster_sync_all(); else __syncthreads();   // the peer may still signal this CTA's barriers / read its smem
     if (warp == 2) {
         tc_fence_after();
-        tmem_dealloc(tmem_base, (uint32_t)a.tmem_cols);
+        if constexpr (CTA2) tmem_dealloc_pair(tmem_base, (uint32_t)a.tmem_cols);
+        else tmem_dealloc(tmem_base, (uint32_t)a.tmem_cols);
+    }
+}
+
+// ---- stem: 3 -> 32, 3x3, stride 1, straight from the caller's NCHW fp32 image ---------------------------
+// Cin = 3 is too narrow for TMA (6-byte pixels), so four producer warps build the im2col rows
+// themselves: thread r of a tile gathers the 27 taps of output pixel r (coalesced along x, L1-resident
+// neighbourhood), converts to fp16, pads K to 32 and writes the 64-byte row in the 64B-swizzled
+// K-major layout the tensor core expects; a proxy fence + mbarrier hands the stage to the MMA warp
+// (one tcgen05.mma pair per tile: M=128, N=32, K=32).  Four TMEM accumulators of 32 columns keep the
+// producers, the tensor core and the epilogue warps (same staged TMA-store epilogue) overlapped.
+constexpr int kStemThreads = 416;          // warps 0-7 producers (two groups), 8 MMA + TMEM alloc, 9-12 epilogue
+constexpr int kStemStages = 8;
+constexpr int kStemAcc = 4;
+
+struct StemArgs {
+    const float* x;
+    int B, H, W;
+    long M;
+    int tiles;
+    TcArgs epi;                             // scale, bias, leaky; staged-epilogue fields
+    const __half* w;                        // [32][32] fp16, k = (ky*3+kx)*3 + c, zero padded
+};
+
+__global__ void __launch_bounds__(kStemThreads, 1)
+stem_tc_kernel(const __grid_constant__ CUtensorMap tmOut, const StemArgs a) {
+    extern __shared__ uint8_t smem_raw[];
+    const uint32_t raw = smem_u32(smem_raw);
+    const uint32_t base = (raw + 1023u) & ~1023u;
+    uint8_t* gen = smem_raw + (base - raw);
+    // header: full[8] | empty[8] | tfull[4] | tempty[4] | sempty[2] | tmem_ptr
+    const uint32_t full0 = base, empty0 = base + 64, tfull0 = base + 128, tempty0 = base + 160, sempty0 = base + 192;
+    volatile uint32_t* tmem_ptr = reinterpret_cast<volatile uint32_t*>(gen + 224);
+    constexpr uint32_t A_BYTES = kBM * 64, STG_BYTES = kBM * 64;
+    const uint32_t wsm = base + 1024;                      // weights 32 x 64 B (2 KB), swizzled
+    const uint32_t stg0 = base + 4096;                     // 2 staging buffers
+    const uint32_t stage0 = stg0 + 2 * STG_BYTES;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+    if (warp == 0 && lane == 0) prefetch_tmap(&tmOut);
+    if (warp == 8 && lane == 0) {
+        for (int s = 0; s < kStemStages; ++s) { mbar_init(full0 + 8 * s, 128); mbar_init(empty0 + 8 * s, 1); }
+        for (int i = 0; i < kStemAcc; ++i) { mbar_init(tfull0 + 8 * i, 1); mbar_init(tempty0 + 8 * i, 128); }
+        for (int i = 0; i < 2; ++i) mbar_init(sempty0 + 8 * i, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 8) tmem_alloc(smem_u32(const_cast<uint32_t*>(tmem_ptr)), 32 * kStemAcc);
+    if (threadIdx.x < 32) {                                // weight rows -> swizzled smem
+        const int r = threadIdx.x;
+        const uint4* src = reinterpret_cast<const uint4*>(a.w + r * 32);
+#pragma unroll
+        for (int c = 0; c < 4; ++c)
+            *reinterpret_cast<uint4*>(gen + 1024 + r * 64 + ((c ^ ((r >> 1) & 3)) << 4)) = __ldg(src + c);
+        fence_async_smem();
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_ptr;
+
+    if (warp < 8) {
+        // ===== producers: one output pixel (im2col row) per thread; two groups of 128 threads take
+        // alternate tiles, and each thread keeps the 27 loads of its next tile in flight while it
+        // converts and stores the current one =====
+        const int grp = warp >> 2;
+        const int r = threadIdx.x & 127;
+        const int xr = (r >> 1) & 3;
+        const long HW = (long)a.H * a.W;
+        auto gather = [&](int tile, float (&v)[27]) {
+#pragma unroll
+            for (int i = 0; i < 27; ++i) v[i] = 0.f;
+            const long m = (long)tile * kBM + r;
+            if (tile < a.tiles && m < a.M) {
+                const int b = (int)(m / HW);
+                const int rem = (int)(m - (long)b * HW);
+                const int y = rem / a.W, x = rem - y * a.W;
+                const float* xb = a.x + (long)b * 3 * HW;
+#pragma unroll
+                for (int ky = 0; ky < 3; ++ky) {
+                    const int iy = y + ky - 1;
+                    const bool oky = iy >= 0 && iy < a.H;
+#pragma unroll
+                    for (int kx = 0; kx < 3; ++kx) {
+                        const int ix = x + kx - 1;
+                        if (oky && ix >= 0 && ix < a.W) {
+#pragma unroll
+                            for (int c = 0; c < 3; ++c) v[(ky * 3 + kx) * 3 + c] = __ldg(xb + c * HW + (long)iy * a.W + ix);
+                        }
+                    }
+                }
+            }
+        };
+        float v[27], vn[27];
+        int i = grp;                                       // index of this CTA's i-th tile
+        gather(blockIdx.x + i * gridDim.x, v);
+        for (; (int)blockIdx.x + i * (int)gridDim.x < a.tiles; i += 2) {
+            gather(blockIdx.x + (i + 2) * gridDim.x, vn);
+            uint4 pk[4];
+            __half2* h = reinterpret_cast<__half2*>(pk);
+#pragma unroll
+            for (int j = 0; j < 13; ++j) h[j] = __floats2half2_rn(v[2 * j], v[2 * j + 1]);
+            h[13] = __floats2half2_rn(v[26], 0.f);
+            h[14] = __floats2half2_rn(0.f, 0.f);
+            h[15] = h[14];
+            const int stage = i % kStemStages;
+            const uint32_t phase = (uint32_t)(i / kStemStages) & 1u;
+            mbar_wait(empty0 + 8 * stage, phase ^ 1, a.epi.dbg, 0, stage);
+            uint8_t* row = gen + (stage0 - base) + stage * A_BYTES + r * 64;
+#pragma unroll
+            for (int c = 0; c < 4; ++c) *reinterpret_cast<uint4*>(row + ((c ^ xr) << 4)) = pk[c];
+            fence_async_smem();
+            mbar_arrive(full0 + 8 * stage);
+#pragma unroll
+            for (int j = 0; j < 27; ++j) v[j] = vn[j];
+        }
+    } else if (warp == 8) {
+        // ===== MMA issuer =====
+        if (lane == 0) {
+            const uint32_t idesc = make_idesc(32);
+            const uint64_t bdesc = make_smem_desc<64>(wsm);
+            int stage = 0;
+            uint32_t phase = 0, acc = 0, acc_phase = 0;
+            for (int tile = blockIdx.x; tile < a.tiles; tile += gridDim.x) {
+                mbar_wait(tempty0 + 8 * acc, acc_phase ^ 1, a.epi.dbg, 1, 100 + (int)acc);
+                mbar_wait(full0 + 8 * stage, phase, a.epi.dbg, 1, stage);
+                tc_fence_after();
+                const uint64_t adesc = make_smem_desc<64>(stage0 + stage * A_BYTES);
+                umma_f16(tmem_base + acc * 32, adesc, bdesc, idesc, 0);
+                umma_f16(tmem_base + acc * 32, adesc + 2, bdesc + 2, idesc, 1);
+                umma_commit(empty0 + 8 * stage);
+                umma_commit(tfull0 + 8 * acc);
+                if (++stage == kStemStages) { stage = 0; phase ^= 1; }
+                if (++acc == kStemAcc) { acc = 0; acc_phase ^= 1; }
+            }
+        }
+        __syncwarp();
+    } else {
+        // ===== epilogue: TMEM -> scale/bias/LeakyReLU -> fp16 -> swizzled smem -> TMA store =====
+        const int q = warp & 3;
+        const int row = q * 32 + lane;
+        const int xr = (row >> 1) & 3;
+        const bool issuer = (warp == 9 && lane == 0);
+        uint32_t acc = 0, acc_phase = 0, g = 0;
+        for (int tile = blockIdx.x; tile < a.tiles; tile += gridDim.x, ++g) {
+            const uint32_t buf = g & 1u, ph = (g >> 1) & 1u;
+            mbar_wait(tfull0 + 8 * acc, acc_phase, a.epi.dbg, 2, 200 + (int)acc);
+            tc_fence_after();
+            uint32_t r0[16], r1[16];
+            const uint32_t taddr = tmem_base + acc * 32 + ((uint32_t)(q * 32) << 16);
+            tmem_ld16(taddr, r0);
+            tmem_ld16(taddr + 16, r1);
+            mbar_wait(sempty0 + 8 * buf, ph ^ 1, a.epi.dbg, 2, 500 + (int)buf);
+            tmem_ld_wait();
+            tc_fence_before();
+            mbar_arrive(tempty0 + 8 * acc);                 // accumulator drained into registers
+            uint8_t* srow = gen + (stg0 - base) + buf * STG_BYTES + row * 64;
+            epilogue16_staged(a.epi, r0, 0, srow, 0, xr);
+            epilogue16_staged(a.epi, r1, 16, srow, 1, xr);
+            fence_async_smem();
+            epi_bar_sync();
+            if (issuer) {
+                tma_store_2d(&tmOut, stg0 + buf * STG_BYTES, 0, tile * kBM);
+                tma_store_commit();
+                if (g > 0) {
+                    tma_store_wait_read<1>();
+                    mbar_arrive(sempty0 + 8 * ((g - 1) & 1u));
+                }
+            }
+            if (++acc == kStemAcc) { acc = 0; acc_phase ^= 1; }
+        }
+        if (issuer) tma_store_wait_all();
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 8) {
+        tc_fence_after();
+        tmem_dealloc(tmem_base, 32 * kStemAcc);
     }
 }
 
@@ -392,7 +878,8 @@ std::string tc_make_plan(TcPlan& p, const ConvArgs& a, const __half* w16, int co
     p.num_kblocks = a.ks * a.ks * p.cin_blocks;
     p.M = (long)a.B * a.Ho * a.Wo;
     p.m_tiles = (int)((p.M + kBM - 1) / kBM);
-    // tile N: the divisor of cout_pad (<= 256, multiple of 16) with the fewest persistent waves x width
+    // tile N: the kernel is bound by bytes brought into the SM (A: 128 rows, B: BN rows per k-block), so
+    // the cost of a candidate is (persistent waves) x (128 + BN); measured in profiles/r01_layer_sweep_v3.txt
     int best_bn = 0;
     double best_cost = 0;
     for (int bn = std::min(cout_pad, 256); bn >= 16; bn -= 16) {
@@ -400,34 +887,76 @@ std::string tc_make_plan(TcPlan& p, const ConvArgs& a, const __half* w16, int co
         if (bn < 64 && bn != cout_pad) break;
         const long tiles = (long)p.m_tiles * (cout_pad / bn);
         const long waves = (tiles + num_sms - 1) / num_sms;
-        const double cost = (double)waves * (bn + 24);      // +24: per-tile fixed cost in units of N columns
+        const double cost = (double)waves * (128 + bn);
         if (!best_bn || cost < best_cost) { best_bn = bn; best_cost = cost; }
     }
     if (!best_bn) return "no valid tile width for cout_pad=" + std::to_string(cout_pad);
     p.BN = best_bn;
+    if (const char* e = getenv("YB_TC_BN")) {
+        const int bn = atoi(e);
+        if (bn >= 16 && bn <= 256 && bn % 16 == 0 && cout_pad % bn == 0) p.BN = bn;
+    }
     p.n_tiles = cout_pad / p.BN;
+    // CTA pairs (cta_group::2): 256-row UMMA tiles, each CTA stages only half of the weight rows, which
+    // both halves the bytes every SM must ingest per FLOP and frees shared memory for deeper pipelines.
+    p.cta2 = p.swz == 128 && p.BN == 256 && !a.upsample && p.m_tiles >= 4 && num_sms % 2 == 0;
+    if (const char* e = getenv("YB_TC_CTA2")) p.cta2 = p.cta2 && atoi(e) != 0;
+    const int ncta = p.cta2 ? 2 : 1;
+    if (p.cta2) p.m_tiles = (p.m_tiles + 1) / 2;            // 256-row units from here on
     int tc = 32;
     while (tc < 2 * p.BN) tc <<= 1;
     p.tmem_cols = tc;
-    const size_t stage_bytes = (size_t)kBM * p.swz + (((size_t)p.BN * p.swz + 1023) & ~(size_t)1023);
-    p.stages = (int)std::min<size_t>(kMaxStages, (kSmemBudget - kSmemHeader - 1024) / stage_bytes);
+    // epilogue: TMA-store staging whenever a tile row splits into whole 128- (or 64-) byte sub-tiles
+    const int esz = a.out_f32 ? 4 : 2;
+    p.epi_staged = 0; p.ring = 0; p.sub_bytes = 128;
+    if (!a.upsample) {
+        if ((p.BN * esz) % 128 == 0) { p.epi_staged = 1; p.sub_bytes = 128; }
+        else if ((p.BN * esz) % 64 == 0) { p.epi_staged = 1; p.sub_bytes = 64; }
+    }
+    p.cs = p.sub_bytes / esz;
+    p.n_sub = p.epi_staged ? p.BN / p.cs : 0;
+    if (p.epi_staged) p.ring = a.res ? 4 : 2;
+    if (const char* e = getenv("YB_TC_RING")) if (p.epi_staged) p.ring = std::max(2, std::min(kMaxRing, atoi(e)));
+    const size_t stg_bytes = ((size_t)kBM * p.sub_bytes + 1023) & ~(size_t)1023;
+    const size_t ring_bytes = p.epi_staged ? p.ring * stg_bytes : 0;
+    p.grid = p.cta2 ? 2 * (int)std::min<long>((long)p.m_tiles * p.n_tiles, num_sms / 2)
+                    : (int)std::min<long>((long)p.m_tiles * p.n_tiles, num_sms);
+    // small-K layers: keep the CTA's whole weight slab resident (halves the L2->SM traffic of 1x1 convs)
+    const size_t b_slot = ((size_t)(p.BN / ncta) * p.swz + 1023) & ~(size_t)1023;
+    const size_t bres_bytes = b_slot * p.num_kblocks;
+    p.b_resident = !p.cta2 && bres_bytes <= 96 * 1024 && p.grid % p.n_tiles == 0 && p.m_tiles > 2 * num_sms;
+    if (const char* e = getenv("YB_TC_BRES")) p.b_resident = p.b_resident && atoi(e) != 0;
+    const size_t kb_bytes = (size_t)kBM * p.swz + (p.b_resident ? 0 : b_slot);
+    const size_t fixed = kSmemHeader + 1024 + ring_bytes + (p.b_resident ? bres_bytes : 0);
+    // k-blocks per pipeline stage: the producer and MMA loops each run on one thread and cost a few hundred
+    // cycles per stage, so a stage should carry >= ~500 tensor-core cycles (one k-block is (BKE/16)*BN/2)
+    p.kps = 1;
+    {
+        const int kb_cycles = (bke / 16) * p.BN / 2;
+        for (int c = 4; c >= 2; --c)
+            if (p.num_kblocks % c == 0 && c * kb_bytes <= 48 * 1024 && kb_cycles * (c - 1) < 768) { p.kps = c; break; }
+        if (const char* e = getenv("YB_TC_KPS")) { const int c = atoi(e); if (c >= 1 && p.num_kblocks % c == 0 && c * kb_bytes <= 96 * 1024) p.kps = c; }
+    }
+    const size_t stage_bytes = kb_bytes * p.kps;
+    p.stages = (int)std::min<size_t>(kMaxStages, (kSmemBudget - fixed) / stage_bytes);
+    if (const char* e = getenv("YB_TC_STAGES")) p.stages = std::max(2, std::min(p.stages, atoi(e)));
     if (p.stages < 2) return "not enough shared memory for two pipeline stages";
-    p.smem = kSmemHeader + 1024 + p.stages * stage_bytes;
-    p.grid = (int)std::min<long>((long)p.m_tiles * p.n_tiles, num_sms);
+    p.smem = fixed + p.stages * stage_bytes;
 
     const CUtensorMapSwizzle swz = p.swz == 128 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B;
     // B: weights [cout_pad][K] fp16, K contiguous; box = one k-block x BN rows
     {
         cuuint64_t dims[2] = {(cuuint64_t)K, (cuuint64_t)cout_pad};
         cuuint64_t strides[1] = {(cuuint64_t)K * sizeof(__half)};
-        cuuint32_t box[2] = {(cuuint32_t)bke, (cuuint32_t)p.BN};
+        cuuint32_t box[2] = {(cuuint32_t)bke, (cuuint32_t)(p.BN / ncta)};   // pair mode: each CTA loads half the rows
         cuuint32_t es[2] = {1, 1};
         CUresult r = g_encode_tiled(&p.tmB, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, const_cast<__half*>(w16), dims, strides, box, es,
                                     CU_TENSOR_MAP_INTERLEAVE_NONE, swz, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
         if (r != CUDA_SUCCESS) return cu_err("cuTensorMapEncodeTiled(weights)", r);
     }
-    if (a.ks == 1) {
+    p.exp_tiled = a.ks == 3 && getenv("YB_TC_EXP_TILED") && atoi(getenv("YB_TC_EXP_TILED")) != 0;
+    if (a.ks == 1 || p.exp_tiled) {
         // A: [M][Cin] with pixel pitch in_ld; rows past M are zero-filled
         cuuint64_t dims[2] = {(cuuint64_t)a.Cin, (cuuint64_t)p.M};
         cuuint64_t strides[1] = {(cuuint64_t)a.in_ld * sizeof(__half)};
@@ -461,32 +990,133 @@ std::string tc_make_plan(TcPlan& p, const ConvArgs& a, const __half* w16, int co
             if (bytes < 131072) reinterpret_cast<uint64_t*>(&p.tmA)[1] &= ~(1ull << 21);
         }
     }
+    if (p.epi_staged) {
+        const CUtensorMapSwizzle eswz = p.sub_bytes == 128 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B;
+        const CUtensorMapDataType dt = a.out_f32 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_FLOAT16;
+        cuuint64_t dims[2] = {(cuuint64_t)a.Cout, (cuuint64_t)p.M};
+        cuuint64_t strides[1] = {(cuuint64_t)a.out_ld * esz};
+        cuuint32_t box[2] = {(cuuint32_t)p.cs, (cuuint32_t)kBM};
+        cuuint32_t es[2] = {1, 1};
+        CUresult r = g_encode_tiled(&p.tmOut, dt, 2, a.out, dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE, eswz,
+                                    CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+        if (r != CUDA_SUCCESS) return cu_err("cuTensorMapEncodeTiled(output)", r);
+        if (a.res) {
+            cuuint64_t rstrides[1] = {(cuuint64_t)a.res_ld * sizeof(__half)};
+            r = g_encode_tiled(&p.tmRes, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, const_cast<void*>(a.res), dims, rstrides, box, es,
+                               CU_TENSOR_MAP_INTERLEAVE_NONE, eswz, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                               CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+            if (r != CUDA_SUCCESS) return cu_err("cuTensorMapEncodeTiled(residual)", r);
+        } else {
+            p.tmRes = p.tmOut;
+        }
+    } else {
+        p.tmOut = p.tmB;
+        p.tmRes = p.tmB;
+    }
     return "";
+}
+
+std::string stem_tc_make_plan(StemTcPlan& p, __half* out, long out_ld, int B, int H, int W, int num_sms) {
+    std::string e = load_driver_entry_points();
+    if (!e.empty()) return e;
+    p.M = (long)B * H * W;
+    p.tiles = (int)((p.M + kBM - 1) / kBM);
+    p.grid = std::min(p.tiles, num_sms);
+    p.smem = 1024 + 4096 + 2 * (size_t)kBM * 64 + (size_t)kStemStages * kBM * 64;
+    cuuint64_t dims[2] = {32, (cuuint64_t)p.M};
+    cuuint64_t strides[1] = {(cuuint64_t)out_ld * sizeof(__half)};
+    cuuint32_t box[2] = {32, (cuuint32_t)kBM};
+    cuuint32_t es[2] = {1, 1};
+    CUresult r = g_encode_tiled(&p.tmOut, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, out, dims, strides, box, es,
+                                CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_NONE,
+                                CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) return cu_err("cuTensorMapEncodeTiled(stem output)", r);
+    return "";
+}
+
+cudaError_t stem_tc_launch(const StemTcPlan& p, const float* x, int B, int H, int W, const __half* w16, const float* scale,
+                           const float* bias, int* dbg, cudaStream_t s) {
+    StemArgs a{};
+    a.x = x; a.B = B; a.H = H; a.W = W; a.M = p.M; a.tiles = p.tiles; a.w = w16;
+    a.epi.scale = scale; a.epi.bias = bias; a.epi.leaky = 1; a.epi.out_f32 = 0; a.epi.has_res = 0; a.epi.dbg = dbg;
+    static bool attr_done = false;
+    if (!attr_done) {
+        cudaError_t e = cudaFuncSetAttribute(stem_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024);
+        if (e != cudaSuccess) return e;
+        attr_done = true;
+    }
+    stem_tc_kernel<<<p.grid, kStemThreads, p.smem, s>>>(p.tmOut, a);
+    return cudaGetLastError();
 }
 
 cudaError_t tc_launch(const TcPlan& p, const ConvArgs& a, int* dbg, cudaStream_t s) {
     TcArgs t;
+    static long long* trace_dev = nullptr;
+    static const bool trace_on = getenv("YB_TC_TRACE") && atoi(getenv("YB_TC_TRACE")) != 0;
+    if (trace_on && !trace_dev) cudaMalloc(&trace_dev, 3 * 64 * 4 * sizeof(long long));
+    if (trace_on) cudaMemsetAsync(trace_dev, 0, 3 * 64 * 4 * sizeof(long long), s);
+    t.trace = trace_on ? trace_dev : nullptr;
     t.M = p.M;
     t.Ho = a.Ho; t.Wo = a.Wo; t.HoWo = a.Ho * a.Wo;
     t.ks = a.ks; t.stride = a.stride; t.pad = a.pad;
     t.cin_blocks = p.cin_blocks; t.num_kblocks = p.num_kblocks;
+    t.kps = p.kps; t.num_iters = p.num_kblocks / p.kps;
     t.BN = p.BN; t.n_tiles = p.n_tiles; t.m_tiles = p.m_tiles;
     t.stages = p.stages; t.tmem_cols = p.tmem_cols;
     t.scale = a.scale; t.bias = a.bias;
     t.out = a.out; t.out_ld = a.out_ld; t.out_f32 = a.out_f32;
     t.res = static_cast<const __half*>(a.res); t.res_ld = a.res_ld;
     t.leaky = a.leaky; t.upsample = a.upsample;
+    t.epi_staged = p.epi_staged; t.ring = p.ring; t.sub_bytes = p.sub_bytes; t.cs = p.cs; t.n_sub = p.n_sub;
+    t.has_res = a.res != nullptr;
+    t.b_resident = p.b_resident;
+    t.exp_tiled = p.exp_tiled;
     t.dbg = dbg;
     static bool attr_done = false;
     if (!attr_done) {
-        cudaError_t e = cudaFuncSetAttribute(conv_tc_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBudget);
+        cudaError_t e = cudaFuncSetAttribute(conv_tc_kernel<128, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBudget);
         if (e != cudaSuccess) return e;
-        e = cudaFuncSetAttribute(conv_tc_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBudget);
+        e = cudaFuncSetAttribute(conv_tc_kernel<64, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBudget);
+        if (e != cudaSuccess) return e;
+        e = cudaFuncSetAttribute(conv_tc_kernel<128, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBudget);
         if (e != cudaSuccess) return e;
         attr_done = true;
     }
-    if (p.swz == 128) conv_tc_kernel<128><<<p.grid, kThreads, p.smem, s>>>(p.tmA, p.tmB, t);
-    else conv_tc_kernel<64><<<p.grid, kThreads, p.smem, s>>>(p.tmA, p.tmB, t);
+    if (p.cta2) {
+        cudaLaunchConfig_t cfg{};
+        cfg.gridDim = dim3(p.grid);
+        cfg.blockDim = dim3(kThreads);
+        cfg.dynamicSmemBytes = p.smem;
+        cfg.stream = s;
+        cudaLaunchAttribute attr[1];
+        attr[0].id = cudaLaunchAttributeClusterDimension;
+        attr[0].val.clusterDim.x = 2;
+        attr[0].val.clusterDim.y = 1;
+        attr[0].val.clusterDim.z = 1;
+        cfg.attrs = attr;
+        cfg.numAttrs = 1;
+        cudaError_t e = cudaLaunchKernelEx(&cfg, conv_tc_kernel<128, true>, p.tmA, p.tmB, p.tmOut, p.tmRes, t);
+        if (e != cudaSuccess) return e;
+    } else if (p.swz == 128) {
+        conv_tc_kernel<128, false><<<p.grid, kThreads, p.smem, s>>>(p.tmA, p.tmB, p.tmOut, p.tmRes, t);
+    } else {
+        conv_tc_kernel<64, false><<<p.grid, kThreads, p.smem, s>>>(p.tmA, p.tmB, p.tmOut, p.tmRes, t);
+    }
+    if (trace_on) {                       // debugging aid: dump CTA 0's per-tile time line (cycles)
+        static int dumps = 0;
+        cudaStreamSynchronize(s);
+        long long h[3 * 64 * 4];
+        cudaMemcpy(h, trace_dev, sizeof(h), cudaMemcpyDeviceToHost);
+        if (dumps++ % 8 == 7) {
+            const long long t0 = h[0];
+            fprintf(stderr, "[tc trace] BN=%d kblocks=%d kps=%d stages=%d ring=%d bres=%d n_sub=%d cta2=%d grid=%d\n", p.BN,
+                    p.num_kblocks, p.kps, p.stages, p.ring, p.b_resident, p.n_sub, p.cta2, p.grid);
+            for (int i = 0; i < 12; ++i)
+                fprintf(stderr, "[tc trace] tile %2d  prod start %7lld end %7lld | mma start %7lld tempty-ok %7lld issued %7lld | epi start %7lld tfull-ok %7lld done %7lld\n",
+                        i, h[(0 * 64 + i) * 4] - t0, h[(0 * 64 + i) * 4 + 1] - t0, h[(1 * 64 + i) * 4] - t0, h[(1 * 64 + i) * 4 + 1] - t0,
+                        h[(1 * 64 + i) * 4 + 2] - t0, h[(2 * 64 + i) * 4] - t0, h[(2 * 64 + i) * 4 + 1] - t0, h[(2 * 64 + i) * 4 + 2] - t0);
+        }
+    }
     return cudaGetLastError();
 }
 

@@ -23,12 +23,19 @@ struct DecodeParams {
 
 __device__ __forceinline__ float sigmoidf_rn(float t) { return __fdiv_rn(1.0f, __fadd_rn(1.0f, expf(-t))); }
 
+// One exponential and one IEEE division per element, no divergent branches: the per-attribute
+// differences are folded into (use_exp, offset, mul).  (s + 0.0f) * 1.0f == s exactly, so conf/cls
+// come out bit-identical to a plain sigmoid.
 __device__ __forceinline__ float decode_one(const DecodeScale& s, int a, int attr, int x, int y, float t) {
-    if (attr >= 4) return sigmoidf_rn(t);
-    if (attr == 0) return __fmul_rn(__fadd_rn(sigmoidf_rn(t), (float)x), s.stride);
-    if (attr == 1) return __fmul_rn(__fadd_rn(sigmoidf_rn(t), (float)y), s.stride);
+    const bool wh = attr == 2 || attr == 3;
+    const float e = expf(wh ? t : -t);
+    const float sig = __fdiv_rn(1.0f, __fadd_rn(1.0f, e));
+    const float off = attr == 0 ? (float)x : (attr == 1 ? (float)y : 0.f);
+    const float mul = attr < 2 ? s.stride : 1.0f;
+    const float r_sig = __fmul_rn(__fadd_rn(sig, off), mul);
     const float anc = attr == 2 ? s.aw[a] : s.ah[a];
-    return __fmul_rn(__fmul_rn(expf(t), anc), s.stride);
+    const float r_wh = __fmul_rn(__fmul_rn(e, anc), s.stride);
+    return wh ? r_wh : r_sig;
 }
 
 // NHWC (engine-internal) input: element (b, p, c) -> out[b][row_off*attrs + p*3*attrs + c]: a flat
@@ -40,15 +47,29 @@ __global__ void __launch_bounds__(256) decode_nhwc_kernel(const __grid_constant_
     const int c1 = (int)P.cells_before[1], c2 = (int)P.cells_before[2];
     for (int c = threadIdx.x; c < ch; c += blockDim.x) {
         const int a = c / P.attrs, attr = c % P.attrs;
-        for (int cell = blockIdx.x; cell < total_cells; cell += gridDim.x) {
-            const int si = cell >= c2 ? 2 : (cell >= c1 ? 1 : 0);
-            const DecodeScale& s = P.sc[si];
-            const int lc = cell - (int)P.cells_before[si];
-            const int hw = s.h * s.w;
-            const int b = lc / hw, p = lc - b * hw;
-            const int y = p / s.w, x = p - y * s.w;
-            const float t = s.logits[((long)b * hw + p) * s.ld + c];
-            det[((long)b * P.n_total + s.row_off) * P.attrs + (long)p * ch + c] = decode_one(s, a, attr, x, y, t);
+        // four cells per iteration with all loads issued first: the kernel is latency-bound otherwise
+        for (int cell0 = blockIdx.x * 4; cell0 < total_cells; cell0 += gridDim.x * 4) {
+            float t[4];
+            long oidx[4];
+            int xs[4], ys[4], sis[4];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                const int cell = cell0 + u;
+                t[u] = 0.f; oidx[u] = -1; xs[u] = ys[u] = sis[u] = 0;
+                if (cell < total_cells) {
+                    const int si = cell >= c2 ? 2 : (cell >= c1 ? 1 : 0);
+                    const DecodeScale& s = P.sc[si];
+                    const int lc = cell - (int)P.cells_before[si];
+                    const int hw = s.h * s.w;
+                    const int b = lc / hw, p = lc - b * hw;
+                    ys[u] = p / s.w; xs[u] = p - ys[u] * s.w; sis[u] = si;
+                    t[u] = __ldg(s.logits + ((long)b * hw + p) * s.ld + c);
+                    oidx[u] = ((long)b * P.n_total + s.row_off) * P.attrs + (long)p * ch + c;
+                }
+            }
+#pragma unroll
+            for (int u = 0; u < 4; ++u)
+                if (oidx[u] >= 0) det[oidx[u]] = decode_one(P.sc[sis[u]], a, attr, xs[u], ys[u], t[u]);
         }
     }
 }
@@ -95,8 +116,8 @@ cudaError_t launch_decode(const DecodeScale sc[3], int nchw, int B, int attrs, i
         P.cells_before[i + 1] = P.cells_before[i] + (long)B * sc[i].h * sc[i].w;
     }
     if (!nchw) {
-        long blocks = P.cells_before[3];
-        if (blocks > 148L * 16) blocks = 148L * 16;       // cell-stride loop, multiple of the SM count
+        long blocks = (P.cells_before[3] + 3) / 4;
+        if (blocks > 148L * 8) blocks = 148L * 8;         // cell-stride loop, multiple of the SM count
         decode_nhwc_kernel<<<(unsigned)blocks, 256, 0, s>>>(P, det);
     } else {
         int nb[3];

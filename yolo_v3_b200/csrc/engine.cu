@@ -27,6 +27,7 @@ struct Op {
     ConvArgs a{};
     bool use_tc = false;
     TcPlan tc;
+    StemTcPlan stem_tc;
 };
 
 struct Plan {
@@ -291,6 +292,10 @@ int build_plan(yb_ctx* c, int B, int H, int W, Plan** out) {
         Op op;
         op.layer = 0; op.stem = true;
         op.a.out = buf[0];
+        if (p->mode == YB_MODE_FP16) {
+            std::string e = stem_tc_make_plan(op.stem_tc, static_cast<__half*>(buf[0]), 32, B, H, W, c->num_sms);
+            if (!e.empty()) return bail("plan: stem: " + e);
+        }
         p->ops.push_back(op);
     }
     int li = 1, ch = 32, h = H, w = W;
@@ -370,7 +375,7 @@ int run_ops(yb_ctx* c, Plan* p, const float* x, int n_ops, cudaStream_t s) {
         cudaError_t e;
         if (op.stem) {
             if (p->mode == YB_MODE_FP16)
-                e = launch_stem<__half>(x, static_cast<__half*>(op.a.out), L.d_w32, L.d_scale, L.d_bias, p->B, p->H, p->W, s);
+                e = stem_tc_launch(op.stem_tc, x, p->B, p->H, p->W, L.d_w16, L.d_scale, L.d_bias, c->dbg, s);
             else
                 e = launch_stem<float>(x, static_cast<float*>(op.a.out), L.d_w32, L.d_scale, L.d_bias, p->B, p->H, p->W, s);
         } else if (op.use_tc) {
@@ -577,7 +582,8 @@ int yb_finalize(yb_ctx* c, int mode) {
         offs[i].bias = place(sizeof(float) * L.cout_pad);
         const bool need32 = mode == YB_MODE_FP32 || i == 0;
         offs[i].w32 = need32 ? place(sizeof(float) * K * L.cout_pad) : (size_t)-1;
-        offs[i].w16 = (mode == YB_MODE_FP16 && i != 0) ? place(sizeof(__half) * K * L.cout_pad) : (size_t)-1;
+        // the stem's fp16 weights are [32][K padded to 32] for the tensor-core stem kernel
+        offs[i].w16 = mode == YB_MODE_FP16 ? place(sizeof(__half) * (i == 0 ? 32 : K) * L.cout_pad) : (size_t)-1;
     }
     if (off != c->blob_bytes || !c->d_blob) {
         cudaFree(c->d_blob);
@@ -613,10 +619,11 @@ int yb_finalize(yb_ctx* c, int mode) {
         }
         if (offs[i].w16 != (size_t)-1) {
             __half* w = reinterpret_cast<__half*>(host.data() + offs[i].w16);  // [cout_pad][tap][cin]
+            const int Kp = i == 0 ? 32 : K;
             for (int n = 0; n < L.cout; ++n)
                 for (int ci = 0; ci < L.cin; ++ci)
                     for (int t = 0; t < taps; ++t)
-                        w[(size_t)n * K + (size_t)t * L.cin + ci] = __float2half_rn(L.w[((size_t)n * L.cin + ci) * taps + t]);
+                        w[(size_t)n * Kp + (size_t)t * L.cin + ci] = __float2half_rn(L.w[((size_t)n * L.cin + ci) * taps + t]);
         }
         L.d_scale = reinterpret_cast<float*>(c->d_blob + offs[i].scale);
         L.d_bias = reinterpret_cast<float*>(c->d_blob + offs[i].bias);
@@ -832,9 +839,15 @@ int yb_run_layer(yb_ctx* c, int li, const void* in, int B, int H, int W, const v
     cudaStream_t s = static_cast<cudaStream_t>(stream);
     const Layer& L = c->layers[li];
     if (li == 0) {
-        cudaError_t e = c->mode == YB_MODE_FP16
-            ? launch_stem<__half>(static_cast<const float*>(in), static_cast<__half*>(out), L.d_w32, L.d_scale, L.d_bias, B, H, W, s)
-            : launch_stem<float>(static_cast<const float*>(in), static_cast<float*>(out), L.d_w32, L.d_scale, L.d_bias, B, H, W, s);
+        cudaError_t e;
+        if (c->mode == YB_MODE_FP16) {
+            StemTcPlan sp;
+            std::string err = stem_tc_make_plan(sp, static_cast<__half*>(out), 32, B, H, W, c->num_sms);
+            if (!err.empty()) return fail(c, YB_E_CUDA, "yb_run_layer: " + err);
+            e = stem_tc_launch(sp, static_cast<const float*>(in), B, H, W, L.d_w16, L.d_scale, L.d_bias, c->dbg, s);
+        } else {
+            e = launch_stem<float>(static_cast<const float*>(in), static_cast<float*>(out), L.d_w32, L.d_scale, L.d_bias, B, H, W, s);
+        }
         ++c->launches;
         YB_CUDA(c, e);
         return YB_OK;

@@ -50,6 +50,82 @@ __device__ __forceinline__ unsigned long long make_key(int cls, float score, int
 }
 
 // ---- K3a ---------------------------------------------------------------------------------------
+// One warp scores kRows consecutive rows per pass: the rows are contiguous in memory, so the warp
+// first issues all its coalesced loads (kRows*(5+C) floats, up to 12 per lane) and only then reduces,
+// which keeps enough bytes in flight to approach HBM bandwidth.
+constexpr int kRows = 4;
+constexpr int kMaxLoads = 12;     // kRows*(5+C) <= 384  <=>  C <= 91; wider rows take the one-row path
+
+__device__ __forceinline__ void pp_emit_row(long row, int N, int lane, float cx, float cy, float w, float h, float obj,
+                                            float best, int bidx, float* __restrict__ rowcand) {
+    const float hw = __fdiv_rn(w, 2.f), hh = __fdiv_rn(h, 2.f);
+    float o = 0.f;
+    switch (lane) {
+        case 0: o = __fsub_rn(cx, hw); break;
+        case 1: o = __fsub_rn(cy, hh); break;
+        case 2: o = __fadd_rn(cx, hw); break;
+        case 3: o = __fadd_rn(cy, hh); break;
+        case 4: o = obj; break;
+        case 5: o = best; break;
+        case 6: o = (float)bidx; break;
+        case 7: o = __int_as_float((int)(row % N)); break;
+        default: break;
+    }
+    if (lane < 8) rowcand[row * 8 + lane] = o;
+}
+
+__global__ void __launch_bounds__(256) pp_score4_kernel(const float* __restrict__ det, long rows, int N, int C,
+                                                        float thr, int is_eval, int* __restrict__ rowcount,
+                                                        float* __restrict__ rowcand) {
+    const int lane = threadIdx.x & 31;
+    const int A = 5 + C;
+    const long row0 = ((long)blockIdx.x * 8 + (threadIdx.x >> 5)) * kRows;
+    if (row0 >= rows) return;
+    const int nrow = (int)min((long)kRows, rows - row0);
+    const int total = nrow * A;
+    const float* r = det + row0 * A;
+    float v[kMaxLoads];
+#pragma unroll
+    for (int k = 0; k < kMaxLoads; ++k) {
+        const int e = lane + 32 * k;
+        v[k] = e < total ? __ldg(r + e) : 0.f;
+    }
+    float hdr[kRows];                              // lanes 0..4 of hdr[j] = cx,cy,w,h,obj of row j (one 20-byte load)
+#pragma unroll
+    for (int j = 0; j < kRows; ++j) hdr[j] = (j < nrow && lane < 5) ? __ldg(r + j * A + lane) : 0.f;
+#pragma unroll
+    for (int j = 0; j < kRows; ++j) {
+        if (j >= nrow) break;
+        const float obj = __shfl_sync(0xffffffffu, hdr[j], 4);
+        float best = -INFINITY;
+        int bidx = 0x7fffffff, cnt = 0;
+#pragma unroll
+        for (int k = 0; k < kMaxLoads; ++k) {
+            const int e = lane + 32 * k - j * A;           // element index inside row j
+            const bool isc = e >= 5 && e < A;
+            const float s = __fmul_rn(v[k], obj);
+            if (is_eval) cnt += __popc(__ballot_sync(0xffffffffu, isc && s > thr));
+            else if (isc && s > best) { best = s; bidx = e - 5; }
+        }
+        const long row = row0 + j;
+        if (is_eval) {
+            if (lane == 0) rowcount[row] = cnt;
+            continue;
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            const float ob = __shfl_xor_sync(0xffffffffu, best, o);
+            const int oi = __shfl_xor_sync(0xffffffffu, bidx, o);
+            if (ob > best || (ob == best && oi < bidx)) { best = ob; bidx = oi; }
+        }
+        const bool pass = best > thr;
+        if (lane == 0) rowcount[row] = pass ? 1 : 0;
+        if (pass)
+            pp_emit_row(row, N, lane, __shfl_sync(0xffffffffu, hdr[j], 0), __shfl_sync(0xffffffffu, hdr[j], 1),
+                        __shfl_sync(0xffffffffu, hdr[j], 2), __shfl_sync(0xffffffffu, hdr[j], 3), obj, best, bidx, rowcand);
+    }
+}
+
 __global__ void __launch_bounds__(256) pp_score_kernel(const float* __restrict__ det, long rows, int N, int C,
                                                        float thr, int is_eval, int* __restrict__ rowcount,
                                                        float* __restrict__ rowcand) {
@@ -87,24 +163,9 @@ __global__ void __launch_bounds__(256) pp_score_kernel(const float* __restrict__
     }
     const bool pass = best > thr;
     if (lane == 0) rowcount[row] = pass ? 1 : 0;
-    if (pass) {
-        const float cx = __shfl_sync(0xffffffffu, v0, 0), cy = __shfl_sync(0xffffffffu, v0, 1);
-        const float w = __shfl_sync(0xffffffffu, v0, 2), h = __shfl_sync(0xffffffffu, v0, 3);
-        const float hw = __fdiv_rn(w, 2.f), hh = __fdiv_rn(h, 2.f);
-        float o = 0.f;
-        switch (lane) {
-            case 0: o = __fsub_rn(cx, hw); break;
-            case 1: o = __fsub_rn(cy, hh); break;
-            case 2: o = __fadd_rn(cx, hw); break;
-            case 3: o = __fadd_rn(cy, hh); break;
-            case 4: o = obj; break;
-            case 5: o = best; break;
-            case 6: o = (float)bidx; break;
-            case 7: o = __int_as_float((int)(row % N)); break;
-            default: break;
-        }
-        if (lane < 8) rowcand[row * 8 + lane] = o;
-    }
+    if (pass)
+        pp_emit_row(row, N, lane, __shfl_sync(0xffffffffu, v0, 0), __shfl_sync(0xffffffffu, v0, 1),
+                    __shfl_sync(0xffffffffu, v0, 2), __shfl_sync(0xffffffffu, v0, 3), obj, best, bidx, rowcand);
 }
 
 // ---- K3b ---------------------------------------------------------------------------------------
@@ -371,7 +432,11 @@ cudaError_t launch_postprocess(const PostArgs& a, PostBuffers& buf, long long* l
         cudaFuncSetAttribute(pp_nms_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kNmsSmemBoxes * 17);
         attrs_set = true;
     }
-    pp_score_kernel<<<(unsigned)((rows + 7) / 8), 256, 0, s>>>(a.det, rows, a.N, a.C, a.conf_thr, a.is_eval, buf.rowcount, buf.rowcand);
+    if (kRows * (5 + a.C) <= 32 * kMaxLoads)
+        pp_score4_kernel<<<(unsigned)((rows + 8 * kRows - 1) / (8 * kRows)), 256, 0, s>>>(a.det, rows, a.N, a.C, a.conf_thr, a.is_eval,
+                                                                                        buf.rowcount, buf.rowcand);
+    else
+        pp_score_kernel<<<(unsigned)((rows + 7) / 8), 256, 0, s>>>(a.det, rows, a.N, a.C, a.conf_thr, a.is_eval, buf.rowcount, buf.rowcand);
     pp_scan_kernel<<<a.B, 1024, 0, s>>>(buf.rowcount, a.N, buf.rowoff, buf.cand_total);
     if (a.is_eval)
         pp_scatter_kernel<<<(unsigned)((rows + 7) / 8), 256, 0, s>>>(a.det, a.N, a.C, a.conf_thr, 1, rows, buf.rowcount, buf.rowoff,

@@ -69,10 +69,11 @@ cudaError_t launch_f32_to_f16(const float* in, __half* out, size_t n, cudaStream
 
 // conv_tc.cu  (tcgen05 + TMA implicit GEMM)
 struct TcPlan {
-    CUtensorMap tmA, tmB;
+    CUtensorMap tmA, tmB, tmOut, tmRes;
+    int epi_staged = 0, ring = 0, sub_bytes = 128, cs = 0, n_sub = 0, b_resident = 0, exp_tiled = 0;
     int swz = 128;        // 128: 64-channel k-blocks, 64: 32-channel k-blocks (Cin == 32)
     int BN = 0, n_tiles = 0, m_tiles = 0, stages = 0, tmem_cols = 0;
-    int num_kblocks = 0, cin_blocks = 0;
+    int num_kblocks = 0, cin_blocks = 0, kps = 1, cta2 = 0;
     int grid = 0;
     size_t smem = 0;
     long M = 0;
@@ -81,6 +82,16 @@ struct TcPlan {
 std::string tc_make_plan(TcPlan& p, const ConvArgs& a, const __half* w16, int cout_pad, int K, int num_sms);
 cudaError_t tc_launch(const TcPlan& p, const ConvArgs& a, int* dbg, cudaStream_t s);
 bool tc_supported(const ConvArgs& a);
+// Cin=3 stem on the tensor cores (producer warps build the im2col rows): NCHW fp32 image -> NHWC fp16 [B,H,W,32]
+struct StemTcPlan {
+    CUtensorMap tmOut;
+    long M = 0;
+    int tiles = 0, grid = 0;
+    size_t smem = 0;
+};
+std::string stem_tc_make_plan(StemTcPlan& p, __half* out, long out_ld, int B, int H, int W, int num_sms);
+cudaError_t stem_tc_launch(const StemTcPlan& p, const float* x, int B, int H, int W, const __half* w16, const float* scale,
+                           const float* bias, int* dbg, cudaStream_t s);
 
 // decode.cu
 struct DecodeScale {
