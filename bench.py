@@ -82,8 +82,8 @@ def cpu_reference(batch, hw, reps, num_threads=None):
     import torch
     from oracle import yolo_oracle as O
     from yolo_v3_b200 import synth
-    if num_threads:
-        torch.set_num_threads(num_threads)
+    # torchrun exports OMP_NUM_THREADS=1; the CPU arm is meant to use every host core
+    torch.set_num_threads(num_threads or os.cpu_count() or 1)
     sd = synth.make_state_dict(seed=1234, recipe="calibrated")
     x = synth.make_images(batch, hw, hw, seed=0)
     best = None
