@@ -72,6 +72,19 @@ struct TcArgs {
 // ---- PTX wrappers --------------------------------------------------------------------------------
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
+// One lane of a converged warp.  The producer and MMA loops are executed by their WHOLE warp with
+// warp-uniform values and only the asynchronous instructions are guarded by this predicate: that lets
+// ptxas keep coordinates / descriptors in uniform registers instead of broadcasting them lane by lane.
+__device__ __forceinline__ bool elect_one() {
+    uint32_t pred;
+    asm volatile(
+        "{\n\t.reg .pred P;\n\t"
+        "elect.sync _|P, 0xffffffff;\n\t"
+        "selp.u32 %0, 1, 0, P;\n\t}"
+        : "=r"(pred));
+    return pred != 0;
+}
+
 __device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
     asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
 }
@@ -86,6 +99,15 @@ __device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
     asm volatile(
         "{\n\t.reg .pred p;\n\t"
         "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
+    return ok != 0;
+}
+__device__ __forceinline__ bool mbar_test_wait(uint32_t bar, uint32_t parity) {   // non-blocking probe
+    uint32_t ok;
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
         "selp.u32 %0, 1, 0, p;\n\t}"
         : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
     return ok != 0;
@@ -374,7 +396,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     const uint32_t full0 = base, empty0 = base + 8 * kMaxStages;
     const uint32_t tfull0 = base + 16 * kMaxStages, tempty0 = tfull0 + 16;
     volatile uint32_t* tmem_ptr = reinterpret_cast<volatile uint32_t*>(gen + 16 * kMaxStages + 32);
-    const uint32_t sfull0 = base + 16 * kMaxStages + 64, sempty0 = sfull0 + 32, bres_bar = sempty0 + 32;
+    const uint32_t sfull0 = base + 16 * kMaxStages + 64, sempty0 = sfull0 + 32, bres_bar = sempty0 + 32, sready0 = bres_bar + 16;
     // staging ring (epilogue), resident weight slab, then the operand pipeline stages; all 1024-byte aligned
     const uint32_t stg_bytes = (uint32_t)kBM * (uint32_t)a.sub_bytes;
     const uint32_t stg0 = base + (uint32_t)kSmemHeader;
@@ -395,7 +417,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     if (warp == 1 && lane == 0) {
         for (int s = 0; s < a.stages; ++s) { mbar_init(full0 + 8 * s, 1); mbar_init(empty0 + 8 * s, 1); }
         for (int i = 0; i < 2; ++i) { mbar_init(tfull0 + 8 * i, 1); mbar_init(tempty0 + 8 * i, (a.epi_staged ? 8 : 4) * NCTA); }
-        for (int i = 0; i < kMaxRing; ++i) { mbar_init(sfull0 + 8 * i, 1); mbar_init(sempty0 + 8 * i, 1); }
+        for (int i = 0; i < kMaxRing; ++i) { mbar_init(sfull0 + 8 * i, 1); mbar_init(sempty0 + 8 * i, 1); mbar_init(sready0 + 8 * i, 8); }
         mbar_init(bres_bar, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
@@ -410,16 +432,17 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     const uint32_t acc_stride = (uint32_t)a.tmem_cols >> 1;
 
     if (warp == 0) {
-        // ===== TMA producer =====
-        if (lane == 0) {
+        // ===== TMA producer (whole warp, one elected lane issues) =====
+        {
             int stage = 0;
             uint32_t phase = 0;
-            if (a.b_resident && tile_first < total_tiles) {
+            if (a.b_resident && tile_first < total_tiles && elect_one()) {
                 // gridDim.x is a multiple of n_tiles, so every tile of this CTA has the same n-tile
                 const int n0 = ((int)blockIdx.x % a.n_tiles) * a.BN;
                 mbar_arrive_expect_tx(bres_bar, (uint32_t)a.num_kblocks * B_BYTES);
                 for (int kb = 0; kb < a.num_kblocks; ++kb) tma_load_2d(&tmB, bres0 + kb * B_SLOT, bres_bar, kb * BKE, n0);
             }
+            __syncwarp();
             // The loop below runs on one thread; everything that can be is carried incrementally
             // (no divisions, no address recomputation) because its latency paces the pipeline.
             const uint32_t tx_bytes = (a.b_resident ? A_BYTES : A_BYTES + B_BYTES) * (uint32_t)a.kps * NCTA;
@@ -435,15 +458,18 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                     int kc = 0, ka = 0;
                     for (int it = 0; it < a.num_iters; ++it) {
                         mbar_wait(eb, phase ^ 1, a.dbg, 0, stage);
-                        if (leader) mbar_arrive_expect_tx(fb, tx_bytes);
+                        const bool el = elect_one();
+                        if (leader && el) mbar_arrive_expect_tx(fb, tx_bytes);
                         uint32_t dst = sA;
                         for (int j = 0; j < a.kps; ++j) {
-                            if constexpr (CTA2) {
-                                tma_load_2d_pair(&tmA, dst, fb, kc, m0);
-                                tma_load_2d_pair(&tmB, dst + A_BYTES, fb, kc, n0);
-                            } else {
-                                tma_load_2d(&tmA, dst, fb, a.exp_tiled ? ka : kc, m0);
-                                if (load_b) tma_load_2d(&tmB, dst + A_BYTES, fb, kc, n0);
+                            if (el) {
+                                if constexpr (CTA2) {
+                                    tma_load_2d_pair(&tmA, dst, fb, kc, m0);
+                                    tma_load_2d_pair(&tmB, dst + A_BYTES, fb, kc, n0);
+                                } else {
+                                    tma_load_2d(&tmA, dst, fb, a.exp_tiled ? ka : kc, m0);
+                                    if (load_b) tma_load_2d(&tmB, dst + A_BYTES, fb, kc, n0);
+                                }
                             }
                             kc += BKE;
                             ka += BKE;
@@ -463,15 +489,18 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                     const int cend = a.cin_blocks * BKE;
                     for (int it = 0; it < a.num_iters; ++it) {
                         mbar_wait(eb, phase ^ 1, a.dbg, 0, stage);
-                        if (leader) mbar_arrive_expect_tx(fb, tx_bytes);
+                        const bool el = elect_one();
+                        if (leader && el) mbar_arrive_expect_tx(fb, tx_bytes);
                         uint32_t dst = sA;
                         for (int j = 0; j < a.kps; ++j) {
-                            if constexpr (CTA2) {
-                                tma_load_im2col_pair(&tmA, dst, fb, cc, cw, chh, cn, kw, kh);
-                                tma_load_2d_pair(&tmB, dst + A_BYTES, fb, kc, n0);
-                            } else {
-                                tma_load_im2col(&tmA, dst, fb, cc, cw, chh, cn, kw, kh);
-                                if (load_b) tma_load_2d(&tmB, dst + A_BYTES, fb, kc, n0);
+                            if (el) {
+                                if constexpr (CTA2) {
+                                    tma_load_im2col_pair(&tmA, dst, fb, cc, cw, chh, cn, kw, kh);
+                                    tma_load_2d_pair(&tmB, dst + A_BYTES, fb, kc, n0);
+                                } else {
+                                    tma_load_im2col(&tmA, dst, fb, cc, cw, chh, cn, kw, kh);
+                                    if (load_b) tma_load_2d(&tmB, dst + A_BYTES, fb, kc, n0);
+                                }
                             }
                             kc += BKE;
                             cc += BKE;
@@ -487,8 +516,8 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         }
         __syncwarp();
     } else if (warp == 1) {
-        // ===== MMA issuer =====
-        if (lane == 0 && leader) {
+        // ===== MMA issuer (whole warp of the leader CTA, one elected lane issues) =====
+        if (leader) {
             const uint32_t idesc = make_idesc(a.BN, kBM * NCTA);
             int stage = 0;
             uint32_t phase = 0, acc = 0, acc_phase = 0;
@@ -498,6 +527,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             const uint64_t bres_desc = make_smem_desc<SWZ>(bres0), bres_inc = B_SLOT >> 4;
             uint64_t adesc = adesc0;
             uint32_t fbar = full0, ebar = empty0;
+            bool ready = false;
             if (a.b_resident && tile_first < total_tiles) mbar_wait(bres_bar, 0, a.dbg, 1, 600);
             int ti = 0;
             for (int tile = tile_first; tile < total_tiles; tile += tile_step, ++ti) {
@@ -508,27 +538,37 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                 const uint32_t d_tmem = tmem_base + acc * acc_stride;
                 int kb = 0;
                 for (int it = 0; it < a.num_iters; ++it) {
-                    mbar_wait(fbar, phase, a.dbg, 1, stage);
+                    if (!ready) mbar_wait(fbar, phase, a.dbg, 1, stage);
                     tc_fence_after();
+                    // probe the NEXT stage's barrier now: its latency overlaps the MMA issue below
+                    const bool wrap = stage + 1 == a.stages;
+                    ready = mbar_test_wait(wrap ? full0 : fbar + 8, wrap ? phase ^ 1 : phase);
+                    const bool el = elect_one();
                     uint64_t ad = adesc;
                     for (int j = 0; j < a.kps; ++j, ++kb) {
                         const uint64_t bd = a.b_resident ? bres_desc + (uint64_t)kb * bres_inc : ad + b_off;
-                        if constexpr (CTA2) {
+                        if (el) {
+                            if constexpr (CTA2) {
 #pragma unroll
-                            for (int k = 0; k < BKE / 16; ++k) umma_f16_pair(d_tmem, ad + 2 * k, bd + 2 * k, idesc, (kb | k) != 0);
-                        } else {
-                            umma_f16(d_tmem, ad, bd, idesc, kb != 0);
+                                for (int k = 0; k < BKE / 16; ++k) umma_f16_pair(d_tmem, ad + 2 * k, bd + 2 * k, idesc, (kb | k) != 0);
+                            } else {
+                                umma_f16(d_tmem, ad, bd, idesc, kb != 0);
 #pragma unroll
-                            for (int k = 1; k < BKE / 16; ++k)   // 16 fp16 = 32 bytes per MMA: descriptor address += 2
-                                umma_f16_imm<1>(d_tmem, ad + 2 * k, bd + 2 * k, idesc);
+                                for (int k = 1; k < BKE / 16; ++k)   // 16 fp16 = 32 bytes per MMA: descriptor address += 2
+                                    umma_f16_imm<1>(d_tmem, ad + 2 * k, bd + 2 * k, idesc);
+                            }
                         }
                         ad += kb_inc;
                     }
-                    if constexpr (CTA2) umma_commit_pair(ebar); else umma_commit(ebar);   // frees the stage (in both CTAs)
+                    if (el) {
+                        if constexpr (CTA2) umma_commit_pair(ebar); else umma_commit(ebar);   // frees the stage (in both CTAs)
+                    }
                     adesc += stage_inc; fbar += 8; ebar += 8;
                     if (++stage == a.stages) { stage = 0; phase ^= 1; adesc = adesc0; fbar = full0; ebar = empty0; }
                 }
-                if constexpr (CTA2) umma_commit_pair(tfull0 + 8 * acc); else umma_commit(tfull0 + 8 * acc);   // accumulator complete
+                if (elect_one()) {
+                    if constexpr (CTA2) umma_commit_pair(tfull0 + 8 * acc); else umma_commit(tfull0 + 8 * acc);   // accumulator complete
+                }
                 YB_TRACE(1, ti, 2);
                 acc ^= 1;
                 if (acc == 0) acc_phase ^= 1;
@@ -549,6 +589,28 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                     tma_load_2d(&tmRes, stg0 + buf * stg_bytes, sfull0 + 8 * buf, n0 + j * a.cs, m0);
                 }
             }
+        }
+        __syncwarp();
+    } else if (warp == 2) {
+        // ===== store issuer: waits until the eight epilogue warps have filled a staging sub-tile, writes it
+        // back with one TMA store and recycles the buffer once the store has drained it =====
+        if (lane == 0 && a.epi_staged) {
+            uint32_t g = 0;
+            for (int tile = tile_first; tile < total_tiles; tile += tile_step) {
+                const int m_unit = tile / a.n_tiles, n_tile = tile - m_unit * a.n_tiles;
+                const int m0 = (m_unit * NCTA + (int)rank) * kBM, n0 = n_tile * a.BN;
+                for (int j = 0; j < a.n_sub; ++j, ++g) {
+                    const uint32_t buf = g % (uint32_t)a.ring, ph = (g / (uint32_t)a.ring) & 1u;
+                    mbar_wait(sready0 + 8 * buf, ph, a.dbg, 4, 700 + (int)buf);
+                    tma_store_2d(&tmOut, stg0 + buf * stg_bytes, n0 + j * a.cs, m0);
+                    tma_store_commit();
+                    if (g > 0) {                              // the previous store has finished reading its buffer
+                        tma_store_wait_read<1>();
+                        mbar_arrive(sempty0 + 8 * ((g - 1) % (uint32_t)a.ring));
+                    }
+                }
+            }
+            tma_store_wait_all();
         }
         __syncwarp();
     } else if (warp >= 4 && a.epi_staged) {
@@ -595,21 +657,13 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                 if (active) epilogue16_staged(a, r0, nb + g0 * 16, srow, g0, xr);
                 if (active && gph > 1) epilogue16_staged(a, r1, nb + g0 * 16 + 16, srow, g0 + 1, xr);
                 fence_async_smem();                           // generic-proxy smem writes -> visible to the TMA engine
-                epi_bar_sync256();
-                if (issuer) {
-                    tma_store_2d(&tmOut, stg0 + buf * stg_bytes, nb, m0);
-                    tma_store_commit();
-                    if (g > 0) {                              // the previous store has finished reading its buffer
-                        tma_store_wait_read<1>();
-                        mbar_arrive(sempty0 + 8 * ((g - 1) % (uint32_t)a.ring));
-                    }
-                }
+                __syncwarp();
+                if (lane == 0) mbar_arrive(sready0 + 8 * buf);   // no block-wide barrier: warps run ahead independently
             }
             if (issuer) YB_TRACE(2, ti, 2);
             acc ^= 1;
             if (acc == 0) acc_phase ^= 1;
         }
-        if (issuer) tma_store_wait_all();
     } else if (warp >= 4 && warp < 8) {
         // ===== epilogue (direct): TMEM -> registers -> global, used by the nearest-upsample layers =====
         const int q = warp - 4;                               // TMEM lane quarter this warp may read

@@ -39,37 +39,38 @@ __device__ __forceinline__ float decode_one(const DecodeScale& s, int a, int att
 }
 
 // NHWC (engine-internal) input: element (b, p, c) -> out[b][row_off*attrs + p*3*attrs + c]: a flat
-// elementwise map.  One thread per channel (so anchor/attr are computed once), blocks stride over cells;
-// consecutive threads touch consecutive addresses on both sides.
-__global__ void __launch_bounds__(256) decode_nhwc_kernel(const __grid_constant__ DecodeParams P, float* __restrict__ det) {
+// elementwise map.  A block owns kCellsPerBlock consecutive cells of one image and scale (so the cell ->
+// (x, y) arithmetic is two scalar divisions per block and increments afterwards); thread t owns channel
+// t (anchor/attr computed once) and walks the cells, four loads in flight at a time; consecutive threads
+// touch consecutive addresses on both sides.
+constexpr int kCellsPerBlock = 16;
+
+__global__ void __launch_bounds__(256) decode_nhwc_kernel(const __grid_constant__ DecodeParams P, float* __restrict__ det,
+                                                          int blocks_s0, int blocks_s1) {
     const int ch = 3 * P.attrs;
-    const int total_cells = (int)P.cells_before[3];
-    const int c1 = (int)P.cells_before[1], c2 = (int)P.cells_before[2];
+    int blk = blockIdx.x;
+    const int si = blk >= blocks_s0 + blocks_s1 ? 2 : (blk >= blocks_s0 ? 1 : 0);
+    blk -= si == 2 ? blocks_s0 + blocks_s1 : (si == 1 ? blocks_s0 : 0);
+    const DecodeScale& s = P.sc[si];
+    const int hw = s.h * s.w;
+    const int per_img = (hw + kCellsPerBlock - 1) / kCellsPerBlock;
+    const int b = blk / per_img, p0 = (blk - b * per_img) * kCellsPerBlock;
+    const int np = min(kCellsPerBlock, hw - p0);
+    const int y0 = p0 / s.w, x0 = p0 - y0 * s.w;
+    const float* in = s.logits + ((long)b * hw + p0) * s.ld;
+    float* out = det + ((long)b * P.n_total + s.row_off) * P.attrs + (long)p0 * ch;
     for (int c = threadIdx.x; c < ch; c += blockDim.x) {
-        const int a = c / P.attrs, attr = c % P.attrs;
-        // four cells per iteration with all loads issued first: the kernel is latency-bound otherwise
-        for (int cell0 = blockIdx.x * 4; cell0 < total_cells; cell0 += gridDim.x * 4) {
+        const int a = c / P.attrs, attr = c - a * P.attrs;
+        int x = x0, y = y0;
+        for (int i0 = 0; i0 < np; i0 += 4) {
             float t[4];
-            long oidx[4];
-            int xs[4], ys[4], sis[4];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) t[u] = i0 + u < np ? __ldg(in + (long)(i0 + u) * s.ld + c) : 0.f;
 #pragma unroll
             for (int u = 0; u < 4; ++u) {
-                const int cell = cell0 + u;
-                t[u] = 0.f; oidx[u] = -1; xs[u] = ys[u] = sis[u] = 0;
-                if (cell < total_cells) {
-                    const int si = cell >= c2 ? 2 : (cell >= c1 ? 1 : 0);
-                    const DecodeScale& s = P.sc[si];
-                    const int lc = cell - (int)P.cells_before[si];
-                    const int hw = s.h * s.w;
-                    const int b = lc / hw, p = lc - b * hw;
-                    ys[u] = p / s.w; xs[u] = p - ys[u] * s.w; sis[u] = si;
-                    t[u] = __ldg(s.logits + ((long)b * hw + p) * s.ld + c);
-                    oidx[u] = ((long)b * P.n_total + s.row_off) * P.attrs + (long)p * ch + c;
-                }
+                if (i0 + u < np) out[(long)(i0 + u) * ch + c] = decode_one(s, a, attr, x, y, t[u]);
+                if (++x == s.w) { x = 0; ++y; }
             }
-#pragma unroll
-            for (int u = 0; u < 4; ++u)
-                if (oidx[u] >= 0) det[oidx[u]] = decode_one(P.sc[sis[u]], a, attr, xs[u], ys[u], t[u]);
         }
     }
 }
@@ -116,9 +117,9 @@ cudaError_t launch_decode(const DecodeScale sc[3], int nchw, int B, int attrs, i
         P.cells_before[i + 1] = P.cells_before[i] + (long)B * sc[i].h * sc[i].w;
     }
     if (!nchw) {
-        long blocks = (P.cells_before[3] + 3) / 4;
-        if (blocks > 148L * 8) blocks = 148L * 8;         // cell-stride loop, multiple of the SM count
-        decode_nhwc_kernel<<<(unsigned)blocks, 256, 0, s>>>(P, det);
+        int nb[3];
+        for (int i = 0; i < 3; ++i) nb[i] = B * ((sc[i].h * sc[i].w + kCellsPerBlock - 1) / kCellsPerBlock);
+        decode_nhwc_kernel<<<nb[0] + nb[1] + nb[2], 256, 0, s>>>(P, det, nb[0], nb[1]);
     } else {
         int nb[3];
         for (int i = 0; i < 3; ++i) nb[i] = B * ((sc[i].h * sc[i].w + 31) / 32);
