@@ -33,7 +33,8 @@ namespace {
 
 constexpr int kBM = 128;
 constexpr int kMaxStages = 16;
-constexpr int kThreads = 384;            // warp 0 TMA, 1 MMA, 2 TMEM alloc, 3 residual TMA, 4-11 epilogue
+constexpr int kThreads = 768;            // warps 0-1 TMA producers, 2 MMA, 3 TMEM alloc + store issuer, 4 residual TMA, 8-23 epilogue
+constexpr int kEpiWarps = 16;
 constexpr int kMaxRing = 4;              // epilogue staging ring depth
 constexpr size_t kSmemBudget = 227 * 1024;
 constexpr size_t kSmemHeader = 1024;     // barriers + tmem pointer
@@ -48,6 +49,8 @@ struct TcArgs {
     int BN, n_tiles, m_tiles;
     int stages, tmem_cols;
     const float* scale; const float* bias;
+    const float* tab;        // device-side: smem copy of scale[cout_pad] | bias[cout_pad] (set inside the kernel)
+    int cout_pad, tab_bytes; // tab_bytes = 2*cout_pad*4 rounded up to 1 KB
     void* out; long out_ld; int out_f32;
     const __half* res; long res_ld;
     int leaky, upsample;
@@ -61,7 +64,7 @@ struct TcArgs {
     int exp_tiled;           // timing experiment: fetch 3x3 A tiles with tiled-mode TMA (results are wrong)
     int b_resident;          // 1: the CTA's whole weight slab [BN][K] is loaded once and stays in smem
     int* dbg;
-    long long* trace;        // optional [3 roles][64 tiles][4] clock64 stamps of CTA 0 (YB_TC_TRACE=1)
+    long long* trace;        // optional [5 roles][64 tiles][4] clock64 stamps of CTA 0 (YB_TC_TRACE=1)
 };
 
 #define YB_TRACE(role, idx, slot)                                                                   \
@@ -271,11 +274,13 @@ __device__ __forceinline__ float leaky(float v) { return v > 0.f ? v : v * kLeak
 __device__ __forceinline__ void epilogue16(const TcArgs& a, const uint32_t (&acc)[16], int n, bool valid, long m,
                                            long o00, long W2ld) {
     float v[16];
-    const float4* sc = reinterpret_cast<const float4*>(a.scale + n);
-    const float4* bi = reinterpret_cast<const float4*>(a.bias + n);
+    // scale/bias come from the shared-memory table: with ~227 KB of smem carved out there is no L1 left,
+    // so global loads here would each pay an L2 round trip
+    const float4* sc = reinterpret_cast<const float4*>(a.tab + n);
+    const float4* bi = reinterpret_cast<const float4*>(a.tab + a.cout_pad + n);
 #pragma unroll
     for (int q = 0; q < 4; ++q) {
-        const float4 s4 = __ldg(sc + q), b4 = __ldg(bi + q);
+        const float4 s4 = sc[q], b4 = bi[q];
         v[4 * q + 0] = fmaf(__uint_as_float(acc[4 * q + 0]), s4.x, b4.x);
         v[4 * q + 1] = fmaf(__uint_as_float(acc[4 * q + 1]), s4.y, b4.y);
         v[4 * q + 2] = fmaf(__uint_as_float(acc[4 * q + 2]), s4.z, b4.z);
@@ -332,11 +337,11 @@ __device__ __forceinline__ void epilogue16(const TcArgs& a, const uint32_t (&acc
 __device__ __forceinline__ void epilogue16_staged(const TcArgs& a, const uint32_t (&acc)[16], int n, uint8_t* srow,
                                                   int grp, int xr) {
     float v[16];
-    const float4* sc = reinterpret_cast<const float4*>(a.scale + n);
-    const float4* bi = reinterpret_cast<const float4*>(a.bias + n);
+    const float4* sc = reinterpret_cast<const float4*>(a.tab + n);            // shared-memory table (see above)
+    const float4* bi = reinterpret_cast<const float4*>(a.tab + a.cout_pad + n);
 #pragma unroll
     for (int q = 0; q < 4; ++q) {
-        const float4 s4 = __ldg(sc + q), b4 = __ldg(bi + q);
+        const float4 s4 = sc[q], b4 = bi[q];
         v[4 * q + 0] = fmaf(__uint_as_float(acc[4 * q + 0]), s4.x, b4.x);
         v[4 * q + 1] = fmaf(__uint_as_float(acc[4 * q + 1]), s4.y, b4.y);
         v[4 * q + 2] = fmaf(__uint_as_float(acc[4 * q + 2]), s4.z, b4.z);
@@ -378,8 +383,9 @@ __device__ __forceinline__ void epilogue16_staged(const TcArgs& a, const uint32_
 template <int SWZ, bool CTA2>
 __global__ void __launch_bounds__(kThreads, 1)
 conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
-               const __grid_constant__ CUtensorMap tmOut, const __grid_constant__ CUtensorMap tmRes, const TcArgs a) {
+               const __grid_constant__ CUtensorMap tmOut, const __grid_constant__ CUtensorMap tmRes, const TcArgs a_in) {
     constexpr int BKE = SWZ / 2;                  // fp16 elements per k-block row
+    TcArgs a = a_in;
     constexpr uint32_t A_BYTES = kBM * SWZ;
     extern __shared__ uint8_t smem_raw[];
     const uint32_t raw = smem_u32(smem_raw);
@@ -399,7 +405,8 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     const uint32_t sfull0 = base + 16 * kMaxStages + 64, sempty0 = sfull0 + 32, bres_bar = sempty0 + 32, sready0 = bres_bar + 16;
     // staging ring (epilogue), resident weight slab, then the operand pipeline stages; all 1024-byte aligned
     const uint32_t stg_bytes = (uint32_t)kBM * (uint32_t)a.sub_bytes;
-    const uint32_t stg0 = base + (uint32_t)kSmemHeader;
+    a.tab = reinterpret_cast<const float*>(gen + kSmemHeader);          // scale | bias table
+    const uint32_t stg0 = base + (uint32_t)kSmemHeader + (uint32_t)a.tab_bytes;
     const uint32_t B_SLOT = (B_BYTES + 1023u) & ~1023u;
     const uint32_t bres0 = stg0 + (a.epi_staged ? (uint32_t)a.ring * ((stg_bytes + 1023u) & ~1023u) : 0u);
     const uint32_t stage0 = bres0 + (a.b_resident ? (uint32_t)a.num_kblocks * B_SLOT : 0u);
@@ -408,20 +415,25 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     const int total_tiles = a.m_tiles * a.n_tiles;          // m_tiles counts 256-row units in pair mode
     const int tile_first = blockIdx.x / NCTA, tile_step = gridDim.x / NCTA;
 
+    for (int i = threadIdx.x; i < a.cout_pad; i += kThreads) {
+        float* tab = reinterpret_cast<float*>(gen + kSmemHeader);
+        tab[i] = __ldg(a.scale + i);
+        tab[a.cout_pad + i] = __ldg(a.bias + i);
+    }
     if (warp == 0 && lane == 0) {
         prefetch_tmap(&tmA);
         prefetch_tmap(&tmB);
         if (a.epi_staged) prefetch_tmap(&tmOut);
         if (a.epi_staged && a.has_res) prefetch_tmap(&tmRes);
     }
-    if (warp == 1 && lane == 0) {
+    if (warp == 2 && lane == 0) {
         for (int s = 0; s < a.stages; ++s) { mbar_init(full0 + 8 * s, 1); mbar_init(empty0 + 8 * s, 1); }
-        for (int i = 0; i < 2; ++i) { mbar_init(tfull0 + 8 * i, 1); mbar_init(tempty0 + 8 * i, (a.epi_staged ? 8 : 4) * NCTA); }
-        for (int i = 0; i < kMaxRing; ++i) { mbar_init(sfull0 + 8 * i, 1); mbar_init(sempty0 + 8 * i, 1); mbar_init(sready0 + 8 * i, 8); }
+        for (int i = 0; i < 2; ++i) { mbar_init(tfull0 + 8 * i, 1); mbar_init(tempty0 + 8 * i, (a.epi_staged ? kEpiWarps : 4) * NCTA); }
+        for (int i = 0; i < kMaxRing; ++i) { mbar_init(sfull0 + 8 * i, 1); mbar_init(sempty0 + 8 * i, 1); mbar_init(sready0 + 8 * i, kEpiWarps); }
         mbar_init(bres_bar, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
-    if (warp == 2) {
+    if (warp == 3) {
         if constexpr (CTA2) tmem_alloc_pair(smem_u32(const_cast<uint32_t*>(tmem_ptr)), (uint32_t)a.tmem_cols);
         else tmem_alloc(smem_u32(const_cast<uint32_t*>(tmem_ptr)), (uint32_t)a.tmem_cols);
     }
@@ -431,12 +443,15 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     const uint32_t tmem_base = *tmem_ptr;
     const uint32_t acc_stride = (uint32_t)a.tmem_cols >> 1;
 
-    if (warp == 0) {
-        // ===== TMA producer (whole warp, one elected lane issues) =====
+    if (warp < 2) {
+        // ===== TMA producers (two warps take alternate pipeline stages; whole warp runs the loop, one
+        // elected lane issues).  Both walk the same stage/coordinate sequence and act on their own parity. =====
         {
+            const uint32_t pw = (uint32_t)warp;
+            uint32_t itg = 0;                             // running stage counter across tiles
             int stage = 0;
             uint32_t phase = 0;
-            if (a.b_resident && tile_first < total_tiles && elect_one()) {
+            if (pw == 0 && a.b_resident && tile_first < total_tiles && elect_one()) {
                 // gridDim.x is a multiple of n_tiles, so every tile of this CTA has the same n-tile
                 const int n0 = ((int)blockIdx.x % a.n_tiles) * a.BN;
                 mbar_arrive_expect_tx(bres_bar, (uint32_t)a.num_kblocks * B_BYTES);
@@ -453,12 +468,13 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                 const int m_unit = tile / a.n_tiles, n_tile = tile - m_unit * a.n_tiles;
                 const int m0 = (m_unit * NCTA + (int)rank) * kBM;
                 const int n0 = n_tile * a.BN + (int)rank * (a.BN / NCTA);   // this CTA's half of the weight rows
-                YB_TRACE(0, ti, 0);
+                if (pw == 0) YB_TRACE(0, ti, 0);
                 if (a.ks == 1 || a.exp_tiled) {
                     int kc = 0, ka = 0;
-                    for (int it = 0; it < a.num_iters; ++it) {
-                        mbar_wait(eb, phase ^ 1, a.dbg, 0, stage);
-                        const bool el = elect_one();
+                    for (int it = 0; it < a.num_iters; ++it, ++itg) {
+                        const bool mine = (itg & 1u) == pw;
+                        if (mine) mbar_wait(eb, phase ^ 1, a.dbg, 0, stage);
+                        const bool el = mine && elect_one();
                         if (leader && el) mbar_arrive_expect_tx(fb, tx_bytes);
                         uint32_t dst = sA;
                         for (int j = 0; j < a.kps; ++j) {
@@ -487,9 +503,10 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                     int kc = 0, cc = 0;                      // k coordinate of the weights, channel coordinate of A
                     uint16_t kw = 0, kh = 0;
                     const int cend = a.cin_blocks * BKE;
-                    for (int it = 0; it < a.num_iters; ++it) {
-                        mbar_wait(eb, phase ^ 1, a.dbg, 0, stage);
-                        const bool el = elect_one();
+                    for (int it = 0; it < a.num_iters; ++it, ++itg) {
+                        const bool mine = (itg & 1u) == pw;
+                        if (mine) mbar_wait(eb, phase ^ 1, a.dbg, 0, stage);
+                        const bool el = mine && elect_one();
                         if (leader && el) mbar_arrive_expect_tx(fb, tx_bytes);
                         uint32_t dst = sA;
                         for (int j = 0; j < a.kps; ++j) {
@@ -511,11 +528,11 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                         if (++stage == a.stages) { stage = 0; phase ^= 1; sA = stage0; fb = full0; eb = empty0; }
                     }
                 }
-                YB_TRACE(0, ti, 1);
+                if (pw == 0) YB_TRACE(0, ti, 1);
             }
         }
         __syncwarp();
-    } else if (warp == 1) {
+    } else if (warp == 2) {
         // ===== MMA issuer (whole warp of the leader CTA, one elected lane issues) =====
         if (leader) {
             const uint32_t idesc = make_idesc(a.BN, kBM * NCTA);
@@ -575,7 +592,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             }
         }
         __syncwarp();
-    } else if (warp == 3) {
+    } else if (warp == 4) {
         // ===== residual prefetch: TMA loads of the residual sub-tiles into the staging ring =====
         if (lane == 0 && a.epi_staged && a.has_res) {
             uint32_t g = 0;
@@ -591,7 +608,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             }
         }
         __syncwarp();
-    } else if (warp == 2) {
+    } else if (warp == 3) {
         // ===== store issuer: waits until the eight epilogue warps have filled a staging sub-tile, writes it
         // back with one TMA store and recycles the buffer once the store has drained it =====
         if (lane == 0 && a.epi_staged) {
@@ -613,18 +630,17 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             tma_store_wait_all();
         }
         __syncwarp();
-    } else if (warp >= 4 && a.epi_staged) {
+    } else if (warp >= 8 && a.epi_staged) {
         // ===== epilogue (staged): TMEM -> registers -> swizzled smem sub-tile -> TMA store =====
-        // Eight warps: warp w reads TMEM lanes 32*(w%4).. (its rows) and, of every sub-tile, the column
-        // half (w-4)/4 -- two warps share each row quarter so the per-thread work is half a sub-tile.
-        const int q = warp & 3, half = (warp - 4) >> 2;
+        // Sixteen warps: warp w reads TMEM lanes 32*(w%4).. (its rows); the four warps of a row quarter each
+        // take one 16-column group of every sub-tile, so a thread's share is 16 values and four warps per
+        // scheduler hide each other's instruction latency (the epilogue is issue-bound, not memory-bound).
+        const int q = warp & 3, part = (warp - 8) >> 2;
         const int row = q * 32 + lane;
         const int xr = a.sub_bytes == 128 ? (row & 7) : ((row >> 1) & 3);
         const int ngrp = a.cs >> 4;                           // 16-column groups per sub-tile: 1, 2 or 4
-        const int gph = ngrp > 1 ? ngrp >> 1 : 1;             // groups per half
-        const int g0 = half * gph;                            // first group of this warp
-        const bool active = g0 < ngrp;
-        const bool issuer = (warp == 4 && lane == 0);
+        const bool active = part < ngrp;
+        const bool issuer = (warp == 8 && lane == 0);
         uint32_t acc = 0, acc_phase = 0, g = 0;
         int ti = 0;
         for (int tile = tile_first; tile < total_tiles; tile += tile_step, ++ti) {
@@ -637,14 +653,15 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             const uint32_t taddr = tmem_base + acc * acc_stride + ((uint32_t)(q * 32) << 16);
             for (int j = 0; j < a.n_sub; ++j, ++g) {
                 const uint32_t buf = g % (uint32_t)a.ring, ph = (g / (uint32_t)a.ring) & 1u;
-                uint32_t r0[16], r1[16];
-                const uint32_t tcol = taddr + (uint32_t)(j * a.cs + g0 * 16);
+                uint32_t r0[16];
+                const uint32_t tcol = taddr + (uint32_t)(j * a.cs + part * 16);
                 if (active) tmem_ld16(tcol, r0);
-                if (active && gph > 1) tmem_ld16(tcol + 16, r1);
                 // the buffer is ours once the residual landed (res layers) or its previous store drained
                 if (a.has_res) mbar_wait(sfull0 + 8 * buf, ph, a.dbg, 2, 400 + (int)buf);
                 else mbar_wait(sempty0 + 8 * buf, ph ^ 1, a.dbg, 2, 500 + (int)buf);
+                if (issuer && j == 0) YB_TRACE(3, ti, 0);
                 tmem_ld_wait();
+                if (issuer && j == 0) YB_TRACE(3, ti, 1);
                 if (j == a.n_sub - 1) {                       // accumulator fully read: hand it back to the MMA warp
                     tc_fence_before();
                     __syncwarp();
@@ -654,19 +671,21 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                 }
                 uint8_t* srow = gen + (stg0 - base) + buf * stg_bytes + (uint32_t)row * (uint32_t)a.sub_bytes;
                 const int nb = n0 + j * a.cs;
-                if (active) epilogue16_staged(a, r0, nb + g0 * 16, srow, g0, xr);
-                if (active && gph > 1) epilogue16_staged(a, r1, nb + g0 * 16 + 16, srow, g0 + 1, xr);
+                if (active) epilogue16_staged(a, r0, nb + part * 16, srow, part, xr);
+                if (issuer && j == 0) YB_TRACE(3, ti, 2);
                 fence_async_smem();                           // generic-proxy smem writes -> visible to the TMA engine
+                if (issuer && j == 0) YB_TRACE(3, ti, 3);
                 __syncwarp();
                 if (lane == 0) mbar_arrive(sready0 + 8 * buf);   // no block-wide barrier: warps run ahead independently
+                if (issuer && j == 0) YB_TRACE(4, ti, 0);
             }
             if (issuer) YB_TRACE(2, ti, 2);
             acc ^= 1;
             if (acc == 0) acc_phase ^= 1;
         }
-    } else if (warp >= 4 && warp < 8) {
-        // ===== epilogue (direct): TMEM -> registers -> global, used by the nearest-upsample layers =====
-        const int q = warp - 4;                               // TMEM lane quarter this warp may read
+    } else if (warp >= 8 && warp < 12) {
+        // ===== epilogue (direct, warps 8-11 only): TMEM -> registers -> global, used by the nearest-upsample layers =====
+        const int q = warp & 3;                               // TMEM lane quarter this warp may read
         const int row = q * 32 + lane;
         uint32_t acc = 0, acc_phase = 0;
         for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
@@ -704,7 +723,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 
     tc_fence_before();
     if constexpr (CTA2) cluster_sync_all(); else __syncthreads();   // the peer may still signal this CTA's barriers / read its smem
-    if (warp == 2) {
+    if (warp == 3) {
         tc_fence_after();
         if constexpr (CTA2) tmem_dealloc_pair(tmem_base, (uint32_t)a.tmem_cols);
         else tmem_dealloc(tmem_base, (uint32_t)a.tmem_cols);
@@ -732,7 +751,8 @@ struct StemArgs {
 };
 
 __global__ void __launch_bounds__(kStemThreads, 1)
-stem_tc_kernel(const __grid_constant__ CUtensorMap tmOut, const StemArgs a) {
+stem_tc_kernel(const __grid_constant__ CUtensorMap tmOut, const StemArgs a_in) {
+    StemArgs a = a_in;
     extern __shared__ uint8_t smem_raw[];
     const uint32_t raw = smem_u32(smem_raw);
     const uint32_t base = (raw + 1023u) & ~1023u;
@@ -754,6 +774,13 @@ stem_tc_kernel(const __grid_constant__ CUtensorMap tmOut, const StemArgs a) {
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 8) tmem_alloc(smem_u32(const_cast<uint32_t*>(tmem_ptr)), 32 * kStemAcc);
+    a.epi.tab = reinterpret_cast<const float*>(gen + 3072);   // scale[32] | bias[32]
+    a.epi.cout_pad = 32;
+    if (threadIdx.x >= 64 && threadIdx.x < 128) {
+        float* tab = reinterpret_cast<float*>(gen + 3072);
+        const int i = threadIdx.x - 64;
+        tab[i] = i < 32 ? __ldg(a.epi.scale + i) : __ldg(a.epi.bias + i - 32);
+    }
     if (threadIdx.x < 32) {                                // weight rows -> swizzled smem
         const int r = threadIdx.x;
         const uint4* src = reinterpret_cast<const uint4*>(a.w + r * 32);
@@ -927,6 +954,7 @@ std::string tc_make_plan(TcPlan& p, const ConvArgs& a, const __half* w16, int co
     std::string e = load_driver_entry_points();
     if (!e.empty()) return e;
     p.swz = a.Cin == 32 ? 64 : 128;
+    p.cout_pad = cout_pad;
     const int bke = p.swz / 2;
     p.cin_blocks = a.Cin / bke;
     p.num_kblocks = a.ks * a.ks * p.cin_blocks;
@@ -981,7 +1009,8 @@ std::string tc_make_plan(TcPlan& p, const ConvArgs& a, const __half* w16, int co
     p.b_resident = !p.cta2 && bres_bytes <= 96 * 1024 && p.grid % p.n_tiles == 0 && p.m_tiles > 2 * num_sms;
     if (const char* e = getenv("YB_TC_BRES")) p.b_resident = p.b_resident && atoi(e) != 0;
     const size_t kb_bytes = (size_t)kBM * p.swz + (p.b_resident ? 0 : b_slot);
-    const size_t fixed = kSmemHeader + 1024 + ring_bytes + (p.b_resident ? bres_bytes : 0);
+    p.tab_bytes = (int)(((size_t)2 * cout_pad * sizeof(float) + 1023) & ~(size_t)1023);
+    const size_t fixed = kSmemHeader + 1024 + p.tab_bytes + ring_bytes + (p.b_resident ? bres_bytes : 0);
     // k-blocks per pipeline stage: the producer and MMA loops each run on one thread and cost a few hundred
     // cycles per stage, so a stage should carry >= ~500 tensor-core cycles (one k-block is (BKE/16)*BN/2)
     p.kps = 1;
@@ -1107,8 +1136,8 @@ cudaError_t tc_launch(const TcPlan& p, const ConvArgs& a, int* dbg, cudaStream_t
     TcArgs t;
     static long long* trace_dev = nullptr;
     static const bool trace_on = getenv("YB_TC_TRACE") && atoi(getenv("YB_TC_TRACE")) != 0;
-    if (trace_on && !trace_dev) cudaMalloc(&trace_dev, 3 * 64 * 4 * sizeof(long long));
-    if (trace_on) cudaMemsetAsync(trace_dev, 0, 3 * 64 * 4 * sizeof(long long), s);
+    if (trace_on && !trace_dev) cudaMalloc(&trace_dev, 5 * 64 * 4 * sizeof(long long));
+    if (trace_on) cudaMemsetAsync(trace_dev, 0, 5 * 64 * 4 * sizeof(long long), s);
     t.trace = trace_on ? trace_dev : nullptr;
     t.M = p.M;
     t.Ho = a.Ho; t.Wo = a.Wo; t.HoWo = a.Ho * a.Wo;
@@ -1118,6 +1147,7 @@ cudaError_t tc_launch(const TcPlan& p, const ConvArgs& a, int* dbg, cudaStream_t
     t.BN = p.BN; t.n_tiles = p.n_tiles; t.m_tiles = p.m_tiles;
     t.stages = p.stages; t.tmem_cols = p.tmem_cols;
     t.scale = a.scale; t.bias = a.bias;
+    t.tab = nullptr; t.cout_pad = p.cout_pad; t.tab_bytes = p.tab_bytes;
     t.out = a.out; t.out_ld = a.out_ld; t.out_f32 = a.out_f32;
     t.res = static_cast<const __half*>(a.res); t.res_ld = a.res_ld;
     t.leaky = a.leaky; t.upsample = a.upsample;
@@ -1159,7 +1189,7 @@ cudaError_t tc_launch(const TcPlan& p, const ConvArgs& a, int* dbg, cudaStream_t
     if (trace_on) {                       // debugging aid: dump CTA 0's per-tile time line (cycles)
         static int dumps = 0;
         cudaStreamSynchronize(s);
-        long long h[3 * 64 * 4];
+        long long h[5 * 64 * 4];
         cudaMemcpy(h, trace_dev, sizeof(h), cudaMemcpyDeviceToHost);
         if (dumps++ % 8 == 7) {
             const long long t0 = h[0];
@@ -1169,6 +1199,10 @@ cudaError_t tc_launch(const TcPlan& p, const ConvArgs& a, int* dbg, cudaStream_t
                 fprintf(stderr, "[tc trace] tile %2d  prod start %7lld end %7lld | mma start %7lld tempty-ok %7lld issued %7lld | epi start %7lld tfull-ok %7lld done %7lld\n",
                         i, h[(0 * 64 + i) * 4] - t0, h[(0 * 64 + i) * 4 + 1] - t0, h[(1 * 64 + i) * 4] - t0, h[(1 * 64 + i) * 4 + 1] - t0,
                         h[(1 * 64 + i) * 4 + 2] - t0, h[(2 * 64 + i) * 4] - t0, h[(2 * 64 + i) * 4 + 1] - t0, h[(2 * 64 + i) * 4 + 2] - t0);
+            for (int i = 0; i < 6; ++i)
+                fprintf(stderr, "[tc trace] tile %2d  epilogue sub-tile 0: buffer-ok %7lld tmem-loaded %7lld math+smem %7lld fence %7lld arrived %7lld\n", i,
+                        h[(3 * 64 + i) * 4] - t0, h[(3 * 64 + i) * 4 + 1] - t0, h[(3 * 64 + i) * 4 + 2] - t0, h[(3 * 64 + i) * 4 + 3] - t0,
+                        h[(4 * 64 + i) * 4] - t0);
         }
     }
     return cudaGetLastError();
