@@ -39,6 +39,26 @@ CONF_THR, NMS_THR = 0.5, 0.4
 METRIC = "images/sec at 608x608 batch-32 (YOLOv3 detect: backbone + 3-scale decode + NMS)"
 
 
+def ncu_conv_traffic():
+    """DRAM bytes (read+write) of the 75 convolution launches of one step, from the committed ncu capture
+    profiles/r01final_conv_metrics.csv (608x608 batch 32 only)."""
+    import csv
+    p = os.path.join(ROOT, "profiles", "r01final_conv_metrics.csv")
+    if not os.path.exists(p):
+        return None
+    rows = list(csv.reader(open(p)))
+    hdr = next((r for r in rows if "Kernel Name" in r), None)
+    if hdr is None:
+        return None
+    i_name, i_val, i_unit = hdr.index("Metric Name"), hdr.index("Metric Value"), hdr.index("Metric Unit")
+    scale = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
+    total = 0.0
+    for r in rows:
+        if len(r) > i_unit and r[i_name] in ("dram__bytes_read.sum", "dram__bytes_write.sum"):
+            total += float(r[i_val].replace(",", "")) * scale.get(r[i_unit], 1.0)
+    return total or None
+
+
 def peaks():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(p):
@@ -232,11 +252,10 @@ def run_ours(args):
     e2e_ms = float(t.item())
 
     # ---- roofline: section times of the same step, CUDA events per section on the launch stream ----
-    _lib.check(lib.yb_set_profiling(ctx, 1), ctx)
-    conv_ms = dec_ms = post_ms = 0.0
     import ctypes
-    reps = min(args.steps, 5)
-    layer_ms = None
+    _lib.check(lib.yb_set_profiling(ctx, 1), ctx)          # events at the section boundaries only
+    conv_ms = dec_ms = post_ms = 0.0
+    reps = min(args.steps, 10)
     for i in range(reps):
         net.detect_raw(xs[i & 1], CONF_THR, NMS_THR, False, True, cap)
         a, b, c = ctypes.c_float(), ctypes.c_float(), ctypes.c_float()
@@ -244,12 +263,17 @@ def run_ours(args):
         conv_ms += a.value / reps
         dec_ms += b.value / reps
         post_ms += c.value / reps
-        buf = (ctypes.c_float * 80)()
-        n = lib.yb_get_layer_ms(ctx, buf, 80)
-        cur = [buf[j] for j in range(min(n, 80))]
-        layer_ms = cur if layer_ms is None else [x + y for x, y in zip(layer_ms, cur)]
+    layer_ms = []
+    if args.layers:
+        _lib.check(lib.yb_set_profiling(ctx, 2), ctx)      # + one event per convolution
+        for i in range(3):
+            net.detect_raw(xs[i & 1], CONF_THR, NMS_THR, False, True, cap)
+            buf = (ctypes.c_float * 80)()
+            n = lib.yb_get_layer_ms(ctx, buf, 80)
+            cur = [buf[j] for j in range(min(n, 80))]
+            layer_ms = cur if not layer_ms else [x + y for x, y in zip(layer_ms, cur)]
+        layer_ms = [v / 3 for v in layer_ms]
     _lib.check(lib.yb_set_profiling(ctx, 0), ctx)
-    layer_ms = [v / reps for v in layer_ms]
 
     if rank != 0:
         if world > 1:
@@ -277,7 +301,10 @@ def run_ours(args):
         "gpu_launches": int(launches),
         "clocks": sampler.summary(),
         "roofline": {"bound": "tensor", "kernel": "conv_tc_kernel (74 launches/step) + stem", "achieved": achieved,
-                     "peak": pk["tensor"], "unit": "TFLOP/s", "frac": achieved / pk["tensor"], "traffic": None,
+                     "peak": pk["tensor"], "unit": "TFLOP/s", "frac": achieved / pk["tensor"],
+                     "traffic": ncu_conv_traffic() if (S == 608 and B == 32) else None,
+                     "traffic_note": "DRAM read+write bytes of the 75 conv launches of one step (ncu, profiles/r01final_conv_metrics.csv); "
+                                     "algorithmic activation+weight bytes: 13.0e9",
                      "peak_source": f"{pk['src']} sustained bf16 (MEASURED_PEAKS.json)",
                      "conv_ms_per_step": conv_ms, "flops_per_step": flops},
         "roofline_hbm": {"decode": {"ms": dec_ms, "achieved_GBps": dec_bytes / (dec_ms * 1e-3) / 1e9 if dec_ms else None,

@@ -136,8 +136,10 @@ int yb_allgather_dets(yb_ctx* ctx, const float* rows7, const int* counts, int B_
 
 /* Number of kernels this library launched on behalf of ctx since creation. */
 long long yb_launch_count(const yb_ctx* ctx);
-/* Average device time (ms) of the convolution stack / decode / post-process sections of the last
- * yb_forward/yb_detect call with profiling enabled; see yb_set_profiling. */
+/* Device time (ms) of the convolution stack / decode / post-process sections of the last
+ * yb_forward/yb_detect call with profiling enabled.  yb_set_profiling level: 0 off, 1 = one CUDA event at
+ * each section boundary (does not disturb the back-to-back launches inside the convolution stack),
+ * 2 = additionally an event after every convolution (per-layer times, serialises the launches). */
 int yb_set_profiling(yb_ctx* ctx, int enabled);
 int yb_get_section_ms(yb_ctx* ctx, float* conv_ms, float* decode_ms, float* post_ms);
 /* Per-layer timing of the last profiled call: ms[i] for the i-th convolution (75), returns count. */

@@ -75,6 +75,11 @@ struct TcArgs {
 // ---- PTX wrappers --------------------------------------------------------------------------------
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
+// Programmatic dependent launch: let the next kernel of the stream be launched while this one runs, and
+// wait for the previous one (completion + memory flush) before touching anything it produced.
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void pdl_wait_prior() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+
 // One lane of a converged warp.  The producer and MMA loops are executed by their WHOLE warp with
 // warp-uniform values and only the asynchronous instructions are guarded by this predicate: that lets
 // ptxas keep coordinates / descriptors in uniform registers instead of broadcasting them lane by lane.
@@ -442,6 +447,8 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     tc_fence_after();
     const uint32_t tmem_base = *tmem_ptr;
     const uint32_t acc_stride = (uint32_t)a.tmem_cols >> 1;
+    pdl_launch_dependents();      // everything above (barriers, TMEM, table) overlaps the previous layer's tail
+    pdl_wait_prior();             // activations written by the previous layer are complete and visible
 
     if (warp < 2) {
         // ===== TMA producers (two warps take alternate pipeline stages; whole warp runs the loop, one
@@ -737,7 +744,8 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 // K-major layout the tensor core expects; a proxy fence + mbarrier hands the stage to the MMA warp
 // (one tcgen05.mma pair per tile: M=128, N=32, K=32).  Four TMEM accumulators of 32 columns keep the
 // producers, the tensor core and the epilogue warps (same staged TMA-store epilogue) overlapped.
-constexpr int kStemThreads = 416;          // warps 0-7 producers (two groups), 8 MMA + TMEM alloc, 9-12 epilogue
+constexpr int kStemGroups = 3;            // producer groups of 128 threads
+constexpr int kStemThreads = 768;          // warps 0-11 producers (three groups), 12 MMA + TMEM alloc, 13 store issuer, 16-23 epilogue
 constexpr int kStemStages = 8;
 constexpr int kStemAcc = 4;
 
@@ -758,7 +766,7 @@ stem_tc_kernel(const __grid_constant__ CUtensorMap tmOut, const StemArgs a_in) {
     const uint32_t base = (raw + 1023u) & ~1023u;
     uint8_t* gen = smem_raw + (base - raw);
     // header: full[8] | empty[8] | tfull[4] | tempty[4] | sempty[2] | tmem_ptr
-    const uint32_t full0 = base, empty0 = base + 64, tfull0 = base + 128, tempty0 = base + 160, sempty0 = base + 192;
+    const uint32_t full0 = base, empty0 = base + 64, tfull0 = base + 128, tempty0 = base + 160, sempty0 = base + 192, sready0 = base + 208;
     volatile uint32_t* tmem_ptr = reinterpret_cast<volatile uint32_t*>(gen + 224);
     constexpr uint32_t A_BYTES = kBM * 64, STG_BYTES = kBM * 64;
     const uint32_t wsm = base + 1024;                      // weights 32 x 64 B (2 KB), swizzled
@@ -767,13 +775,13 @@ stem_tc_kernel(const __grid_constant__ CUtensorMap tmOut, const StemArgs a_in) {
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
     if (warp == 0 && lane == 0) prefetch_tmap(&tmOut);
-    if (warp == 8 && lane == 0) {
+    if (warp == 12 && lane == 0) {
         for (int s = 0; s < kStemStages; ++s) { mbar_init(full0 + 8 * s, 128); mbar_init(empty0 + 8 * s, 1); }
-        for (int i = 0; i < kStemAcc; ++i) { mbar_init(tfull0 + 8 * i, 1); mbar_init(tempty0 + 8 * i, 128); }
-        for (int i = 0; i < 2; ++i) mbar_init(sempty0 + 8 * i, 1);
+        for (int i = 0; i < kStemAcc; ++i) { mbar_init(tfull0 + 8 * i, 1); mbar_init(tempty0 + 8 * i, 8); }
+        for (int i = 0; i < 2; ++i) { mbar_init(sempty0 + 8 * i, 1); mbar_init(sready0 + 8 * i, 8); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
-    if (warp == 8) tmem_alloc(smem_u32(const_cast<uint32_t*>(tmem_ptr)), 32 * kStemAcc);
+    if (warp == 12) tmem_alloc(smem_u32(const_cast<uint32_t*>(tmem_ptr)), 32 * kStemAcc);
     a.epi.tab = reinterpret_cast<const float*>(gen + 3072);   // scale[32] | bias[32]
     a.epi.cout_pad = 32;
     if (threadIdx.x >= 64 && threadIdx.x < 128) {
@@ -793,10 +801,12 @@ stem_tc_kernel(const __grid_constant__ CUtensorMap tmOut, const StemArgs a_in) {
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_ptr;
+    pdl_launch_dependents();
+    pdl_wait_prior();             // the output buffer may still be read by the previous step's kernels
 
-    if (warp < 8) {
-        // ===== producers: one output pixel (im2col row) per thread; two groups of 128 threads take
-        // alternate tiles, and each thread keeps the 27 loads of its next tile in flight while it
+    if (warp < 4 * kStemGroups) {
+        // ===== producers: one output pixel (im2col row) per thread; kStemGroups groups of 128 threads take
+        // tiles round-robin, and each thread keeps the 27 loads of its next tile in flight while it
         // converts and stores the current one =====
         const int grp = warp >> 2;
         const int r = threadIdx.x & 127;
@@ -829,8 +839,8 @@ stem_tc_kernel(const __grid_constant__ CUtensorMap tmOut, const StemArgs a_in) {
         float v[27], vn[27];
         int i = grp;                                       // index of this CTA's i-th tile
         gather(blockIdx.x + i * gridDim.x, v);
-        for (; (int)blockIdx.x + i * (int)gridDim.x < a.tiles; i += 2) {
-            gather(blockIdx.x + (i + 2) * gridDim.x, vn);
+        for (; (int)blockIdx.x + i * (int)gridDim.x < a.tiles; i += kStemGroups) {
+            gather(blockIdx.x + (i + kStemGroups) * gridDim.x, vn);
             uint4 pk[4];
             __half2* h = reinterpret_cast<__half2*>(pk);
 #pragma unroll
@@ -849,7 +859,7 @@ stem_tc_kernel(const __grid_constant__ CUtensorMap tmOut, const StemArgs a_in) {
 #pragma unroll
             for (int j = 0; j < 27; ++j) v[j] = vn[j];
         }
-    } else if (warp == 8) {
+    } else if (warp == 12) {
         // ===== MMA issuer =====
         if (lane == 0) {
             const uint32_t idesc = make_idesc(32);
@@ -870,31 +880,13 @@ stem_tc_kernel(const __grid_constant__ CUtensorMap tmOut, const StemArgs a_in) {
             }
         }
         __syncwarp();
-    } else {
-        // ===== epilogue: TMEM -> scale/bias/LeakyReLU -> fp16 -> swizzled smem -> TMA store =====
-        const int q = warp & 3;
-        const int row = q * 32 + lane;
-        const int xr = (row >> 1) & 3;
-        const bool issuer = (warp == 9 && lane == 0);
-        uint32_t acc = 0, acc_phase = 0, g = 0;
-        for (int tile = blockIdx.x; tile < a.tiles; tile += gridDim.x, ++g) {
-            const uint32_t buf = g & 1u, ph = (g >> 1) & 1u;
-            mbar_wait(tfull0 + 8 * acc, acc_phase, a.epi.dbg, 2, 200 + (int)acc);
-            tc_fence_after();
-            uint32_t r0[16], r1[16];
-            const uint32_t taddr = tmem_base + acc * 32 + ((uint32_t)(q * 32) << 16);
-            tmem_ld16(taddr, r0);
-            tmem_ld16(taddr + 16, r1);
-            mbar_wait(sempty0 + 8 * buf, ph ^ 1, a.epi.dbg, 2, 500 + (int)buf);
-            tmem_ld_wait();
-            tc_fence_before();
-            mbar_arrive(tempty0 + 8 * acc);                 // accumulator drained into registers
-            uint8_t* srow = gen + (stg0 - base) + buf * STG_BYTES + row * 64;
-            epilogue16_staged(a.epi, r0, 0, srow, 0, xr);
-            epilogue16_staged(a.epi, r1, 16, srow, 1, xr);
-            fence_async_smem();
-            epi_bar_sync();
-            if (issuer) {
+    } else if (warp == 13) {
+        // ===== store issuer =====
+        if (lane == 0) {
+            uint32_t g = 0;
+            for (int tile = blockIdx.x; tile < a.tiles; tile += gridDim.x, ++g) {
+                const uint32_t buf = g & 1u, ph = (g >> 1) & 1u;
+                mbar_wait(sready0 + 8 * buf, ph, a.epi.dbg, 4, 700 + (int)buf);
                 tma_store_2d(&tmOut, stg0 + buf * STG_BYTES, 0, tile * kBM);
                 tma_store_commit();
                 if (g > 0) {
@@ -902,13 +894,38 @@ stem_tc_kernel(const __grid_constant__ CUtensorMap tmOut, const StemArgs a_in) {
                     mbar_arrive(sempty0 + 8 * ((g - 1) & 1u));
                 }
             }
+            tma_store_wait_all();
+        }
+        __syncwarp();
+    } else if (warp >= 16) {
+        // ===== epilogue (8 warps, 16 columns per thread): TMEM -> scale/bias/LeakyReLU -> fp16 -> swizzled smem =====
+        const int q = warp & 3, part = (warp - 16) >> 2;
+        const int row = q * 32 + lane;
+        const int xr = (row >> 1) & 3;
+        uint32_t acc = 0, acc_phase = 0, g = 0;
+        for (int tile = blockIdx.x; tile < a.tiles; tile += gridDim.x, ++g) {
+            const uint32_t buf = g & 1u, ph = (g >> 1) & 1u;
+            mbar_wait(tfull0 + 8 * acc, acc_phase, a.epi.dbg, 2, 200 + (int)acc);
+            tc_fence_after();
+            uint32_t r0[16];
+            const uint32_t taddr = tmem_base + acc * 32 + ((uint32_t)(q * 32) << 16);
+            tmem_ld16(taddr + part * 16, r0);
+            mbar_wait(sempty0 + 8 * buf, ph ^ 1, a.epi.dbg, 2, 500 + (int)buf);
+            tmem_ld_wait();
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(tempty0 + 8 * acc);   // accumulator drained into registers
+            uint8_t* srow = gen + (stg0 - base) + buf * STG_BYTES + row * 64;
+            epilogue16_staged(a.epi, r0, part * 16, srow, part, xr);
+            fence_async_smem();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(sready0 + 8 * buf);
             if (++acc == kStemAcc) { acc = 0; acc_phase ^= 1; }
         }
-        if (issuer) tma_store_wait_all();
     }
     tc_fence_before();
     __syncthreads();
-    if (warp == 8) {
+    if (warp == 12) {
         tc_fence_after();
         tmem_dealloc(tmem_base, 32 * kStemAcc);
     }
@@ -1128,7 +1145,21 @@ cudaError_t stem_tc_launch(const StemTcPlan& p, const float* x, int B, int H, in
         if (e != cudaSuccess) return e;
         attr_done = true;
     }
-    stem_tc_kernel<<<p.grid, kStemThreads, p.smem, s>>>(p.tmOut, a);
+    {
+        static const bool pdl = !(getenv("YB_TC_PDL") && atoi(getenv("YB_TC_PDL")) == 0);
+        cudaLaunchConfig_t cfg{};
+        cfg.gridDim = dim3(p.grid);
+        cfg.blockDim = dim3(kStemThreads);
+        cfg.dynamicSmemBytes = p.smem;
+        cfg.stream = s;
+        cudaLaunchAttribute attr[1];
+        attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+        attr[0].val.programmaticStreamSerializationAllowed = 1;
+        cfg.attrs = attr;
+        cfg.numAttrs = pdl ? 1 : 0;
+        cudaError_t e = cudaLaunchKernelEx(&cfg, stem_tc_kernel, p.tmOut, a);
+        if (e != cudaSuccess) return e;
+    }
     return cudaGetLastError();
 }
 
@@ -1166,25 +1197,34 @@ cudaError_t tc_launch(const TcPlan& p, const ConvArgs& a, int* dbg, cudaStream_t
         if (e != cudaSuccess) return e;
         attr_done = true;
     }
-    if (p.cta2) {
+    {
+        static const bool pdl = !(getenv("YB_TC_PDL") && atoi(getenv("YB_TC_PDL")) == 0);
         cudaLaunchConfig_t cfg{};
         cfg.gridDim = dim3(p.grid);
         cfg.blockDim = dim3(kThreads);
         cfg.dynamicSmemBytes = p.smem;
         cfg.stream = s;
-        cudaLaunchAttribute attr[1];
-        attr[0].id = cudaLaunchAttributeClusterDimension;
-        attr[0].val.clusterDim.x = 2;
-        attr[0].val.clusterDim.y = 1;
-        attr[0].val.clusterDim.z = 1;
+        cudaLaunchAttribute attr[2];
+        int na = 0;
+        if (pdl) {
+            attr[na].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+            attr[na].val.programmaticStreamSerializationAllowed = 1;
+            ++na;
+        }
+        if (p.cta2) {
+            attr[na].id = cudaLaunchAttributeClusterDimension;
+            attr[na].val.clusterDim.x = 2;
+            attr[na].val.clusterDim.y = 1;
+            attr[na].val.clusterDim.z = 1;
+            ++na;
+        }
         cfg.attrs = attr;
-        cfg.numAttrs = 1;
-        cudaError_t e = cudaLaunchKernelEx(&cfg, conv_tc_kernel<128, true>, p.tmA, p.tmB, p.tmOut, p.tmRes, t);
+        cfg.numAttrs = na;
+        cudaError_t e;
+        if (p.cta2) e = cudaLaunchKernelEx(&cfg, conv_tc_kernel<128, true>, p.tmA, p.tmB, p.tmOut, p.tmRes, t);
+        else if (p.swz == 128) e = cudaLaunchKernelEx(&cfg, conv_tc_kernel<128, false>, p.tmA, p.tmB, p.tmOut, p.tmRes, t);
+        else e = cudaLaunchKernelEx(&cfg, conv_tc_kernel<64, false>, p.tmA, p.tmB, p.tmOut, p.tmRes, t);
         if (e != cudaSuccess) return e;
-    } else if (p.swz == 128) {
-        conv_tc_kernel<128, false><<<p.grid, kThreads, p.smem, s>>>(p.tmA, p.tmB, p.tmOut, p.tmRes, t);
-    } else {
-        conv_tc_kernel<64, false><<<p.grid, kThreads, p.smem, s>>>(p.tmA, p.tmB, p.tmOut, p.tmRes, t);
     }
     if (trace_on) {                       // debugging aid: dump CTA 0's per-tile time line (cycles)
         static int dumps = 0;

@@ -44,6 +44,7 @@ __device__ __forceinline__ float decode_one(const DecodeScale& s, int a, int att
 // t (anchor/attr computed once) and walks the cells, four loads in flight at a time; consecutive threads
 // touch consecutive addresses on both sides.
 constexpr int kCellsPerBlock = 16;
+constexpr int kDecodeUnroll = 4;
 
 __global__ void __launch_bounds__(256) decode_nhwc_kernel(const __grid_constant__ DecodeParams P, float* __restrict__ det,
                                                           int blocks_s0, int blocks_s1) {
@@ -62,12 +63,12 @@ __global__ void __launch_bounds__(256) decode_nhwc_kernel(const __grid_constant_
     for (int c = threadIdx.x; c < ch; c += blockDim.x) {
         const int a = c / P.attrs, attr = c - a * P.attrs;
         int x = x0, y = y0;
-        for (int i0 = 0; i0 < np; i0 += 4) {
-            float t[4];
+        for (int i0 = 0; i0 < np; i0 += kDecodeUnroll) {
+            float t[kDecodeUnroll];
 #pragma unroll
-            for (int u = 0; u < 4; ++u) t[u] = i0 + u < np ? __ldg(in + (long)(i0 + u) * s.ld + c) : 0.f;
+            for (int u = 0; u < kDecodeUnroll; ++u) t[u] = i0 + u < np ? __ldg(in + (long)(i0 + u) * s.ld + c) : 0.f;
 #pragma unroll
-            for (int u = 0; u < 4; ++u) {
+            for (int u = 0; u < kDecodeUnroll; ++u) {
                 if (i0 + u < np) out[(long)(i0 + u) * ch + c] = decode_one(s, a, attr, x, y, t[u]);
                 if (++x == s.w) { x = 0; ++y; }
             }

@@ -69,6 +69,7 @@ struct yb_ctx {
     mutable std::string err;
     long long launches = 0;
     bool profiling = false;
+    bool profile_layers = false;      // profiling level 2: an event after every convolution (perturbs PDL overlap)
     std::vector<cudaEvent_t> ev;
     float sec_ms[3] = {0, 0, 0};
     std::vector<float> layer_ms;
@@ -385,7 +386,7 @@ int run_ops(yb_ctx* c, Plan* p, const float* x, int n_ops, cudaStream_t s) {
         }
         if (e != cudaSuccess) return fail(c, YB_E_CUDA, "launch of layer " + L.key + ": " + cudaGetErrorString(e));
         ++c->launches;
-        if (prof) YB_CUDA(c, cudaEventRecord(c->ev[i + 1], s));
+        if (prof && (c->profile_layers || i == n_ops - 1)) YB_CUDA(c, cudaEventRecord(c->ev[i + 1], s));
     }
     return YB_OK;
 }
@@ -423,8 +424,9 @@ int total_rows(int H, int W) { return 3 * ((H / 32) * (W / 32) + (H / 16) * (W /
 int record_sections(yb_ctx* c, int n_ops, bool have_decode, bool have_post, cudaStream_t s) {
     // events: [0]=start, [1..n_ops]=after each op, [n_ops+1]=after decode, [n_ops+2]=after post
     YB_CUDA(c, cudaStreamSynchronize(s));
-    c->layer_ms.assign(n_ops, 0.f);
-    for (int i = 0; i < n_ops; ++i) YB_CUDA(c, cudaEventElapsedTime(&c->layer_ms[i], c->ev[i], c->ev[i + 1]));
+    c->layer_ms.assign(c->profile_layers ? n_ops : 0, 0.f);
+    if (c->profile_layers)
+        for (int i = 0; i < n_ops; ++i) YB_CUDA(c, cudaEventElapsedTime(&c->layer_ms[i], c->ev[i], c->ev[i + 1]));
     YB_CUDA(c, cudaEventElapsedTime(&c->sec_ms[0], c->ev[0], c->ev[n_ops]));
     c->sec_ms[1] = c->sec_ms[2] = 0.f;
     if (have_decode) YB_CUDA(c, cudaEventElapsedTime(&c->sec_ms[1], c->ev[n_ops], c->ev[n_ops + 1]));
@@ -813,6 +815,7 @@ int yb_debug_words(const yb_ctx* c, int* out, int n) {
 int yb_set_profiling(yb_ctx* c, int enabled) {
     if (!c) return fail(nullptr, YB_E_ARG, "null ctx");
     c->profiling = enabled != 0;
+    c->profile_layers = enabled >= 2;
     return YB_OK;
 }
 
