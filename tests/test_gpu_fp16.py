@@ -169,3 +169,38 @@ def test_fp16_detect_matches_own_postprocess(sd):
     assert len(a) == len(b) == 2
     for p, q in zip(a, b):
         assert torch.equal(p, q)
+
+
+def test_fp16_other_shapes_and_class_counts(oracle):
+    """Non-square input, batch 3, and a 20-class head (75 channels -> padded 80: the narrow fp32 staging path)."""
+    from yolo_v3_b200 import YoloNet, postprocessing
+    for nc, (h, w), B in ((20, (160, 224), 3), (80, (320, 192), 1)):
+        sd = synth.make_state_dict(seed=7, num_classes=nc, recipe="calibrated", calib_hw=96)
+        x = synth.make_images(B, h, w, seed=9)
+        net = YoloNet((w, h), numClass=nc, precision="fp16")
+        net.load_state_dict(sd)
+        net = net.cuda().eval()
+        det = torch.cat(net(x.cuda(), None), 1)
+        ref = torch.cat(oracle.forward(sd, x, num_classes=nc), 1)
+        assert det.shape == ref.shape == (B, topology.num_boxes(h, w), 5 + nc)
+        d = (det.cpu() - ref).abs()
+        assert float(d[..., :2].max()) < 4.0 and float(d[..., 4:].max()) < 0.15
+        res, idx = postprocessing(det, nc, 0.05, 0.4, return_index=True)
+        ref_res, ref_idx = oracle.postprocessing_c(det.cpu(), nc, 0.05, 0.4)
+        for r, e, i, ei in zip(res, ref_res, idx, ref_idx):
+            assert np.array_equal(i, ei) and torch.equal(r, e)
+
+
+def test_fp16_plan_cache_two_shapes(sd):
+    """Alternating shapes reuses cached plans and keeps results identical."""
+    from yolo_v3_b200 import YoloNet
+    net = YoloNet((416, 416), precision="fp16")
+    net.load_state_dict(sd)
+    net = net.cuda().eval()
+    xa = synth.make_images(1, 416, 416, seed=1).cuda()
+    xb = synth.make_images(2, 224, 224, seed=2).cuda()
+    a1 = torch.cat(net(xa, None), 1).clone()
+    b1 = torch.cat(net(xb, None), 1).clone()
+    a2 = torch.cat(net(xa, None), 1)
+    b2 = torch.cat(net(xb, None), 1)
+    assert torch.equal(a1, a2) and torch.equal(b1, b2)
