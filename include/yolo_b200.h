@@ -118,6 +118,17 @@ int yb_detect(yb_ctx* ctx, const float* x_nchw, int B, int H, int W, float obj_c
               int is_eval, int use_nms, float* rows7, int* counts, int* src_index, int* cand_counts,
               int cap, void* stream);
 
+/* Replaces boundingbox.correct_yolo_boxes(bboxes, org_w, org_h, img_w, img_h, is_letterbox)
+ * (boundingbox.py:139-149 = letterbox_reverse :95-116 or rescale_bbox :119-137, then x1y1x2y2 -> xywh,
+ * :10-15), the step every caller applies right after postprocessing (test.py:41, evaluate.py:187), for a
+ * whole batch on the device.  boxes: dev, B x cap rows of `row_stride` floats whose first four are
+ * x1,y1,x2,y2 in network-input pixels (row_stride 7 for rows7, 4 for bare boxes); counts: dev [B] valid rows
+ * per image, or NULL for "all cap rows"; org_wh_host: HOST int[B][2] = original (w,h) of every image;
+ * out_xywh: dev [B,cap,4] = x,y,w,h in original-image pixels.  Rows whose four coordinates sum to 0 are
+ * passed through unchanged, as in the reference. */
+int yb_correct_boxes(yb_ctx* ctx, const float* boxes, int row_stride, const int* counts, int B, int cap,
+                     const int* org_wh_host, int img_w, int img_h, int is_letterbox, float* out_xywh, void* stream);
+
 /* ---- multi-GPU (absent in the reference; batch sharding) ------------------------- */
 
 /* 128-byte NCCL unique id, created on rank 0 and shipped to the other ranks by the host plumbing

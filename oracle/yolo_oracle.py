@@ -7,7 +7,8 @@ reference implements in
                                      PreDetectionConvGroup :107-150, UpsampleGroup :153-162,
                                      YoloNet.forward :198-231, WeightManager :249-303)
     /root/reference/yololayer.py    (YoloLayer.forward inference branch :31-59, :97-105)
-    /root/reference/boundingbox.py  (bbox_cxcywh_to_x1y1x2y2 :25-29)
+    /root/reference/boundingbox.py  (bbox_cxcywh_to_x1y1x2y2 :25-29; correct_yolo_boxes :139-149 with
+                                     letterbox_reverse :95-116, rescale_bbox :119-137)
     /root/reference/utils.py        (iou_vectorized :98-119, get_nms_detections :148-202,
                                      get_raw_detections :204-224, postprocessing :226-258)
 
@@ -260,6 +261,31 @@ def postprocessing(det: torch.Tensor, num_classes: int, obj_conf_thr: float = 0.
         results.append(torch.cat(rows, 0))
         src.append(np.concatenate(idxs))
     return (results, src) if return_index else results
+
+
+def correct_yolo_boxes(bboxes: torch.Tensor, org_w, org_h, img_w, img_h, is_letterbox=False) -> torch.Tensor:
+    """boundingbox.correct_yolo_boxes (boundingbox.py:139-149): letterbox_reverse (:95-116) or rescale_bbox
+    (:119-137) with clipping to the original image, then x1y1x2y2 -> xywh (:10-15).  fp32 tensor arithmetic
+    with python-float ratios, as the reference."""
+    if len(bboxes) == 0:
+        return bboxes
+    b = bboxes.clone().float()
+    if is_letterbox:
+        ratio = min(img_w / org_w, img_h / org_h)
+        rw, rh = int(org_w * ratio), int(org_h * ratio)
+        xp, yp = (img_w - rw) // 2, (img_h - rh) // 2
+        rx = ry = ratio
+    else:
+        rx, ry, xp, yp = img_w / org_w, img_h / org_h, 0, 0
+    m = b.sum(-1) != 0
+    b[m, 0] = torch.clamp((b[m, 0] - xp) / rx, 0, org_w)
+    b[m, 2] = torch.clamp((b[m, 2] - xp) / rx, 0, org_w)
+    b[m, 1] = torch.clamp((b[m, 1] - yp) / ry, 0, org_h)
+    b[m, 3] = torch.clamp((b[m, 3] - yp) / ry, 0, org_h)
+    out = b.clone()
+    out[:, 2] = b[:, 2] - b[:, 0]
+    out[:, 3] = b[:, 3] - b[:, 1]
+    return out
 
 
 # --------------------------------------------------------------------------------------

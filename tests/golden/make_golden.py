@@ -179,7 +179,27 @@ def make_net():
     print("darknet consumed", consumed, "of", len(blob), "roundtrip equal", same)
 
 
+def make_boxes():
+    """correct_yolo_boxes (boundingbox.py:139-149) on network-space boxes, letterbox and plain resize."""
+    import boundingbox as ref_bb   # noqa: E402  (reference)
+    out = {}
+    rs = np.random.RandomState(21)
+    cases = [(602, 452, 416, 416), (1280, 720, 608, 608), (333, 500, 416, 416), (640, 640, 608, 608)]
+    out["cases"] = np.array(cases)
+    for i, (ow, oh, iw, ih) in enumerate(cases):
+        k = 64
+        x1 = rs.uniform(-20, iw, k); y1 = rs.uniform(-20, ih, k)
+        b = np.stack([x1, y1, x1 + rs.uniform(1, 300, k), y1 + rs.uniform(1, 300, k)], 1).astype(np.float32)
+        b[5] = 0.0                                     # all-zero row: passed through by the mask
+        t = torch.from_numpy(b)
+        out[f"in{i}"] = b
+        out[f"letterbox{i}"] = ref_bb.correct_yolo_boxes(t.clone(), ow, oh, iw, ih, True).numpy()
+        out[f"resize{i}"] = ref_bb.correct_yolo_boxes(t.clone(), ow, oh, iw, ih, False).numpy()
+    np.savez_compressed(os.path.join(HERE, "boxes_golden.npz"), **out)
+
+
 if __name__ == "__main__":
+    make_boxes()
     make_decode()
     make_postprocess()
     make_net()

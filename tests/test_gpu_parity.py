@@ -356,3 +356,24 @@ def test_c_abi_error_codes():
     assert lib.yb_forward(ctx, vp(x), 1, 64, 64, vp(det), stream()) == 0
     assert lib.yb_launch_count(ctx) == 76
     lib.yb_destroy(ctx)
+
+
+# ---------------------------------------------------------------------------------------------
+# N2: correct_yolo_boxes (the step right after the path)
+# ---------------------------------------------------------------------------------------------
+def test_correct_yolo_boxes_bit_exact(golden, oracle):
+    from yolo_v3_b200.boundingbox import correct_yolo_boxes, correct_yolo_boxes_batch
+    g = golden("boxes_golden.npz")
+    for i, (ow, oh, iw, ih) in enumerate(g["cases"]):
+        b = torch.from_numpy(g[f"in{i}"])
+        for mode, flag in (("letterbox", True), ("resize", False)):
+            y = correct_yolo_boxes(b, int(ow), int(oh), int(iw), int(ih), flag)            # CPU in -> CPU out
+            assert not y.is_cuda and np.array_equal(y.numpy(), g[f"{mode}{i}"]), (i, mode)
+    # batch form on device rows7 with counts: two images of different original size
+    rows = torch.zeros(2, 64, 7)
+    rows[0, :, :4] = torch.from_numpy(g["in0"]); rows[1, :, :4] = torch.from_numpy(g["in1"])
+    counts = torch.tensor([64, 40], dtype=torch.int32)
+    out = correct_yolo_boxes_batch(rows.cuda(), counts.cuda(), [(602, 452), (602, 452)], 416, 416, True).cpu()
+    assert np.array_equal(out[0].numpy(), g["letterbox0"])
+    ref1 = oracle.correct_yolo_boxes(torch.from_numpy(g["in1"]), 602, 452, 416, 416, True)
+    assert torch.equal(out[1, :40], ref1[:40]) and float(out[1, 40:].abs().sum()) == 0.0

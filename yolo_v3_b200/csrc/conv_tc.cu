@@ -1035,6 +1035,10 @@ std::string tc_make_plan(TcPlan& p, const ConvArgs& a, const __half* w16, int co
         const int kb_cycles = (bke / 16) * p.BN / 2;
         for (int c = 4; c >= 2; --c)
             if (p.num_kblocks % c == 0 && c * kb_bytes <= 48 * 1024 && kb_cycles * (c - 1) < 768) { p.kps = c; break; }
+        // resident weights, no residual ring: two stages holding ALL taps of a tile fit -> one barrier round
+        // trip per tile (measured on the 32->64 stride-2 layer: 0.286 -> 0.247 ms, profiles/README.md)
+        if (p.b_resident && !a.res && p.num_kblocks <= 9 && fixed + 2 * p.num_kblocks * kb_bytes <= kSmemBudget)
+            p.kps = p.num_kblocks;
         if (const char* e = getenv("YB_TC_KPS")) { const int c = atoi(e); if (c >= 1 && p.num_kblocks % c == 0 && c * kb_bytes <= 96 * 1024) p.kps = c; }
     }
     const size_t stage_bytes = kb_bytes * p.kps;

@@ -62,6 +62,8 @@ struct yb_ctx {
     size_t blob_bytes = 0;
     std::vector<std::unique_ptr<Plan>> plans;
     PostBuffers post;
+    float* box_params = nullptr;      // [B][6] per-image parameters of yb_correct_boxes
+    int box_params_cap = 0;
     float* det_scratch = nullptr;     // for yb_detect
     size_t det_scratch_bytes = 0;
     int* dbg = nullptr;               // device alias of dbg_host (mapped pinned memory): watchdog words of the
@@ -475,6 +477,7 @@ void yb_destroy(yb_ctx* c) {
     free_post(c);
     cudaFree(c->d_blob);
     cudaFree(c->det_scratch);
+    cudaFree(c->box_params);
     cudaFreeHost(c->dbg_host);
     for (cudaEvent_t e : c->ev) cudaEventDestroy(e);
     if (c->nccl_comm) comm_destroy(c->nccl_comm);
@@ -766,6 +769,46 @@ int yb_detect(yb_ctx* c, const float* x, int B, int H, int W, float conf, float 
         rc = record_sections(c, (int)p->ops.size(), true, true, s);
     }
     return rc;
+}
+
+int yb_correct_boxes(yb_ctx* c, const float* boxes, int row_stride, const int* counts, int B, int cap, const int* org_wh,
+                     int img_w, int img_h, int is_letterbox, float* out_xywh, void* stream) {
+    if (!c) return fail(nullptr, YB_E_ARG, "null ctx");
+    if (!boxes || !org_wh || !out_xywh || B <= 0 || cap <= 0 || row_stride < 4 || img_w <= 0 || img_h <= 0)
+        return fail(c, YB_E_ARG, "yb_correct_boxes: bad arguments");
+    YB_CUDA(c, cudaSetDevice(c->device));
+    if (B > c->box_params_cap) {
+        cudaFree(c->box_params);
+        c->box_params = nullptr;
+        c->box_params_cap = 0;
+        YB_CUDA(c, cudaMalloc(&c->box_params, sizeof(float) * 6 * (size_t)B));
+        c->box_params_cap = B;
+    }
+    // host arithmetic exactly as the reference does it in python floats (doubles) and ints
+    std::vector<float> prm((size_t)B * 6);
+    for (int b = 0; b < B; ++b) {
+        const int ow = org_wh[2 * b], oh = org_wh[2 * b + 1];
+        if (ow <= 0 || oh <= 0) return fail(c, YB_E_ARG, "yb_correct_boxes: original sizes must be positive");
+        double rx, ry;
+        long xpad = 0, ypad = 0;
+        if (is_letterbox) {                                               // boundingbox.py:106-108
+            const double ratio = std::min((double)img_w / ow, (double)img_h / oh);
+            const long rw = (long)(ow * ratio), rh = (long)(oh * ratio);
+            xpad = (img_w - rw) / 2;
+            ypad = (img_h - rh) / 2;
+            rx = ry = ratio;
+        } else {                                                          // boundingbox.py:130
+            rx = (double)img_w / ow;
+            ry = (double)img_h / oh;
+        }
+        float* p = &prm[(size_t)b * 6];
+        p[0] = (float)rx; p[1] = (float)ry; p[2] = (float)xpad; p[3] = (float)ypad; p[4] = (float)ow; p[5] = (float)oh;
+    }
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    YB_CUDA(c, cudaMemcpyAsync(c->box_params, prm.data(), prm.size() * sizeof(float), cudaMemcpyHostToDevice, s));
+    YB_CUDA(c, launch_correct_boxes(boxes, row_stride, counts, B, cap, c->box_params, out_xywh, s));
+    ++c->launches;
+    return YB_OK;
 }
 
 int yb_comm_unique_id(uint8_t id_out[128]) {

@@ -421,7 +421,35 @@ __global__ void __launch_bounds__(1024) pp_emit_kernel(const unsigned long long*
     }
 }
 
+// ---- N2: correct_yolo_boxes (boundingbox.py:95-149) ---------------------------------------------
+// params per image: ratio_x, ratio_y (fp32, as torch casts the python float), x_pad, y_pad, org_w, org_h
+__global__ void __launch_bounds__(256) correct_boxes_kernel(const float* __restrict__ boxes, int row_stride,
+                                                            const int* __restrict__ counts, int B, int cap,
+                                                            const float* __restrict__ params, float* __restrict__ out) {
+    const long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= (long)B * cap) return;
+    const int b = (int)(i / cap), k = (int)(i - (long)b * cap);
+    if (counts && k >= counts[b]) return;
+    const float* r = boxes + i * row_stride;
+    float x1 = r[0], y1 = r[1], x2 = r[2], y2 = r[3];
+    const float* p = params + b * 6;
+    if (__fadd_rn(__fadd_rn(__fadd_rn(x1, y1), x2), y2) != 0.f) {        // mask = labels.sum(-1) != 0
+        x1 = fminf(fmaxf(__fdiv_rn(__fsub_rn(x1, p[2]), p[0]), 0.f), p[4]);
+        x2 = fminf(fmaxf(__fdiv_rn(__fsub_rn(x2, p[2]), p[0]), 0.f), p[4]);
+        y1 = fminf(fmaxf(__fdiv_rn(__fsub_rn(y1, p[3]), p[1]), 0.f), p[5]);
+        y2 = fminf(fmaxf(__fdiv_rn(__fsub_rn(y2, p[3]), p[1]), 0.f), p[5]);
+    }
+    *reinterpret_cast<float4*>(out + i * 4) = make_float4(x1, y1, __fsub_rn(x2, x1), __fsub_rn(y2, y1));
+}
+
 }  // namespace
+
+cudaError_t launch_correct_boxes(const float* boxes, int row_stride, const int* counts, int B, int cap, const float* params_dev,
+                                 float* out, cudaStream_t s) {
+    const long n = (long)B * cap;
+    correct_boxes_kernel<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(boxes, row_stride, counts, B, cap, params_dev, out);
+    return cudaGetLastError();
+}
 
 cudaError_t launch_postprocess(const PostArgs& a, PostBuffers& buf, long long* launches, cudaStream_t s) {
     const long rows = (long)a.B * a.N;

@@ -125,5 +125,7 @@ struct PostArgs {
     float* rows7; int* counts; int* src_index; int* cand_counts; int cap;
 };
 cudaError_t launch_postprocess(const PostArgs& a, PostBuffers& buf, long long* launches, cudaStream_t s);
+cudaError_t launch_correct_boxes(const float* boxes, int row_stride, const int* counts, int B, int cap, const float* params_dev,
+                                 float* out, cudaStream_t s);
 
 }  // namespace yb
