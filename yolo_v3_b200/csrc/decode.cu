@@ -40,11 +40,12 @@ __device__ __forceinline__ float decode_one(const DecodeScale& s, int a, int att
 
 // NHWC (engine-internal) input: element (b, p, c) -> out[b][row_off*attrs + p*3*attrs + c]: a flat
 // elementwise map.  A block owns kCellsPerBlock consecutive cells of one image and scale (so the cell ->
-// (x, y) arithmetic is two scalar divisions per block and increments afterwards); thread t owns channel
-// t (anchor/attr computed once) and walks the cells, four loads in flight at a time; consecutive threads
-// touch consecutive addresses on both sides.
-constexpr int kCellsPerBlock = 16;
-constexpr int kDecodeUnroll = 4;
+// (x, y) arithmetic is two scalar divisions per block).  64 threads cover one cell with a 16-byte load of
+// four consecutive channels each (the head maps are padded to a multiple of 16 channels, so the loads are
+// aligned); the four 64-thread groups of a block take every fourth cell, with four such loads in flight
+// per thread -- the kernel is latency-bound otherwise.  Stores are scalar (the 3*(5+C)-float output rows
+// are only 4-byte aligned) but consecutive threads still write consecutive addresses.
+constexpr int kCellsPerBlock = 32;
 
 __global__ void __launch_bounds__(256) decode_nhwc_kernel(const __grid_constant__ DecodeParams P, float* __restrict__ det,
                                                           int blocks_s0, int blocks_s1) {
@@ -57,20 +58,31 @@ __global__ void __launch_bounds__(256) decode_nhwc_kernel(const __grid_constant_
     const int per_img = (hw + kCellsPerBlock - 1) / kCellsPerBlock;
     const int b = blk / per_img, p0 = (blk - b * per_img) * kCellsPerBlock;
     const int np = min(kCellsPerBlock, hw - p0);
-    const int y0 = p0 / s.w, x0 = p0 - y0 * s.w;
     const float* in = s.logits + ((long)b * hw + p0) * s.ld;
     float* out = det + ((long)b * P.n_total + s.row_off) * P.attrs + (long)p0 * ch;
-    for (int c = threadIdx.x; c < ch; c += blockDim.x) {
-        const int a = c / P.attrs, attr = c - a * P.attrs;
-        int x = x0, y = y0;
-        for (int i0 = 0; i0 < np; i0 += kDecodeUnroll) {
-            float t[kDecodeUnroll];
+    const int grp = threadIdx.x >> 6, q = threadIdx.x & 63;
+    for (int c0 = q * 4; c0 < ch; c0 += 256) {                     // one pass for up to 256 channels
+        int a[4], attr[4];
 #pragma unroll
-            for (int u = 0; u < kDecodeUnroll; ++u) t[u] = i0 + u < np ? __ldg(in + (long)(i0 + u) * s.ld + c) : 0.f;
+        for (int u = 0; u < 4; ++u) { a[u] = (c0 + u) / P.attrs; attr[u] = (c0 + u) - a[u] * P.attrs; }
+        for (int i0 = grp; i0 < np; i0 += 16) {                    // cells i0, i0+4, i0+8, i0+12 of this group
+            float4 t[4];
 #pragma unroll
-            for (int u = 0; u < kDecodeUnroll; ++u) {
-                if (i0 + u < np) out[(long)(i0 + u) * ch + c] = decode_one(s, a, attr, x, y, t[u]);
-                if (++x == s.w) { x = 0; ++y; }
+            for (int u = 0; u < 4; ++u) {
+                const int i = i0 + 4 * u;
+                t[u] = i < np ? __ldg(reinterpret_cast<const float4*>(in + (long)i * s.ld + c0)) : make_float4(0.f, 0.f, 0.f, 0.f);
+            }
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                const int i = i0 + 4 * u;
+                if (i >= np) break;
+                const int p = p0 + i;
+                const int y = p / s.w, x = p - y * s.w;
+                float* o = out + (long)i * ch + c0;
+                const float v[4] = {t[u].x, t[u].y, t[u].z, t[u].w};
+#pragma unroll
+                for (int e = 0; e < 4; ++e)
+                    if (c0 + e < ch) o[e] = decode_one(s, a[e], attr[e], x, y, v[e]);
             }
         }
     }

@@ -74,11 +74,14 @@ __device__ __forceinline__ void pp_emit_row(long row, int N, int lane, float cx,
     if (lane < 8) rowcand[row * 8 + lane] = o;
 }
 
+// CS > 0: number of classes known at compile time (80 for COCO), so each row's window of loaded values
+// [j*A/32, (j*A+A-1)/32] is static and only those ~4 of the 12 values per lane are examined.
+template <int CS>
 __global__ void __launch_bounds__(256) pp_score4_kernel(const float* __restrict__ det, long rows, int N, int C,
                                                         float thr, int is_eval, int* __restrict__ rowcount,
                                                         float* __restrict__ rowcand) {
     const int lane = threadIdx.x & 31;
-    const int A = 5 + C;
+    const int A = CS > 0 ? 5 + CS : 5 + C;
     const long row0 = ((long)blockIdx.x * 8 + (threadIdx.x >> 5)) * kRows;
     if (row0 >= rows) return;
     const int nrow = (int)min((long)kRows, rows - row0);
@@ -101,6 +104,7 @@ __global__ void __launch_bounds__(256) pp_score4_kernel(const float* __restrict_
         int bidx = 0x7fffffff, cnt = 0;
 #pragma unroll
         for (int k = 0; k < kMaxLoads; ++k) {
+            if (CS > 0 && (k < (j * (5 + CS)) / 32 || k > (j * (5 + CS) + 4 + CS) / 32)) continue;   // static window
             const int e = lane + 32 * k - j * A;           // element index inside row j
             const bool isc = e >= 5 && e < A;
             const float s = __fmul_rn(v[k], obj);
@@ -460,9 +464,12 @@ cudaError_t launch_postprocess(const PostArgs& a, PostBuffers& buf, long long* l
         cudaFuncSetAttribute(pp_nms_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kNmsSmemBoxes * 17);
         attrs_set = true;
     }
-    if (kRows * (5 + a.C) <= 32 * kMaxLoads)
-        pp_score4_kernel<<<(unsigned)((rows + 8 * kRows - 1) / (8 * kRows)), 256, 0, s>>>(a.det, rows, a.N, a.C, a.conf_thr, a.is_eval,
-                                                                                        buf.rowcount, buf.rowcand);
+    if (a.C == 80)
+        pp_score4_kernel<80><<<(unsigned)((rows + 8 * kRows - 1) / (8 * kRows)), 256, 0, s>>>(a.det, rows, a.N, a.C, a.conf_thr, a.is_eval,
+                                                                                            buf.rowcount, buf.rowcand);
+    else if (kRows * (5 + a.C) <= 32 * kMaxLoads)
+        pp_score4_kernel<0><<<(unsigned)((rows + 8 * kRows - 1) / (8 * kRows)), 256, 0, s>>>(a.det, rows, a.N, a.C, a.conf_thr, a.is_eval,
+                                                                                           buf.rowcount, buf.rowcand);
     else
         pp_score_kernel<<<(unsigned)((rows + 7) / 8), 256, 0, s>>>(a.det, rows, a.N, a.C, a.conf_thr, a.is_eval, buf.rowcount, buf.rowcand);
     pp_scan_kernel<<<a.B, 1024, 0, s>>>(buf.rowcount, a.N, buf.rowoff, buf.cand_total);
