@@ -31,7 +31,7 @@ def input_hw(specs, size):
     return out
 
 
-def run(layers, batch, size, reps):
+def run(layers, batch, size, reps, b2b=1):
     import torch
     from yolo_v3_b200 import _lib, synth, topology
     specs = topology.layer_specs(80)
@@ -65,10 +65,11 @@ def run(layers, batch, size, reps):
             flush.zero_()                              # evict L2 between repetitions
             a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             a.record()
-            _lib.check(lib.yb_run_layer(ctx, li, ctypes.c_void_p(x.data_ptr()), batch, h, h, rp, ctypes.c_void_p(out.data_ptr()), st), ctx)
+            for _k in range(b2b):
+                _lib.check(lib.yb_run_layer(ctx, li, ctypes.c_void_p(x.data_ptr()), batch, h, h, rp, ctypes.c_void_p(out.data_ptr()), st), ctx)
             b.record()
             torch.cuda.synchronize()
-            ts.append(a.elapsed_time(b))
+            ts.append(a.elapsed_time(b) / b2b)
         ts.sort()
         ms = ts[len(ts) // 2]
         fl = 2.0 * batch * ho * ho * e["cout"] * e["cin"] * e["ks"] ** 2
@@ -86,10 +87,11 @@ if __name__ == "__main__":
     ap.add_argument("--reps", type=int, default=7)
     ap.add_argument("--sweep", default="")
     ap.add_argument("--child", action="store_true")
+    ap.add_argument("--b2b", type=int, default=1, help="launches per timed region (back to back)")
     a = ap.parse_args()
     layers = [int(v) for v in a.layers.split(",")]
     if a.child or not a.sweep:
-        run(layers, a.batch, a.size, a.reps)
+        run(layers, a.batch, a.size, a.reps, a.b2b)
         sys.exit(0)
     axes = []
     for part in a.sweep.split(";"):
@@ -100,4 +102,4 @@ if __name__ == "__main__":
         env.update({k: v for k, v in combo})
         print("== " + " ".join(f"{k}={v}" for k, v in combo), flush=True)
         subprocess.run([sys.executable, os.path.abspath(__file__), "--child", "--layers", a.layers, "--batch", str(a.batch),
-                        "--size", str(a.size), "--reps", str(a.reps)], env=env, timeout=600)
+                        "--size", str(a.size), "--reps", str(a.reps), "--b2b", str(a.b2b)], env=env, timeout=600)

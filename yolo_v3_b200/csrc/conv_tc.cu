@@ -64,7 +64,7 @@ struct TcArgs {
     int exp_tiled;           // timing experiment: fetch 3x3 A tiles with tiled-mode TMA (results are wrong)
     int b_resident;          // 1: the CTA's whole weight slab [BN][K] is loaded once and stays in smem
     int* dbg;
-    long long* trace;        // optional [5 roles][64 tiles][4] clock64 stamps of CTA 0 (YB_TC_TRACE=1)
+    long long* trace;        // optional [6 roles][64 tiles][4] clock64 stamps of CTA 0 (YB_TC_TRACE=1)
 };
 
 #define YB_TRACE(role, idx, slot)                                                                   \
@@ -447,8 +447,10 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     tc_fence_after();
     const uint32_t tmem_base = *tmem_ptr;
     const uint32_t acc_stride = (uint32_t)a.tmem_cols >> 1;
+    if (threadIdx.x == 0) YB_TRACE(5, 0, 1);
     pdl_launch_dependents();      // everything above (barriers, TMEM, table) overlaps the previous layer's tail
     pdl_wait_prior();             // activations written by the previous layer are complete and visible
+    if (threadIdx.x == 0) YB_TRACE(5, 0, 2);
 
     if (warp < 2) {
         // ===== TMA producers (two warps take alternate pipeline stages; whole warp runs the loop, one
@@ -735,6 +737,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         if constexpr (CTA2) tmem_dealloc_pair(tmem_base, (uint32_t)a.tmem_cols);
         else tmem_dealloc(tmem_base, (uint32_t)a.tmem_cols);
     }
+    if (threadIdx.x == 0) YB_TRACE(5, 0, 3);
 }
 
 // ---- stem: 3 -> 32, 3x3, stride 1, straight from the caller's NCHW fp32 image ---------------------------
@@ -1171,8 +1174,8 @@ cudaError_t tc_launch(const TcPlan& p, const ConvArgs& a, int* dbg, cudaStream_t
     TcArgs t;
     static long long* trace_dev = nullptr;
     static const bool trace_on = getenv("YB_TC_TRACE") && atoi(getenv("YB_TC_TRACE")) != 0;
-    if (trace_on && !trace_dev) cudaMalloc(&trace_dev, 5 * 64 * 4 * sizeof(long long));
-    if (trace_on) cudaMemsetAsync(trace_dev, 0, 5 * 64 * 4 * sizeof(long long), s);
+    if (trace_on && !trace_dev) cudaMalloc(&trace_dev, 6 * 64 * 4 * sizeof(long long));
+    if (trace_on) cudaMemsetAsync(trace_dev, 0, 6 * 64 * 4 * sizeof(long long), s);
     t.trace = trace_on ? trace_dev : nullptr;
     t.M = p.M;
     t.Ho = a.Ho; t.Wo = a.Wo; t.HoWo = a.Ho * a.Wo;
@@ -1233,7 +1236,7 @@ cudaError_t tc_launch(const TcPlan& p, const ConvArgs& a, int* dbg, cudaStream_t
     if (trace_on) {                       // debugging aid: dump CTA 0's per-tile time line (cycles)
         static int dumps = 0;
         cudaStreamSynchronize(s);
-        long long h[5 * 64 * 4];
+        long long h[6 * 64 * 4];
         cudaMemcpy(h, trace_dev, sizeof(h), cudaMemcpyDeviceToHost);
         if (dumps++ % 8 == 7) {
             const long long t0 = h[0];
@@ -1243,6 +1246,14 @@ cudaError_t tc_launch(const TcPlan& p, const ConvArgs& a, int* dbg, cudaStream_t
                 fprintf(stderr, "[tc trace] tile %2d  prod start %7lld end %7lld | mma start %7lld tempty-ok %7lld issued %7lld | epi start %7lld tfull-ok %7lld done %7lld\n",
                         i, h[(0 * 64 + i) * 4] - t0, h[(0 * 64 + i) * 4 + 1] - t0, h[(1 * 64 + i) * 4] - t0, h[(1 * 64 + i) * 4 + 1] - t0,
                         h[(1 * 64 + i) * 4 + 2] - t0, h[(2 * 64 + i) * 4] - t0, h[(2 * 64 + i) * 4 + 1] - t0, h[(2 * 64 + i) * 4 + 2] - t0);
+            {
+                int last = 0;
+                for (int i = 0; i < 64; ++i) if (h[(2 * 64 + i) * 4 + 2]) last = i;
+                // (the entry stamp is taken before griddepcontrol.wait, so the preceding memset may erase it)
+                fprintf(stderr, "[tc trace] kernel: setup-done %7lld pdl-wait-done %7lld | first tile MMAs issued %7lld | last tile (%d) epilogue done %7lld | exit %7lld\n",
+                        h[(5 * 64) * 4 + 1] - t0, h[(5 * 64) * 4 + 2] - t0, h[(1 * 64) * 4 + 2] - t0, last,
+                        h[(2 * 64 + last) * 4 + 2] - t0, h[(5 * 64) * 4 + 3] - t0);
+            }
             for (int i = 0; i < 6; ++i)
                 fprintf(stderr, "[tc trace] tile %2d  epilogue sub-tile 0: buffer-ok %7lld tmem-loaded %7lld math+smem %7lld fence %7lld arrived %7lld\n", i,
                         h[(3 * 64 + i) * 4] - t0, h[(3 * 64 + i) * 4 + 1] - t0, h[(3 * 64 + i) * 4 + 2] - t0, h[(3 * 64 + i) * 4 + 3] - t0,
