@@ -10,7 +10,9 @@ reference implements in
     /root/reference/boundingbox.py  (bbox_cxcywh_to_x1y1x2y2 :25-29; correct_yolo_boxes :139-149 with
                                      letterbox_reverse :95-116, rescale_bbox :119-137)
     /root/reference/utils.py        (iou_vectorized :98-119, get_nms_detections :148-202,
-                                     get_raw_detections :204-224, postprocessing :226-258)
+                                     get_raw_detections :204-224, postprocessing :226-258;
+                                     letterbox_transforms :34-42, letterbox_image :44-57, load_image :60-72,
+                                     whose cv2.resize arithmetic is OpenCV's -- see the pre-process section)
 
 It is the *checker* for the CUDA path.  Only tests/, __graft_entry__.smoke() and the
 cpu_baseline / --impl reference legs of bench.py may import it; nothing under
@@ -286,6 +288,99 @@ def correct_yolo_boxes(bboxes: torch.Tensor, org_w, org_h, img_w, img_h, is_lett
     out[:, 2] = b[:, 2] - b[:, 0]
     out[:, 3] = b[:, 3] - b[:, 1]
     return out
+
+
+# --------------------------------------------------------------------------------------
+# Pre-process: letterbox (utils.letterbox_transforms :34-42, letterbox_image :44-57, load_image :60-72)
+# --------------------------------------------------------------------------------------
+# The arithmetic of the resize lives in a third-party dependency that is not vendored in the reference:
+# OpenCV (cv2.resize(..., interpolation=cv2.INTER_CUBIC), utils.py:50; this image has opencv-python 4.13.0).
+# Restated here is OpenCV's own portable implementation for 8-bit images (modules/imgproc/src/resize.cpp:
+# resizeGeneric_ with HResizeCubic<uchar,int,short> and VResizeCubic<..., FixedPtCast<int,uchar,22>,
+# VResizeCubicVec_32s8u>), pinned bit-for-bit against cv2.resize with cv2.ipp.setUseIPP(False) through
+# tests/golden/letterbox_golden.npz.  OpenCV builds that carry Intel IPP (the pip wheel does) route this call to
+# ippiResizeCubic instead, whose results differ from OpenCV's own code by at most one grey level on ~4 % of the
+# pixels; the golden file holds both variants and the tests check "bit-exact" against the former and
+# "<= 1 level" against the latter.
+_CUBIC_A = np.float32(-0.75)
+_COEF_SCALE = 2048                                   # INTER_RESIZE_COEF_SCALE = 1 << 11
+_VEC = 8                                             # elements per iteration of VResizeCubicVec_32s8u (2 x 128-bit)
+
+
+def letterbox_transforms(inner_dim, outer_dim):
+    """utils.letterbox_transforms (utils.py:34-42), python-float arithmetic."""
+    outer_w, outer_h = outer_dim
+    inner_w, inner_h = inner_dim
+    ratio = min(outer_w / inner_w, outer_h / inner_h)
+    box_w = int(inner_w * ratio)
+    box_h = int(inner_h * ratio)
+    return box_w, box_h, (outer_w // 2) - (box_w // 2), (outer_h // 2) - (box_h // 2), ratio
+
+
+def _cubic_coeffs(x: np.ndarray) -> np.ndarray:
+    """interpolateCubic(float x, float* coeffs), A = -0.75, every operation rounded to fp32."""
+    A, one = _CUBIC_A, np.float32(1)
+    x = x.astype(np.float32)
+    c0 = ((A * (x + one) - np.float32(5) * A) * (x + one) + np.float32(8) * A) * (x + one) - np.float32(4) * A
+    c1 = ((A + np.float32(2)) * x - (A + np.float32(3))) * x * x + one
+    c2 = ((A + np.float32(2)) * (one - x) - (A + np.float32(3))) * (one - x) * (one - x) + one
+    c3 = one - c0 - c1 - c2
+    return np.stack([c0, c1, c2, c3], -1).astype(np.float32)
+
+
+def _cubic_axis(ssize: int, dsize: int):
+    """Source offsets and 11-bit fixed-point taps of one axis (resizeGeneric set-up loop):
+    f = (float)((d + 0.5) * scale - 0.5) in double then fp32, s = floor(f), taps = cvRound(coeff * 2048)."""
+    scale = 1.0 / (dsize / ssize)                    # resize(): inv_scale = dsize/ssize; scale = 1./inv_scale
+    f = ((np.arange(dsize, dtype=np.float64) + 0.5) * scale - 0.5).astype(np.float32)
+    s = np.floor(f)
+    frac = (f - s.astype(np.float32)).astype(np.float32)
+    taps = np.clip(np.rint(_cubic_coeffs(frac) * np.float32(_COEF_SCALE)), -32768, 32767).astype(np.int32)
+    return s.astype(np.int64), taps
+
+
+def resize_cubic_u8(img: np.ndarray, dw: int, dh: int) -> np.ndarray:
+    """cv2.resize(img, (dw, dh), interpolation=cv2.INTER_CUBIC) for uint8 HxWxC, OpenCV's portable code path.
+    Horizontal pass: exact int32 sums of 4 border-replicated taps.  Vertical pass: fp32
+    S0*b0 + (S1*b1 + (S2*b2 + S3*b3)) with b = tap/2^22, separate roundings, round-half-even, saturate -- except the
+    last (dw*C) % 8 elements of every row, which the scalar tail computes as (sum + 2^21) >> 22."""
+    sh, sw, cn = img.shape
+    xofs, xa = _cubic_axis(sw, dw)
+    yofs, yb = _cubic_axis(sh, dh)
+    S = img.astype(np.int32)
+    xi = np.clip(xofs[:, None] + np.arange(-1, 3)[None, :], 0, sw - 1)
+    H = (S[:, xi, :] * xa[None, :, :, None]).sum(2)                  # [sh, dw, cn] int32, exact
+    yi = np.clip(yofs[:, None] + np.arange(-1, 3)[None, :], 0, sh - 1)
+    R = H[yi]                                                        # [dh, 4, dw, cn]
+    b = yb.astype(np.float32) * (np.float32(1.0) / np.float32(_COEF_SCALE * _COEF_SCALE))
+    Rf = R.astype(np.float32)
+    t = (Rf[:, 3] * b[:, 3, None, None]).astype(np.float32)
+    for k in (2, 1, 0):
+        t = ((Rf[:, k] * b[:, k, None, None]).astype(np.float32) + t).astype(np.float32)
+    out = np.clip(np.rint(t), 0, 255).astype(np.uint8).reshape(dh, dw * cn)
+    tail = (dw * cn) // _VEC * _VEC
+    if tail < dw * cn:
+        v = (R.astype(np.int64) * yb[:, :, None, None]).sum(1).reshape(dh, dw * cn)
+        out[:, tail:] = np.clip((v[:, tail:] + (1 << 21)) >> 22, 0, 255).astype(np.uint8)
+    return out.reshape(dh, dw, cn)
+
+
+def letterbox_image(img: np.ndarray, dim) -> Tuple[np.ndarray, torch.Tensor]:
+    """utils.letterbox_image (utils.py:44-57): grey (128) canvas np.full(dim + (3,)), bicubic-resized image pasted
+    at the centred offset; returns the canvas (int64, as np.full gives) and Tensor([box_w, box_h, box_x, box_y, ratio])."""
+    image = np.full(tuple(dim) + (3,), 128)
+    img_dim = (img.shape[1], img.shape[0])
+    box_w, box_h, box_x, box_y, ratio = letterbox_transforms(img_dim, dim)
+    box_image = resize_cubic_u8(img, box_w, box_h)
+    image[box_y:box_y + box_h, box_x:box_x + box_w] = box_image
+    return image, torch.Tensor([box_w, box_h, box_x, box_y, ratio])
+
+
+def load_image_letterbox(img_rgb_u8: np.ndarray, dim) -> Tuple[torch.Tensor, torch.Tensor]:
+    """utils.load_image(path, 'letterbox', dim) after the file decode (utils.py:60-72): letterbox, then
+    torch.from_numpy(img).float().permute(2,0,1) / 255."""
+    image, trans = letterbox_image(img_rgb_u8, dim)
+    return torch.from_numpy(image).float().permute(2, 0, 1) / 255, trans
 
 
 # --------------------------------------------------------------------------------------

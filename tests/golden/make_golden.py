@@ -198,7 +198,36 @@ def make_boxes():
     np.savez_compressed(os.path.join(HERE, "boxes_golden.npz"), **out)
 
 
+LETTERBOX_CASES = [  # (src_h, src_w, dim, seed): the dog-cycle-car.png shape, VGA -> 608, tall, upscale, 720p
+    (452, 602, 416, 31), (480, 640, 608, 32), (500, 333, 416, 33), (97, 131, 160, 34), (720, 1280, 320, 35), (64, 64, 96, 36)]
+
+
+def make_letterbox():
+    """utils.letterbox_image / load_image (utils.py:44-72) on seeded uint8 images (synth.make_photo, regenerated by
+    the tests from the seed).  Stored per case: the canvas with cv2's own implementation (cv2.ipp.setUseIPP(False)),
+    the difference of the IPP-accelerated build to it (int8, |d| <= 1), and `trans`."""
+    import cv2
+    out = {"cases": np.array(LETTERBOX_CASES)}
+    for i, (sh, sw, dim, seed) in enumerate(LETTERBOX_CASES):
+        img = synth.make_photo(sh, sw, seed)
+        cv2.ipp.setUseIPP(False)
+        canvas, trans = ref_utils.letterbox_image(img, (dim, dim))
+        cv2.ipp.setUseIPP(True)
+        canvas_ipp, _ = ref_utils.letterbox_image(img, (dim, dim))
+        assert canvas.min() >= 0 and canvas.max() <= 255
+        out[f"canvas{i}"] = canvas.astype(np.uint8)
+        out[f"ipp_delta{i}"] = (canvas_ipp - canvas).astype(np.int8)
+        out[f"trans{i}"] = trans.numpy()
+        # what load_image returns after the decode: float CHW / 255 (utils.py:71) -- digest only
+        x = torch.from_numpy(canvas).float().permute(2, 0, 1) / 255
+        out[f"sum{i}"] = np.array(float(x.double().sum()))
+    np.savez_compressed(os.path.join(HERE, "letterbox_golden.npz"), **out)
+
+
 if __name__ == "__main__":
+    make_letterbox()
+    if "--letterbox-only" in sys.argv:
+        sys.exit(0)
     make_boxes()
     make_decode()
     make_postprocess()

@@ -63,6 +63,9 @@ struct TcArgs {
     int has_res;
     int exp_tiled;           // timing experiment: fetch 3x3 A tiles with tiled-mode TMA (results are wrong)
     int b_resident;          // 1: the CTA's whole weight slab [BN][K] is loaded once and stays in smem
+    int pf_dist;             // L2 prefetch distance of the A operand, in tiles of this CTA (0 = off)
+    int b_early;             // weights are touched (resident load / L2 prefetch) before griddepcontrol.wait
+    int srel;                // store issuer: staging-buffer stores allowed to stay unread (0, 1 or 2)
     int* dbg;
     long long* trace;        // optional [6 roles][64 tiles][4] clock64 stamps of CTA 0 (YB_TC_TRACE=1)
 };
@@ -152,6 +155,14 @@ __device__ __forceinline__ void tma_load_im2col(const CUtensorMap* tm, uint32_t 
     asm volatile(
         "cp.async.bulk.tensor.4d.shared::cluster.global.im2col.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2], {%7, %8};"
         ::"r"(dst), "l"(tm), "r"(bar), "r"(c), "r"(w), "r"(h), "r"(n), "h"(off_w), "h"(off_h) : "memory");
+}
+// L2 prefetch of a box (no shared-memory destination, no completion to wait for)
+__device__ __forceinline__ void tma_prefetch_2d(const CUtensorMap* tm, int c0, int c1) {
+    asm volatile("cp.async.bulk.prefetch.tensor.2d.L2.global.tile [%0, {%1, %2}];" ::"l"(tm), "r"(c0), "r"(c1) : "memory");
+}
+__device__ __forceinline__ void tma_prefetch_im2col(const CUtensorMap* tm, int c, int w, int h, int n, uint16_t off_w, uint16_t off_h) {
+    asm volatile("cp.async.bulk.prefetch.tensor.4d.L2.global.im2col [%0, {%1, %2, %3, %4}], {%5, %6};"
+                 ::"l"(tm), "r"(c), "r"(w), "r"(h), "r"(n), "h"(off_w), "h"(off_h) : "memory");
 }
 __device__ __forceinline__ void tma_store_2d(const CUtensorMap* tm, uint32_t src, int c0, int c1) {
     asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];"
@@ -449,6 +460,22 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     const uint32_t acc_stride = (uint32_t)a.tmem_cols >> 1;
     if (threadIdx.x == 0) YB_TRACE(5, 0, 1);
     pdl_launch_dependents();      // everything above (barriers, TMEM, table) overlaps the previous layer's tail
+    // The weights do not depend on the previous layer: touch them before waiting for it, so that the resident
+    // slab (or, through an L2 prefetch, the first pipeline's worth of weight k-blocks) arrives under its tail.
+    if (warp == 0 && a.b_early && tile_first < total_tiles && elect_one()) {
+        if (a.b_resident) {
+            const int n0 = ((int)blockIdx.x % a.n_tiles) * a.BN;   // gridDim.x is a multiple of n_tiles
+            mbar_arrive_expect_tx(bres_bar, (uint32_t)a.num_kblocks * B_BYTES);
+#pragma unroll 1
+            for (int kb = 0; kb < a.num_kblocks; ++kb) tma_load_2d(&tmB, bres0 + kb * B_SLOT, bres_bar, kb * BKE, n0);
+        } else {
+            const int n0 = (tile_first % a.n_tiles) * a.BN + (int)rank * (a.BN / NCTA);
+            const int npf = min(a.num_kblocks, a.stages * a.kps);
+#pragma unroll 1
+            for (int kb = 0; kb < npf; ++kb) tma_prefetch_2d(&tmB, kb * BKE, n0);
+        }
+    }
+    __syncwarp();
     pdl_wait_prior();             // activations written by the previous layer are complete and visible
     if (threadIdx.x == 0) YB_TRACE(5, 0, 2);
 
@@ -460,7 +487,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             uint32_t itg = 0;                             // running stage counter across tiles
             int stage = 0;
             uint32_t phase = 0;
-            if (pw == 0 && a.b_resident && tile_first < total_tiles && elect_one()) {
+            if (pw == 0 && a.b_resident && !a.b_early && tile_first < total_tiles && elect_one()) {
                 // gridDim.x is a multiple of n_tiles, so every tile of this CTA has the same n-tile
                 const int n0 = ((int)blockIdx.x % a.n_tiles) * a.BN;
                 mbar_arrive_expect_tx(bres_bar, (uint32_t)a.num_kblocks * B_BYTES);
@@ -478,6 +505,40 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                 const int m0 = (m_unit * NCTA + (int)rank) * kBM;
                 const int n0 = n_tile * a.BN + (int)rank * (a.BN / NCTA);   // this CTA's half of the weight rows
                 if (pw == 0) YB_TRACE(0, ti, 0);
+                if (a.pf_dist && pw == 1 && !a.exp_tiled) {
+                    // L2 prefetch of the A operand of this CTA's tile pf_dist rounds ahead: the memory-bound layers
+                    // keep only one or two tiles in flight in shared memory, which leaves them DRAM-latency-bound;
+                    // the prefetch moves the DRAM round trip out of the pipeline (one CTA per m-tile issues it).
+                    const int tp = tile + a.pf_dist * tile_step;
+                    if (tp < total_tiles) {
+                        const int mu = tp / a.n_tiles;
+                        if (tp - mu * a.n_tiles == 0 && elect_one()) {
+                            const int m0p = (mu * NCTA + (int)rank) * kBM;
+                            if (a.ks == 1) {
+#pragma unroll 1
+                                for (int kb = 0; kb < a.num_kblocks; ++kb) tma_prefetch_2d(&tmA, kb * BKE, m0p);
+                            } else {
+                                const int cn = m0p / a.HoWo;
+                                const int r = m0p - cn * a.HoWo;
+                                const int p = r / a.Wo, q = r - p * a.Wo;
+                                const int cw = q * a.stride - a.pad, chh = p * a.stride - a.pad;
+                                // stride 1: the centre tap is the tile's own pixels (the rows above / below belong to
+                                // neighbouring tiles, prefetched by their CTAs at the same time); stride 2: the four
+                                // taps (1..2, 1..2) tile the input without overlap
+#pragma unroll 1
+                                for (int cb = 0; cb < a.cin_blocks; ++cb) {
+                                    tma_prefetch_im2col(&tmA, cb * BKE, cw, chh, cn, 1, 1);
+                                    if (a.stride == 2) {
+                                        tma_prefetch_im2col(&tmA, cb * BKE, cw, chh, cn, 2, 1);
+                                        tma_prefetch_im2col(&tmA, cb * BKE, cw, chh, cn, 1, 2);
+                                        tma_prefetch_im2col(&tmA, cb * BKE, cw, chh, cn, 2, 2);
+                                    }
+                                }
+                            }
+                        }
+                    }
+                    __syncwarp();
+                }
                 if (a.ks == 1 || a.exp_tiled) {
                     int kc = 0, ka = 0;
                     for (int it = 0; it < a.num_iters; ++it, ++itg) {
@@ -608,6 +669,14 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             for (int tile = tile_first; tile < total_tiles; tile += tile_step) {
                 const int m_unit = tile / a.n_tiles, n_tile = tile - m_unit * a.n_tiles;
                 const int m0 = (m_unit * NCTA + (int)rank) * kBM, n0 = n_tile * a.BN;
+                if (a.pf_dist) {                              // residual tile of a later round -> L2
+                    const int tp = tile + a.pf_dist * tile_step;
+                    if (tp < total_tiles) {
+                        const int mu = tp / a.n_tiles, nt = tp - mu * a.n_tiles;
+#pragma unroll 1
+                        for (int j = 0; j < a.n_sub; ++j) tma_prefetch_2d(&tmRes, nt * a.BN + j * a.cs, (mu * NCTA + (int)rank) * kBM);
+                    }
+                }
                 for (int j = 0; j < a.n_sub; ++j, ++g) {
                     const uint32_t buf = g % (uint32_t)a.ring, ph = (g / (uint32_t)a.ring) & 1u;
                     mbar_wait(sempty0 + 8 * buf, ph ^ 1, a.dbg, 3, 300 + (int)buf);
@@ -630,9 +699,17 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                     mbar_wait(sready0 + 8 * buf, ph, a.dbg, 4, 700 + (int)buf);
                     tma_store_2d(&tmOut, stg0 + buf * stg_bytes, n0 + j * a.cs, m0);
                     tma_store_commit();
-                    if (g > 0) {                              // the previous store has finished reading its buffer
-                        tma_store_wait_read<1>();
-                        mbar_arrive(sempty0 + 8 * ((g - 1) % (uint32_t)a.ring));
+                    // Recycle buffers: keep at most `srel` stores unread.  srel = ring - 2 is the latest release that
+                    // still lets the epilogue warps start sub-tile g+1 while sub-tile g is being finished; with the
+                    // two-deep ring that means handing the buffer back as soon as THIS store has read it (releasing
+                    // buffer g-1 only after store g was issued chained the sub-tiles one after another).
+                    if (a.srel == 0) {
+                        tma_store_wait_read<0>();
+                        mbar_arrive(sempty0 + 8 * buf);
+                    } else if (a.srel == 1) {
+                        if (g >= 1) { tma_store_wait_read<1>(); mbar_arrive(sempty0 + 8 * ((g - 1) % (uint32_t)a.ring)); }
+                    } else {
+                        if (g >= 2) { tma_store_wait_read<2>(); mbar_arrive(sempty0 + 8 * ((g - 2) % (uint32_t)a.ring)); }
                     }
                 }
             }
@@ -751,6 +828,7 @@ constexpr int kStemGroups = 3;            // producer groups of 128 threads
 constexpr int kStemThreads = 768;          // warps 0-11 producers (three groups), 12 MMA + TMEM alloc, 13 store issuer, 16-23 epilogue
 constexpr int kStemStages = 8;
 constexpr int kStemAcc = 4;
+constexpr int kStemRing = 4;              // epilogue staging buffers (a two-deep ring chained the tiles one after another)
 
 struct StemArgs {
     const float* x;
@@ -758,6 +836,7 @@ struct StemArgs {
     long M;
     int tiles;
     TcArgs epi;                             // scale, bias, leaky; staged-epilogue fields
+    int pf_dist;                            // L2 prefetch distance of the input image, in rounds of a producer group (0 = off)
     const __half* w;                        // [32][32] fp16, k = (ky*3+kx)*3 + c, zero padded
 };
 
@@ -768,20 +847,20 @@ stem_tc_kernel(const __grid_constant__ CUtensorMap tmOut, const StemArgs a_in) {
     const uint32_t raw = smem_u32(smem_raw);
     const uint32_t base = (raw + 1023u) & ~1023u;
     uint8_t* gen = smem_raw + (base - raw);
-    // header: full[8] | empty[8] | tfull[4] | tempty[4] | sempty[2] | tmem_ptr
-    const uint32_t full0 = base, empty0 = base + 64, tfull0 = base + 128, tempty0 = base + 160, sempty0 = base + 192, sready0 = base + 208;
-    volatile uint32_t* tmem_ptr = reinterpret_cast<volatile uint32_t*>(gen + 224);
+    // header: full[8] | empty[8] | tfull[4] | tempty[4] | sempty[4] | sready[4] | tmem_ptr
+    const uint32_t full0 = base, empty0 = base + 64, tfull0 = base + 128, tempty0 = base + 160, sempty0 = base + 192, sready0 = base + 224;
+    volatile uint32_t* tmem_ptr = reinterpret_cast<volatile uint32_t*>(gen + 256);
     constexpr uint32_t A_BYTES = kBM * 64, STG_BYTES = kBM * 64;
     const uint32_t wsm = base + 1024;                      // weights 32 x 64 B (2 KB), swizzled
-    const uint32_t stg0 = base + 4096;                     // 2 staging buffers
-    const uint32_t stage0 = stg0 + 2 * STG_BYTES;
+    const uint32_t stg0 = base + 4096;                     // kStemRing staging buffers
+    const uint32_t stage0 = stg0 + kStemRing * STG_BYTES;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
     if (warp == 0 && lane == 0) prefetch_tmap(&tmOut);
     if (warp == 12 && lane == 0) {
         for (int s = 0; s < kStemStages; ++s) { mbar_init(full0 + 8 * s, 128); mbar_init(empty0 + 8 * s, 1); }
         for (int i = 0; i < kStemAcc; ++i) { mbar_init(tfull0 + 8 * i, 1); mbar_init(tempty0 + 8 * i, 8); }
-        for (int i = 0; i < 2; ++i) { mbar_init(sempty0 + 8 * i, 1); mbar_init(sready0 + 8 * i, 8); }
+        for (int i = 0; i < kStemRing; ++i) { mbar_init(sempty0 + 8 * i, 1); mbar_init(sready0 + 8 * i, 8); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 12) tmem_alloc(smem_u32(const_cast<uint32_t*>(tmem_ptr)), 32 * kStemAcc);
@@ -839,10 +918,22 @@ stem_tc_kernel(const __grid_constant__ CUtensorMap tmOut, const StemArgs a_in) {
                 }
             }
         };
+        // L2 prefetch of this thread's own pixel (3 channel planes) a few rounds ahead: a group has one tile of
+        // loads in flight, so without it every iteration waits out a full DRAM round trip
+        auto prefetch_l2 = [&](int tile) {
+            const long m = (long)tile * kBM + r;
+            if (tile < a.tiles && m < a.M) {
+                const int b = (int)(m / HW);
+                const float* px = a.x + (long)b * 3 * HW + (m - (long)b * HW);
+#pragma unroll
+                for (int c = 0; c < 3; ++c) asm volatile("prefetch.global.L2 [%0];" ::"l"(px + c * HW));
+            }
+        };
         float v[27], vn[27];
         int i = grp;                                       // index of this CTA's i-th tile
         gather(blockIdx.x + i * gridDim.x, v);
         for (; (int)blockIdx.x + i * (int)gridDim.x < a.tiles; i += kStemGroups) {
+            if (a.pf_dist) prefetch_l2(blockIdx.x + (i + kStemGroups * (1 + a.pf_dist)) * gridDim.x);
             gather(blockIdx.x + (i + kStemGroups) * gridDim.x, vn);
             uint4 pk[4];
             __half2* h = reinterpret_cast<__half2*>(pk);
@@ -888,13 +979,13 @@ stem_tc_kernel(const __grid_constant__ CUtensorMap tmOut, const StemArgs a_in) {
         if (lane == 0) {
             uint32_t g = 0;
             for (int tile = blockIdx.x; tile < a.tiles; tile += gridDim.x, ++g) {
-                const uint32_t buf = g & 1u, ph = (g >> 1) & 1u;
+                const uint32_t buf = g % kStemRing, ph = (g / kStemRing) & 1u;
                 mbar_wait(sready0 + 8 * buf, ph, a.epi.dbg, 4, 700 + (int)buf);
                 tma_store_2d(&tmOut, stg0 + buf * STG_BYTES, 0, tile * kBM);
                 tma_store_commit();
-                if (g > 0) {
-                    tma_store_wait_read<1>();
-                    mbar_arrive(sempty0 + 8 * ((g - 1) & 1u));
+                if (g >= 2) {                              // two stores may stay unread; buffer g-2 goes back to the epilogue
+                    tma_store_wait_read<2>();
+                    mbar_arrive(sempty0 + 8 * ((g - 2) % kStemRing));
                 }
             }
             tma_store_wait_all();
@@ -907,7 +998,7 @@ stem_tc_kernel(const __grid_constant__ CUtensorMap tmOut, const StemArgs a_in) {
         const int xr = (row >> 1) & 3;
         uint32_t acc = 0, acc_phase = 0, g = 0;
         for (int tile = blockIdx.x; tile < a.tiles; tile += gridDim.x, ++g) {
-            const uint32_t buf = g & 1u, ph = (g >> 1) & 1u;
+            const uint32_t buf = g % kStemRing, ph = (g / kStemRing) & 1u;
             mbar_wait(tfull0 + 8 * acc, acc_phase, a.epi.dbg, 2, 200 + (int)acc);
             tc_fence_after();
             uint32_t r0[16];
@@ -1028,6 +1119,16 @@ std::string tc_make_plan(TcPlan& p, const ConvArgs& a, const __half* w16, int co
     const size_t bres_bytes = b_slot * p.num_kblocks;
     p.b_resident = !p.cta2 && bres_bytes <= 96 * 1024 && p.grid % p.n_tiles == 0 && p.m_tiles > 2 * num_sms;
     if (const char* e = getenv("YB_TC_BRES")) p.b_resident = p.b_resident && atoi(e) != 0;
+    // Experiments kept behind overrides (profiles/r01b_sweep_prefetch.txt): an L2 prefetch of the A operand
+    // pf_dist tiles ahead makes the memory-bound layers SLOWER (32->64 s2: 0.25 -> 0.30 ms; the TMA request
+    // path, not DRAM latency, is what limits them), touching the weights before griddepcontrol.wait and the
+    // earlier staging-buffer release change nothing measurable.  Defaults = the validated behaviour.
+    p.pf_dist = 0;
+    if (const char* e = getenv("YB_TC_PF")) p.pf_dist = std::max(0, std::min(16, atoi(e)));
+    p.srel = 1;
+    if (const char* e = getenv("YB_TC_SREL")) p.srel = std::max(0, std::min(std::min(2, p.ring - 1), atoi(e)));
+    p.b_early = 0;
+    if (const char* e = getenv("YB_TC_BEARLY")) p.b_early = atoi(e) != 0;
     const size_t kb_bytes = (size_t)kBM * p.swz + (p.b_resident ? 0 : b_slot);
     p.tab_bytes = (int)(((size_t)2 * cout_pad * sizeof(float) + 1023) & ~(size_t)1023);
     const size_t fixed = kSmemHeader + 1024 + p.tab_bytes + ring_bytes + (p.b_resident ? bres_bytes : 0);
@@ -1129,7 +1230,7 @@ std::string stem_tc_make_plan(StemTcPlan& p, __half* out, long out_ld, int B, in
     p.M = (long)B * H * W;
     p.tiles = (int)((p.M + kBM - 1) / kBM);
     p.grid = std::min(p.tiles, num_sms);
-    p.smem = 1024 + 4096 + 2 * (size_t)kBM * 64 + (size_t)kStemStages * kBM * 64;
+    p.smem = 1024 + 4096 + kStemRing * (size_t)kBM * 64 + (size_t)kStemStages * kBM * 64;
     cuuint64_t dims[2] = {32, (cuuint64_t)p.M};
     cuuint64_t strides[1] = {(cuuint64_t)out_ld * sizeof(__half)};
     cuuint32_t box[2] = {32, (cuuint32_t)kBM};
@@ -1145,10 +1246,14 @@ cudaError_t stem_tc_launch(const StemTcPlan& p, const float* x, int B, int H, in
                            const float* bias, int* dbg, cudaStream_t s) {
     StemArgs a{};
     a.x = x; a.B = B; a.H = H; a.W = W; a.M = p.M; a.tiles = p.tiles; a.w = w16;
+    {
+        static const int pf = getenv("YB_STEM_PF") ? std::max(0, std::min(64, atoi(getenv("YB_STEM_PF")))) : 0;
+        a.pf_dist = pf;
+    }
     a.epi.scale = scale; a.epi.bias = bias; a.epi.leaky = 1; a.epi.out_f32 = 0; a.epi.has_res = 0; a.epi.dbg = dbg;
     static bool attr_done = false;
     if (!attr_done) {
-        cudaError_t e = cudaFuncSetAttribute(stem_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024);
+        cudaError_t e = cudaFuncSetAttribute(stem_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 128 * 1024);
         if (e != cudaSuccess) return e;
         attr_done = true;
     }
@@ -1192,6 +1297,9 @@ cudaError_t tc_launch(const TcPlan& p, const ConvArgs& a, int* dbg, cudaStream_t
     t.epi_staged = p.epi_staged; t.ring = p.ring; t.sub_bytes = p.sub_bytes; t.cs = p.cs; t.n_sub = p.n_sub;
     t.has_res = a.res != nullptr;
     t.b_resident = p.b_resident;
+    t.pf_dist = p.pf_dist;
+    t.b_early = p.b_early;
+    t.srel = p.srel;
     t.exp_tiled = p.exp_tiled;
     t.dbg = dbg;
     static bool attr_done = false;

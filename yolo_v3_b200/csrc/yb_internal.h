@@ -74,6 +74,7 @@ struct TcPlan {
     int swz = 128;        // 128: 64-channel k-blocks, 64: 32-channel k-blocks (Cin == 32)
     int BN = 0, n_tiles = 0, m_tiles = 0, stages = 0, tmem_cols = 0;
     int num_kblocks = 0, cin_blocks = 0, kps = 1, cta2 = 0, cout_pad = 0, tab_bytes = 0;
+    int pf_dist = 0, b_early = 0, srel = 0;
     int grid = 0;
     size_t smem = 0;
     long M = 0;

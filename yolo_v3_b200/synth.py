@@ -108,6 +108,20 @@ def make_images(batch: int, h: int, w: int, seed: int = 0) -> torch.Tensor:
     return torch.from_numpy(np.random.RandomState(seed).rand(batch, 3, h, w).astype(np.float32))
 
 
+def make_photo(h: int, w: int, seed: int = 0) -> np.ndarray:
+    """Seeded uint8 RGB image [h,w,3] with photo-like content (smooth structure, edges, mild noise): the
+    input of the letterbox pre-process (what cv2.imread + cvtColor hand to utils.letterbox_image, utils.py:61-67)."""
+    rs = np.random.RandomState(seed)
+    yy, xx = np.mgrid[0:h, 0:w].astype(np.float64)
+    ph = rs.uniform(0, 6.28, (3, 3))
+    img = np.empty((h, w, 3), np.float64)
+    for c in range(3):
+        img[..., c] = (128 + 55 * np.sin(xx / 17.0 + ph[c, 0]) * np.cos(yy / 23.0 + ph[c, 1])
+                       + 35 * np.sin((xx + 2 * yy) / 7.0 + ph[c, 2]) + 40 * (((xx // 37) + (yy // 29)) % 2))
+    img += rs.randint(-6, 7, (h, w, 3))
+    return np.clip(np.rint(img), 0, 255).astype(np.uint8)
+
+
 def make_head_logits(batch: int, h: int, w: int, num_classes: int = 80, seed: int = 7,
                      obj_mu: float = -6.5, dense: bool = False):
     """Seeded raw head maps [B,255,h/32..h/8,...] for the post-process stress configs
