@@ -129,6 +129,21 @@ int yb_detect(yb_ctx* ctx, const float* x_nchw, int B, int H, int W, float obj_c
 int yb_correct_boxes(yb_ctx* ctx, const float* boxes, int row_stride, const int* counts, int B, int cap,
                      const int* org_wh_host, int img_w, int img_h, int is_letterbox, float* out_xywh, void* stream);
 
+/* Replaces utils.load_image(path, 'letterbox', dim) after the file decode (utils.py:60-72) for a batch of images of
+ * different sizes: letterbox_image (utils.py:44-57 = letterbox_transforms :34-42, cv2.resize(..., INTER_CUBIC) to the
+ * box, paste on a grey-128 canvas) followed by torch.from_numpy(img).float().permute(2,0,1) / 255.  The resize
+ * arithmetic is OpenCV's portable 8-bit path, bit for bit (csrc/preprocess.cu).
+ * imgs_dev: HOST array of B device pointers to uint8 RGB HWC images (row pitch w*3); hw_host: HOST int[B][2] = (h, w)
+ * of every image; dim_w, dim_h: the reference's `dim` = (outer_w, outer_h), from which every image's box is derived;
+ * canvas_h, canvas_w: the canvas.  The reference allocates np.full(dim + (3,)), i.e. canvas_h = dim[0], canvas_w =
+ * dim[1] -- the same thing for the square sizes it uses; a box that does not fit the canvas makes numpy raise and this
+ * call return YB_E_ARG.  (dim = (w, h) of the image itself with canvas (h, w) is the plain float()/255 + HWC->CHW of
+ * load_image(mode=None).)  out_nchw: dev [B,3,canvas_h,canvas_w] fp32; canvas_hwc: dev uint8 [B,canvas_h,canvas_w,3],
+ * the canvas letterbox_image itself returns (either output may be NULL, not both); trans_host: HOST float[B][5] =
+ * box_w, box_h, box_x, box_y, ratio (the reference's `trans`), may be NULL. */
+int yb_letterbox(yb_ctx* ctx, const uint8_t* const* imgs_dev, const int* hw_host, int B, int dim_w, int dim_h,
+                 int canvas_h, int canvas_w, float* out_nchw, uint8_t* canvas_hwc, float* trans_host, void* stream);
+
 /* ---- multi-GPU (absent in the reference; batch sharding) ------------------------- */
 
 /* 128-byte NCCL unique id, created on rank 0 and shipped to the other ranks by the host plumbing

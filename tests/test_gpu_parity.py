@@ -377,3 +377,80 @@ def test_correct_yolo_boxes_bit_exact(golden, oracle):
     assert np.array_equal(out[0].numpy(), g["letterbox0"])
     ref1 = oracle.correct_yolo_boxes(torch.from_numpy(g["in1"]), 602, 452, 416, 416, True)
     assert torch.equal(out[1, :40], ref1[:40]) and float(out[1, 40:].abs().sum()) == 0.0
+
+
+# ---------------------------------------------------------------------------------------------
+# N1: letterbox pre-process (the step right before the path)
+# ---------------------------------------------------------------------------------------------
+def test_letterbox_bit_exact(golden, oracle):
+    """yb_letterbox against the canvases the reference's own letterbox_image produced (OpenCV's portable code path:
+    bit-exact; the IPP-accelerated build: within one grey level), one launch for the whole ragged batch."""
+    from yolo_v3_b200.utils import letterbox_batch, letterbox_image
+    g = golden("letterbox_golden.npz")
+    by_dim = {}
+    for i, (sh, sw, dim, seed) in enumerate(g["cases"]):
+        by_dim.setdefault(int(dim), []).append((i, synth.make_photo(int(sh), int(sw), int(seed))))
+    for dim, items in by_dim.items():
+        canv, trans = letterbox_batch([im for _, im in items], (dim, dim), want_canvas=True)
+        x, trans2 = letterbox_batch([im for _, im in items], (dim, dim))
+        canv, x = canv.cpu().numpy(), x.cpu()
+        assert torch.equal(trans, trans2)
+        for k, (i, im) in enumerate(items):
+            assert np.array_equal(canv[k], g[f"canvas{i}"]), i                                  # bit-exact (bytes)
+            assert np.array_equal(trans[k].numpy(), g[f"trans{i}"]), i
+            ref = torch.from_numpy(g[f"canvas{i}"].astype(np.int64)).float().permute(2, 0, 1) / 255   # utils.py:71
+            assert torch.equal(x[k], ref), i
+            ipp = g[f"canvas{i}"].astype(np.int64) + g[f"ipp_delta{i}"]
+            assert np.abs(canv[k].astype(np.int64) - ipp).max() <= 1
+    # reference signature: numpy integer canvas + 5-element transform
+    img = synth.make_photo(97, 131, 34)
+    canvas, t = letterbox_image(img, (160, 160))
+    ref_canvas, ref_t = oracle.letterbox_image(img, (160, 160))
+    assert canvas.dtype == np.int64 and np.array_equal(canvas, ref_canvas) and torch.equal(t, ref_t)
+
+
+def test_letterbox_edge_cases(oracle):
+    from yolo_v3_b200.utils import letterbox_batch, letterbox_image
+    rs = np.random.RandomState(3)
+    # ragged, tiny, strongly up- and down-scaled noise images against the oracle (which is pinned to cv2 on the CPU side)
+    shapes = [(1, 1), (2, 7), (5, 3), (33, 257), (301, 17), (64, 64), (240, 427)]
+    imgs = [rs.randint(0, 256, (h, w, 3)).astype(np.uint8) for h, w in shapes]
+    for dim in (32, 96, 224):
+        canv, trans = letterbox_batch(imgs, (dim, dim), want_canvas=True)
+        for k, im in enumerate(imgs):
+            h, w = im.shape[:2]
+            if int(w * min(dim / w, dim / h)) == 0 or int(h * min(dim / w, dim / h)) == 0:
+                continue
+            ref, rt = oracle.letterbox_image(im, (dim, dim))
+            assert np.array_equal(canv[k].cpu().numpy(), ref), (dim, k)
+            assert torch.equal(trans[k], rt)
+    # an image that collapses to an empty box, and a non-square dim whose box does not fit the reference's
+    # transposed canvas: the reference raises (cv2 / numpy), so does the mirror
+    with pytest.raises(Exception):
+        letterbox_batch([np.zeros((1, 400, 3), np.uint8)], (32, 32))
+    with pytest.raises(ValueError):
+        letterbox_image(np.zeros((100, 300, 3), np.uint8), (320, 96))
+    # identity geometry = load_image(mode=None): exact copy, /255, HWC -> CHW
+    im = imgs[-1]
+    x, _ = letterbox_batch([im], (im.shape[1], im.shape[0]), canvas_hw=im.shape[:2])
+    assert torch.equal(x[0].cpu(), torch.from_numpy(im).float().permute(2, 0, 1) / 255)
+
+
+def test_detect_fused_equals_two_kernel_path(oracle, sd_calibrated):
+    """yb_detect (decode + score fused, det never materialised) == yb_forward + yb_postprocess, bit for bit, in fp32
+    mode at a low threshold (most anchors take the full path) and a high one (most are skipped on objectness)."""
+    from yolo_v3_b200 import YoloNet, postprocessing
+    net = YoloNet((96, 160), precision="fp32")
+    net.load_state_dict(sd_calibrated)
+    net = net.cuda().eval()
+    x = synth.make_images(3, 160, 96, seed=11).cuda()
+    det = torch.cat(net(x, None), 1)
+    ref_det = torch.cat(oracle.forward(sd_calibrated, x.cpu()), 1)
+    np.testing.assert_allclose(det.cpu().numpy(), ref_det.numpy(), rtol=1e-3, atol=2e-3)
+    for thr in (0.001, 0.05, 0.5, 0.999):
+        a = net.detect(x, thr, 0.4)
+        b = postprocessing(det, 80, thr, 0.4)
+        assert len(a) == len(b)
+        assert all(torch.equal(p, q) for p, q in zip(a, b)), thr
+        ref, _ = oracle.postprocessing_c(det.cpu(), 80, thr, 0.4)
+        assert len(ref) == len(b) and all(torch.equal(p, q) for p, q in zip(ref, b)), thr

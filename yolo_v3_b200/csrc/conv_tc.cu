@@ -825,7 +825,8 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 // (one tcgen05.mma pair per tile: M=128, N=32, K=32).  Four TMEM accumulators of 32 columns keep the
 // producers, the tensor core and the epilogue warps (same staged TMA-store epilogue) overlapped.
 constexpr int kStemGroups = 3;            // producer groups of 128 threads
-constexpr int kStemThreads = 768;          // warps 0-11 producers (three groups), 12 MMA + TMEM alloc, 13 store issuer, 16-23 epilogue
+constexpr int kStemThreads = 704;          // warps 0-11 producers (three groups), 12-19 epilogue, 20 MMA + TMEM alloc, 21 store issuer
+                                           // (22 warps)
 constexpr int kStemStages = 8;
 constexpr int kStemAcc = 4;
 constexpr int kStemRing = 4;              // epilogue staging buffers (a two-deep ring chained the tiles one after another)
@@ -857,13 +858,13 @@ stem_tc_kernel(const __grid_constant__ CUtensorMap tmOut, const StemArgs a_in) {
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
     if (warp == 0 && lane == 0) prefetch_tmap(&tmOut);
-    if (warp == 12 && lane == 0) {
+    if (warp == 20 && lane == 0) {
         for (int s = 0; s < kStemStages; ++s) { mbar_init(full0 + 8 * s, 128); mbar_init(empty0 + 8 * s, 1); }
         for (int i = 0; i < kStemAcc; ++i) { mbar_init(tfull0 + 8 * i, 1); mbar_init(tempty0 + 8 * i, 8); }
         for (int i = 0; i < kStemRing; ++i) { mbar_init(sempty0 + 8 * i, 1); mbar_init(sready0 + 8 * i, 8); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
-    if (warp == 12) tmem_alloc(smem_u32(const_cast<uint32_t*>(tmem_ptr)), 32 * kStemAcc);
+    if (warp == 20) tmem_alloc(smem_u32(const_cast<uint32_t*>(tmem_ptr)), 32 * kStemAcc);
     a.epi.tab = reinterpret_cast<const float*>(gen + 3072);   // scale[32] | bias[32]
     a.epi.cout_pad = 32;
     if (threadIdx.x >= 64 && threadIdx.x < 128) {
@@ -888,60 +889,82 @@ stem_tc_kernel(const __grid_constant__ CUtensorMap tmOut, const StemArgs a_in) {
 
     if (warp < 4 * kStemGroups) {
         // ===== producers: one output pixel (im2col row) per thread; kStemGroups groups of 128 threads take
-        // tiles round-robin, and each thread keeps the 27 loads of its next tile in flight while it
-        // converts and stores the current one =====
+        // tiles round-robin, and each thread keeps the 27 loads of its next tile in flight while it converts
+        // and stores the current one.  The kernel is instruction-issue-bound (ncu: 71 % issue-active, 840
+        // warp instructions per 32 pixels in the first version), so the loop is kept lean: the pixel's
+        // (image, y, x) is carried incrementally instead of divided out per tile, interior pixels take an
+        // unpredicated path (nine row pointers, immediate +-1 offsets), and the taps are packed to fp16
+        // before the next tile's loads are issued into the same registers (one set instead of two + a copy) =====
         const int grp = warp >> 2;
         const int r = threadIdx.x & 127;
         const int xr = (r >> 1) & 3;
-        const long HW = (long)a.H * a.W;
-        auto gather = [&](int tile, float (&v)[27]) {
+        const int HW = a.H * a.W;
+        const long img_stride = 3L * HW;
+        const int tstep = kStemGroups * (int)gridDim.x;
+        int i = grp;                                       // index of this CTA's i-th tile
+        int tile = (int)blockIdx.x + i * (int)gridDim.x;
+        long m = (long)tile * kBM + r;                     // this thread's pixel in the tile being gathered
+        const long dm = (long)tstep * kBM;
+        int pb = (int)(m / HW), py, px;
+        {
+            const int rem = (int)(m - (long)pb * HW);
+            py = rem / a.W; px = rem - py * a.W;
+        }
+        const int db = (int)(dm / HW);
+        const int drem = (int)(dm - (long)db * HW);
+        const int dy = drem / a.W, dx = drem - dy * a.W;
+        auto advance = [&]() {
+            m += dm;
+            px += dx; if (px >= a.W) { px -= a.W; ++py; }
+            py += dy; if (py >= a.H) { py -= a.H; ++pb; }
+            pb += db;
+        };
+        auto gather = [&](float (&v)[27]) {
+            if (m < a.M) {
+                const float* p = a.x + (long)pb * img_stride + py * a.W + px;
+                if (py >= 1 && py < a.H - 1 && px >= 1 && px < a.W - 1) {
 #pragma unroll
-            for (int i = 0; i < 27; ++i) v[i] = 0.f;
-            const long m = (long)tile * kBM + r;
-            if (tile < a.tiles && m < a.M) {
-                const int b = (int)(m / HW);
-                const int rem = (int)(m - (long)b * HW);
-                const int y = rem / a.W, x = rem - y * a.W;
-                const float* xb = a.x + (long)b * 3 * HW;
+                    for (int c = 0; c < 3; ++c) {
 #pragma unroll
-                for (int ky = 0; ky < 3; ++ky) {
-                    const int iy = y + ky - 1;
-                    const bool oky = iy >= 0 && iy < a.H;
+                        for (int ky = 0; ky < 3; ++ky) {
+                            const float* q = p + c * HW + (ky - 1) * a.W;
+                            v[(ky * 3 + 0) * 3 + c] = __ldg(q - 1);
+                            v[(ky * 3 + 1) * 3 + c] = __ldg(q);
+                            v[(ky * 3 + 2) * 3 + c] = __ldg(q + 1);
+                        }
+                    }
+                } else {
 #pragma unroll
-                    for (int kx = 0; kx < 3; ++kx) {
-                        const int ix = x + kx - 1;
-                        if (oky && ix >= 0 && ix < a.W) {
+                    for (int ky = 0; ky < 3; ++ky) {
+                        const int iy = py + ky - 1;
+                        const bool oky = iy >= 0 && iy < a.H;
 #pragma unroll
-                            for (int c = 0; c < 3; ++c) v[(ky * 3 + kx) * 3 + c] = __ldg(xb + c * HW + (long)iy * a.W + ix);
+                        for (int kx = 0; kx < 3; ++kx) {
+                            const int ix = px + kx - 1;
+                            const bool ok = oky && ix >= 0 && ix < a.W;
+#pragma unroll
+                            for (int c = 0; c < 3; ++c)
+                                v[(ky * 3 + kx) * 3 + c] = ok ? __ldg(p + c * HW + (ky - 1) * a.W + (kx - 1)) : 0.f;
                         }
                     }
                 }
-            }
-        };
-        // L2 prefetch of this thread's own pixel (3 channel planes) a few rounds ahead: a group has one tile of
-        // loads in flight, so without it every iteration waits out a full DRAM round trip
-        auto prefetch_l2 = [&](int tile) {
-            const long m = (long)tile * kBM + r;
-            if (tile < a.tiles && m < a.M) {
-                const int b = (int)(m / HW);
-                const float* px = a.x + (long)b * 3 * HW + (m - (long)b * HW);
+            } else {
 #pragma unroll
-                for (int c = 0; c < 3; ++c) asm volatile("prefetch.global.L2 [%0];" ::"l"(px + c * HW));
+                for (int k = 0; k < 27; ++k) v[k] = 0.f;
             }
         };
-        float v[27], vn[27];
-        int i = grp;                                       // index of this CTA's i-th tile
-        gather(blockIdx.x + i * gridDim.x, v);
-        for (; (int)blockIdx.x + i * (int)gridDim.x < a.tiles; i += kStemGroups) {
-            if (a.pf_dist) prefetch_l2(blockIdx.x + (i + kStemGroups * (1 + a.pf_dist)) * gridDim.x);
-            gather(blockIdx.x + (i + kStemGroups) * gridDim.x, vn);
-            uint4 pk[4];
+        float v[27];
+        if (tile < a.tiles) gather(v);
+        while (tile < a.tiles) {
+            uint4 pk[4];                                   // waits for the loads issued one iteration ago
             __half2* h = reinterpret_cast<__half2*>(pk);
 #pragma unroll
             for (int j = 0; j < 13; ++j) h[j] = __floats2half2_rn(v[2 * j], v[2 * j + 1]);
             h[13] = __floats2half2_rn(v[26], 0.f);
             h[14] = __floats2half2_rn(0.f, 0.f);
             h[15] = h[14];
+            advance();
+            gather(v);                                     // next tile's loads in flight (zeros past the end)
             const int stage = i % kStemStages;
             const uint32_t phase = (uint32_t)(i / kStemStages) & 1u;
             mbar_wait(empty0 + 8 * stage, phase ^ 1, a.epi.dbg, 0, stage);
@@ -950,10 +973,9 @@ stem_tc_kernel(const __grid_constant__ CUtensorMap tmOut, const StemArgs a_in) {
             for (int c = 0; c < 4; ++c) *reinterpret_cast<uint4*>(row + ((c ^ xr) << 4)) = pk[c];
             fence_async_smem();
             mbar_arrive(full0 + 8 * stage);
-#pragma unroll
-            for (int j = 0; j < 27; ++j) v[j] = vn[j];
+            i += kStemGroups; tile += tstep;
         }
-    } else if (warp == 12) {
+    } else if (warp == 20) {
         // ===== MMA issuer =====
         if (lane == 0) {
             const uint32_t idesc = make_idesc(32);
@@ -974,7 +996,7 @@ stem_tc_kernel(const __grid_constant__ CUtensorMap tmOut, const StemArgs a_in) {
             }
         }
         __syncwarp();
-    } else if (warp == 13) {
+    } else if (warp == 21) {
         // ===== store issuer =====
         if (lane == 0) {
             uint32_t g = 0;
@@ -991,11 +1013,15 @@ stem_tc_kernel(const __grid_constant__ CUtensorMap tmOut, const StemArgs a_in) {
             tma_store_wait_all();
         }
         __syncwarp();
-    } else if (warp >= 16) {
-        // ===== epilogue (8 warps, 16 columns per thread): TMEM -> scale/bias/LeakyReLU -> fp16 -> swizzled smem =====
-        const int q = warp & 3, part = (warp - 16) >> 2;
+    } else if (warp >= 12 && warp < 20) {
+        // ===== epilogue (8 warps, 16 columns per thread): TMEM -> scale/bias/LeakyReLU -> fp16 -> swizzled smem.
+        // A thread owns the same 16 channels in every tile, so their scale/bias live in registers. =====
+        const int q = warp & 3, part = (warp - 12) >> 2;
         const int row = q * 32 + lane;
         const int xr = (row >> 1) & 3;
+        float sc[16], bi[16];
+#pragma unroll
+        for (int j = 0; j < 16; ++j) { sc[j] = a.epi.tab[part * 16 + j]; bi[j] = a.epi.tab[32 + part * 16 + j]; }
         uint32_t acc = 0, acc_phase = 0, g = 0;
         for (int tile = blockIdx.x; tile < a.tiles; tile += gridDim.x, ++g) {
             const uint32_t buf = g % kStemRing, ph = (g / kStemRing) & 1u;
@@ -1010,7 +1036,19 @@ stem_tc_kernel(const __grid_constant__ CUtensorMap tmOut, const StemArgs a_in) {
             __syncwarp();
             if (lane == 0) mbar_arrive(tempty0 + 8 * acc);   // accumulator drained into registers
             uint8_t* srow = gen + (stg0 - base) + buf * STG_BYTES + row * 64;
-            epilogue16_staged(a.epi, r0, part * 16, srow, part, xr);
+#pragma unroll
+            for (int h = 0; h < 2; ++h) {
+                uint4 pk;
+                __half2* ph2 = reinterpret_cast<__half2*>(&pk);
+#pragma unroll
+                for (int e = 0; e < 4; ++e) {
+                    const int j = 8 * h + 2 * e;
+                    const float v0 = leaky(fmaf(__uint_as_float(r0[j]), sc[j], bi[j]));
+                    const float v1 = leaky(fmaf(__uint_as_float(r0[j + 1]), sc[j + 1], bi[j + 1]));
+                    ph2[e] = __floats2half2_rn(v0, v1);
+                }
+                *reinterpret_cast<uint4*>(srow + (((part * 2 + h) ^ xr) << 4)) = pk;
+            }
             fence_async_smem();
             __syncwarp();
             if (lane == 0) mbar_arrive(sready0 + 8 * buf);
@@ -1019,7 +1057,7 @@ stem_tc_kernel(const __grid_constant__ CUtensorMap tmOut, const StemArgs a_in) {
     }
     tc_fence_before();
     __syncthreads();
-    if (warp == 12) {
+    if (warp == 20) {
         tc_fence_after();
         tmem_dealloc(tmem_base, 32 * kStemAcc);
     }

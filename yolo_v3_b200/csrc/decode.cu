@@ -10,6 +10,8 @@
 //
 // Full-precision expf and IEEE division (no -use_fast_math); every product is a separate rounding
 // as in the reference.  HBM-bound: reads 4 B and writes 4 B per element, both fully coalesced.
+#include <algorithm>
+
 #include "yb_internal.h"
 
 namespace yb {
@@ -119,7 +121,137 @@ __global__ void __launch_bounds__(256) decode_nchw_kernel(const __grid_constant_
     for (int i = threadIdx.x; i < n; i += blockDim.x) o[i] = tile[(i % ch) * 33 + i / ch];
 }
 
+// ---- fused decode + score (the yb_detect path) ---------------------------------------------------------
+// One warp per grid cell.  The cell's 3*(5+C) raw logits are one aligned, padded run of the NHWC head map:
+// the warp loads it with 16-byte loads, parks it in shared memory, and then
+//   * (kWriteDet) decodes every element and writes the cell's three rows of det_cat with coalesced stores
+//     -- the standalone decode, without the strided scalar stores of decode_nhwc_kernel;
+//   * (kScore) does what pp_score does on those rows without the [B,N,5+C] tensor ever being written or
+//     re-read: score_c = cls_c * obj, row max with the lowest-index tie-break, strict '>' threshold, box
+//     convert, -> rowcount / rowcand for pp_scan / pp_scatter.  Since cls_c <= 1, score_c <= obj in fp32 as
+//     well (rounding is monotonic), so an anchor whose objectness does not pass cannot pass: its class
+//     sigmoids are never evaluated (at conf 0.5 that is >99 % of the anchors; at conf 0.001 almost none).
+// Arithmetic is decode_one / __fmul_rn exactly as in the two-kernel path, so the results are bit-identical.
+constexpr int kFusedWarps = 8;
+
+template <bool kWriteDet, bool kScore>
+__global__ void __launch_bounds__(kFusedWarps * 32, 4)
+decode_cells_kernel(const __grid_constant__ DecodeParams P, float* __restrict__ det, float thr, int* __restrict__ rowcount,
+                    float* __restrict__ rowcand, int ch_pad) {
+    extern __shared__ __align__(16) float cell_smem[];      // [kFusedWarps][ch_pad]
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    float* sm = cell_smem + warp * ch_pad;
+    const int attrs = P.attrs, ch = 3 * attrs;
+    const long total = P.cells_before[3];
+    const long wstride = (long)gridDim.x * kFusedWarps;
+    int ca[8], cattr[8];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) { ca[k] = (lane + 32 * k) / attrs; cattr[k] = (lane + 32 * k) - ca[k] * attrs; }
+    for (long g = (long)blockIdx.x * kFusedWarps + warp; g < total; g += wstride) {
+        const int si = g >= P.cells_before[2] ? 2 : (g >= P.cells_before[1] ? 1 : 0);
+        const DecodeScale& s = P.sc[si];
+        const int hw = s.h * s.w;
+        const long gl = g - P.cells_before[si];
+        const int b = (int)(gl / hw), p = (int)(gl - (long)b * hw);
+        const int y = p / s.w, x = p - y * s.w;
+        const float* in = s.logits + gl * s.ld;              // (b*hw + p) * ld
+        __syncwarp();                                        // previous cell's readers are done with sm
+        for (int c0 = lane * 4; c0 < ch_pad; c0 += 128)
+            *reinterpret_cast<float4*>(sm + c0) = __ldg(reinterpret_cast<const float4*>(in + c0));
+        __syncwarp();
+        const long row0 = (long)b * P.n_total + s.row_off + (long)p * 3;
+        bool need[3] = {true, true, true};
+        float obj[3];
+        if (kScore && !kWriteDet) {
+#pragma unroll
+            for (int a = 0; a < 3; ++a) {
+                obj[a] = decode_one(s, a, 4, x, y, sm[a * attrs + 4]);
+                need[a] = obj[a] > thr;
+                if (!need[a] && lane == 0) rowcount[row0 + a] = 0;
+            }
+            if (!(need[0] || need[1] || need[2])) continue;
+        }
+        __syncwarp();                                        // everyone has read the raw objectness logits
+        // decode in place: lane takes channels lane, lane+32, ... (anchor / attribute of the first eight are
+        // per-thread constants, computed once outside the cell loop)
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+            const int c = lane + 32 * k;
+            if (c < ch) {
+                const float v = decode_one(s, ca[k], cattr[k], x, y, sm[c]);
+                sm[c] = v;
+                if (kWriteDet) det[row0 * attrs + c] = v;
+            }
+        }
+        for (int c = lane + 256; c < ch; c += 32) {
+            const int a = c / attrs, attr = c - a * attrs;
+            const float v = decode_one(s, a, attr, x, y, sm[c]);
+            sm[c] = v;
+            if (kWriteDet) det[row0 * attrs + c] = v;
+        }
+        if (!kScore) continue;
+        __syncwarp();
+#pragma unroll
+        for (int a = 0; a < 3; ++a) {
+            if (!need[a]) continue;
+            const float* r = sm + a * attrs;
+            const float o = r[4];
+            float best = -INFINITY;
+            int bidx = 0x7fffffff;
+            for (int e = 5 + lane; e < attrs; e += 32) {
+                const float sc = __fmul_rn(r[e], o);
+                if (sc > best) { best = sc; bidx = e - 5; }
+            }
+#pragma unroll
+            for (int d = 16; d > 0; d >>= 1) {
+                const float ob = __shfl_xor_sync(0xffffffffu, best, d);
+                const int oi = __shfl_xor_sync(0xffffffffu, bidx, d);
+                if (ob > best || (ob == best && oi < bidx)) { best = ob; bidx = oi; }
+            }
+            const bool pass = best > thr;
+            const long row = row0 + a;
+            if (lane == 0) rowcount[row] = pass ? 1 : 0;
+            if (pass && lane < 8) {                          // same 8 floats pp_score emits (postprocess.cu: pp_emit_row)
+                const float cx = r[0], cy = r[1], hw2 = __fdiv_rn(r[2], 2.f), hh2 = __fdiv_rn(r[3], 2.f);
+                float v = 0.f;
+                switch (lane) {
+                    case 0: v = __fsub_rn(cx, hw2); break;
+                    case 1: v = __fsub_rn(cy, hh2); break;
+                    case 2: v = __fadd_rn(cx, hw2); break;
+                    case 3: v = __fadd_rn(cy, hh2); break;
+                    case 4: v = o; break;
+                    case 5: v = best; break;
+                    case 6: v = (float)bidx; break;
+                    default: v = __int_as_float((int)(row - (long)b * P.n_total)); break;
+                }
+                rowcand[row * 8 + lane] = v;
+            }
+        }
+    }
+}
+
 }  // namespace
+
+// mode bit 0: write det_cat, bit 1: score into rowcount / rowcand (non-eval post-process front end).
+// Requires the NHWC head maps with pixel pitch ld == ch_pad (a multiple of 4 floats, 16-byte aligned cells).
+cudaError_t launch_decode_cells(const DecodeScale sc[3], int B, int attrs, int n_total, int mode, float* det, float thr,
+                                int* rowcount, float* rowcand, int num_sms, cudaStream_t s) {
+    DecodeParams P;
+    P.B = B; P.attrs = attrs; P.n_total = n_total;
+    P.cells_before[0] = 0;
+    for (int i = 0; i < 3; ++i) {
+        P.sc[i] = sc[i];
+        P.cells_before[i + 1] = P.cells_before[i] + (long)B * sc[i].h * sc[i].w;
+    }
+    const int ch_pad = (int)sc[0].ld;
+    const size_t smem = (size_t)kFusedWarps * ch_pad * sizeof(float);
+    const long blocks_needed = (P.cells_before[3] + kFusedWarps - 1) / kFusedWarps;
+    const unsigned grid = (unsigned)std::min<long>(blocks_needed, (long)num_sms * 4);
+    if (mode == 1) decode_cells_kernel<true, false><<<grid, kFusedWarps * 32, smem, s>>>(P, det, thr, rowcount, rowcand, ch_pad);
+    else if (mode == 2) decode_cells_kernel<false, true><<<grid, kFusedWarps * 32, smem, s>>>(P, det, thr, rowcount, rowcand, ch_pad);
+    else decode_cells_kernel<true, true><<<grid, kFusedWarps * 32, smem, s>>>(P, det, thr, rowcount, rowcand, ch_pad);
+    return cudaGetLastError();
+}
 
 cudaError_t launch_decode(const DecodeScale sc[3], int nchw, int B, int attrs, int n_total, float* det, cudaStream_t s) {
     DecodeParams P;

@@ -15,6 +15,8 @@
 #include <cstring>
 #include <memory>
 
+#include <cstdlib>
+
 #include "yb_internal.h"
 
 namespace yb {
@@ -64,6 +66,8 @@ struct yb_ctx {
     PostBuffers post;
     float* box_params = nullptr;      // [B][6] per-image parameters of yb_correct_boxes
     int box_params_cap = 0;
+    LbImage* lb_params = nullptr;     // [B] per-image parameters of yb_letterbox
+    int lb_params_cap = 0;
     float* det_scratch = nullptr;     // for yb_detect
     size_t det_scratch_bytes = 0;
     int* dbg = nullptr;               // device alias of dbg_host (mapped pinned memory): watchdog words of the
@@ -478,6 +482,7 @@ void yb_destroy(yb_ctx* c) {
     cudaFree(c->d_blob);
     cudaFree(c->det_scratch);
     cudaFree(c->box_params);
+    cudaFree(c->lb_params);
     cudaFreeHost(c->dbg_host);
     for (cudaEvent_t e : c->ev) cudaEventDestroy(e);
     if (c->nccl_comm) comm_destroy(c->nccl_comm);
@@ -652,7 +657,12 @@ int yb_forward(yb_ctx* c, const float* x, int B, int H, int W, float* det, void*
     if ((rc = run_ops(c, p, x, (int)p->ops.size(), s))) return rc;
     DecodeScale sc[3];
     fill_decode(c, H, W, p->logits[0], p->logits[1], p->logits[2], c->layers.back().cout_pad, sc);
-    YB_CUDA(c, launch_decode(sc, 0, B, c->attrs, total_rows(H, W), det, s));
+    // decode: one warp per grid cell (coalesced row stores); YB_DECODE_V2=0 selects the first, flat-map kernel
+    static const bool decode_v2 = !(getenv("YB_DECODE_V2") && atoi(getenv("YB_DECODE_V2")) == 0);
+    if (decode_v2)
+        YB_CUDA(c, launch_decode_cells(sc, B, c->attrs, total_rows(H, W), 1, det, 0.f, nullptr, nullptr, c->num_sms, s));
+    else
+        YB_CUDA(c, launch_decode(sc, 0, B, c->attrs, total_rows(H, W), det, s));
     ++c->launches;
     if (c->profiling) {
         YB_CUDA(c, cudaEventRecord(c->ev[p->ops.size() + 1], s));
@@ -733,42 +743,47 @@ int yb_detect(yb_ctx* c, const float* x, int B, int H, int W, float conf, float 
               float* rows7, int* counts, int* src_index, int* cand_counts, int cap, void* stream) {
     int rc = check_shape(c, B, H, W);
     if (rc) return rc;
+    if (!x || !rows7 || !counts || cap <= 0) return fail(c, YB_E_ARG, "yb_detect: bad arguments");
     const int N = total_rows(H, W);
-    const size_t need = sizeof(float) * (size_t)B * N * c->attrs;
-    if (need > c->det_scratch_bytes) {
-        cudaFree(c->det_scratch);
-        c->det_scratch = nullptr;
-        c->det_scratch_bytes = 0;
-        YB_CUDA(c, cudaMalloc(&c->det_scratch, need));
-        c->det_scratch_bytes = need;
-    }
-    const bool prof = c->profiling;
-    c->profiling = false;               // sections are recorded here, not inside yb_forward
-    cudaStream_t s = static_cast<cudaStream_t>(stream);
-    Plan* p = nullptr;
-    if (prof) {
-        if ((rc = build_plan(c, B, H, W, &p))) { c->profiling = prof; return rc; }
-        c->profiling = true;
-        rc = run_ops(c, p, x, (int)p->ops.size(), s);
-        c->profiling = false;
-        if (!rc) {
-            DecodeScale sc[3];
-            fill_decode(c, H, W, p->logits[0], p->logits[1], p->logits[2], c->layers.back().cout_pad, sc);
-            cudaError_t e = launch_decode(sc, 0, B, c->attrs, N, c->det_scratch, s);
-            ++c->launches;
-            if (e != cudaSuccess) rc = fail(c, YB_E_CUDA, cudaGetErrorString(e));
-            cudaEventRecord(c->ev[p->ops.size() + 1], s);
+    // Non-eval mode never materialises the [B,N,5+C] tensor: the decode kernel scores each cell's three rows while
+    // they are in shared memory and hands pp_scan / pp_scatter the per-row candidates directly.  Eval mode (one
+    // candidate per passing (box, class) pair, gathered from det by pp_scatter) keeps the two-kernel path.
+    static const bool fused_ok = !(getenv("YB_FUSED_DETECT") && atoi(getenv("YB_FUSED_DETECT")) == 0);
+    const bool fused = fused_ok && !is_eval;
+    if (!fused) {
+        const size_t need = sizeof(float) * (size_t)B * N * c->attrs;
+        if (need > c->det_scratch_bytes) {
+            cudaFree(c->det_scratch);
+            c->det_scratch = nullptr;
+            c->det_scratch_bytes = 0;
+            YB_CUDA(c, cudaMalloc(&c->det_scratch, need));
+            c->det_scratch_bytes = need;
         }
-    } else {
-        rc = yb_forward(c, x, B, H, W, c->det_scratch, stream);
     }
-    if (!rc) rc = yb_postprocess(c, c->det_scratch, B, N, conf, nms, is_eval, use_nms, rows7, counts, src_index, cand_counts, cap, stream);
-    c->profiling = prof;
-    if (!rc && prof) {
-        cudaEventRecord(c->ev[p->ops.size() + 2], s);
-        rc = record_sections(c, (int)p->ops.size(), true, true, s);
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    YB_CUDA(c, cudaSetDevice(c->device));
+    Plan* p = nullptr;
+    if ((rc = build_plan(c, B, H, W, &p))) return rc;
+    if ((rc = ensure_post(c, B, N, is_eval))) return rc;
+    const int n_ops = (int)p->ops.size();
+    if ((rc = run_ops(c, p, x, n_ops, s))) return rc;       // records events [0] and [n_ops] when profiling
+    DecodeScale sc[3];
+    fill_decode(c, H, W, p->logits[0], p->logits[1], p->logits[2], c->layers.back().cout_pad, sc);
+    if (fused)
+        YB_CUDA(c, launch_decode_cells(sc, B, c->attrs, N, 2, nullptr, conf, c->post.rowcount, c->post.rowcand, c->num_sms, s));
+    else
+        YB_CUDA(c, launch_decode(sc, 0, B, c->attrs, N, c->det_scratch, s));
+    ++c->launches;
+    if (c->profiling) YB_CUDA(c, cudaEventRecord(c->ev[n_ops + 1], s));
+    PostArgs a{fused ? nullptr : c->det_scratch, B, N, c->num_classes, conf, nms, is_eval, use_nms, rows7, counts, src_index,
+               cand_counts, cap};
+    a.pre_scored = fused ? 1 : 0;
+    YB_CUDA(c, launch_postprocess(a, c->post, &c->launches, s));
+    if (c->profiling) {
+        YB_CUDA(c, cudaEventRecord(c->ev[n_ops + 2], s));
+        return record_sections(c, n_ops, true, true, s);
     }
-    return rc;
+    return YB_OK;
 }
 
 int yb_correct_boxes(yb_ctx* c, const float* boxes, int row_stride, const int* counts, int B, int cap, const int* org_wh,
@@ -807,6 +822,51 @@ int yb_correct_boxes(yb_ctx* c, const float* boxes, int row_stride, const int* c
     cudaStream_t s = static_cast<cudaStream_t>(stream);
     YB_CUDA(c, cudaMemcpyAsync(c->box_params, prm.data(), prm.size() * sizeof(float), cudaMemcpyHostToDevice, s));
     YB_CUDA(c, launch_correct_boxes(boxes, row_stride, counts, B, cap, c->box_params, out_xywh, s));
+    ++c->launches;
+    return YB_OK;
+}
+
+int yb_letterbox(yb_ctx* c, const uint8_t* const* imgs_dev, const int* hw_host, int B, int dim_w, int dim_h, int canvas_h,
+                 int canvas_w, float* out_nchw, uint8_t* canvas_hwc, float* trans_host, void* stream) {
+    if (!c) return fail(nullptr, YB_E_ARG, "null ctx");
+    if (!imgs_dev || !hw_host || (!out_nchw && !canvas_hwc) || B <= 0 || dim_w <= 0 || dim_h <= 0 || canvas_h <= 0 || canvas_w <= 0)
+        return fail(c, YB_E_ARG, "yb_letterbox: bad arguments");
+    YB_CUDA(c, cudaSetDevice(c->device));
+    if (B > c->lb_params_cap) {
+        cudaFree(c->lb_params);
+        c->lb_params = nullptr;
+        c->lb_params_cap = 0;
+        YB_CUDA(c, cudaMalloc(&c->lb_params, sizeof(LbImage) * (size_t)B));
+        c->lb_params_cap = B;
+    }
+    // The reference's canvas is np.full(dim + (3,), 128) (utils.py:46), i.e. canvas_h = dim[0] = outer_w and canvas_w =
+    // dim[1] = outer_h, while the box is placed with letterbox_transforms' (w, h) reading of dim (utils.py:34-42):
+    // identical for the square sizes the reference uses; for other sizes the paste must fit or numpy raises, and so
+    // does this call.  The caller states the canvas explicitly.
+    std::vector<LbImage> prm((size_t)B);
+    for (int b = 0; b < B; ++b) {
+        const int sh = hw_host[2 * b], sw = hw_host[2 * b + 1];
+        if (sh <= 0 || sw <= 0 || !imgs_dev[b]) return fail(c, YB_E_ARG, "yb_letterbox: image " + std::to_string(b) + " is empty");
+        // letterbox_transforms, python-float (double) arithmetic and int() truncation
+        const double ratio = std::min((double)dim_w / sw, (double)dim_h / sh);
+        const int box_w = (int)(sw * ratio), box_h = (int)(sh * ratio);
+        const int box_x = dim_w / 2 - box_w / 2, box_y = dim_h / 2 - box_h / 2;
+        if (box_w <= 0 || box_h <= 0) return fail(c, YB_E_ARG, "yb_letterbox: image " + std::to_string(b) + " collapses to an empty box");
+        if (box_x < 0 || box_y < 0 || box_y + box_h > canvas_h || box_x + box_w > canvas_w)
+            return fail(c, YB_E_ARG, "yb_letterbox: the resized image does not fit the canvas (non-square dim, see utils.py:46)");
+        LbImage& q = prm[b];
+        q.src = imgs_dev[b]; q.sh = sh; q.sw = sw;
+        q.box_w = box_w; q.box_h = box_h; q.box_x = box_x; q.box_y = box_y;
+        q.scale_x = 1.0 / ((double)box_w / sw);                           // cv::resize: inv_scale = dsize/ssize; scale = 1/inv_scale
+        q.scale_y = 1.0 / ((double)box_h / sh);
+        if (trans_host) {
+            float* t = trans_host + 5 * (size_t)b;
+            t[0] = (float)box_w; t[1] = (float)box_h; t[2] = (float)box_x; t[3] = (float)box_y; t[4] = (float)ratio;
+        }
+    }
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    YB_CUDA(c, cudaMemcpyAsync(c->lb_params, prm.data(), prm.size() * sizeof(LbImage), cudaMemcpyHostToDevice, s));
+    YB_CUDA(c, launch_letterbox(c->lb_params, B, canvas_h, canvas_w, out_nchw, canvas_hwc, s));
     ++c->launches;
     return YB_OK;
 }

@@ -464,7 +464,9 @@ cudaError_t launch_postprocess(const PostArgs& a, PostBuffers& buf, long long* l
         cudaFuncSetAttribute(pp_nms_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kNmsSmemBoxes * 17);
         attrs_set = true;
     }
-    if (a.C == 80)
+    if (a.pre_scored) {
+        *launches -= 1;                 // the scoring ran inside the fused decode kernel (counted by the caller)
+    } else if (a.C == 80)
         pp_score4_kernel<80><<<(unsigned)((rows + 8 * kRows - 1) / (8 * kRows)), 256, 0, s>>>(a.det, rows, a.N, a.C, a.conf_thr, a.is_eval,
                                                                                             buf.rowcount, buf.rowcand);
     else if (kRows * (5 + a.C) <= 32 * kMaxLoads)

@@ -1,0 +1,112 @@
+// N1: letterbox pre-process -- utils.load_image(path, 'letterbox', dim) after the file decode
+// (reference utils.py:60-72): letterbox_image (utils.py:44-57) = cv2.resize(img, (box_w, box_h), INTER_CUBIC) pasted
+// at the centred offset of a grey (128) canvas, then torch.from_numpy(img).float().permute(2,0,1) / 255.
+//
+// The resize arithmetic is OpenCV's (third-party, not vendored in the reference; opencv-python 4.13.0 in this image).
+// This kernel restates OpenCV's own portable code path for 8-bit images bit for bit (modules/imgproc/src/resize.cpp:
+// resizeGeneric_ + HResizeCubic<uchar,int,short> + VResizeCubic<..., VResizeCubicVec_32s8u>):
+//   * per axis: f = (float)((d + 0.5) * scale - 0.5) evaluated in double, s = floor(f), four taps
+//     cvRound(interpolateCubic(f - s) * 2048) with A = -0.75, every fp32 operation rounded separately;
+//   * horizontal pass: exact int32 sum of the four border-replicated taps;
+//   * vertical pass: fp32  S0*b0 + (S1*b1 + (S2*b2 + S3*b3)),  b = tap / 2^22, no FMA, round-half-even, saturate --
+//     except the last (box_w*3) % 8 elements of every row, which OpenCV's scalar tail computes as
+//     (S0*b0 + S1*b1 + S2*b2 + S3*b3 + 2^21) >> 22 in int32.
+// (OpenCV builds with Intel IPP route the call to ippiResizeCubic, which differs from this by at most one grey level;
+// tests/golden/letterbox_golden.npz holds both, see oracle/yolo_oracle.py.)
+//
+// HBM-bound byte work: one thread per canvas pixel reads its 4x4 source neighbourhood (3 bytes per pixel, L1/L2
+// resident: neighbouring threads share 3/4 of it) and writes the three fp32 planes with coalesced stores;
+// algorithmic traffic = source bytes + 12 bytes per canvas pixel.
+#include "yb_internal.h"
+
+namespace yb {
+namespace {
+
+__device__ __forceinline__ void cubic_taps(int d, double scale, int& s0, int (&tap)[4]) {
+    const double fd = __dsub_rn(__dmul_rn(__dadd_rn((double)d, 0.5), scale), 0.5);
+    float f = __double2float_rn(fd);
+    const float fl = floorf(f);
+    s0 = (int)fl;
+    const float x = __fsub_rn(f, fl);
+    const float A = -0.75f;
+    const float x1 = __fadd_rn(x, 1.f), xm = __fsub_rn(1.f, x);
+    float c[4];
+    // ((A*(x+1) - 5A)*(x+1) + 8A)*(x+1) - 4A
+    c[0] = __fsub_rn(__fmul_rn(__fadd_rn(__fmul_rn(__fsub_rn(__fmul_rn(A, x1), -3.75f), x1), -6.0f), x1), -3.0f);
+    // ((A+2)*x - (A+3))*x*x + 1
+    c[1] = __fadd_rn(__fmul_rn(__fmul_rn(__fsub_rn(__fmul_rn(1.25f, x), 2.25f), x), x), 1.f);
+    // ((A+2)*(1-x) - (A+3))*(1-x)*(1-x) + 1
+    c[2] = __fadd_rn(__fmul_rn(__fmul_rn(__fsub_rn(__fmul_rn(1.25f, xm), 2.25f), xm), xm), 1.f);
+    c[3] = __fsub_rn(__fsub_rn(__fsub_rn(1.f, c[0]), c[1]), c[2]);
+#pragma unroll
+    for (int k = 0; k < 4; ++k) tap[k] = max(-32768, min(32767, __float2int_rn(__fmul_rn(c[k], 2048.f))));   // saturate_cast<short>
+}
+
+__global__ void __launch_bounds__(256) letterbox_kernel(const LbImage* __restrict__ imgs, int canvas_h, int canvas_w,
+                                                        float* __restrict__ out, unsigned char* __restrict__ canvas) {
+    const int x = blockIdx.x * 32 + (threadIdx.x & 31), y = blockIdx.y * 8 + (threadIdx.x >> 5), b = blockIdx.z;
+    if (x >= canvas_w || y >= canvas_h) return;
+    const LbImage im = imgs[b];
+    const size_t plane = (size_t)canvas_h * canvas_w;
+    const int dx = x - im.box_x, dy = y - im.box_y;
+    int val[3] = {128, 128, 128};
+    if (dx >= 0 && dx < im.box_w && dy >= 0 && dy < im.box_h) {
+        int sx, sy, xa[4], yb[4];
+        cubic_taps(dx, im.scale_x, sx, xa);
+        cubic_taps(dy, im.scale_y, sy, yb);
+        int H[4][3];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            const int ry = max(0, min(im.sh - 1, sy - 1 + k));
+            const unsigned char* row = im.src + (size_t)ry * im.sw * 3;
+            H[k][0] = H[k][1] = H[k][2] = 0;
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                const int rx = max(0, min(im.sw - 1, sx - 1 + j));
+                const unsigned char* px = row + rx * 3;
+#pragma unroll
+                for (int c = 0; c < 3; ++c) H[k][c] += (int)__ldg(px + c) * xa[j];
+            }
+        }
+        const int vec_end = (im.box_w * 3) / 8 * 8;
+        const float sc = 1.f / 4194304.f;                                  // 1 / (2048 * 2048)
+        float bf[4];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) bf[k] = __fmul_rn((float)yb[k], sc);
+#pragma unroll
+        for (int c = 0; c < 3; ++c) {
+            int r;
+            if (dx * 3 + c < vec_end) {
+                float t = __fmul_rn((float)H[3][c], bf[3]);
+                t = __fadd_rn(__fmul_rn((float)H[2][c], bf[2]), t);
+                t = __fadd_rn(__fmul_rn((float)H[1][c], bf[1]), t);
+                t = __fadd_rn(__fmul_rn((float)H[0][c], bf[0]), t);
+                r = __float2int_rn(t);
+            } else {
+                r = (H[0][c] * yb[0] + H[1][c] * yb[1] + H[2][c] * yb[2] + H[3][c] * yb[3] + (1 << 21)) >> 22;
+            }
+            val[c] = max(0, min(255, r));
+        }
+    }
+    if (out) {                                                             // float() / 255, HWC -> CHW (utils.py:71)
+        float* o = out + (size_t)b * 3 * plane + (size_t)y * canvas_w + x;
+#pragma unroll
+        for (int c = 0; c < 3; ++c) o[c * plane] = __fdiv_rn((float)val[c], 255.f);
+    }
+    if (canvas) {                                                          // the HWC canvas letterbox_image returns
+        unsigned char* q = canvas + ((size_t)b * plane + (size_t)y * canvas_w + x) * 3;
+#pragma unroll
+        for (int c = 0; c < 3; ++c) q[c] = (unsigned char)val[c];
+    }
+}
+
+}  // namespace
+
+cudaError_t launch_letterbox(const LbImage* imgs_dev, int B, int canvas_h, int canvas_w, float* out, unsigned char* canvas,
+                             cudaStream_t s) {
+    const dim3 grid((canvas_w + 31) / 32, (canvas_h + 7) / 8, B);
+    letterbox_kernel<<<grid, 256, 0, s>>>(imgs_dev, canvas_h, canvas_w, out, canvas);
+    return cudaGetLastError();
+}
+
+}  // namespace yb

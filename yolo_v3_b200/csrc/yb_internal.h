@@ -104,6 +104,10 @@ struct DecodeScale {
     float aw[3], ah[3];   // anchors / stride, fp32 (reference yololayer.py:37-38)
 };
 cudaError_t launch_decode(const DecodeScale sc[3], int nchw, int B, int attrs, int n_total, float* det, cudaStream_t s);
+// One warp per grid cell over the NHWC head maps (pixel pitch sc[].ld, a multiple of 4 floats).  mode bit 0: write
+// det_cat (standalone decode), bit 1: score the rows into rowcount / rowcand (front end of the non-eval post-process).
+cudaError_t launch_decode_cells(const DecodeScale sc[3], int B, int attrs, int n_total, int mode, float* det, float thr,
+                                int* rowcount, float* rowcand, int num_sms, cudaStream_t s);
 
 // postprocess.cu
 struct PostBuffers {
@@ -120,13 +124,25 @@ struct PostBuffers {
     size_t bytes = 0;
 };
 struct PostArgs {
-    const float* det; int B, N, C;
+    const float* det; int B, N, C;      // det may be NULL when pre_scored
+
     float conf_thr, nms_thr;
     int is_eval, use_nms;
     float* rows7; int* counts; int* src_index; int* cand_counts; int cap;
+    int pre_scored = 0;                 // rowcount / rowcand were already filled by launch_decode_cells (non-eval only)
 };
 cudaError_t launch_postprocess(const PostArgs& a, PostBuffers& buf, long long* launches, cudaStream_t s);
 cudaError_t launch_correct_boxes(const float* boxes, int row_stride, const int* counts, int B, int cap, const float* params_dev,
                                  float* out, cudaStream_t s);
+
+// preprocess.cu
+struct LbImage {
+    const unsigned char* src;   // dev, uint8 RGB HWC, row pitch sw*3
+    int sh, sw;                 // source size
+    int box_w, box_h, box_x, box_y;
+    double scale_x, scale_y;    // 1.0 / ((double)box / src), as cv::resize computes it
+};
+cudaError_t launch_letterbox(const LbImage* imgs_dev, int B, int canvas_h, int canvas_w, float* out, unsigned char* canvas,
+                             cudaStream_t s);
 
 }  // namespace yb

@@ -1,4 +1,6 @@
-"""Host mirror of the reference's post-process entry point (reference utils.py:226-258).
+"""Host mirror of the reference's utils.py entry points on the inference path: ``postprocessing``
+(reference utils.py:226-258) and the letterbox pre-process ``letterbox_transforms`` / ``letterbox_image`` /
+``load_image`` (utils.py:34-72).
 
 ``postprocessing(detections, num_classes, obj_conf_thr=0.5, nms_thr=0.4, is_eval=False, use_nms=True)``
 keeps the reference's signature and return convention -- a list (one entry per image) of CPU fp32
@@ -15,8 +17,9 @@ candidate order ascending) where the reference's unstable CPU sort is arbitrary.
 from __future__ import annotations
 
 import ctypes
-from typing import Dict, Tuple
+from typing import Dict, Sequence, Tuple
 
+import numpy as np
 import torch
 
 from . import _lib
@@ -96,3 +99,99 @@ def postprocessing(detections, num_classes, obj_conf_thr=0.5, nms_thr=0.4, is_ev
         return res, []
     src_h = src[:, :max(mx, 1)].cpu()
     return res, [src_h[b, :int(counts_h[b])].long().numpy() for b in range(rows.shape[0])]
+
+
+# ---- pre-process: letterbox (reference utils.py:34-72) -------------------------------------------------------
+def letterbox_transforms(inner_dim, outer_dim):
+    """Reference utils.letterbox_transforms (utils.py:34-42); pure host integer / float arithmetic."""
+    outer_w, outer_h = outer_dim
+    inner_w, inner_h = inner_dim
+    ratio = min(outer_w / inner_w, outer_h / inner_h)
+    box_w = int(inner_w * ratio)
+    box_h = int(inner_h * ratio)
+    box_x_offset = (outer_w // 2) - (box_w // 2)
+    box_y_offset = (outer_h // 2) - (box_h // 2)
+    return box_w, box_h, box_x_offset, box_y_offset, ratio
+
+
+def _as_cuda_u8(img, device):
+    if isinstance(img, torch.Tensor):
+        t = img
+    else:
+        a = np.ascontiguousarray(img)
+        if a.dtype != np.uint8:
+            raise TypeError("letterbox expects uint8 images (what cv2.imread returns)")
+        t = torch.from_numpy(a)
+    if t.dtype != torch.uint8 or t.dim() != 3 or t.shape[2] != 3:
+        raise ValueError("letterbox expects [H,W,3] uint8 images")
+    return t.to(device, non_blocking=True).contiguous()
+
+
+def letterbox_batch(imgs: Sequence, dim, device=None, want_canvas=False, canvas_hw=None):
+    """Letterboxes a list of [H,W,3] uint8 RGB images (numpy arrays or tensors, sizes may differ) on the GPU in one
+    launch (yb_letterbox).  Returns (x, trans): x = CUDA fp32 [B,3,dim[0],dim[1]] = what ``load_image(path,
+    'letterbox', dim)[0]`` holds for every image, trans = CPU fp32 [B,5] = box_w, box_h, box_x, box_y, ratio.
+    With want_canvas=True the uint8 [B,dim[0],dim[1],3] canvases are returned instead of x.  The canvas is
+    dim[0] rows by dim[1] columns exactly as the reference's np.full(dim + (3,), 128) (utils.py:46) unless canvas_hw
+    overrides it."""
+    if not torch.cuda.is_available():
+        raise RuntimeError("yolo_v3_b200 runs on CUDA devices only (no CPU fallback)")
+    if device is None:
+        device = torch.device("cuda", torch.cuda.current_device())
+    device = torch.device(device)
+    index = device.index if device.index is not None else torch.cuda.current_device()
+    B = len(imgs)
+    if B == 0:
+        raise ValueError("empty image list")
+    dev_imgs = [_as_cuda_u8(im, device) for im in imgs]
+    ptrs = (ctypes.c_void_p * B)(*[t.data_ptr() for t in dev_imgs])
+    hw = (ctypes.c_int * (2 * B))(*[int(v) for t in dev_imgs for v in t.shape[:2]])
+    trans = (ctypes.c_float * (5 * B))()
+    dim_w, dim_h = int(dim[0]), int(dim[1])
+    ch, cw = (dim_w, dim_h) if canvas_hw is None else (int(canvas_hw[0]), int(canvas_hw[1]))
+    out = canvas = None
+    if want_canvas:
+        canvas = torch.empty(B, ch, cw, 3, device=device, dtype=torch.uint8)
+    else:
+        out = torch.empty(B, 3, ch, cw, device=device, dtype=torch.float32)
+    lib = _lib.load()
+    ctx = _ctx_for(index, 80)
+    with torch.cuda.device(device):
+        _lib.check(lib.yb_letterbox(ctx, ptrs, hw, B, dim_w, dim_h, ch, cw,
+                                    ctypes.c_void_p(out.data_ptr()) if out is not None else None,
+                                    ctypes.c_void_p(canvas.data_ptr()) if canvas is not None else None,
+                                    trans, ctypes.c_void_p(torch.cuda.current_stream(device).cuda_stream)), ctx)
+    t = torch.tensor(list(trans), dtype=torch.float32).reshape(B, 5)
+    return (canvas if want_canvas else out), t
+
+
+def letterbox_image(img, dim):
+    """Reference signature (utils.py:44-57): [H,W,3] uint8 image -> (canvas, transform).  The canvas is the numpy
+    integer array the reference builds with np.full(dim + (3,), 128); the resize + paste run on the GPU."""
+    try:
+        canvas, trans = letterbox_batch([img], dim, want_canvas=True)
+    except _lib.YbError as e:
+        if e.code == -1:                               # numpy's error for a paste that does not fit the canvas
+            raise ValueError(str(e)) from None
+        raise
+    return canvas[0].cpu().numpy().astype(np.int64), torch.Tensor(trans[0].tolist())
+
+
+def load_image(img_path, mode=None, dim=None):
+    """Reference signature (utils.py:60-72).  The file decode (cv2.imread + BGR->RGB) stays on the host -- it is not
+    part of the path -- and the letterbox / scaling / HWC->CHW run on the GPU.  Returns (CUDA fp32 [3,H,W], trans)."""
+    import cv2
+    img = cv2.imread(img_path)
+    if img is None:
+        raise FileNotFoundError(img_path)
+    img = cv2.cvtColor(img, cv2.COLOR_BGR2RGB)
+    if mode is not None and dim is not None:
+        if mode == "letterbox":
+            x, trans = letterbox_batch([img], dim)
+            return x[0], torch.Tensor(trans[0].tolist())
+        if mode == "resize":
+            raise NotImplementedError("load_image(mode='resize') (cv2 INTER_LINEAR) is not on the GPU path yet; use 'letterbox'")
+    # no geometric change: the same kernel with a full-size box (taps 0,1,0,0) is an exact copy, /255, HWC->CHW
+    h, w = img.shape[:2]
+    x, _ = letterbox_batch([img], (w, h), canvas_hw=(h, w))
+    return x[0], None
