@@ -113,6 +113,15 @@ int yb_postprocess(yb_ctx* ctx, const float* det_cat, int B, int N, float obj_co
                    int is_eval, int use_nms, float* rows7, int* counts, int* src_index, int* cand_counts,
                    int cap, void* stream);
 
+/* Replaces the notebook's own inline post-process (yolo_detect.ipynb cell 35 with its helpers in cells 30 and 33:
+ * torch_unique, iou_vectorized, reduce_row_by_column, nms), which differs from utils.postprocessing: a box is a
+ * candidate when its OBJECTNESS > obj_conf_thr (>= 0), its class is the arg-max of the raw class probabilities,
+ * x2 = (cx - w/2) + w, boxes of a class are ordered by objectness (descending, ties in candidate order) and the
+ * pair-list reduction of cells 33 is greedy NMS in that order.  Same outputs as yb_postprocess; rows7 column 5 holds
+ * the winning class probability. */
+int yb_postprocess_notebook(yb_ctx* ctx, const float* det_cat, int B, int N, float obj_conf_thr, float nms_thr,
+                            float* rows7, int* counts, int* src_index, int* cand_counts, int cap, void* stream);
+
 /* forward + postprocess with no intermediate host round trip (what test.py:35-36 does per batch). */
 int yb_detect(yb_ctx* ctx, const float* x_nchw, int B, int H, int W, float obj_conf_thr, float nms_thr,
               int is_eval, int use_nms, float* rows7, int* counts, int* src_index, int* cand_counts,
@@ -143,6 +152,13 @@ int yb_correct_boxes(yb_ctx* ctx, const float* boxes, int row_stride, const int*
  * box_w, box_h, box_x, box_y, ratio (the reference's `trans`), may be NULL. */
 int yb_letterbox(yb_ctx* ctx, const uint8_t* const* imgs_dev, const int* hw_host, int B, int dim_w, int dim_h,
                  int canvas_h, int canvas_w, float* out_nchw, uint8_t* canvas_hwc, float* trans_host, void* stream);
+
+/* Replaces utils.load_image(path, 'resize', dim) after the file decode (utils.py:68-71): cv2.resize(img, dim) (default
+ * INTER_LINEAR; OpenCV's 8-bit fixed-point path, bit for bit) then float()/255 and HWC->CHW, for a batch.  dim_w, dim_h:
+ * the reference's `dim` = cv2's dsize (w, h); out_nchw: dev [B,3,dim_h,dim_w] fp32; out_hwc: dev uint8 [B,dim_h,dim_w,3]
+ * (either may be NULL, not both); other arguments as yb_letterbox. */
+int yb_resize(yb_ctx* ctx, const uint8_t* const* imgs_dev, const int* hw_host, int B, int dim_w, int dim_h,
+              float* out_nchw, uint8_t* out_hwc, void* stream);
 
 /* ---- multi-GPU (absent in the reference; batch sharding) ------------------------- */
 

@@ -265,6 +265,56 @@ def postprocessing(det: torch.Tensor, num_classes: int, obj_conf_thr: float = 0.
     return (results, src) if return_index else results
 
 
+def _reduce_row_by_column(pairs: np.ndarray) -> np.ndarray:
+    """reduce_row_by_column (yolo_detect.ipynb cell 33), literally: walk the (row, column) pair list of `iou > thr`;
+    a pair (i, j) with j != i deletes every pair whose row is j; the cursor advances by one either way."""
+    i = 0
+    while i < pairs.shape[0]:
+        j = pairs[i, 1]
+        if pairs[i, 0] != j:
+            pairs = pairs[pairs[:, 0] != j]
+        i += 1
+    return pairs
+
+
+def notebook_postprocessing(det: torch.Tensor, num_classes: int, obj_conf_thr: float = 0.5, nms_thr: float = 0.4,
+                            return_index: bool = False):
+    """The notebook's own inline post-process (yolo_detect.ipynb cell 35 + helpers in cells 30, 33), which is NOT
+    utils.postprocessing: objectness threshold (rows failing it are zeroed and dropped by nonzero()), x2 = x1 + w,
+    class = arg-max of the raw class probabilities, per class (ascending) sort by objectness (descending; stable =
+    the fixed tie-break) and the pair-list NMS of cell 33.  Returns a list (len B) of [K,7] tensors
+    [x1,y1,x2,y2,obj,class_prob,cls] (an empty tensor for an image without detections)."""
+    det = det.detach().cpu().float()
+    results, src = [], []
+    for b in range(det.shape[0]):
+        d = det[b]
+        ci = ((d[:, 4] > obj_conf_thr) & (d[:, 4] != 0)).nonzero().squeeze(1)
+        if len(ci) == 0:
+            results.append(torch.Tensor())
+            src.append(np.zeros(0, np.int64))
+            continue
+        x1 = d[ci, 0] - d[ci, 2] / 2
+        y1 = d[ci, 1] - d[ci, 3] / 2
+        x2 = x1 + d[ci, 2]
+        y2 = y1 + d[ci, 3]
+        prob, cls = torch.max(d[ci, 5:5 + num_classes], 1)
+        rows = torch.stack((x1, y1, x2, y2, d[ci, 4], prob, cls.float()), 1)
+        out, idxs = [], []
+        for c in torch.unique(rows[:, 6]):
+            sel = (rows[:, 6] == c).nonzero().squeeze(1)
+            r = rows[sel]
+            _, order = r[:, 4].sort(descending=True, stable=True)
+            r = r[order]
+            pairs = (iou_matrix(r[:, :4]) > nms_thr).nonzero().numpy()
+            pairs = _reduce_row_by_column(pairs)
+            keep = np.unique(pairs[:, 0])
+            out.append(r[keep])
+            idxs.append(ci[sel][order][keep].numpy().astype(np.int64))
+        results.append(torch.cat(out, 0))
+        src.append(np.concatenate(idxs))
+    return (results, src) if return_index else results
+
+
 def correct_yolo_boxes(bboxes: torch.Tensor, org_w, org_h, img_w, img_h, is_letterbox=False) -> torch.Tensor:
     """boundingbox.correct_yolo_boxes (boundingbox.py:139-149): letterbox_reverse (:95-116) or rescale_bbox
     (:119-137) with clipping to the original image, then x1y1x2y2 -> xywh (:10-15).  fp32 tensor arithmetic
@@ -363,6 +413,45 @@ def resize_cubic_u8(img: np.ndarray, dw: int, dh: int) -> np.ndarray:
         v = (R.astype(np.int64) * yb[:, :, None, None]).sum(1).reshape(dh, dw * cn)
         out[:, tail:] = np.clip((v[:, tail:] + (1 << 21)) >> 22, 0, 255).astype(np.uint8)
     return out.reshape(dh, dw, cn)
+
+
+def _linear_axis(ssize: int, dsize: int, clamp: bool):
+    """Offsets and 11-bit taps of one axis for INTER_LINEAR.  The x axis clamps (s < 0 -> s = 0, f = 0;
+    s >= ssize-1 -> s = ssize-1, f = 0); the y axis keeps its fraction and only clips the two row indices."""
+    scale = 1.0 / (dsize / ssize)
+    f = ((np.arange(dsize, dtype=np.float64) + 0.5) * scale - 0.5).astype(np.float32)
+    s = np.floor(f).astype(np.int64)
+    frac = (f - s.astype(np.float32)).astype(np.float32)
+    if clamp:
+        lo, hi = s < 0, s >= ssize - 1
+        frac[lo] = 0
+        s[lo] = 0
+        frac[hi] = 0
+        s[hi] = ssize - 1
+    taps = np.stack([(np.float32(1) - frac).astype(np.float32), frac], -1)
+    return s, np.clip(np.rint(taps * np.float32(_COEF_SCALE)), -32768, 32767).astype(np.int32)
+
+
+def resize_linear_u8(img: np.ndarray, dw: int, dh: int) -> np.ndarray:
+    """cv2.resize(img, (dw, dh)) (default INTER_LINEAR) for uint8 HxWxC, OpenCV's own 8-bit path (resize.cpp:
+    HResizeLinear<uchar,int,short> + VResizeLinear<uchar,int,short,...,VResizeLinearVec_32s8u>): exact int32
+    horizontal pass, then ((b0*(S0>>4))>>16) + ((b1*(S1>>4))>>16) + 2) >> 2, vector body and scalar tail alike.
+    IPP builds do not divert this call (8-bit linear is excluded there), so one golden covers both."""
+    sh, sw, cn = img.shape
+    xofs, xa = _linear_axis(sw, dw, True)
+    yofs, yb = _linear_axis(sh, dh, False)
+    S = img.astype(np.int32)
+    H = S[:, xofs, :] * xa[None, :, 0, None] + S[:, np.clip(xofs + 1, 0, sw - 1), :] * xa[None, :, 1, None]
+    S0, S1 = H[np.clip(yofs, 0, sh - 1)], H[np.clip(yofs + 1, 0, sh - 1)]
+    b0, b1 = yb[:, 0][:, None, None], yb[:, 1][:, None, None]
+    t = ((b0 * (S0 >> 4)) >> 16) + ((b1 * (S1 >> 4)) >> 16)
+    return np.clip((t + 2) >> 2, 0, 255).astype(np.uint8)
+
+
+def load_image_resize(img_rgb_u8: np.ndarray, dim) -> torch.Tensor:
+    """utils.load_image(path, 'resize', dim) after the file decode (utils.py:68-71): cv2.resize(img, dim), /255, CHW."""
+    out = resize_linear_u8(img_rgb_u8, int(dim[0]), int(dim[1]))
+    return torch.from_numpy(out).float().permute(2, 0, 1) / 255
 
 
 def letterbox_image(img: np.ndarray, dim) -> Tuple[np.ndarray, torch.Tensor]:

@@ -198,8 +198,11 @@ def make_boxes():
     np.savez_compressed(os.path.join(HERE, "boxes_golden.npz"), **out)
 
 
-LETTERBOX_CASES = [  # (src_h, src_w, dim, seed): the dog-cycle-car.png shape, VGA -> 608, tall, upscale, 720p
-    (452, 602, 416, 31), (480, 640, 608, 32), (500, 333, 416, 33), (97, 131, 160, 34), (720, 1280, 320, 35), (64, 64, 96, 36)]
+LETTERBOX_CASES = [  # (src_h, src_w, dim, seed): the dog-cycle-car.png shape, VGA, tall, upscale, 720p, square upscale
+    (452, 602, 416, 31), (480, 640, 224, 32), (500, 333, 192, 33), (97, 131, 160, 34), (720, 1280, 160, 35), (64, 64, 96, 36)]
+
+
+RESIZE_CASES = [(480, 640, 224, 224, 41), (97, 131, 160, 96, 42), (720, 1280, 192, 128, 43), (60, 40, 33, 77, 44)]  # sh, sw, dim_w, dim_h, seed
 
 
 def make_letterbox():
@@ -221,10 +224,61 @@ def make_letterbox():
         # what load_image returns after the decode: float CHW / 255 (utils.py:71) -- digest only
         x = torch.from_numpy(canvas).float().permute(2, 0, 1) / 255
         out[f"sum{i}"] = np.array(float(x.double().sum()))
+    # load_image end to end (utils.py:60-72) through a lossless PNG: 'resize' (cv2.resize(img, dim), INTER_LINEAR; IPP
+    # does not divert 8-bit linear, so both builds agree), 'letterbox' and mode=None
+    import tempfile
+    out["resize_cases"] = np.array(RESIZE_CASES)
+    with tempfile.TemporaryDirectory() as td:
+        for i, (sh, sw, dw, dh, seed) in enumerate(RESIZE_CASES):
+            img = synth.make_photo(sh, sw, seed)
+            path = os.path.join(td, f"img{i}.png")
+            cv2.imwrite(path, cv2.cvtColor(img, cv2.COLOR_RGB2BGR))
+            res = {}
+            for ipp in (False, True):
+                cv2.ipp.setUseIPP(ipp)
+                res[ipp], trans = ref_utils.load_image(path, "resize", (dw, dh))
+                assert trans is None
+            assert torch.equal(res[False], res[True])
+            x = res[False]
+            assert tuple(x.shape) == (3, dh, dw)
+            out[f"resize{i}"] = torch.round(x * 255).permute(1, 2, 0).numpy().astype(np.uint8)
+            out[f"resize_sum{i}"] = np.array(float(x.double().sum()))
+            plain, _ = ref_utils.load_image(path)                   # mode=None: /255 + CHW only
+            out[f"plain_sum{i}"] = np.array(float(plain.double().sum()))
     np.savez_compressed(os.path.join(HERE, "letterbox_golden.npz"), **out)
 
 
+def make_notebook():
+    """The notebook's own post-process: cells 30 (torch_unique), 33 (iou_vectorized, reduce_row_by_column, nms) and
+    35 (postprocessing) of /root/reference/yolo_detect.ipynb are executed as they are (Tensor.cuda is the identity
+    shim above, Tensor.sort is stable) on the synthetic detections of the post-process fixtures."""
+    import json
+    nb = json.load(open("/root/reference/yolo_detect.ipynb"))
+    ns = {"torch": torch, "np": np, "Tensor": torch.Tensor}
+    for i in (30, 33, 35):
+        src = "".join(nb["cells"][i]["source"])
+        assert any(k in src for k in ("def torch_unique", "def iou_vectorized", "def postprocessing")), i
+        exec(compile(src, f"yolo_detect.ipynb#cell{i}", "exec"), ns)
+    out = {}
+    rs = np.random.RandomState(9)
+    cases = {"c80": (synth_det(rs, 2, 300, 80), 80), "c20": (synth_det(rs, 3, 200, 20), 20)}
+    cases["c20"][0][1, :, 4] = 0.0                     # an image without detections
+    for tag, (det, nc) in cases.items():
+        out[f"{tag}_det"] = det
+        out[f"{tag}_num_classes"] = np.array(nc)
+        for m, (ct, nt) in {"default": (0.5, 0.4), "low": (0.02, 0.45), "none": (2.0, 0.4)}.items():
+            res = ns["postprocessing"](torch.from_numpy(det).clone(), nc, obj_conf_thr=ct, nms_thr=nt)
+            assert isinstance(res, list) and len(res) == det.shape[0]
+            pack_results(res, f"{tag}_{m}", out)
+            out[f"{tag}_{m}_kw"] = np.array([ct, nt])
+    np.savez_compressed(os.path.join(HERE, "notebook_golden.npz"), **out)
+
+
 if __name__ == "__main__":
+    if "--notebook-only" in sys.argv:
+        make_notebook()
+        sys.exit(0)
+    make_notebook()
     make_letterbox()
     if "--letterbox-only" in sys.argv:
         sys.exit(0)

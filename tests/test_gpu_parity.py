@@ -454,3 +454,58 @@ def test_detect_fused_equals_two_kernel_path(oracle, sd_calibrated):
         assert all(torch.equal(p, q) for p, q in zip(a, b)), thr
         ref, _ = oracle.postprocessing_c(det.cpu(), 80, thr, 0.4)
         assert len(ref) == len(b) and all(torch.equal(p, q) for p, q in zip(ref, b)), thr
+
+
+# ---------------------------------------------------------------------------------------------
+# N4: the notebook's own inline post-process (yolo_detect.ipynb cell 35)
+# ---------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("tag", ["c80", "c20"])
+@pytest.mark.parametrize("mode", ["default", "low", "none"])
+def test_notebook_postprocess_vs_reference_golden(golden, tag, mode):
+    from yolo_v3_b200.notebook import postprocessing as nb_post
+    g = golden("notebook_golden.npz")
+    det = torch.from_numpy(g[f"{tag}_det"])
+    ct, nt = g[f"{tag}_{mode}_kw"]
+    res = nb_post(det, int(g[f"{tag}_num_classes"]), float(ct), float(nt))
+    ref = unpack(g, f"{tag}_{mode}")
+    assert isinstance(res, list) and len(res) == len(ref)
+    for a, b in zip(res, ref):
+        assert not a.is_cuda
+        assert np.array_equal(a.numpy().reshape(-1, 7), b)          # bit-exact rows in the notebook's order
+
+
+def test_notebook_postprocess_608_vs_oracle(oracle):
+    """A 608x608 head (22 743 boxes, 2 images) through the notebook variant against its oracle: identical rows
+    and source indices."""
+    from yolo_v3_b200.notebook import postprocessing as nb_post
+    logits = synth.make_head_logits(2, 608, 608, 80, seed=7, obj_mu=-3.0)
+    det = torch.cat([oracle.decode(l, ANCHORS, MASKS[i], (608, 608), 80) for i, l in enumerate(logits)], 1)
+    res, idx = nb_post(det, 80, 0.3, 0.4, return_index=True)
+    ref, ridx = oracle.notebook_postprocessing(det, 80, 0.3, 0.4, return_index=True)
+    assert sum(len(r) for r in ref) > 200
+    for a, b, i, j in zip(res, ref, idx, ridx):
+        assert torch.equal(a, b) and np.array_equal(i, j)
+
+
+def test_resize_mode_bit_exact(golden, oracle, tmp_path):
+    """yb_resize (load_image mode 'resize') against the reference's own output, and load_image end to end through a
+    PNG file for the three modes."""
+    from yolo_v3_b200.utils import load_image, resize_batch
+    g = golden("letterbox_golden.npz")
+    for i, (sh, sw, dw, dh, seed) in enumerate(g["resize_cases"]):
+        img = synth.make_photo(int(sh), int(sw), int(seed))
+        u8 = resize_batch([img], (int(dw), int(dh)), want_u8=True)[0].cpu().numpy()
+        assert np.array_equal(u8, g[f"resize{i}"]), i
+        x = resize_batch([img], (int(dw), int(dh)))[0].cpu()
+        assert torch.equal(x, torch.from_numpy(g[f"resize{i}"]).float().permute(2, 0, 1) / 255)
+    cv2 = pytest.importorskip("cv2")
+    img = synth.make_photo(97, 131, 42)
+    path = str(tmp_path / "img.png")
+    cv2.imwrite(path, cv2.cvtColor(img, cv2.COLOR_RGB2BGR))
+    x, t = load_image(path, "resize", (160, 96))
+    assert t is None and x.is_cuda and torch.equal(x.cpu(), oracle.load_image_resize(img, (160, 96)))
+    x, t = load_image(path, "letterbox", (160, 160))
+    rx, rt = oracle.load_image_letterbox(img, (160, 160))
+    assert torch.equal(x.cpu(), rx) and torch.equal(t, rt)
+    x, t = load_image(path)
+    assert t is None and torch.equal(x.cpu(), torch.from_numpy(img).float().permute(2, 0, 1) / 255)

@@ -14,7 +14,7 @@ def __getattr__(name):
                 "PreDetectionConvGroup", "UpsampleGroup"):
         from . import darknet
         return getattr(darknet, name)
-    if name in ("postprocessing", "postprocessing_raw", "letterbox_transforms", "letterbox_image", "letterbox_batch", "load_image"):
+    if name in ("postprocessing", "postprocessing_raw", "letterbox_transforms", "letterbox_image", "letterbox_batch", "resize_batch", "load_image"):
         from . import utils
         return getattr(utils, name)
     if name == "YoloLayer":

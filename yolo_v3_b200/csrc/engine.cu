@@ -657,8 +657,9 @@ int yb_forward(yb_ctx* c, const float* x, int B, int H, int W, float* det, void*
     if ((rc = run_ops(c, p, x, (int)p->ops.size(), s))) return rc;
     DecodeScale sc[3];
     fill_decode(c, H, W, p->logits[0], p->logits[1], p->logits[2], c->layers.back().cout_pad, sc);
-    // decode: one warp per grid cell (coalesced row stores); YB_DECODE_V2=0 selects the first, flat-map kernel
-    static const bool decode_v2 = !(getenv("YB_DECODE_V2") && atoi(getenv("YB_DECODE_V2")) == 0);
+    // decode: the flat-map kernel; YB_DECODE_V2=1 selects the one-warp-per-cell kernel (coalesced row stores, but one
+    // cell in flight per warp: measured 0.194 ms against 0.170 ms at 608x608 batch 32, profiles/README.md)
+    static const bool decode_v2 = getenv("YB_DECODE_V2") && atoi(getenv("YB_DECODE_V2")) != 0;
     if (decode_v2)
         YB_CUDA(c, launch_decode_cells(sc, B, c->attrs, total_rows(H, W), 1, det, 0.f, nullptr, nullptr, c->num_sms, s));
     else
@@ -735,6 +736,19 @@ int yb_postprocess(yb_ctx* c, const float* det, int B, int N, float conf, float 
     int rc = ensure_post(c, B, N, is_eval);
     if (rc) return rc;
     PostArgs a{det, B, N, c->num_classes, conf, nms, is_eval, use_nms, rows7, counts, src_index, cand_counts, cap};
+    YB_CUDA(c, launch_postprocess(a, c->post, &c->launches, static_cast<cudaStream_t>(stream)));
+    return YB_OK;
+}
+
+int yb_postprocess_notebook(yb_ctx* c, const float* det, int B, int N, float conf, float nms, float* rows7, int* counts,
+                            int* src_index, int* cand_counts, int cap, void* stream) {
+    if (!c) return fail(nullptr, YB_E_ARG, "null ctx");
+    if (!det || !rows7 || !counts || B <= 0 || N <= 0 || cap <= 0) return fail(c, YB_E_ARG, "yb_postprocess_notebook: bad arguments");
+    YB_CUDA(c, cudaSetDevice(c->device));
+    int rc = ensure_post(c, B, N, 0);
+    if (rc) return rc;
+    PostArgs a{det, B, N, c->num_classes, conf, nms, 0, 1, rows7, counts, src_index, cand_counts, cap};
+    a.variant = 1;
     YB_CUDA(c, launch_postprocess(a, c->post, &c->launches, static_cast<cudaStream_t>(stream)));
     return YB_OK;
 }
@@ -826,6 +840,36 @@ int yb_correct_boxes(yb_ctx* c, const float* boxes, int row_stride, const int* c
     return YB_OK;
 }
 
+int yb_resize(yb_ctx* c, const uint8_t* const* imgs_dev, const int* hw_host, int B, int dim_w, int dim_h, float* out_nchw,
+              uint8_t* out_hwc, void* stream) {
+    if (!c) return fail(nullptr, YB_E_ARG, "null ctx");
+    if (!imgs_dev || !hw_host || (!out_nchw && !out_hwc) || B <= 0 || dim_w <= 0 || dim_h <= 0) return fail(c, YB_E_ARG, "yb_resize: bad arguments");
+    YB_CUDA(c, cudaSetDevice(c->device));
+    if (B > c->lb_params_cap) {
+        cudaFree(c->lb_params);
+        c->lb_params = nullptr;
+        c->lb_params_cap = 0;
+        YB_CUDA(c, cudaMalloc(&c->lb_params, sizeof(LbImage) * (size_t)B));
+        c->lb_params_cap = B;
+    }
+    std::vector<LbImage> prm((size_t)B);
+    for (int b = 0; b < B; ++b) {
+        const int sh = hw_host[2 * b], sw = hw_host[2 * b + 1];
+        if (sh <= 0 || sw <= 0 || !imgs_dev[b]) return fail(c, YB_E_ARG, "yb_resize: image " + std::to_string(b) + " is empty");
+        LbImage& q = prm[b];
+        q.src = imgs_dev[b]; q.sh = sh; q.sw = sw;
+        q.box_w = dim_w; q.box_h = dim_h; q.box_x = 0; q.box_y = 0;      // cv2.resize(img, dim): dsize = (w, h)
+        q.scale_x = 1.0 / ((double)dim_w / sw);
+        q.scale_y = 1.0 / ((double)dim_h / sh);
+        q.interp = 1;
+    }
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    YB_CUDA(c, cudaMemcpyAsync(c->lb_params, prm.data(), prm.size() * sizeof(LbImage), cudaMemcpyHostToDevice, s));
+    YB_CUDA(c, launch_letterbox(c->lb_params, B, dim_h, dim_w, out_nchw, out_hwc, s));
+    ++c->launches;
+    return YB_OK;
+}
+
 int yb_letterbox(yb_ctx* c, const uint8_t* const* imgs_dev, const int* hw_host, int B, int dim_w, int dim_h, int canvas_h,
                  int canvas_w, float* out_nchw, uint8_t* canvas_hwc, float* trans_host, void* stream) {
     if (!c) return fail(nullptr, YB_E_ARG, "null ctx");
@@ -859,6 +903,7 @@ int yb_letterbox(yb_ctx* c, const uint8_t* const* imgs_dev, const int* hw_host, 
         q.box_w = box_w; q.box_h = box_h; q.box_x = box_x; q.box_y = box_y;
         q.scale_x = 1.0 / ((double)box_w / sw);                           // cv::resize: inv_scale = dsize/ssize; scale = 1/inv_scale
         q.scale_y = 1.0 / ((double)box_h / sh);
+        q.interp = 0;
         if (trans_host) {
             float* t = trans_host + 5 * (size_t)b;
             t[0] = (float)box_w; t[1] = (float)box_h; t[2] = (float)box_x; t[3] = (float)box_y; t[4] = (float)ratio;

@@ -56,15 +56,17 @@ __device__ __forceinline__ unsigned long long make_key(int cls, float score, int
 constexpr int kRows = 4;
 constexpr int kMaxLoads = 12;     // kRows*(5+C) <= 384  <=>  C <= 91; wider rows take the one-row path
 
+// variant 0: utils.postprocessing (x2 = cx + w/2, boundingbox.py:25-29); variant 1: the notebook's inline
+// post-process (yolo_detect.ipynb cell 35: x1 = cx - w/2, x2 = x1 + w).
 __device__ __forceinline__ void pp_emit_row(long row, int N, int lane, float cx, float cy, float w, float h, float obj,
-                                            float best, int bidx, float* __restrict__ rowcand) {
+                                            float best, int bidx, float* __restrict__ rowcand, int variant = 0) {
     const float hw = __fdiv_rn(w, 2.f), hh = __fdiv_rn(h, 2.f);
     float o = 0.f;
     switch (lane) {
         case 0: o = __fsub_rn(cx, hw); break;
         case 1: o = __fsub_rn(cy, hh); break;
-        case 2: o = __fadd_rn(cx, hw); break;
-        case 3: o = __fadd_rn(cy, hh); break;
+        case 2: o = variant ? __fadd_rn(__fsub_rn(cx, hw), w) : __fadd_rn(cx, hw); break;
+        case 3: o = variant ? __fadd_rn(__fsub_rn(cy, hh), h) : __fadd_rn(cy, hh); break;
         case 4: o = obj; break;
         case 5: o = best; break;
         case 6: o = (float)bidx; break;
@@ -79,7 +81,7 @@ __device__ __forceinline__ void pp_emit_row(long row, int N, int lane, float cx,
 template <int CS>
 __global__ void __launch_bounds__(256) pp_score4_kernel(const float* __restrict__ det, long rows, int N, int C,
                                                         float thr, int is_eval, int* __restrict__ rowcount,
-                                                        float* __restrict__ rowcand) {
+                                                        float* __restrict__ rowcand, int variant) {
     const int lane = threadIdx.x & 31;
     const int A = CS > 0 ? 5 + CS : 5 + C;
     const long row0 = ((long)blockIdx.x * 8 + (threadIdx.x >> 5)) * kRows;
@@ -107,7 +109,7 @@ __global__ void __launch_bounds__(256) pp_score4_kernel(const float* __restrict_
             if (CS > 0 && (k < (j * (5 + CS)) / 32 || k > (j * (5 + CS) + 4 + CS) / 32)) continue;   // static window
             const int e = lane + 32 * k - j * A;           // element index inside row j
             const bool isc = e >= 5 && e < A;
-            const float s = __fmul_rn(v[k], obj);
+            const float s = variant ? v[k] : __fmul_rn(v[k], obj);      // notebook: arg-max of the raw class probability
             if (is_eval) cnt += __popc(__ballot_sync(0xffffffffu, isc && s > thr));
             else if (isc && s > best) { best = s; bidx = e - 5; }
         }
@@ -122,17 +124,17 @@ __global__ void __launch_bounds__(256) pp_score4_kernel(const float* __restrict_
             const int oi = __shfl_xor_sync(0xffffffffu, bidx, o);
             if (ob > best || (ob == best && oi < bidx)) { best = ob; bidx = oi; }
         }
-        const bool pass = best > thr;
+        const bool pass = variant ? obj > thr : best > thr;             // notebook: objectness threshold (cell 35)
         if (lane == 0) rowcount[row] = pass ? 1 : 0;
         if (pass)
             pp_emit_row(row, N, lane, __shfl_sync(0xffffffffu, hdr[j], 0), __shfl_sync(0xffffffffu, hdr[j], 1),
-                        __shfl_sync(0xffffffffu, hdr[j], 2), __shfl_sync(0xffffffffu, hdr[j], 3), obj, best, bidx, rowcand);
+                        __shfl_sync(0xffffffffu, hdr[j], 2), __shfl_sync(0xffffffffu, hdr[j], 3), obj, best, bidx, rowcand, variant);
     }
 }
 
 __global__ void __launch_bounds__(256) pp_score_kernel(const float* __restrict__ det, long rows, int N, int C,
                                                        float thr, int is_eval, int* __restrict__ rowcount,
-                                                       float* __restrict__ rowcand) {
+                                                       float* __restrict__ rowcand, int variant) {
     const int lane = threadIdx.x & 31;
     const long row = (long)blockIdx.x * 8 + (threadIdx.x >> 5);
     if (row >= rows) return;
@@ -147,7 +149,7 @@ __global__ void __launch_bounds__(256) pp_score_kernel(const float* __restrict__
         const int e = e0 + lane;
         const float v = e0 == 0 ? v0 : (e < A ? __ldg(r + e) : 0.f);
         const bool isc = e >= 5 && e < A;
-        const float s = __fmul_rn(v, obj);
+        const float s = variant ? v : __fmul_rn(v, obj);
         if (is_eval) {
             cnt += __popc(__ballot_sync(0xffffffffu, isc && s > thr));
         } else if (isc && s > best) {
@@ -165,11 +167,11 @@ __global__ void __launch_bounds__(256) pp_score_kernel(const float* __restrict__
         const int oi = __shfl_xor_sync(0xffffffffu, bidx, o);
         if (ob > best || (ob == best && oi < bidx)) { best = ob; bidx = oi; }
     }
-    const bool pass = best > thr;
+    const bool pass = variant ? obj > thr : best > thr;
     if (lane == 0) rowcount[row] = pass ? 1 : 0;
     if (pass)
         pp_emit_row(row, N, lane, __shfl_sync(0xffffffffu, v0, 0), __shfl_sync(0xffffffffu, v0, 1),
-                    __shfl_sync(0xffffffffu, v0, 2), __shfl_sync(0xffffffffu, v0, 3), obj, best, bidx, rowcand);
+                    __shfl_sync(0xffffffffu, v0, 2), __shfl_sync(0xffffffffu, v0, 3), obj, best, bidx, rowcand, variant);
 }
 
 // ---- K3b ---------------------------------------------------------------------------------------
@@ -220,7 +222,7 @@ __global__ void __launch_bounds__(256) pp_scatter_kernel(const float* __restrict
                                                          long rows, const int* __restrict__ rowcount,
                                                          const int* __restrict__ rowoff, const float* __restrict__ rowcand,
                                                          float* __restrict__ cand, unsigned long long* __restrict__ keys,
-                                                         int cand_cap, int sort_cap) {
+                                                         int cand_cap, int sort_cap, int variant) {
     if (!is_eval) {
         const long row = (long)blockIdx.x * blockDim.x + threadIdx.x;
         if (row >= rows || rowcount[row] == 0) return;
@@ -232,7 +234,7 @@ __global__ void __launch_bounds__(256) pp_scatter_kernel(const float* __restrict
         float* o = cand + ((long)b * cand_cap + off) * 8;
         *reinterpret_cast<float4*>(o) = lo;
         *reinterpret_cast<float4*>(o + 4) = hi;
-        keys[(long)b * sort_cap + off] = make_key((int)hi.z, hi.y, off);
+        keys[(long)b * sort_cap + off] = make_key((int)hi.z, variant ? hi.x : hi.y, off);   // notebook sorts by objectness
         return;
     }
     const int lane = threadIdx.x & 31;
@@ -468,19 +470,19 @@ cudaError_t launch_postprocess(const PostArgs& a, PostBuffers& buf, long long* l
         *launches -= 1;                 // the scoring ran inside the fused decode kernel (counted by the caller)
     } else if (a.C == 80)
         pp_score4_kernel<80><<<(unsigned)((rows + 8 * kRows - 1) / (8 * kRows)), 256, 0, s>>>(a.det, rows, a.N, a.C, a.conf_thr, a.is_eval,
-                                                                                            buf.rowcount, buf.rowcand);
+                                                                                            buf.rowcount, buf.rowcand, a.variant);
     else if (kRows * (5 + a.C) <= 32 * kMaxLoads)
         pp_score4_kernel<0><<<(unsigned)((rows + 8 * kRows - 1) / (8 * kRows)), 256, 0, s>>>(a.det, rows, a.N, a.C, a.conf_thr, a.is_eval,
-                                                                                           buf.rowcount, buf.rowcand);
+                                                                                           buf.rowcount, buf.rowcand, a.variant);
     else
-        pp_score_kernel<<<(unsigned)((rows + 7) / 8), 256, 0, s>>>(a.det, rows, a.N, a.C, a.conf_thr, a.is_eval, buf.rowcount, buf.rowcand);
+        pp_score_kernel<<<(unsigned)((rows + 7) / 8), 256, 0, s>>>(a.det, rows, a.N, a.C, a.conf_thr, a.is_eval, buf.rowcount, buf.rowcand, a.variant);
     pp_scan_kernel<<<a.B, 1024, 0, s>>>(buf.rowcount, a.N, buf.rowoff, buf.cand_total);
     if (a.is_eval)
         pp_scatter_kernel<<<(unsigned)((rows + 7) / 8), 256, 0, s>>>(a.det, a.N, a.C, a.conf_thr, 1, rows, buf.rowcount, buf.rowoff,
-                                                                    buf.rowcand, buf.cand, buf.keys, cand_cap, sort_cap);
+                                                                    buf.rowcand, buf.cand, buf.keys, cand_cap, sort_cap, a.variant);
     else
         pp_scatter_kernel<<<(unsigned)((rows + 255) / 256), 256, 0, s>>>(a.det, a.N, a.C, a.conf_thr, 0, rows, buf.rowcount, buf.rowoff,
-                                                                        buf.rowcand, buf.cand, buf.keys, cand_cap, sort_cap);
+                                                                        buf.rowcand, buf.cand, buf.keys, cand_cap, sort_cap, a.variant);
     *launches += 3;
     if (a.use_nms) {
         pp_sort_kernel<<<a.B, 1024, kSortSmemKeys * 8, s>>>(buf.keys, buf.cand, buf.cand_total, cand_cap, sort_cap, a.C, buf.sbox, buf.seg);

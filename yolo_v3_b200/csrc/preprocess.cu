@@ -1,6 +1,7 @@
-// N1: letterbox pre-process -- utils.load_image(path, 'letterbox', dim) after the file decode
-// (reference utils.py:60-72): letterbox_image (utils.py:44-57) = cv2.resize(img, (box_w, box_h), INTER_CUBIC) pasted
-// at the centred offset of a grey (128) canvas, then torch.from_numpy(img).float().permute(2,0,1) / 255.
+// N1: pre-process -- utils.load_image(path, mode, dim) after the file decode (reference utils.py:60-72):
+//   'letterbox': letterbox_image (utils.py:44-57) = cv2.resize(img, (box_w, box_h), INTER_CUBIC) pasted at the centred
+//                offset of a grey (128) canvas;   'resize': cv2.resize(img, dim) (INTER_LINEAR, utils.py:69);
+// then torch.from_numpy(img).float().permute(2,0,1) / 255.
 //
 // The resize arithmetic is OpenCV's (third-party, not vendored in the reference; opencv-python 4.13.0 in this image).
 // This kernel restates OpenCV's own portable code path for 8-bit images bit for bit (modules/imgproc/src/resize.cpp:
@@ -42,6 +43,22 @@ __device__ __forceinline__ void cubic_taps(int d, double scale, int& s0, int (&t
     for (int k = 0; k < 4; ++k) tap[k] = max(-32768, min(32767, __float2int_rn(__fmul_rn(c[k], 2048.f))));   // saturate_cast<short>
 }
 
+// INTER_LINEAR taps (cv2.resize(img, dim), utils.py:69): the x axis clamps offset and fraction at the borders, the y
+// axis keeps its fraction and clips only the row indices (resize.cpp set-up loops).
+__device__ __forceinline__ void linear_taps(int d, double scale, int ssize, bool clamp, int& s0, int (&tap)[2]) {
+    const double fd = __dsub_rn(__dmul_rn(__dadd_rn((double)d, 0.5), scale), 0.5);
+    const float f = __double2float_rn(fd);
+    const float fl = floorf(f);
+    s0 = (int)fl;
+    float x = __fsub_rn(f, fl);
+    if (clamp) {
+        if (s0 < 0) { x = 0.f; s0 = 0; }
+        if (s0 >= ssize - 1) { x = 0.f; s0 = ssize - 1; }
+    }
+    tap[0] = max(-32768, min(32767, __float2int_rn(__fmul_rn(__fsub_rn(1.f, x), 2048.f))));
+    tap[1] = max(-32768, min(32767, __float2int_rn(__fmul_rn(x, 2048.f))));
+}
+
 __global__ void __launch_bounds__(256) letterbox_kernel(const LbImage* __restrict__ imgs, int canvas_h, int canvas_w,
                                                         float* __restrict__ out, unsigned char* __restrict__ canvas) {
     const int x = blockIdx.x * 32 + (threadIdx.x & 31), y = blockIdx.y * 8 + (threadIdx.x >> 5), b = blockIdx.z;
@@ -50,7 +67,23 @@ __global__ void __launch_bounds__(256) letterbox_kernel(const LbImage* __restric
     const size_t plane = (size_t)canvas_h * canvas_w;
     const int dx = x - im.box_x, dy = y - im.box_y;
     int val[3] = {128, 128, 128};
-    if (dx >= 0 && dx < im.box_w && dy >= 0 && dy < im.box_h) {
+    if (im.interp == 1 && dx >= 0 && dx < im.box_w && dy >= 0 && dy < im.box_h) {
+        // bilinear: exact int32 horizontal pass, then ((b0*(S0>>4))>>16) + ((b1*(S1>>4))>>16) + 2) >> 2
+        // (VResizeLinearVec_32s8u and its scalar tail compute the same expression)
+        int sx, sy, xa[2], yb[2];
+        linear_taps(dx, im.scale_x, im.sw, true, sx, xa);
+        linear_taps(dy, im.scale_y, im.sh, false, sy, yb);
+        const int x0 = sx, x1 = min(sx + 1, im.sw - 1);
+        const unsigned char* r0 = im.src + (size_t)max(0, min(im.sh - 1, sy)) * im.sw * 3;
+        const unsigned char* r1 = im.src + (size_t)max(0, min(im.sh - 1, sy + 1)) * im.sw * 3;
+#pragma unroll
+        for (int c = 0; c < 3; ++c) {
+            const int S0 = (int)__ldg(r0 + x0 * 3 + c) * xa[0] + (int)__ldg(r0 + x1 * 3 + c) * xa[1];
+            const int S1 = (int)__ldg(r1 + x0 * 3 + c) * xa[0] + (int)__ldg(r1 + x1 * 3 + c) * xa[1];
+            const int t = ((yb[0] * (S0 >> 4)) >> 16) + ((yb[1] * (S1 >> 4)) >> 16);
+            val[c] = max(0, min(255, (t + 2) >> 2));
+        }
+    } else if (dx >= 0 && dx < im.box_w && dy >= 0 && dy < im.box_h) {
         int sx, sy, xa[4], yb[4];
         cubic_taps(dx, im.scale_x, sx, xa);
         cubic_taps(dy, im.scale_y, sy, yb);

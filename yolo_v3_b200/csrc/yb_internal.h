@@ -130,6 +130,7 @@ struct PostArgs {
     int is_eval, use_nms;
     float* rows7; int* counts; int* src_index; int* cand_counts; int cap;
     int pre_scored = 0;                 // rowcount / rowcand were already filled by launch_decode_cells (non-eval only)
+    int variant = 0;                    // 1: the notebook's inline post-process (yolo_detect.ipynb cell 35), non-eval only
 };
 cudaError_t launch_postprocess(const PostArgs& a, PostBuffers& buf, long long* launches, cudaStream_t s);
 cudaError_t launch_correct_boxes(const float* boxes, int row_stride, const int* counts, int B, int cap, const float* params_dev,
@@ -141,6 +142,7 @@ struct LbImage {
     int sh, sw;                 // source size
     int box_w, box_h, box_x, box_y;
     double scale_x, scale_y;    // 1.0 / ((double)box / src), as cv::resize computes it
+    int interp;                 // 0: INTER_CUBIC (letterbox), 1: INTER_LINEAR (plain resize)
 };
 cudaError_t launch_letterbox(const LbImage* imgs_dev, int B, int canvas_h, int canvas_w, float* out, unsigned char* canvas,
                              cudaStream_t s);

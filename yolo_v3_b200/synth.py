@@ -118,7 +118,7 @@ def make_photo(h: int, w: int, seed: int = 0) -> np.ndarray:
     for c in range(3):
         img[..., c] = (128 + 55 * np.sin(xx / 17.0 + ph[c, 0]) * np.cos(yy / 23.0 + ph[c, 1])
                        + 35 * np.sin((xx + 2 * yy) / 7.0 + ph[c, 2]) + 40 * (((xx // 37) + (yy // 29)) % 2))
-    img += rs.randint(-6, 7, (h, w, 3))
+    img += rs.randint(-3, 4, (h, w, 3))
     return np.clip(np.rint(img), 0, 255).astype(np.uint8)
 
 

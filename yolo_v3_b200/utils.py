@@ -165,6 +165,37 @@ def letterbox_batch(imgs: Sequence, dim, device=None, want_canvas=False, canvas_
     return (canvas if want_canvas else out), t
 
 
+def resize_batch(imgs: Sequence, dim, device=None, want_u8=False):
+    """cv2.resize(img, dim) (INTER_LINEAR) + float()/255 + HWC->CHW for a list of [H,W,3] uint8 images in one launch
+    (yb_resize).  Returns CUDA fp32 [B,3,dim[1],dim[0]] (or the uint8 [B,dim[1],dim[0],3] images with want_u8)."""
+    if not torch.cuda.is_available():
+        raise RuntimeError("yolo_v3_b200 runs on CUDA devices only (no CPU fallback)")
+    if device is None:
+        device = torch.device("cuda", torch.cuda.current_device())
+    device = torch.device(device)
+    index = device.index if device.index is not None else torch.cuda.current_device()
+    B = len(imgs)
+    if B == 0:
+        raise ValueError("empty image list")
+    dev_imgs = [_as_cuda_u8(im, device) for im in imgs]
+    ptrs = (ctypes.c_void_p * B)(*[t.data_ptr() for t in dev_imgs])
+    hw = (ctypes.c_int * (2 * B))(*[int(v) for t in dev_imgs for v in t.shape[:2]])
+    dim_w, dim_h = int(dim[0]), int(dim[1])
+    out = u8 = None
+    if want_u8:
+        u8 = torch.empty(B, dim_h, dim_w, 3, device=device, dtype=torch.uint8)
+    else:
+        out = torch.empty(B, 3, dim_h, dim_w, device=device, dtype=torch.float32)
+    lib = _lib.load()
+    ctx = _ctx_for(index, 80)
+    with torch.cuda.device(device):
+        _lib.check(lib.yb_resize(ctx, ptrs, hw, B, dim_w, dim_h,
+                                 ctypes.c_void_p(out.data_ptr()) if out is not None else None,
+                                 ctypes.c_void_p(u8.data_ptr()) if u8 is not None else None,
+                                 ctypes.c_void_p(torch.cuda.current_stream(device).cuda_stream)), ctx)
+    return u8 if want_u8 else out
+
+
 def letterbox_image(img, dim):
     """Reference signature (utils.py:44-57): [H,W,3] uint8 image -> (canvas, transform).  The canvas is the numpy
     integer array the reference builds with np.full(dim + (3,), 128); the resize + paste run on the GPU."""
@@ -190,7 +221,7 @@ def load_image(img_path, mode=None, dim=None):
             x, trans = letterbox_batch([img], dim)
             return x[0], torch.Tensor(trans[0].tolist())
         if mode == "resize":
-            raise NotImplementedError("load_image(mode='resize') (cv2 INTER_LINEAR) is not on the GPU path yet; use 'letterbox'")
+            return resize_batch([img], dim)[0], None
     # no geometric change: the same kernel with a full-size box (taps 0,1,0,0) is an exact copy, /255, HWC->CHW
     h, w = img.shape[:2]
     x, _ = letterbox_batch([img], (w, h), canvas_hw=(h, w))
