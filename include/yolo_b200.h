@@ -147,11 +147,14 @@ int yb_correct_boxes(yb_ctx* ctx, const float* boxes, int row_stride, const int*
  * canvas_h, canvas_w: the canvas.  The reference allocates np.full(dim + (3,)), i.e. canvas_h = dim[0], canvas_w =
  * dim[1] -- the same thing for the square sizes it uses; a box that does not fit the canvas makes numpy raise and this
  * call return YB_E_ARG.  (dim = (w, h) of the image itself with canvas (h, w) is the plain float()/255 + HWC->CHW of
- * load_image(mode=None).)  out_nchw: dev [B,3,canvas_h,canvas_w] fp32; canvas_hwc: dev uint8 [B,canvas_h,canvas_w,3],
- * the canvas letterbox_image itself returns (either output may be NULL, not both); trans_host: HOST float[B][5] =
- * box_w, box_h, box_x, box_y, ratio (the reference's `trans`), may be NULL. */
+ * load_image(mode=None).)  offset_rule 0: box offsets as utils.letterbox_transforms (w//2 - box_w//2); 1: as the
+ * dataset transform IaaLetterbox (transforms.py:144-212: same cubic resize, offsets (w - box_w)//2, canvas [dim_h,dim_w]).
+ * out_nchw: dev [B,3,canvas_h,canvas_w] fp32; canvas_hwc: dev uint8 [B,canvas_h,canvas_w,3], the canvas
+ * letterbox_image itself returns (either output may be NULL, not both); trans_host: HOST float[B][5] = box_w, box_h,
+ * box_x, box_y, ratio (the reference's `trans`), may be NULL. */
 int yb_letterbox(yb_ctx* ctx, const uint8_t* const* imgs_dev, const int* hw_host, int B, int dim_w, int dim_h,
-                 int canvas_h, int canvas_w, float* out_nchw, uint8_t* canvas_hwc, float* trans_host, void* stream);
+                 int canvas_h, int canvas_w, int offset_rule, float* out_nchw, uint8_t* canvas_hwc, float* trans_host,
+                 void* stream);
 
 /* Replaces utils.load_image(path, 'resize', dim) after the file decode (utils.py:68-71): cv2.resize(img, dim) (default
  * INTER_LINEAR; OpenCV's 8-bit fixed-point path, bit for bit) then float()/255 and HWC->CHW, for a batch.  dim_w, dim_h:

@@ -465,6 +465,20 @@ def letterbox_image(img: np.ndarray, dim) -> Tuple[np.ndarray, torch.Tensor]:
     return image, torch.Tensor([box_w, box_h, box_x, box_y, ratio])
 
 
+def iaa_letterbox(img: np.ndarray, dim) -> np.ndarray:
+    """IaaLetterbox._augment_images (transforms.py:153-176) for one uint8 image, dim = (width, height): bicubic
+    resize (imgaug.imresize_single_image(..., 'cubic') is cv2.resize(..., INTER_CUBIC); imgaug itself is not in
+    this image, so this leg is pinned through the cv2-pinned resize above), then np.pad with 128 using
+    _compute_height_width_pad's offsets (:203-210)."""
+    width, height = int(dim[0]), int(dim[1])
+    img_h, img_w = img.shape[:2]
+    ratio = min(width / img_w, height / img_h)
+    rw, rh = int(img_w * ratio), int(img_h * ratio)
+    x_pad, y_pad = (width - rw) // 2, (height - rh) // 2
+    rs = resize_cubic_u8(img, rw, rh)
+    return np.pad(rs, ((y_pad, height - rh - y_pad), (x_pad, width - rw - x_pad), (0, 0)), mode="constant", constant_values=128)
+
+
 def load_image_letterbox(img_rgb_u8: np.ndarray, dim) -> Tuple[torch.Tensor, torch.Tensor]:
     """utils.load_image(path, 'letterbox', dim) after the file decode (utils.py:60-72): letterbox, then
     torch.from_numpy(img).float().permute(2,0,1) / 255."""

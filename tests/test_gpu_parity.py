@@ -509,3 +509,14 @@ def test_resize_mode_bit_exact(golden, oracle, tmp_path):
     assert torch.equal(x.cpu(), rx) and torch.equal(t, rt)
     x, t = load_image(path)
     assert t is None and torch.equal(x.cpu(), torch.from_numpy(img).float().permute(2, 0, 1) / 255)
+
+
+def test_iaa_letterbox_variant(oracle):
+    """The dataset transform's letterbox (transforms.IaaLetterbox): same bicubic resize, (w - bw)//2 offsets, [h,w] canvas."""
+    from yolo_v3_b200.utils import letterbox_batch
+    imgs = [synth.make_photo(500, 333, 33), synth.make_photo(97, 131, 34), synth.make_photo(240, 427, 5)]
+    for dim in ((416, 416), (320, 224)):
+        canv, _ = letterbox_batch(imgs, dim, want_canvas=True, iaa=True)
+        assert tuple(canv.shape) == (3, dim[1], dim[0], 3)
+        for k, im in enumerate(imgs):
+            assert np.array_equal(canv[k].cpu().numpy(), oracle.iaa_letterbox(im, dim)), (dim, k)

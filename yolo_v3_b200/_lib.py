@@ -41,8 +41,8 @@ PROTOTYPES = {
                           c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_void_p]),
     "yb_correct_boxes": (c_int, [c_void_p, c_void_p, c_int, c_void_p, c_int, c_int, POINTER(c_int), c_int, c_int, c_int,
                                  c_void_p, c_void_p]),
-    "yb_letterbox": (c_int, [c_void_p, POINTER(c_void_p), POINTER(c_int), c_int, c_int, c_int, c_int, c_int, c_void_p, c_void_p,
-                             POINTER(c_float), c_void_p]),
+    "yb_letterbox": (c_int, [c_void_p, POINTER(c_void_p), POINTER(c_int), c_int, c_int, c_int, c_int, c_int, c_int, c_void_p,
+                             c_void_p, POINTER(c_float), c_void_p]),
     "yb_resize": (c_int, [c_void_p, POINTER(c_void_p), POINTER(c_int), c_int, c_int, c_int, c_void_p, c_void_p, c_void_p]),
     "yb_comm_unique_id": (c_int, [POINTER(c_uint8)]),
     "yb_comm_init": (c_int, [c_void_p, POINTER(c_uint8), c_int, c_int]),

@@ -871,7 +871,7 @@ int yb_resize(yb_ctx* c, const uint8_t* const* imgs_dev, const int* hw_host, int
 }
 
 int yb_letterbox(yb_ctx* c, const uint8_t* const* imgs_dev, const int* hw_host, int B, int dim_w, int dim_h, int canvas_h,
-                 int canvas_w, float* out_nchw, uint8_t* canvas_hwc, float* trans_host, void* stream) {
+                 int canvas_w, int offset_rule, float* out_nchw, uint8_t* canvas_hwc, float* trans_host, void* stream) {
     if (!c) return fail(nullptr, YB_E_ARG, "null ctx");
     if (!imgs_dev || !hw_host || (!out_nchw && !canvas_hwc) || B <= 0 || dim_w <= 0 || dim_h <= 0 || canvas_h <= 0 || canvas_w <= 0)
         return fail(c, YB_E_ARG, "yb_letterbox: bad arguments");
@@ -894,7 +894,10 @@ int yb_letterbox(yb_ctx* c, const uint8_t* const* imgs_dev, const int* hw_host, 
         // letterbox_transforms, python-float (double) arithmetic and int() truncation
         const double ratio = std::min((double)dim_w / sw, (double)dim_h / sh);
         const int box_w = (int)(sw * ratio), box_h = (int)(sh * ratio);
-        const int box_x = dim_w / 2 - box_w / 2, box_y = dim_h / 2 - box_h / 2;
+        // utils.letterbox_transforms (utils.py:40-41) centres with w//2 - bw//2, IaaLetterbox._compute_height_width_pad
+        // (transforms.py:203-210) with (w - bw)//2: one pixel apart when the box size is odd
+        const int box_x = offset_rule ? (dim_w - box_w) / 2 : dim_w / 2 - box_w / 2;
+        const int box_y = offset_rule ? (dim_h - box_h) / 2 : dim_h / 2 - box_h / 2;
         if (box_w <= 0 || box_h <= 0) return fail(c, YB_E_ARG, "yb_letterbox: image " + std::to_string(b) + " collapses to an empty box");
         if (box_x < 0 || box_y < 0 || box_y + box_h > canvas_h || box_x + box_w > canvas_w)
             return fail(c, YB_E_ARG, "yb_letterbox: the resized image does not fit the canvas (non-square dim, see utils.py:46)");

@@ -18,6 +18,8 @@
 // HBM-bound byte work: one thread per canvas pixel reads its 4x4 source neighbourhood (3 bytes per pixel, L1/L2
 // resident: neighbouring threads share 3/4 of it) and writes the three fp32 planes with coalesced stores;
 // algorithmic traffic = source bytes + 12 bytes per canvas pixel.
+#include <cstdlib>
+
 #include "yb_internal.h"
 
 namespace yb {
@@ -133,12 +135,196 @@ __global__ void __launch_bounds__(256) letterbox_kernel(const LbImage* __restric
     }
 }
 
+// ---- two-pass tiled version -------------------------------------------------------------------------------
+// The direct kernel above recomputes the horizontal pass of every source row four times (once per vertical tap
+// of every output row that uses it) and is instruction-bound (48 byte loads + 48 integer MACs per pixel).  Here a
+// block owns a 32 x 32 tile of the canvas: pass 1 computes the int32 horizontal sums of exactly the source rows the
+// tile needs, once each, into shared memory; pass 2 combines them vertically.  Same arithmetic, same results.
+constexpr int kLbTile = 32;
+constexpr int kLbMaxRows = 100;            // source rows a tile may need: up to ~3x vertical downscale (else: direct kernel)
+
+__device__ __forceinline__ void store_pixel(float* __restrict__ out, unsigned char* __restrict__ canvas, size_t plane, int b,
+                                            int canvas_w, int x, int y, const int (&val)[3]) {
+    if (out) {
+        float* o = out + (size_t)b * 3 * plane + (size_t)y * canvas_w + x;
+#pragma unroll
+        for (int c = 0; c < 3; ++c) o[c * plane] = __fdiv_rn((float)val[c], 255.f);
+    }
+    if (canvas) {
+        unsigned char* q = canvas + ((size_t)b * plane + (size_t)y * canvas_w + x) * 3;
+#pragma unroll
+        for (int c = 0; c < 3; ++c) q[c] = (unsigned char)val[c];
+    }
+}
+
+__global__ void __launch_bounds__(256) letterbox_tiled_kernel(const LbImage* __restrict__ imgs, int canvas_h, int canvas_w,
+                                                              float* __restrict__ out, unsigned char* __restrict__ canvas) {
+    __shared__ int Hs[kLbMaxRows * kLbTile * 3];
+    const int b = blockIdx.z;
+    const LbImage im = imgs[b];
+    const size_t plane = (size_t)canvas_h * canvas_w;
+    const int tx0 = blockIdx.x * kLbTile, ty0 = blockIdx.y * kLbTile;
+    const int lx = threadIdx.x & 31, ly = threadIdx.x >> 5;             // 32 columns x 8 rows of threads
+    const int x = tx0 + lx;
+    // the part of the tile that lies inside the box, in box coordinates
+    const int dy_lo = max(ty0 - im.box_y, 0);
+    const int dy_hi = min(min(ty0 + kLbTile, canvas_h) - im.box_y, im.box_h);                   // rows [dy_lo, dy_hi)
+    const int dx = x - im.box_x;
+    const bool col_in = x < canvas_w && dx >= 0 && dx < im.box_w;
+    const bool tile_in = dy_lo < dy_hi && tx0 + kLbTile > im.box_x && tx0 < im.box_x + im.box_w;
+    const int ntap = im.interp == 1 ? 2 : 4;
+    int r_lo = 0, r_hi = -1;
+    if (tile_in) {
+        int s_first, s_last, tmp4[4], tmp2[2];
+        if (im.interp == 1) {
+            linear_taps(dy_lo, im.scale_y, im.sh, false, s_first, tmp2);
+            linear_taps(dy_hi - 1, im.scale_y, im.sh, false, s_last, tmp2);
+            r_lo = max(0, min(im.sh - 1, s_first));
+            r_hi = max(0, min(im.sh - 1, s_last + 1));
+        } else {
+            cubic_taps(dy_lo, im.scale_y, s_first, tmp4);
+            cubic_taps(dy_hi - 1, im.scale_y, s_last, tmp4);
+            r_lo = max(0, min(im.sh - 1, s_first - 1));
+            r_hi = max(0, min(im.sh - 1, s_last + 2));
+        }
+    }
+    const int nrows = r_hi - r_lo + 1;
+    const bool staged = tile_in && nrows <= kLbMaxRows;
+    // ---- pass 1: horizontal sums of source rows r_lo..r_hi for this thread's column
+    if (staged && col_in) {
+        int sx, xa[4] = {0, 0, 0, 0}, xi[4];
+        if (im.interp == 1) {
+            int t2[2];
+            linear_taps(dx, im.scale_x, im.sw, true, sx, t2);
+            xa[0] = t2[0]; xa[1] = t2[1];
+            xi[0] = sx; xi[1] = min(sx + 1, im.sw - 1); xi[2] = xi[3] = 0;
+        } else {
+            cubic_taps(dx, im.scale_x, sx, xa);
+#pragma unroll
+            for (int j = 0; j < 4; ++j) xi[j] = max(0, min(im.sw - 1, sx - 1 + j));
+        }
+        for (int r = ly; r < nrows; r += 8) {
+            const unsigned char* row = im.src + (size_t)(r_lo + r) * im.sw * 3;
+            int h0 = 0, h1 = 0, h2 = 0;
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                if (j < ntap) {
+                    const unsigned char* px = row + xi[j] * 3;
+                    h0 += (int)__ldg(px) * xa[j];
+                    h1 += (int)__ldg(px + 1) * xa[j];
+                    h2 += (int)__ldg(px + 2) * xa[j];
+                }
+            }
+            int* h = Hs + (r * kLbTile + lx) * 3;
+            h[0] = h0; h[1] = h1; h[2] = h2;
+        }
+    }
+    __syncthreads();
+    // ---- pass 2: vertical combination, four output rows per thread
+    if (x >= canvas_w) return;
+    const int vec_end = (im.box_w * 3) / 8 * 8;
+    for (int yy = ly; yy < kLbTile; yy += 8) {
+        const int y = ty0 + yy;
+        if (y >= canvas_h) break;
+        const int dy = y - im.box_y;
+        int val[3] = {128, 128, 128};
+        if (col_in && dy >= 0 && dy < im.box_h) {
+            if (!staged) {
+                // a tile that needs more source rows than the staging buffer holds (strong downscale): direct evaluation
+                int sx, sy;
+                if (im.interp == 1) {
+                    int xa[2], yb[2];
+                    linear_taps(dx, im.scale_x, im.sw, true, sx, xa);
+                    linear_taps(dy, im.scale_y, im.sh, false, sy, yb);
+                    const int x0 = sx, x1 = min(sx + 1, im.sw - 1);
+                    const unsigned char* r0 = im.src + (size_t)max(0, min(im.sh - 1, sy)) * im.sw * 3;
+                    const unsigned char* r1 = im.src + (size_t)max(0, min(im.sh - 1, sy + 1)) * im.sw * 3;
+#pragma unroll
+                    for (int c = 0; c < 3; ++c) {
+                        const int S0 = (int)__ldg(r0 + x0 * 3 + c) * xa[0] + (int)__ldg(r0 + x1 * 3 + c) * xa[1];
+                        const int S1 = (int)__ldg(r1 + x0 * 3 + c) * xa[0] + (int)__ldg(r1 + x1 * 3 + c) * xa[1];
+                        val[c] = max(0, min(255, ((((yb[0] * (S0 >> 4)) >> 16) + ((yb[1] * (S1 >> 4)) >> 16)) + 2) >> 2));
+                    }
+                } else {
+                    int xa[4], yb[4], H[4][3];
+                    cubic_taps(dx, im.scale_x, sx, xa);
+                    cubic_taps(dy, im.scale_y, sy, yb);
+#pragma unroll
+                    for (int k = 0; k < 4; ++k) {
+                        const unsigned char* row = im.src + (size_t)max(0, min(im.sh - 1, sy - 1 + k)) * im.sw * 3;
+                        H[k][0] = H[k][1] = H[k][2] = 0;
+#pragma unroll
+                        for (int j = 0; j < 4; ++j) {
+                            const unsigned char* px = row + max(0, min(im.sw - 1, sx - 1 + j)) * 3;
+#pragma unroll
+                            for (int c = 0; c < 3; ++c) H[k][c] += (int)__ldg(px + c) * xa[j];
+                        }
+                    }
+#pragma unroll
+                    for (int c = 0; c < 3; ++c) {
+                        int r;
+                        if (dx * 3 + c < vec_end) {
+                            float t = __fmul_rn((float)H[3][c], __fmul_rn((float)yb[3], 1.f / 4194304.f));
+                            t = __fadd_rn(__fmul_rn((float)H[2][c], __fmul_rn((float)yb[2], 1.f / 4194304.f)), t);
+                            t = __fadd_rn(__fmul_rn((float)H[1][c], __fmul_rn((float)yb[1], 1.f / 4194304.f)), t);
+                            t = __fadd_rn(__fmul_rn((float)H[0][c], __fmul_rn((float)yb[0], 1.f / 4194304.f)), t);
+                            r = __float2int_rn(t);
+                        } else {
+                            r = (H[0][c] * yb[0] + H[1][c] * yb[1] + H[2][c] * yb[2] + H[3][c] * yb[3] + (1 << 21)) >> 22;
+                        }
+                        val[c] = max(0, min(255, r));
+                    }
+                }
+            } else if (im.interp == 1) {
+                int sy, yb[2];
+                linear_taps(dy, im.scale_y, im.sh, false, sy, yb);
+                const int* h0 = Hs + ((max(0, min(im.sh - 1, sy)) - r_lo) * kLbTile + lx) * 3;
+                const int* h1 = Hs + ((max(0, min(im.sh - 1, sy + 1)) - r_lo) * kLbTile + lx) * 3;
+#pragma unroll
+                for (int c = 0; c < 3; ++c)
+                    val[c] = max(0, min(255, ((((yb[0] * (h0[c] >> 4)) >> 16) + ((yb[1] * (h1[c] >> 4)) >> 16)) + 2) >> 2));
+            } else {
+                int sy, yb[4];
+                cubic_taps(dy, im.scale_y, sy, yb);
+                const int* h[4];
+#pragma unroll
+                for (int k = 0; k < 4; ++k) h[k] = Hs + ((max(0, min(im.sh - 1, sy - 1 + k)) - r_lo) * kLbTile + lx) * 3;
+                float bf[4];
+#pragma unroll
+                for (int k = 0; k < 4; ++k) bf[k] = __fmul_rn((float)yb[k], 1.f / 4194304.f);
+#pragma unroll
+                for (int c = 0; c < 3; ++c) {
+                    const int H0 = h[0][c], H1 = h[1][c], H2 = h[2][c], H3 = h[3][c];
+                    int r;
+                    if (dx * 3 + c < vec_end) {
+                        float t = __fmul_rn((float)H3, bf[3]);
+                        t = __fadd_rn(__fmul_rn((float)H2, bf[2]), t);
+                        t = __fadd_rn(__fmul_rn((float)H1, bf[1]), t);
+                        t = __fadd_rn(__fmul_rn((float)H0, bf[0]), t);
+                        r = __float2int_rn(t);
+                    } else {
+                        r = (H0 * yb[0] + H1 * yb[1] + H2 * yb[2] + H3 * yb[3] + (1 << 21)) >> 22;
+                    }
+                    val[c] = max(0, min(255, r));
+                }
+            }
+        }
+        store_pixel(out, canvas, plane, b, canvas_w, x, y, val);
+    }
+}
+
 }  // namespace
 
 cudaError_t launch_letterbox(const LbImage* imgs_dev, int B, int canvas_h, int canvas_w, float* out, unsigned char* canvas,
                              cudaStream_t s) {
-    const dim3 grid((canvas_w + 31) / 32, (canvas_h + 7) / 8, B);
-    letterbox_kernel<<<grid, 256, 0, s>>>(imgs_dev, canvas_h, canvas_w, out, canvas);
+    static const bool direct = getenv("YB_LB_DIRECT") && atoi(getenv("YB_LB_DIRECT")) != 0;   // first version, kept for A/B timing
+    if (direct) {
+        const dim3 grid((canvas_w + 31) / 32, (canvas_h + 7) / 8, B);
+        letterbox_kernel<<<grid, 256, 0, s>>>(imgs_dev, canvas_h, canvas_w, out, canvas);
+    } else {
+        const dim3 grid((canvas_w + kLbTile - 1) / kLbTile, (canvas_h + kLbTile - 1) / kLbTile, B);
+        letterbox_tiled_kernel<<<grid, 256, 0, s>>>(imgs_dev, canvas_h, canvas_w, out, canvas);
+    }
     return cudaGetLastError();
 }
 

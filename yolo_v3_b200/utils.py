@@ -127,13 +127,14 @@ def _as_cuda_u8(img, device):
     return t.to(device, non_blocking=True).contiguous()
 
 
-def letterbox_batch(imgs: Sequence, dim, device=None, want_canvas=False, canvas_hw=None):
+def letterbox_batch(imgs: Sequence, dim, device=None, want_canvas=False, canvas_hw=None, iaa=False):
     """Letterboxes a list of [H,W,3] uint8 RGB images (numpy arrays or tensors, sizes may differ) on the GPU in one
     launch (yb_letterbox).  Returns (x, trans): x = CUDA fp32 [B,3,dim[0],dim[1]] = what ``load_image(path,
     'letterbox', dim)[0]`` holds for every image, trans = CPU fp32 [B,5] = box_w, box_h, box_x, box_y, ratio.
     With want_canvas=True the uint8 [B,dim[0],dim[1],3] canvases are returned instead of x.  The canvas is
     dim[0] rows by dim[1] columns exactly as the reference's np.full(dim + (3,), 128) (utils.py:46) unless canvas_hw
-    overrides it."""
+    overrides it.  iaa=True is the dataset transform IaaLetterbox (transforms.py:144-212): the same bicubic resize,
+    offsets (w - box_w)//2 instead of w//2 - box_w//2 and a [dim[1], dim[0]] canvas."""
     if not torch.cuda.is_available():
         raise RuntimeError("yolo_v3_b200 runs on CUDA devices only (no CPU fallback)")
     if device is None:
@@ -148,7 +149,10 @@ def letterbox_batch(imgs: Sequence, dim, device=None, want_canvas=False, canvas_
     hw = (ctypes.c_int * (2 * B))(*[int(v) for t in dev_imgs for v in t.shape[:2]])
     trans = (ctypes.c_float * (5 * B))()
     dim_w, dim_h = int(dim[0]), int(dim[1])
-    ch, cw = (dim_w, dim_h) if canvas_hw is None else (int(canvas_hw[0]), int(canvas_hw[1]))
+    if canvas_hw is not None:
+        ch, cw = int(canvas_hw[0]), int(canvas_hw[1])
+    else:
+        ch, cw = (dim_h, dim_w) if iaa else (dim_w, dim_h)
     out = canvas = None
     if want_canvas:
         canvas = torch.empty(B, ch, cw, 3, device=device, dtype=torch.uint8)
@@ -157,7 +161,7 @@ def letterbox_batch(imgs: Sequence, dim, device=None, want_canvas=False, canvas_
     lib = _lib.load()
     ctx = _ctx_for(index, 80)
     with torch.cuda.device(device):
-        _lib.check(lib.yb_letterbox(ctx, ptrs, hw, B, dim_w, dim_h, ch, cw,
+        _lib.check(lib.yb_letterbox(ctx, ptrs, hw, B, dim_w, dim_h, ch, cw, int(bool(iaa)),
                                     ctypes.c_void_p(out.data_ptr()) if out is not None else None,
                                     ctypes.c_void_p(canvas.data_ptr()) if canvas is not None else None,
                                     trans, ctypes.c_void_p(torch.cuda.current_stream(device).cuda_stream)), ctx)
