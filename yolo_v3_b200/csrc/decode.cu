@@ -239,105 +239,149 @@ decode_cells_kernel(const __grid_constant__ DecodeParams P, float* __restrict__ 
 // At conf 0.5 almost no cell reaches phase 2 and the kernel reads ~10 % of the head maps; at conf 0.001 nearly
 // every cell does and the cost is that of decode_cells_kernel plus the three probes.  Results are bit-identical
 // to decode + pp_score in both regimes (same decode_one / __fmul_rn arithmetic, same tie-break).
+// Decode + score one cell with the whole warp (phase 2 of the scoring kernels): nd = bit mask of the anchors
+// whose objectness passed.
+__device__ __forceinline__ void score_cell(const DecodeParams& P, float* sm, int lane, long gc, int nd, float thr,
+                                           int* __restrict__ rowcount, float* __restrict__ rowcand, int ch_pad,
+                                           const int (&ca)[8], const int (&cattr)[8]) {
+    const int attrs = P.attrs, ch = 3 * attrs;
+    const int si = gc >= P.cells_before[2] ? 2 : (gc >= P.cells_before[1] ? 1 : 0);
+    const DecodeScale& s = P.sc[si];
+    const long gl = gc - P.cells_before[si];
+    const int hw = s.h * s.w;
+    const int b = (int)(gl / hw), p = (int)(gl - (long)b * hw);
+    const int y = p / s.w, x = p - y * s.w;
+    const float* in = s.logits + gl * s.ld;
+    const long row0 = (long)b * P.n_total + s.row_off + (long)p * 3;
+    __syncwarp();                                        // previous cell's readers are done with sm
+    for (int c0 = lane * 4; c0 < ch_pad; c0 += 128)
+        *reinterpret_cast<float4*>(sm + c0) = __ldg(reinterpret_cast<const float4*>(in + c0));
+    __syncwarp();
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+        const int c = lane + 32 * k;
+        if (c < ch) sm[c] = decode_one(s, ca[k], cattr[k], x, y, sm[c]);
+    }
+    for (int c = lane + 256; c < ch; c += 32) {
+        const int a = c / attrs;
+        sm[c] = decode_one(s, a, c - a * attrs, x, y, sm[c]);
+    }
+    __syncwarp();
+#pragma unroll
+    for (int a = 0; a < 3; ++a) {
+        if (!((nd >> a) & 1)) continue;
+        const float* r = sm + a * attrs;
+        const float o = r[4];
+        float best = -INFINITY;
+        int bidx = 0x7fffffff;
+        for (int e = 5 + lane; e < attrs; e += 32) {
+            const float sc = __fmul_rn(r[e], o);
+            if (sc > best) { best = sc; bidx = e - 5; }
+        }
+#pragma unroll
+        for (int d = 16; d > 0; d >>= 1) {
+            const float ob = __shfl_xor_sync(0xffffffffu, best, d);
+            const int oi = __shfl_xor_sync(0xffffffffu, bidx, d);
+            if (ob > best || (ob == best && oi < bidx)) { best = ob; bidx = oi; }
+        }
+        const bool pass = best > thr;
+        const long row = row0 + a;
+        if (lane == 0) rowcount[row] = pass ? 1 : 0;
+        if (pass && lane < 8) {                          // same 8 floats pp_score emits (postprocess.cu: pp_emit_row)
+            const float cx = r[0], cy = r[1], hw2 = __fdiv_rn(r[2], 2.f), hh2 = __fdiv_rn(r[3], 2.f);
+            float v = 0.f;
+            switch (lane) {
+                case 0: v = __fsub_rn(cx, hw2); break;
+                case 1: v = __fsub_rn(cy, hh2); break;
+                case 2: v = __fadd_rn(cx, hw2); break;
+                case 3: v = __fadd_rn(cy, hh2); break;
+                case 4: v = o; break;
+                case 5: v = best; break;
+                case 6: v = (float)bidx; break;
+                default: v = __int_as_float((int)(row - (long)b * P.n_total)); break;
+            }
+            rowcand[row * 8 + lane] = v;
+        }
+    }
+}
+
+// Phase 1 for one cell (one lane): the three objectness probes.  Returns the mask of live anchors and settles
+// the dead ones (rowcount = 0).
+__device__ __forceinline__ int probe_cell(const DecodeParams& P, long g, float thr, int* __restrict__ rowcount) {
+    const int si = g >= P.cells_before[2] ? 2 : (g >= P.cells_before[1] ? 1 : 0);
+    const long gl = g - P.cells_before[si];
+    const int hw = P.sc[si].h * P.sc[si].w;
+    const int b = (int)(gl / hw), p = (int)(gl - (long)b * hw);
+    const float* in = P.sc[si].logits + gl * P.sc[si].ld;
+    const long row0 = (long)b * P.n_total + P.sc[si].row_off + (long)p * 3;
+    float t[3];
+#pragma unroll
+    for (int a = 0; a < 3; ++a) t[a] = __ldg(in + a * P.attrs + 4);
+    int need = 0;
+#pragma unroll
+    for (int a = 0; a < 3; ++a) {
+        // decode_one(attr = 4) is (sigmoid + 0) * 1 == sigmoid exactly
+        if (sigmoidf_rn(t[a]) > thr) need |= 1 << a;
+        else rowcount[row0 + a] = 0;
+    }
+    return need;
+}
+
+// Single-kernel form: a warp probes 32 cells, then walks its own live cells.
 __global__ void __launch_bounds__(kFusedWarps * 32, 4)
 score_cells_kernel(const __grid_constant__ DecodeParams P, float thr, int* __restrict__ rowcount, float* __restrict__ rowcand,
                    int ch_pad) {
     extern __shared__ __align__(16) float cell_smem[];      // [kFusedWarps][ch_pad]
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     float* sm = cell_smem + warp * ch_pad;
-    const int attrs = P.attrs, ch = 3 * attrs;
+    const int attrs = P.attrs;
     const long total = P.cells_before[3];
     const long wstride = (long)gridDim.x * kFusedWarps * 32;
     int ca[8], cattr[8];
 #pragma unroll
     for (int k = 0; k < 8; ++k) { ca[k] = (lane + 32 * k) / attrs; cattr[k] = (lane + 32 * k) - ca[k] * attrs; }
     for (long g0 = ((long)blockIdx.x * kFusedWarps + warp) * 32; g0 < total; g0 += wstride) {
-        // ---- phase 1: three objectness probes per cell, one cell per lane
         const long g = g0 + lane;
-        int need = 0;
-        if (g < total) {
-            const int si = g >= P.cells_before[2] ? 2 : (g >= P.cells_before[1] ? 1 : 0);
-            const long gl = g - P.cells_before[si];
-            const int hw = P.sc[si].h * P.sc[si].w;
-            const int b = (int)(gl / hw), p = (int)(gl - (long)b * hw);
-            const float* in = P.sc[si].logits + gl * P.sc[si].ld;
-            const long row0 = (long)b * P.n_total + P.sc[si].row_off + (long)p * 3;
-            float t[3];
-#pragma unroll
-            for (int a = 0; a < 3; ++a) t[a] = __ldg(in + a * attrs + 4);
-#pragma unroll
-            for (int a = 0; a < 3; ++a) {
-                // decode_one(attr = 4) is (sigmoid + 0) * 1 == sigmoid exactly
-                if (sigmoidf_rn(t[a]) > thr) need |= 1 << a;
-                else rowcount[row0 + a] = 0;
-            }
-        }
-        // ---- phase 2: cells with a live anchor, one at a time, whole warp
+        const int need = g < total ? probe_cell(P, g, thr, rowcount) : 0;
         unsigned live = __ballot_sync(0xffffffffu, need != 0);
         while (live) {
             const int src = __ffs(live) - 1;
             live &= live - 1;
-            const int nd = __shfl_sync(0xffffffffu, need, src);
-            const long gc = g0 + src;
-            const int si = gc >= P.cells_before[2] ? 2 : (gc >= P.cells_before[1] ? 1 : 0);
-            const DecodeScale& s = P.sc[si];
-            const long gl = gc - P.cells_before[si];
-            const int hw = s.h * s.w;
-            const int b = (int)(gl / hw), p = (int)(gl - (long)b * hw);
-            const int y = p / s.w, x = p - y * s.w;
-            const float* in = s.logits + gl * s.ld;
-            const long row0 = (long)b * P.n_total + s.row_off + (long)p * 3;
-            __syncwarp();                                    // previous cell's readers are done with sm
-            for (int c0 = lane * 4; c0 < ch_pad; c0 += 128)
-                *reinterpret_cast<float4*>(sm + c0) = __ldg(reinterpret_cast<const float4*>(in + c0));
-            __syncwarp();
-#pragma unroll
-            for (int k = 0; k < 8; ++k) {
-                const int c = lane + 32 * k;
-                if (c < ch) sm[c] = decode_one(s, ca[k], cattr[k], x, y, sm[c]);
-            }
-            for (int c = lane + 256; c < ch; c += 32) {
-                const int a = c / attrs;
-                sm[c] = decode_one(s, a, c - a * attrs, x, y, sm[c]);
-            }
-            __syncwarp();
-#pragma unroll
-            for (int a = 0; a < 3; ++a) {
-                if (!((nd >> a) & 1)) continue;
-                const float* r = sm + a * attrs;
-                const float o = r[4];
-                float best = -INFINITY;
-                int bidx = 0x7fffffff;
-                for (int e = 5 + lane; e < attrs; e += 32) {
-                    const float sc = __fmul_rn(r[e], o);
-                    if (sc > best) { best = sc; bidx = e - 5; }
-                }
-#pragma unroll
-                for (int d = 16; d > 0; d >>= 1) {
-                    const float ob = __shfl_xor_sync(0xffffffffu, best, d);
-                    const int oi = __shfl_xor_sync(0xffffffffu, bidx, d);
-                    if (ob > best || (ob == best && oi < bidx)) { best = ob; bidx = oi; }
-                }
-                const bool pass = best > thr;
-                const long row = row0 + a;
-                if (lane == 0) rowcount[row] = pass ? 1 : 0;
-                if (pass && lane < 8) {                      // same 8 floats pp_score emits (postprocess.cu: pp_emit_row)
-                    const float cx = r[0], cy = r[1], hw2 = __fdiv_rn(r[2], 2.f), hh2 = __fdiv_rn(r[3], 2.f);
-                    float v = 0.f;
-                    switch (lane) {
-                        case 0: v = __fsub_rn(cx, hw2); break;
-                        case 1: v = __fsub_rn(cy, hh2); break;
-                        case 2: v = __fadd_rn(cx, hw2); break;
-                        case 3: v = __fadd_rn(cy, hh2); break;
-                        case 4: v = o; break;
-                        case 5: v = best; break;
-                        case 6: v = (float)bidx; break;
-                        default: v = __int_as_float((int)(row - (long)b * P.n_total)); break;
-                    }
-                    rowcand[row * 8 + lane] = v;
-                }
-            }
+            score_cell(P, sm, lane, g0 + src, __shfl_sync(0xffffffffu, need, src), thr, rowcount, rowcand, ch_pad, ca, cattr);
         }
+    }
+}
+
+// Two-kernel form (default): the probe appends live cells to a list, and the scoring kernel spreads that list over
+// every warp of the GPU -- in the single-kernel form a warp walks its own live cells one after another, and the
+// slowest warp sets the time.  list[0] = count (zeroed by the host), entries (cell << 3 | anchor mask) follow.
+__global__ void __launch_bounds__(256) probe_cells_kernel(const __grid_constant__ DecodeParams P, float thr,
+                                                          int* __restrict__ rowcount, int* __restrict__ list) {
+    const long g = (long)blockIdx.x * blockDim.x + threadIdx.x;
+    const int lane = threadIdx.x & 31;
+    const int need = g < P.cells_before[3] ? probe_cell(P, g, thr, rowcount) : 0;
+    const unsigned live = __ballot_sync(0xffffffffu, need != 0);
+    if (!live) return;
+    int base = 0;
+    if (lane == __ffs(live) - 1) base = atomicAdd(list, __popc(live));
+    base = __shfl_sync(0xffffffffu, base, __ffs(live) - 1);
+    if (need) list[1 + base + __popc(live & ((1u << lane) - 1))] = (int)(g << 3) | need;
+}
+
+__global__ void __launch_bounds__(kFusedWarps * 32, 4)
+score_list_kernel(const __grid_constant__ DecodeParams P, float thr, int* __restrict__ rowcount, float* __restrict__ rowcand,
+                  const int* __restrict__ list, int ch_pad) {
+    extern __shared__ __align__(16) float cell_smem[];      // [kFusedWarps][ch_pad]
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    float* sm = cell_smem + warp * ch_pad;
+    const int attrs = P.attrs;
+    const int count = list[0];
+    int ca[8], cattr[8];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) { ca[k] = (lane + 32 * k) / attrs; cattr[k] = (lane + 32 * k) - ca[k] * attrs; }
+    for (int i = blockIdx.x * kFusedWarps + warp; i < count; i += gridDim.x * kFusedWarps) {
+        const int e = list[1 + i];
+        score_cell(P, sm, lane, (long)(e >> 3), e & 7, thr, rowcount, rowcand, ch_pad, ca, cattr);
     }
 }
 
@@ -346,7 +390,8 @@ score_cells_kernel(const __grid_constant__ DecodeParams P, float thr, int* __res
 // mode bit 0: write det_cat, bit 1: score into rowcount / rowcand (non-eval post-process front end).
 // Requires the NHWC head maps with pixel pitch ld == ch_pad (a multiple of 4 floats, 16-byte aligned cells).
 cudaError_t launch_decode_cells(const DecodeScale sc[3], int B, int attrs, int n_total, int mode, float* det, float thr,
-                                int* rowcount, float* rowcand, int num_sms, cudaStream_t s) {
+                                int* rowcount, float* rowcand, int* list, int* extra_launches, int num_sms, cudaStream_t s) {
+    if (extra_launches) *extra_launches = 0;
     DecodeParams P;
     P.B = B; P.attrs = attrs; P.n_total = n_total;
     P.cells_before[0] = 0;
@@ -360,11 +405,22 @@ cudaError_t launch_decode_cells(const DecodeScale sc[3], int B, int attrs, int n
     const unsigned grid = (unsigned)std::min<long>(blocks_needed, (long)num_sms * 4);
     if (mode == 1) decode_cells_kernel<true, false><<<grid, kFusedWarps * 32, smem, s>>>(P, det, thr, rowcount, rowcand, ch_pad);
     else if (mode == 2) {
-        static const bool obj_first = !(getenv("YB_SCORE_OBJ_FIRST") && atoi(getenv("YB_SCORE_OBJ_FIRST")) == 0);
-        const long groups = (P.cells_before[3] + 31) / 32;
+        // YB_SCORE_MODE: 0 one cell per warp at a time, everything decoded; 1 objectness-first in one kernel;
+        // 2 (default) objectness probe -> live-cell list -> scoring kernel over the list
+        static const int score_mode = getenv("YB_SCORE_MODE") ? atoi(getenv("YB_SCORE_MODE")) : 2;
+        const long cells = P.cells_before[3];
+        const long groups = (cells + 31) / 32;
         const unsigned grid2 = (unsigned)std::min<long>((groups + kFusedWarps - 1) / kFusedWarps, (long)num_sms * 4);
-        if (obj_first) score_cells_kernel<<<grid2, kFusedWarps * 32, smem, s>>>(P, thr, rowcount, rowcand, ch_pad);
-        else decode_cells_kernel<false, true><<<grid, kFusedWarps * 32, smem, s>>>(P, det, thr, rowcount, rowcand, ch_pad);
+        if (score_mode == 2 && list && cells < (1L << 28)) {
+            cudaMemsetAsync(list, 0, sizeof(int), s);
+            probe_cells_kernel<<<(unsigned)((cells + 255) / 256), 256, 0, s>>>(P, thr, rowcount, list);
+            score_list_kernel<<<num_sms * 4, kFusedWarps * 32, smem, s>>>(P, thr, rowcount, rowcand, list, ch_pad);
+            if (extra_launches) *extra_launches = 1;
+        } else if (score_mode >= 1) {
+            score_cells_kernel<<<grid2, kFusedWarps * 32, smem, s>>>(P, thr, rowcount, rowcand, ch_pad);
+        } else {
+            decode_cells_kernel<false, true><<<grid, kFusedWarps * 32, smem, s>>>(P, det, thr, rowcount, rowcand, ch_pad);
+        }
     }
     else decode_cells_kernel<true, true><<<grid, kFusedWarps * 32, smem, s>>>(P, det, thr, rowcount, rowcand, ch_pad);
     return cudaGetLastError();

@@ -661,7 +661,7 @@ int yb_forward(yb_ctx* c, const float* x, int B, int H, int W, float* det, void*
     // cell in flight per warp: measured 0.194 ms against 0.170 ms at 608x608 batch 32, profiles/README.md)
     static const bool decode_v2 = getenv("YB_DECODE_V2") && atoi(getenv("YB_DECODE_V2")) != 0;
     if (decode_v2)
-        YB_CUDA(c, launch_decode_cells(sc, B, c->attrs, total_rows(H, W), 1, det, 0.f, nullptr, nullptr, c->num_sms, s));
+        YB_CUDA(c, launch_decode_cells(sc, B, c->attrs, total_rows(H, W), 1, det, 0.f, nullptr, nullptr, nullptr, nullptr, c->num_sms, s));
     else
         YB_CUDA(c, launch_decode(sc, 0, B, c->attrs, total_rows(H, W), det, s));
     ++c->launches;
@@ -783,10 +783,15 @@ int yb_detect(yb_ctx* c, const float* x, int B, int H, int W, float conf, float 
     if ((rc = run_ops(c, p, x, n_ops, s))) return rc;       // records events [0] and [n_ops] when profiling
     DecodeScale sc[3];
     fill_decode(c, H, W, p->logits[0], p->logits[1], p->logits[2], c->layers.back().cout_pad, sc);
-    if (fused)
-        YB_CUDA(c, launch_decode_cells(sc, B, c->attrs, N, 2, nullptr, conf, c->post.rowcount, c->post.rowcand, c->num_sms, s));
-    else
+    if (fused) {
+        // the live-cell list borrows rowoff (B*N ints >= 1 + cells; pp_scan overwrites it afterwards)
+        int extra = 0;
+        YB_CUDA(c, launch_decode_cells(sc, B, c->attrs, N, 2, nullptr, conf, c->post.rowcount, c->post.rowcand, c->post.rowoff, &extra,
+                                       c->num_sms, s));
+        c->launches += extra;
+    } else {
         YB_CUDA(c, launch_decode(sc, 0, B, c->attrs, N, c->det_scratch, s));
+    }
     ++c->launches;
     if (c->profiling) YB_CUDA(c, cudaEventRecord(c->ev[n_ops + 1], s));
     PostArgs a{fused ? nullptr : c->det_scratch, B, N, c->num_classes, conf, nms, is_eval, use_nms, rows7, counts, src_index,

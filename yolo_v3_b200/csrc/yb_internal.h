@@ -106,8 +106,10 @@ struct DecodeScale {
 cudaError_t launch_decode(const DecodeScale sc[3], int nchw, int B, int attrs, int n_total, float* det, cudaStream_t s);
 // One warp per grid cell over the NHWC head maps (pixel pitch sc[].ld, a multiple of 4 floats).  mode bit 0: write
 // det_cat (standalone decode), bit 1: score the rows into rowcount / rowcand (front end of the non-eval post-process).
+// `list`: scratch of at least 1 + (cells of the batch) ints for the live-cell list of the two-kernel scoring form (may be
+// NULL: single-kernel form); *extra_launches <- kernels launched beyond the first.
 cudaError_t launch_decode_cells(const DecodeScale sc[3], int B, int attrs, int n_total, int mode, float* det, float thr,
-                                int* rowcount, float* rowcand, int num_sms, cudaStream_t s);
+                                int* rowcount, float* rowcand, int* list, int* extra_launches, int num_sms, cudaStream_t s);
 
 // postprocess.cu
 struct PostBuffers {
