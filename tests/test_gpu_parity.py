@@ -520,3 +520,32 @@ def test_iaa_letterbox_variant(oracle):
         assert tuple(canv.shape) == (3, dim[1], dim[0], 3)
         for k, im in enumerate(imgs):
             assert np.array_equal(canv[k].cpu().numpy(), oracle.iaa_letterbox(im, dim)), (dim, k)
+
+
+def test_eval_json_writer(tmp_path, oracle, sd_calibrated):
+    """evaluate.py's results writer on the device path: eval-mode detect (conf 0.005 / nms 0.45) + correct_yolo_boxes,
+    JSON text identical to the reference's format built from the oracle's rows."""
+    import json
+    from collections import OrderedDict
+    from yolo_v3_b200 import YoloNet
+    from yolo_v3_b200.evaluate import open_json_pred_writer, predict_and_process
+    net = YoloNet((96, 96), precision="fp32")
+    net.load_state_dict(sd_calibrated)
+    net = net.cuda().eval()
+    x = synth.make_images(2, 96, 96, seed=4)
+    sample = {"img": x, "org_img": torch.zeros(2, 3, 120, 160), "img_path": ["a/COCO_val2014_000000000042.jpg", "b/000000000139.jpg"]}
+    out = tmp_path / "res.json"
+    with open_json_pred_writer(str(out), ["c"] * 80, is_letterbox=True) as w:
+        predict_and_process([sample], net, 80, w)
+    got = json.loads(out.read_text())
+    det = torch.cat(net(x.cuda(), None), 1).cpu()
+    ref, _ = oracle.postprocessing_c(det, 80, 0.005, 0.45, is_eval=True)
+    exp = []
+    for b, (iid, rows) in enumerate(zip((42, 139), ref)):
+        boxes = oracle.correct_yolo_boxes(rows[:, :4], 160, 120, 96, 96, True)
+        for r, bb in zip(rows.tolist(), boxes.tolist()):
+            exp.append(OrderedDict(image_id=iid, category_id=int(r[6]), bbox=bb, score=r[5]))
+    assert len(got) == len(exp) > 50
+    assert got == json.loads(json.dumps(exp))
+    text = out.read_text()
+    assert text.startswith('[{\n    "image_id":42,') and text.endswith("}]")

@@ -61,15 +61,9 @@ __device__ __forceinline__ void linear_taps(int d, double scale, int ssize, bool
     tap[1] = max(-32768, min(32767, __float2int_rn(__fmul_rn(x, 2048.f))));
 }
 
-__global__ void __launch_bounds__(256) letterbox_kernel(const LbImage* __restrict__ imgs, int canvas_h, int canvas_w,
-                                                        float* __restrict__ out, unsigned char* __restrict__ canvas) {
-    const int x = blockIdx.x * 32 + (threadIdx.x & 31), y = blockIdx.y * 8 + (threadIdx.x >> 5), b = blockIdx.z;
-    if (x >= canvas_w || y >= canvas_h) return;
-    const LbImage im = imgs[b];
-    const size_t plane = (size_t)canvas_h * canvas_w;
-    const int dx = x - im.box_x, dy = y - im.box_y;
-    int val[3] = {128, 128, 128};
-    if (im.interp == 1 && dx >= 0 && dx < im.box_w && dy >= 0 && dy < im.box_h) {
+// One canvas pixel inside the box, evaluated directly from the source image (4x4 / 2x2 neighbourhood).
+__device__ __forceinline__ void direct_pixel(const LbImage& im, int dx, int dy, int (&val)[3]) {
+    if (im.interp == 1) {
         // bilinear: exact int32 horizontal pass, then ((b0*(S0>>4))>>16) + ((b1*(S1>>4))>>16) + 2) >> 2
         // (VResizeLinearVec_32s8u and its scalar tail compute the same expression)
         int sx, sy, xa[2], yb[2];
@@ -85,44 +79,48 @@ __global__ void __launch_bounds__(256) letterbox_kernel(const LbImage* __restric
             const int t = ((yb[0] * (S0 >> 4)) >> 16) + ((yb[1] * (S1 >> 4)) >> 16);
             val[c] = max(0, min(255, (t + 2) >> 2));
         }
-    } else if (dx >= 0 && dx < im.box_w && dy >= 0 && dy < im.box_h) {
-        int sx, sy, xa[4], yb[4];
-        cubic_taps(dx, im.scale_x, sx, xa);
-        cubic_taps(dy, im.scale_y, sy, yb);
-        int H[4][3];
+        return;
+    }
+    int sx, sy, xa[4], yb[4];
+    cubic_taps(dx, im.scale_x, sx, xa);
+    cubic_taps(dy, im.scale_y, sy, yb);
+    int H[4][3];
 #pragma unroll
-        for (int k = 0; k < 4; ++k) {
-            const int ry = max(0, min(im.sh - 1, sy - 1 + k));
-            const unsigned char* row = im.src + (size_t)ry * im.sw * 3;
-            H[k][0] = H[k][1] = H[k][2] = 0;
+    for (int k = 0; k < 4; ++k) {
+        const int ry = max(0, min(im.sh - 1, sy - 1 + k));
+        const unsigned char* row = im.src + (size_t)ry * im.sw * 3;
+        H[k][0] = H[k][1] = H[k][2] = 0;
 #pragma unroll
-            for (int j = 0; j < 4; ++j) {
-                const int rx = max(0, min(im.sw - 1, sx - 1 + j));
-                const unsigned char* px = row + rx * 3;
+        for (int j = 0; j < 4; ++j) {
+            const int rx = max(0, min(im.sw - 1, sx - 1 + j));
+            const unsigned char* px = row + rx * 3;
 #pragma unroll
-                for (int c = 0; c < 3; ++c) H[k][c] += (int)__ldg(px + c) * xa[j];
-            }
-        }
-        const int vec_end = (im.box_w * 3) / 8 * 8;
-        const float sc = 1.f / 4194304.f;                                  // 1 / (2048 * 2048)
-        float bf[4];
-#pragma unroll
-        for (int k = 0; k < 4; ++k) bf[k] = __fmul_rn((float)yb[k], sc);
-#pragma unroll
-        for (int c = 0; c < 3; ++c) {
-            int r;
-            if (dx * 3 + c < vec_end) {
-                float t = __fmul_rn((float)H[3][c], bf[3]);
-                t = __fadd_rn(__fmul_rn((float)H[2][c], bf[2]), t);
-                t = __fadd_rn(__fmul_rn((float)H[1][c], bf[1]), t);
-                t = __fadd_rn(__fmul_rn((float)H[0][c], bf[0]), t);
-                r = __float2int_rn(t);
-            } else {
-                r = (H[0][c] * yb[0] + H[1][c] * yb[1] + H[2][c] * yb[2] + H[3][c] * yb[3] + (1 << 21)) >> 22;
-            }
-            val[c] = max(0, min(255, r));
+            for (int c = 0; c < 3; ++c) H[k][c] += (int)__ldg(px + c) * xa[j];
         }
     }
+    const int vec_end = (im.box_w * 3) / 8 * 8;
+    const float sc = 1.f / 4194304.f;                                  // 1 / (2048 * 2048)
+    float bf[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) bf[k] = __fmul_rn((float)yb[k], sc);
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+        int r;
+        if (dx * 3 + c < vec_end) {
+            float t = __fmul_rn((float)H[3][c], bf[3]);
+            t = __fadd_rn(__fmul_rn((float)H[2][c], bf[2]), t);
+            t = __fadd_rn(__fmul_rn((float)H[1][c], bf[1]), t);
+            t = __fadd_rn(__fmul_rn((float)H[0][c], bf[0]), t);
+            r = __float2int_rn(t);
+        } else {
+            r = (H[0][c] * yb[0] + H[1][c] * yb[1] + H[2][c] * yb[2] + H[3][c] * yb[3] + (1 << 21)) >> 22;
+        }
+        val[c] = max(0, min(255, r));
+    }
+}
+
+__device__ __forceinline__ void store_pixel(float* __restrict__ out, unsigned char* __restrict__ canvas, size_t plane, int b,
+                                            int canvas_w, int x, int y, const int (&val)[3]) {
     if (out) {                                                             // float() / 255, HWC -> CHW (utils.py:71)
         float* o = out + (size_t)b * 3 * plane + (size_t)y * canvas_w + x;
 #pragma unroll
@@ -135,88 +133,111 @@ __global__ void __launch_bounds__(256) letterbox_kernel(const LbImage* __restric
     }
 }
 
-// ---- two-pass tiled version -------------------------------------------------------------------------------
-// The direct kernel above recomputes the horizontal pass of every source row four times (once per vertical tap
-// of every output row that uses it) and is instruction-bound (48 byte loads + 48 integer MACs per pixel).  Here a
-// block owns a 32 x 32 tile of the canvas: pass 1 computes the int32 horizontal sums of exactly the source rows the
-// tile needs, once each, into shared memory; pass 2 combines them vertically.  Same arithmetic, same results.
-constexpr int kLbTile = 32;
-constexpr int kLbMaxRows = 100;            // source rows a tile may need: up to ~3x vertical downscale (else: direct kernel)
-
-__device__ __forceinline__ void store_pixel(float* __restrict__ out, unsigned char* __restrict__ canvas, size_t plane, int b,
-                                            int canvas_w, int x, int y, const int (&val)[3]) {
-    if (out) {
-        float* o = out + (size_t)b * 3 * plane + (size_t)y * canvas_w + x;
-#pragma unroll
-        for (int c = 0; c < 3; ++c) o[c * plane] = __fdiv_rn((float)val[c], 255.f);
-    }
-    if (canvas) {
-        unsigned char* q = canvas + ((size_t)b * plane + (size_t)y * canvas_w + x) * 3;
-#pragma unroll
-        for (int c = 0; c < 3; ++c) q[c] = (unsigned char)val[c];
-    }
+// First version: one thread per canvas pixel.  Kept for A/B timing (YB_LB_DIRECT=1).
+__global__ void __launch_bounds__(256) letterbox_kernel(const LbImage* __restrict__ imgs, int canvas_h, int canvas_w,
+                                                        float* __restrict__ out, unsigned char* __restrict__ canvas) {
+    const int x = blockIdx.x * 32 + (threadIdx.x & 31), y = blockIdx.y * 8 + (threadIdx.x >> 5), b = blockIdx.z;
+    if (x >= canvas_w || y >= canvas_h) return;
+    const LbImage im = imgs[b];
+    const int dx = x - im.box_x, dy = y - im.box_y;
+    int val[3] = {128, 128, 128};
+    if (dx >= 0 && dx < im.box_w && dy >= 0 && dy < im.box_h) direct_pixel(im, dx, dy, val);
+    store_pixel(out, canvas, (size_t)canvas_h * canvas_w, b, canvas_w, x, y, val);
 }
+
+// ---- two-pass tiled version -------------------------------------------------------------------------------
+// The direct kernel recomputes the horizontal pass of every source row four times (once per vertical tap of every
+// output row that uses it) and every thread re-derives taps its neighbours share; ncu shows it instruction-issue-
+// bound (84 % issue-active at 11 % of DRAM throughput).  Here a block owns a 32 x 32 tile of the canvas: the taps
+// of its 32 columns and 32 rows are computed once into shared memory, pass 1 computes the horizontal sums of
+// exactly the source rows the tile needs, once each (kept as fp32: |sum| < 2^24, so exact), pass 2 combines them
+// vertically, and the /255 comes from a 256-entry table of the IEEE quotients.  Same arithmetic, same results.
+constexpr int kLbTile = 32;
+constexpr int kLbMaxRows = 100;            // source rows a tile may need: up to ~3x vertical downscale (else: direct)
 
 __global__ void __launch_bounds__(256) letterbox_tiled_kernel(const LbImage* __restrict__ imgs, int canvas_h, int canvas_w,
                                                               float* __restrict__ out, unsigned char* __restrict__ canvas) {
-    __shared__ int Hs[kLbMaxRows * kLbTile * 3];
-    const int b = blockIdx.z;
+    __shared__ float Hs[kLbMaxRows * kLbTile * 3];
+    __shared__ int xtap[kLbTile][4], xoff[kLbTile][4];       // per column: taps, byte offset of the (clamped) source pixel
+    __shared__ int ytap[kLbTile][4], ysrc[kLbTile];          // per row: taps, unclamped first source row (sy)
+    __shared__ float ybf[kLbTile][4];                        // per row: taps / 2^22 (cubic vector path)
+    __shared__ float lut[256];
+    const int b = blockIdx.z, tid = threadIdx.x;
     const LbImage im = imgs[b];
     const size_t plane = (size_t)canvas_h * canvas_w;
     const int tx0 = blockIdx.x * kLbTile, ty0 = blockIdx.y * kLbTile;
-    const int lx = threadIdx.x & 31, ly = threadIdx.x >> 5;             // 32 columns x 8 rows of threads
+    const int lx = tid & 31, ly = tid >> 5;                  // 32 columns x 8 rows of threads
     const int x = tx0 + lx;
-    // the part of the tile that lies inside the box, in box coordinates
+    const int ntap = im.interp == 1 ? 2 : 4;
+    // the rows / columns of the tile that lie inside the box, in box coordinates
     const int dy_lo = max(ty0 - im.box_y, 0);
     const int dy_hi = min(min(ty0 + kLbTile, canvas_h) - im.box_y, im.box_h);                   // rows [dy_lo, dy_hi)
     const int dx = x - im.box_x;
     const bool col_in = x < canvas_w && dx >= 0 && dx < im.box_w;
     const bool tile_in = dy_lo < dy_hi && tx0 + kLbTile > im.box_x && tx0 < im.box_x + im.box_w;
-    const int ntap = im.interp == 1 ? 2 : 4;
+    lut[tid] = __fdiv_rn((float)tid, 255.f);
+    if (tile_in && ly == 0) {                                // warp 0: taps of the tile's columns
+        int sx = 0, t4[4] = {0, 0, 0, 0}, o4[4] = {0, 0, 0, 0};
+        if (col_in) {
+            if (im.interp == 1) {
+                int t2[2];
+                linear_taps(dx, im.scale_x, im.sw, true, sx, t2);
+                t4[0] = t2[0]; t4[1] = t2[1];
+                o4[0] = sx * 3; o4[1] = min(sx + 1, im.sw - 1) * 3;
+            } else {
+                cubic_taps(dx, im.scale_x, sx, t4);
+#pragma unroll
+                for (int j = 0; j < 4; ++j) o4[j] = max(0, min(im.sw - 1, sx - 1 + j)) * 3;
+            }
+        }
+#pragma unroll
+        for (int j = 0; j < 4; ++j) { xtap[lx][j] = t4[j]; xoff[lx][j] = o4[j]; }
+    }
+    if (tile_in && ly == 1) {                                // warp 1: taps of the tile's rows
+        const int dy = ty0 + lx - im.box_y;
+        int sy = 0, t4[4] = {0, 0, 0, 0};
+        if (dy >= dy_lo && dy < dy_hi) {
+            if (im.interp == 1) {
+                int t2[2];
+                linear_taps(dy, im.scale_y, im.sh, false, sy, t2);
+                t4[0] = t2[0]; t4[1] = t2[1];
+            } else {
+                cubic_taps(dy, im.scale_y, sy, t4);
+            }
+        }
+        ysrc[lx] = sy;
+#pragma unroll
+        for (int k = 0; k < 4; ++k) { ytap[lx][k] = t4[k]; ybf[lx][k] = __fmul_rn((float)t4[k], 1.f / 4194304.f); }
+    }
+    __syncthreads();
     int r_lo = 0, r_hi = -1;
     if (tile_in) {
-        int s_first, s_last, tmp4[4], tmp2[2];
-        if (im.interp == 1) {
-            linear_taps(dy_lo, im.scale_y, im.sh, false, s_first, tmp2);
-            linear_taps(dy_hi - 1, im.scale_y, im.sh, false, s_last, tmp2);
-            r_lo = max(0, min(im.sh - 1, s_first));
-            r_hi = max(0, min(im.sh - 1, s_last + 1));
-        } else {
-            cubic_taps(dy_lo, im.scale_y, s_first, tmp4);
-            cubic_taps(dy_hi - 1, im.scale_y, s_last, tmp4);
-            r_lo = max(0, min(im.sh - 1, s_first - 1));
-            r_hi = max(0, min(im.sh - 1, s_last + 2));
-        }
+        const int s_first = ysrc[dy_lo + im.box_y - ty0], s_last = ysrc[dy_hi - 1 + im.box_y - ty0];
+        const int first = im.interp == 1 ? s_first : s_first - 1, last = im.interp == 1 ? s_last + 1 : s_last + 2;
+        r_lo = max(0, min(im.sh - 1, first));
+        r_hi = max(0, min(im.sh - 1, last));
     }
     const int nrows = r_hi - r_lo + 1;
     const bool staged = tile_in && nrows <= kLbMaxRows;
     // ---- pass 1: horizontal sums of source rows r_lo..r_hi for this thread's column
     if (staged && col_in) {
-        int sx, xa[4] = {0, 0, 0, 0}, xi[4];
-        if (im.interp == 1) {
-            int t2[2];
-            linear_taps(dx, im.scale_x, im.sw, true, sx, t2);
-            xa[0] = t2[0]; xa[1] = t2[1];
-            xi[0] = sx; xi[1] = min(sx + 1, im.sw - 1); xi[2] = xi[3] = 0;
-        } else {
-            cubic_taps(dx, im.scale_x, sx, xa);
+        int xa[4], xo[4];
 #pragma unroll
-            for (int j = 0; j < 4; ++j) xi[j] = max(0, min(im.sw - 1, sx - 1 + j));
-        }
+        for (int j = 0; j < 4; ++j) { xa[j] = xtap[lx][j]; xo[j] = xoff[lx][j]; }
         for (int r = ly; r < nrows; r += 8) {
             const unsigned char* row = im.src + (size_t)(r_lo + r) * im.sw * 3;
             int h0 = 0, h1 = 0, h2 = 0;
 #pragma unroll
             for (int j = 0; j < 4; ++j) {
                 if (j < ntap) {
-                    const unsigned char* px = row + xi[j] * 3;
+                    const unsigned char* px = row + xo[j];
                     h0 += (int)__ldg(px) * xa[j];
                     h1 += (int)__ldg(px + 1) * xa[j];
                     h2 += (int)__ldg(px + 2) * xa[j];
                 }
             }
-            int* h = Hs + (r * kLbTile + lx) * 3;
-            h[0] = h0; h[1] = h1; h[2] = h2;
+            float* h = Hs + (r * kLbTile + lx) * 3;
+            h[0] = (float)h0; h[1] = (float)h1; h[2] = (float)h2;
         }
     }
     __syncthreads();
@@ -230,86 +251,49 @@ __global__ void __launch_bounds__(256) letterbox_tiled_kernel(const LbImage* __r
         int val[3] = {128, 128, 128};
         if (col_in && dy >= 0 && dy < im.box_h) {
             if (!staged) {
-                // a tile that needs more source rows than the staging buffer holds (strong downscale): direct evaluation
-                int sx, sy;
-                if (im.interp == 1) {
-                    int xa[2], yb[2];
-                    linear_taps(dx, im.scale_x, im.sw, true, sx, xa);
-                    linear_taps(dy, im.scale_y, im.sh, false, sy, yb);
-                    const int x0 = sx, x1 = min(sx + 1, im.sw - 1);
-                    const unsigned char* r0 = im.src + (size_t)max(0, min(im.sh - 1, sy)) * im.sw * 3;
-                    const unsigned char* r1 = im.src + (size_t)max(0, min(im.sh - 1, sy + 1)) * im.sw * 3;
-#pragma unroll
-                    for (int c = 0; c < 3; ++c) {
-                        const int S0 = (int)__ldg(r0 + x0 * 3 + c) * xa[0] + (int)__ldg(r0 + x1 * 3 + c) * xa[1];
-                        const int S1 = (int)__ldg(r1 + x0 * 3 + c) * xa[0] + (int)__ldg(r1 + x1 * 3 + c) * xa[1];
-                        val[c] = max(0, min(255, ((((yb[0] * (S0 >> 4)) >> 16) + ((yb[1] * (S1 >> 4)) >> 16)) + 2) >> 2));
-                    }
-                } else {
-                    int xa[4], yb[4], H[4][3];
-                    cubic_taps(dx, im.scale_x, sx, xa);
-                    cubic_taps(dy, im.scale_y, sy, yb);
-#pragma unroll
-                    for (int k = 0; k < 4; ++k) {
-                        const unsigned char* row = im.src + (size_t)max(0, min(im.sh - 1, sy - 1 + k)) * im.sw * 3;
-                        H[k][0] = H[k][1] = H[k][2] = 0;
-#pragma unroll
-                        for (int j = 0; j < 4; ++j) {
-                            const unsigned char* px = row + max(0, min(im.sw - 1, sx - 1 + j)) * 3;
-#pragma unroll
-                            for (int c = 0; c < 3; ++c) H[k][c] += (int)__ldg(px + c) * xa[j];
-                        }
-                    }
-#pragma unroll
-                    for (int c = 0; c < 3; ++c) {
-                        int r;
-                        if (dx * 3 + c < vec_end) {
-                            float t = __fmul_rn((float)H[3][c], __fmul_rn((float)yb[3], 1.f / 4194304.f));
-                            t = __fadd_rn(__fmul_rn((float)H[2][c], __fmul_rn((float)yb[2], 1.f / 4194304.f)), t);
-                            t = __fadd_rn(__fmul_rn((float)H[1][c], __fmul_rn((float)yb[1], 1.f / 4194304.f)), t);
-                            t = __fadd_rn(__fmul_rn((float)H[0][c], __fmul_rn((float)yb[0], 1.f / 4194304.f)), t);
-                            r = __float2int_rn(t);
-                        } else {
-                            r = (H[0][c] * yb[0] + H[1][c] * yb[1] + H[2][c] * yb[2] + H[3][c] * yb[3] + (1 << 21)) >> 22;
-                        }
-                        val[c] = max(0, min(255, r));
-                    }
-                }
+                direct_pixel(im, dx, dy, val);              // strong downscale: more source rows than the buffer holds
             } else if (im.interp == 1) {
-                int sy, yb[2];
-                linear_taps(dy, im.scale_y, im.sh, false, sy, yb);
-                const int* h0 = Hs + ((max(0, min(im.sh - 1, sy)) - r_lo) * kLbTile + lx) * 3;
-                const int* h1 = Hs + ((max(0, min(im.sh - 1, sy + 1)) - r_lo) * kLbTile + lx) * 3;
-#pragma unroll
-                for (int c = 0; c < 3; ++c)
-                    val[c] = max(0, min(255, ((((yb[0] * (h0[c] >> 4)) >> 16) + ((yb[1] * (h1[c] >> 4)) >> 16)) + 2) >> 2));
-            } else {
-                int sy, yb[4];
-                cubic_taps(dy, im.scale_y, sy, yb);
-                const int* h[4];
-#pragma unroll
-                for (int k = 0; k < 4; ++k) h[k] = Hs + ((max(0, min(im.sh - 1, sy - 1 + k)) - r_lo) * kLbTile + lx) * 3;
-                float bf[4];
-#pragma unroll
-                for (int k = 0; k < 4; ++k) bf[k] = __fmul_rn((float)yb[k], 1.f / 4194304.f);
+                const int sy = ysrc[yy], b0 = ytap[yy][0], b1 = ytap[yy][1];
+                const float* h0 = Hs + ((max(0, min(im.sh - 1, sy)) - r_lo) * kLbTile + lx) * 3;
+                const float* h1 = Hs + ((max(0, min(im.sh - 1, sy + 1)) - r_lo) * kLbTile + lx) * 3;
 #pragma unroll
                 for (int c = 0; c < 3; ++c) {
-                    const int H0 = h[0][c], H1 = h[1][c], H2 = h[2][c], H3 = h[3][c];
+                    const int S0 = __float2int_rn(h0[c]), S1 = __float2int_rn(h1[c]);
+                    val[c] = max(0, min(255, ((((b0 * (S0 >> 4)) >> 16) + ((b1 * (S1 >> 4)) >> 16)) + 2) >> 2));
+                }
+            } else {
+                const int sy = ysrc[yy];
+                const float* h[4];
+#pragma unroll
+                for (int k = 0; k < 4; ++k) h[k] = Hs + ((max(0, min(im.sh - 1, sy - 1 + k)) - r_lo) * kLbTile + lx) * 3;
+#pragma unroll
+                for (int c = 0; c < 3; ++c) {
+                    const float H0 = h[0][c], H1 = h[1][c], H2 = h[2][c], H3 = h[3][c];
                     int r;
                     if (dx * 3 + c < vec_end) {
-                        float t = __fmul_rn((float)H3, bf[3]);
-                        t = __fadd_rn(__fmul_rn((float)H2, bf[2]), t);
-                        t = __fadd_rn(__fmul_rn((float)H1, bf[1]), t);
-                        t = __fadd_rn(__fmul_rn((float)H0, bf[0]), t);
+                        float t = __fmul_rn(H3, ybf[yy][3]);
+                        t = __fadd_rn(__fmul_rn(H2, ybf[yy][2]), t);
+                        t = __fadd_rn(__fmul_rn(H1, ybf[yy][1]), t);
+                        t = __fadd_rn(__fmul_rn(H0, ybf[yy][0]), t);
                         r = __float2int_rn(t);
                     } else {
-                        r = (H0 * yb[0] + H1 * yb[1] + H2 * yb[2] + H3 * yb[3] + (1 << 21)) >> 22;
+                        r = (__float2int_rn(H0) * ytap[yy][0] + __float2int_rn(H1) * ytap[yy][1] + __float2int_rn(H2) * ytap[yy][2] +
+                             __float2int_rn(H3) * ytap[yy][3] + (1 << 21)) >> 22;
                     }
                     val[c] = max(0, min(255, r));
                 }
             }
         }
-        store_pixel(out, canvas, plane, b, canvas_w, x, y, val);
+        if (out) {
+            float* o = out + (size_t)b * 3 * plane + (size_t)y * canvas_w + x;
+#pragma unroll
+            for (int c = 0; c < 3; ++c) o[c * plane] = lut[val[c]];
+        }
+        if (canvas) {
+            unsigned char* q = canvas + ((size_t)b * plane + (size_t)y * canvas_w + x) * 3;
+#pragma unroll
+            for (int c = 0; c < 3; ++c) q[c] = (unsigned char)val[c];
+        }
     }
 }
 
