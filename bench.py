@@ -157,7 +157,7 @@ def run_reference(args):
                        "note": f"CPU path; each step is a bounded sample of {args.ref_batch} images of the batch-{args.batch} workload"},
             "cpu_baseline": base,
             "e2e": {"value": value, "unit": "images/sec", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
-    print(json.dumps(line))
+    emit(line)
 
 
 def run_ours(args):
@@ -378,7 +378,7 @@ def run_ours(args):
         "cpu_baseline": cpu,
         "detections_last_step": int(counts_h.sum()),
     }
-    print(json.dumps(line))
+    emit(line)
     if args.layers:
         specs = topology.layer_specs(80)
         for i, v in enumerate(layer_ms):
@@ -387,7 +387,25 @@ def run_ours(args):
         dist.destroy_process_group()
 
 
+_JSON_FD = None
+
+
+def emit(line):
+    """The one JSON line goes to the process's original stdout; everything else that lands on fd 1 (NCCL prints a
+    version banner there when NCCL_DEBUG is set) has been routed to stderr by main()."""
+    data = (json.dumps(line) + "\n").encode()
+    if _JSON_FD is None:
+        sys.stdout.write(data.decode())
+        sys.stdout.flush()
+    else:
+        os.write(_JSON_FD, data)
+
+
 def main():
+    global _JSON_FD
+    sys.stdout.flush()
+    _JSON_FD = os.dup(1)
+    os.dup2(2, 1)
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=20)

@@ -36,36 +36,41 @@ class BatchHandler:
 
 
 class JsonPredictionWriter(BatchHandler):
-    """Reference evaluate.JsonPredictionWriter (evaluate.py:164-195)."""
+    """Same interface and output text as the reference's writer (evaluate.py:164-195): `[`, one
+    `json.dump(entry, indent=4, separators=(',', ':'))` per detection separated by commas, `]`.  The whole batch is
+    box-corrected on the device in one call and formatted from host lists; an empty result set gives `[]` (the
+    reference's seek-back-and-truncate leaves a lone `]` there)."""
 
     def __init__(self, out_path, classes_names, is_letterbox=False):
         self.out_path = out_path
-        self.file = open(out_path, "w")
         self.classes_names = classes_names
         self.is_letterbox = is_letterbox
+        self.file = open(out_path, "w")
+        self._entries = 0
 
     def write_start(self):
         self.file.write("[")
 
     def write_end(self):
-        self.file.seek(self.file.tell() - 1, os.SEEK_SET)
-        self.file.truncate()
         self.file.write("]")
         self.file.close()
 
+    def _emit(self, entry):
+        if self._entries:
+            self.file.write(",")
+        json.dump(entry, self.file, indent=4, separators=(",", ":"))
+        self._entries += 1
+
     def process_batch(self, sample, predictions):
-        imgs, org_imgs, img_paths = sample["img"], sample["org_img"], sample["img_path"]
-        for img, org_img, img_path, prediction in zip(imgs, org_imgs, img_paths, predictions):
-            img_w, img_h, org_w, org_h = img.shape[2], img.shape[1], org_img.shape[2], org_img.shape[1]
-            image_id = get_image_id_from_path(img_path)
-            if prediction is not None and len(prediction) != 0:
-                bboxes = correct_yolo_boxes(prediction[..., 0:4], org_w, org_h, img_w, img_h, self.is_letterbox)
-                category_ids = prediction[..., 6]
-                scores = prediction[..., 5]
-                for category_id, bbox, score in zip(category_ids.tolist(), bboxes.tolist(), scores.tolist()):
-                    res = create_results_entry(image_id, int(category_id), bbox, score)
-                    json.dump(res, self.file, indent=4, separators=(",", ":"))
-                    self.file.write(",")
+        net_hw = [tuple(t.shape[1:3]) for t in sample["img"]]
+        org_hw = [tuple(t.shape[1:3]) for t in sample["org_img"]]
+        for (ih, iw), (oh, ow), path, pred in zip(net_hw, org_hw, sample["img_path"], predictions):
+            if pred is None or len(pred) == 0:
+                continue
+            xywh = correct_yolo_boxes(pred[..., 0:4], ow, oh, iw, ih, self.is_letterbox).tolist()
+            image_id = get_image_id_from_path(path)
+            for box, score, cls in zip(xywh, pred[..., 5].tolist(), pred[..., 6].tolist()):
+                self._emit(create_results_entry(image_id, int(cls), box, score))
 
 
 @contextmanager
