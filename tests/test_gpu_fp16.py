@@ -85,6 +85,11 @@ CASES = [
     (59, 2, 19, 19, False),    # up1 512->256 1x1
     (60, 1, 38, 38, False),    # 768->256 1x1 (concat input width)
     (74, 1, 76, 76, False),    # head 256->255 @ /8
+    # widths that are multiples of 38 take the halo-tile kernel (conv_halo.cu): 3 x 38 tiles, nine shifted views of one patch
+    (3, 2, 10, 76, True),      # 32->64, Cin=32 (64-byte pixels), residual, last row strip partial (10 = 3*3 + 1)
+    (3, 1, 5, 38, False),      # same without residual (two-deep staging ring), single column tile
+    (6, 2, 7, 114, True),      # 64->128, Cin=64, two 64-channel halves per tile, residual
+    (6, 1, 152, 152, True),    # the real stage-1 map
 ]
 
 

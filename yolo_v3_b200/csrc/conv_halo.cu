@@ -1,0 +1,394 @@
+// K1h: 3x3 stride-1 convolution of the wide, shallow layers (Cin = 32 or 64 at 304x304 / 152x152) from a HALO TILE.
+//
+// conv_tc.cu fetches the A operand of a 3x3 layer with nine im2col TMA loads per tile, i.e. every input pixel travels
+// from L2 to shared memory nine times.  For the layers with few channels that traffic, not DRAM and not the tensor
+// pipe, is the bound (profiles/README.md: 6-8 TB/s through L2 at 30-47 % tensor-pipe activity).  Here each input
+// pixel is staged ONCE: a tile is 3 output rows x 38 output columns, its input patch (5 x 40 pixels, zero-filled
+// outside the image by TMA) is one tiled TMA load, and the nine taps are nine views of that patch -- the UMMA
+// descriptor of tap (ky, kx) simply starts (ky*40 + kx) pixels into it.  That works because a K-major descriptor
+// may start at any row of a TMA-written swizzled tile (base_offset 0; tools/probes/umma_shift_probe.cu).
+//
+//   * GEMM rows follow the PATCH pitch: row m = r*40 + c (r < 3, c < 40), so that tap (ky, kx) of row m is patch
+//     pixel m + ky*40 + kx for every m: one descriptor, 128 consecutive 128-byte (Cin = 64) or 64-byte (Cin = 32)
+//     rows.  Rows with c >= 38 or m >= 120 are by-products (they read the neighbour's pixels) and are dropped.
+//   * weights: the CTA's whole [BN = 64][9*Cin] slab is resident in shared memory (36 / 72 KB);
+//   * epilogue as in conv_tc.cu (TMEM -> scale/bias -> LeakyReLU -> +residual -> fp16 -> swizzled staging -> TMA
+//     store), except that the staging row of GEMM row m is the COMPACT index r*38 + c and the residual load / output
+//     store are 4-D boxes {64 ch, 38, 3, 1} of the NHWC tensor (rows past the image are clipped by the tensor map).
+//
+// Same warp roles, barriers, TMEM double buffering, watchdog and programmatic dependent launch as conv_tc.cu.
+#include <algorithm>
+#include <cstdlib>
+
+#include "tc_ptx.cuh"
+#include "yb_internal.h"
+
+namespace yb {
+namespace {
+
+constexpr int kHP = 40;                       // patch pitch in pixels = tile columns + 2
+constexpr int kHC = 38;                       // output columns per tile
+constexpr int kHR = 3;                        // output rows per tile
+constexpr int kHPatchPix = (kHR + 2) * kHP;   // 200 pixels per TMA load
+constexpr int kHSlotPix = 216;                // rows reserved per stage: the last tap reads up to row 2*40+2+127 = 209
+constexpr int kHValid = kHR * kHC;            // 114 output pixels per tile
+constexpr int kHBN = 64;                      // output channels per tile
+constexpr int kHThreads = 768;                // warp 0 producer, 2 MMA, 3 TMEM alloc + store issuer, 4 residual, 8-23 epilogue
+constexpr int kHEpiWarps = 16;
+constexpr int kHMaxStages = 12;
+constexpr int kHMaxRing = 4;
+constexpr size_t kHSmemBudget = 227 * 1024;
+constexpr uint32_t kHStgBytes = 128 * 128;    // one staging sub-tile: 128 rows x 64 fp16
+
+struct HaloArgs {
+    int tiles_x, tiles_y, n_tiles, total_tiles;
+    int stages, slot_bytes;
+    const float* scale; const float* bias;
+    int cout_pad, tab_bytes;
+    int leaky, has_res, ring;
+    int* dbg;
+};
+
+__device__ __forceinline__ void tma_load_4d(const CUtensorMap* tm, uint32_t dst, uint32_t bar, int c0, int c1, int c2, int c3) {
+    asm volatile(
+        "cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
+        ::"r"(dst), "l"(tm), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "r"(c3) : "memory");
+}
+__device__ __forceinline__ void tma_store_4d(const CUtensorMap* tm, uint32_t src, int c0, int c1, int c2, int c3) {
+    asm volatile("cp.async.bulk.tensor.4d.global.shared::cta.bulk_group [%0, {%2, %3, %4, %5}], [%1];"
+                 ::"l"(tm), "r"(src), "r"(c0), "r"(c1), "r"(c2), "r"(c3) : "memory");
+}
+
+struct TileXY { int n_tile, x0, y0, img; };
+__device__ __forceinline__ TileXY tile_xy(const HaloArgs& a, int tile) {
+    TileXY t;
+    t.n_tile = tile % a.n_tiles;
+    const int mt = tile / a.n_tiles;
+    const int xt = mt % a.tiles_x, rest = mt / a.tiles_x;
+    t.x0 = xt * kHC;
+    t.y0 = (rest % a.tiles_y) * kHR;
+    t.img = rest / a.tiles_y;
+    return t;
+}
+
+template <int SWZ>
+__global__ void __launch_bounds__(kHThreads, 1)
+conv_halo_kernel(const __grid_constant__ CUtensorMap tmIn, const __grid_constant__ CUtensorMap tmB,
+                 const __grid_constant__ CUtensorMap tmOut, const __grid_constant__ CUtensorMap tmRes, const HaloArgs a) {
+    constexpr int BKE = SWZ / 2;                                // fp16 per pixel = Cin
+    constexpr uint32_t B_SLOT = kHBN * SWZ;                     // one tap of the weight slab: 64 rows x Cin
+    extern __shared__ uint8_t smem_raw[];
+    const uint32_t raw = smem_u32(smem_raw);
+    const uint32_t base = (raw + 1023u) & ~1023u;
+    uint8_t* gen = smem_raw + (base - raw);
+    // header: full[12] | empty[12] | tfull[2] | tempty[2] | tmem_ptr | sfull[4] | sempty[4] | sready[4] | bres
+    const uint32_t full0 = base, empty0 = base + 8 * kHMaxStages;
+    const uint32_t tfull0 = base + 16 * kHMaxStages, tempty0 = tfull0 + 16;
+    volatile uint32_t* tmem_ptr = reinterpret_cast<volatile uint32_t*>(gen + 16 * kHMaxStages + 32);
+    const uint32_t sfull0 = base + 16 * kHMaxStages + 64, sempty0 = sfull0 + 32, sready0 = sempty0 + 32, bres_bar = sready0 + 32;
+    const float* tab = reinterpret_cast<const float*>(gen + 1024);         // scale[cout_pad] | bias[cout_pad]
+    const uint32_t stg0 = base + 1024 + (uint32_t)a.tab_bytes;
+    const uint32_t bres0 = stg0 + (uint32_t)a.ring * kHStgBytes;
+    const uint32_t stage0 = bres0 + 9 * B_SLOT;
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int tile_first = blockIdx.x, tile_step = gridDim.x;
+
+    for (int i = threadIdx.x; i < a.cout_pad; i += kHThreads) {
+        float* t = reinterpret_cast<float*>(gen + 1024);
+        t[i] = __ldg(a.scale + i);
+        t[a.cout_pad + i] = __ldg(a.bias + i);
+    }
+    if (warp == 0 && lane == 0) {
+        prefetch_tmap(&tmIn); prefetch_tmap(&tmB); prefetch_tmap(&tmOut);
+        if (a.has_res) prefetch_tmap(&tmRes);
+    }
+    if (warp == 2 && lane == 0) {
+        for (int s = 0; s < a.stages; ++s) { mbar_init(full0 + 8 * s, 1); mbar_init(empty0 + 8 * s, 1); }
+        for (int i = 0; i < 2; ++i) { mbar_init(tfull0 + 8 * i, 1); mbar_init(tempty0 + 8 * i, kHEpiWarps); }
+        for (int i = 0; i < kHMaxRing; ++i) { mbar_init(sfull0 + 8 * i, 1); mbar_init(sempty0 + 8 * i, 1); mbar_init(sready0 + 8 * i, kHEpiWarps); }
+        mbar_init(bres_bar, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 3) tmem_alloc(smem_u32(const_cast<uint32_t*>(tmem_ptr)), 2 * kHBN);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_ptr;
+    pdl_launch_dependents();
+    pdl_wait_prior();
+
+    if (warp == 0) {
+        // ===== TMA producer: the resident weight slab once, then one patch per tile =====
+        if (tile_first < a.total_tiles && elect_one()) {
+            const int n0 = (tile_first % a.n_tiles) * kHBN;                // gridDim.x is a multiple of n_tiles
+            mbar_arrive_expect_tx(bres_bar, 9 * B_SLOT);
+#pragma unroll 1
+            for (int t = 0; t < 9; ++t) tma_load_2d(&tmB, bres0 + t * B_SLOT, bres_bar, t * BKE, n0);
+        }
+        __syncwarp();
+        int stage = 0;
+        uint32_t phase = 0;
+        for (int tile = tile_first; tile < a.total_tiles; tile += tile_step) {
+            const TileXY t = tile_xy(a, tile);
+            mbar_wait(empty0 + 8 * stage, phase ^ 1, a.dbg, 0, stage);
+            if (elect_one()) {
+                mbar_arrive_expect_tx(full0 + 8 * stage, (uint32_t)kHPatchPix * SWZ);
+                tma_load_4d(&tmIn, stage0 + stage * a.slot_bytes, full0 + 8 * stage, 0, t.x0 - 1, t.y0 - 1, t.img);
+            }
+            __syncwarp();
+            if (++stage == a.stages) { stage = 0; phase ^= 1; }
+        }
+    } else if (warp == 2) {
+        // ===== MMA issuer: nine taps = nine shifted views of the patch =====
+        const uint32_t idesc = make_idesc(kHBN, 128);
+        int stage = 0;
+        uint32_t phase = 0, acc = 0, acc_phase = 0;
+        if (tile_first < a.total_tiles) mbar_wait(bres_bar, 0, a.dbg, 1, 600);
+        const uint64_t bdesc0 = make_smem_desc<SWZ>(bres0);
+        for (int tile = tile_first; tile < a.total_tiles; tile += tile_step) {
+            mbar_wait(tempty0 + 8 * acc, acc_phase ^ 1, a.dbg, 1, 100 + (int)acc);
+            mbar_wait(full0 + 8 * stage, phase, a.dbg, 1, stage);
+            tc_fence_after();
+            if (elect_one()) {
+                const uint32_t d_tmem = tmem_base + acc * kHBN;
+                const uint64_t adesc0 = make_smem_desc<SWZ>(stage0 + stage * a.slot_bytes);
+#pragma unroll
+                for (int t = 0; t < 9; ++t) {
+                    const uint64_t ad = adesc0 + (uint64_t)(((t / 3) * kHP + (t % 3)) * SWZ >> 4);
+                    const uint64_t bd = bdesc0 + (uint64_t)(t * (B_SLOT >> 4));
+#pragma unroll
+                    for (int k = 0; k < BKE / 16; ++k) umma_f16(d_tmem, ad + 2 * k, bd + 2 * k, idesc, (t | k) != 0);
+                }
+                umma_commit(empty0 + 8 * stage);
+                umma_commit(tfull0 + 8 * acc);
+            }
+            __syncwarp();
+            if (++stage == a.stages) { stage = 0; phase ^= 1; }
+            acc ^= 1;
+            if (acc == 0) acc_phase ^= 1;
+        }
+    } else if (warp == 4) {
+        // ===== residual prefetch into the staging ring (compact 3 x 38 pixel rows) =====
+        if (lane == 0 && a.has_res) {
+            uint32_t g = 0;
+            for (int tile = tile_first; tile < a.total_tiles; tile += tile_step, ++g) {
+                const TileXY t = tile_xy(a, tile);
+                const uint32_t buf = g % (uint32_t)a.ring, ph = (g / (uint32_t)a.ring) & 1u;
+                mbar_wait(sempty0 + 8 * buf, ph ^ 1, a.dbg, 3, 300 + (int)buf);
+                mbar_arrive_expect_tx(sfull0 + 8 * buf, (uint32_t)kHValid * 128u);
+                tma_load_4d(&tmRes, stg0 + buf * kHStgBytes, sfull0 + 8 * buf, t.n_tile * kHBN, t.x0, t.y0, t.img);
+            }
+        }
+        __syncwarp();
+    } else if (warp == 3) {
+        // ===== store issuer =====
+        if (lane == 0) {
+            uint32_t g = 0;
+            for (int tile = tile_first; tile < a.total_tiles; tile += tile_step, ++g) {
+                const TileXY t = tile_xy(a, tile);
+                const uint32_t buf = g % (uint32_t)a.ring, ph = (g / (uint32_t)a.ring) & 1u;
+                mbar_wait(sready0 + 8 * buf, ph, a.dbg, 4, 700 + (int)buf);
+                tma_store_4d(&tmOut, stg0 + buf * kHStgBytes, t.n_tile * kHBN, t.x0, t.y0, t.img);
+                tma_store_commit();
+                if (g > 0) {                                  // the previous store has finished reading its buffer
+                    tma_store_wait_read<1>();
+                    mbar_arrive(sempty0 + 8 * ((g - 1) % (uint32_t)a.ring));
+                }
+            }
+            tma_store_wait_all();
+        }
+        __syncwarp();
+    } else if (warp >= 8) {
+        // ===== epilogue: TMEM lane m = GEMM row m = patch-pitch pixel (r, c); staging row = r*38 + c =====
+        const int q = warp & 3, part = (warp - 8) >> 2;        // TMEM lane quarter, 16-column group of the 64
+        const int m = q * 32 + lane;
+        const int r = m / kHP, c = m - r * kHP;
+        const bool valid = r < kHR && c < kHC;
+        const int mp = r * kHC + c;                             // compact row (only used when valid)
+        const int xr = mp & 7;
+        uint32_t acc = 0, acc_phase = 0, g = 0;
+        for (int tile = tile_first; tile < a.total_tiles; tile += tile_step, ++g) {
+            const int n0 = (tile % a.n_tiles) * kHBN;
+            const uint32_t buf = g % (uint32_t)a.ring, ph = (g / (uint32_t)a.ring) & 1u;
+            mbar_wait(tfull0 + 8 * acc, acc_phase, a.dbg, 2, 200 + (int)acc);
+            tc_fence_after();
+            uint32_t r0[16];
+            tmem_ld16(tmem_base + acc * kHBN + ((uint32_t)(q * 32) << 16) + (uint32_t)(part * 16), r0);
+            if (a.has_res) mbar_wait(sfull0 + 8 * buf, ph, a.dbg, 2, 400 + (int)buf);
+            else mbar_wait(sempty0 + 8 * buf, ph ^ 1, a.dbg, 2, 500 + (int)buf);
+            tmem_ld_wait();
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(tempty0 + 8 * acc);      // accumulator drained into registers
+            if (valid) {
+                uint8_t* srow = gen + (stg0 - base) + buf * kHStgBytes + (uint32_t)mp * 128u;
+                const int n = n0 + part * 16;
+                const float4* sc = reinterpret_cast<const float4*>(tab + n);
+                const float4* bi = reinterpret_cast<const float4*>(tab + a.cout_pad + n);
+                float v[16];
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                    const float4 s4 = sc[i], b4 = bi[i];
+                    v[4 * i + 0] = fmaf(__uint_as_float(r0[4 * i + 0]), s4.x, b4.x);
+                    v[4 * i + 1] = fmaf(__uint_as_float(r0[4 * i + 1]), s4.y, b4.y);
+                    v[4 * i + 2] = fmaf(__uint_as_float(r0[4 * i + 2]), s4.z, b4.z);
+                    v[4 * i + 3] = fmaf(__uint_as_float(r0[4 * i + 3]), s4.w, b4.w);
+                }
+                if (a.leaky) {
+#pragma unroll
+                    for (int i = 0; i < 16; ++i) v[i] = leaky(v[i]);
+                }
+#pragma unroll
+                for (int h = 0; h < 2; ++h) {
+                    uint4* p = reinterpret_cast<uint4*>(srow + (((part * 2 + h) ^ xr) << 4));
+                    if (a.has_res) {
+                        const uint4 rr = *p;
+                        const __half2* hh = reinterpret_cast<const __half2*>(&rr);
+#pragma unroll
+                        for (int i = 0; i < 4; ++i) {
+                            const float2 f = __half22float2(hh[i]);
+                            v[8 * h + 2 * i] += f.x;
+                            v[8 * h + 2 * i + 1] += f.y;
+                        }
+                    }
+                    uint4 pk;
+                    __half2* ph2 = reinterpret_cast<__half2*>(&pk);
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) ph2[i] = __floats2half2_rn(v[8 * h + 2 * i], v[8 * h + 2 * i + 1]);
+                    *p = pk;
+                }
+            }
+            fence_async_smem();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(sready0 + 8 * buf);
+            acc ^= 1;
+            if (acc == 0) acc_phase ^= 1;
+        }
+    }
+
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 3) {
+        tc_fence_after();
+        tmem_dealloc(tmem_base, 2 * kHBN);
+    }
+}
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+EncodeTiledFn g_enc = nullptr;
+
+std::string halo_err(const char* what, CUresult r) { return std::string(what) + " failed with CUresult " + std::to_string((int)r); }
+
+}  // namespace
+
+bool halo_supported(const ConvArgs& a) {
+    static const bool enabled = !(getenv("YB_HALO") && atoi(getenv("YB_HALO")) == 0);
+    if (!enabled) return false;
+    if (a.ks != 3 || a.stride != 1 || a.pad != 1 || a.upsample || a.out_f32) return false;
+    if (a.Cin != 32 && a.Cin != 64) return false;
+    if (a.W % kHC != 0 || a.Cout % kHBN != 0 || a.Cout > 128) return false;
+    // (the scheme trades 11 % of the tensor work -- 114 useful rows of 128 -- for ~5x less L2->SM traffic; with these
+    // channel counts the im2col kernel is traffic-bound, so every eligible shape takes it)
+    return !(a.in_ld % 8 || a.out_ld % 8 || (a.res && a.res_ld % 8));
+}
+
+std::string halo_make_plan(HaloPlan& p, const ConvArgs& a, const __half* w16, int cout_pad, int K, int num_sms) {
+    if (!g_enc) {
+        void* f = nullptr;
+        cudaDriverEntryPointQueryResult qr;
+        cudaError_t e = cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &f, cudaEnableDefault, &qr);
+        if (e != cudaSuccess || qr != cudaDriverEntryPointSuccess || !f) return "cuTensorMapEncodeTiled not available from the driver";
+        g_enc = reinterpret_cast<EncodeTiledFn>(f);
+    }
+    p.swz = a.Cin == 32 ? 64 : 128;
+    p.cout_pad = cout_pad;
+    p.tiles_x = a.W / kHC;
+    p.tiles_y = (a.H + kHR - 1) / kHR;
+    p.n_tiles = a.Cout / kHBN;
+    p.total_tiles = a.B * p.tiles_x * p.tiles_y * p.n_tiles;
+    p.ring = a.res ? 4 : 2;
+    p.tab_bytes = (int)(((size_t)2 * cout_pad * sizeof(float) + 1023) & ~(size_t)1023);
+    p.slot_bytes = (int)(((size_t)kHSlotPix * p.swz + 1023) & ~(size_t)1023);
+    const size_t fixed = 1024 + 1024 + p.tab_bytes + (size_t)p.ring * kHStgBytes + (size_t)9 * kHBN * p.swz;
+    p.stages = (int)std::min<size_t>(kHMaxStages, (kHSmemBudget - fixed) / p.slot_bytes);
+    if (p.stages < 2) return "not enough shared memory for two patch stages";
+    p.smem = fixed + (size_t)p.stages * p.slot_bytes;
+    p.grid = std::min(p.total_tiles, num_sms);
+    p.grid -= p.grid % p.n_tiles;
+    if (p.grid <= 0) return "grid too small for the tile split";
+    const CUtensorMapSwizzle swz = p.swz == 128 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B;
+    const cuuint32_t es4[4] = {1, 1, 1, 1};
+    const cuuint32_t es2[2] = {1, 1};
+    {   // input patch: NHWC as (C, W, H, N); box = Cin x 40 x 5 x 1, out-of-image pixels read as zero (the conv padding)
+        cuuint64_t dims[4] = {(cuuint64_t)a.Cin, (cuuint64_t)a.W, (cuuint64_t)a.H, (cuuint64_t)a.B};
+        cuuint64_t st[3] = {(cuuint64_t)a.in_ld * 2, (cuuint64_t)a.W * a.in_ld * 2, (cuuint64_t)a.H * a.W * a.in_ld * 2};
+        cuuint32_t box[4] = {(cuuint32_t)a.Cin, (cuuint32_t)kHP, (cuuint32_t)(kHR + 2), 1};
+        CUresult r = g_enc(&p.tmIn, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 4, const_cast<void*>(a.in), dims, st, box, es4,
+                           CU_TENSOR_MAP_INTERLEAVE_NONE, swz, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+        if (r != CUDA_SUCCESS) return halo_err("cuTensorMapEncodeTiled(halo input)", r);
+    }
+    {   // weights [cout_pad][K], one tap x 64 rows per box
+        cuuint64_t dims[2] = {(cuuint64_t)K, (cuuint64_t)cout_pad};
+        cuuint64_t st[1] = {(cuuint64_t)K * 2};
+        cuuint32_t box[2] = {(cuuint32_t)a.Cin, (cuuint32_t)kHBN};
+        CUresult r = g_enc(&p.tmB, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, const_cast<__half*>(w16), dims, st, box, es2,
+                           CU_TENSOR_MAP_INTERLEAVE_NONE, swz, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+        if (r != CUDA_SUCCESS) return halo_err("cuTensorMapEncodeTiled(halo weights)", r);
+    }
+    {   // output / residual: box = 64 ch x 38 x 3 x 1, 128B swizzle (staging rows are 128 bytes)
+        cuuint64_t dims[4] = {(cuuint64_t)a.Cout, (cuuint64_t)a.W, (cuuint64_t)a.H, (cuuint64_t)a.B};
+        cuuint64_t st[3] = {(cuuint64_t)a.out_ld * 2, (cuuint64_t)a.W * a.out_ld * 2, (cuuint64_t)a.H * a.W * a.out_ld * 2};
+        cuuint32_t box[4] = {(cuuint32_t)kHBN, (cuuint32_t)kHC, (cuuint32_t)kHR, 1};
+        CUresult r = g_enc(&p.tmOut, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 4, a.out, dims, st, box, es4, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                           CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+        if (r != CUDA_SUCCESS) return halo_err("cuTensorMapEncodeTiled(halo output)", r);
+        if (a.res) {
+            cuuint64_t rst[3] = {(cuuint64_t)a.res_ld * 2, (cuuint64_t)a.W * a.res_ld * 2, (cuuint64_t)a.H * a.W * a.res_ld * 2};
+            r = g_enc(&p.tmRes, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 4, const_cast<void*>(a.res), dims, rst, box, es4,
+                      CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                      CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+            if (r != CUDA_SUCCESS) return halo_err("cuTensorMapEncodeTiled(halo residual)", r);
+        } else {
+            p.tmRes = p.tmOut;
+        }
+    }
+    return "";
+}
+
+cudaError_t halo_launch(const HaloPlan& p, const ConvArgs& a, int* dbg, cudaStream_t s) {
+    HaloArgs h;
+    h.tiles_x = p.tiles_x; h.tiles_y = p.tiles_y; h.n_tiles = p.n_tiles; h.total_tiles = p.total_tiles;
+    h.stages = p.stages; h.slot_bytes = p.slot_bytes;
+    h.scale = a.scale; h.bias = a.bias;
+    h.cout_pad = p.cout_pad; h.tab_bytes = p.tab_bytes;
+    h.leaky = a.leaky; h.has_res = a.res != nullptr; h.ring = p.ring;
+    h.dbg = dbg;
+    static bool attr_done = false;
+    if (!attr_done) {
+        cudaError_t e = cudaFuncSetAttribute(conv_halo_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kHSmemBudget);
+        if (e != cudaSuccess) return e;
+        e = cudaFuncSetAttribute(conv_halo_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kHSmemBudget);
+        if (e != cudaSuccess) return e;
+        attr_done = true;
+    }
+    static const bool pdl = !(getenv("YB_TC_PDL") && atoi(getenv("YB_TC_PDL")) == 0);
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = dim3(p.grid);
+    cfg.blockDim = dim3(kHThreads);
+    cfg.dynamicSmemBytes = p.smem;
+    cfg.stream = s;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = pdl ? 1 : 0;
+    cudaError_t e = p.swz == 128 ? cudaLaunchKernelEx(&cfg, conv_halo_kernel<128>, p.tmIn, p.tmB, p.tmOut, p.tmRes, h)
+                                 : cudaLaunchKernelEx(&cfg, conv_halo_kernel<64>, p.tmIn, p.tmB, p.tmOut, p.tmRes, h);
+    if (e != cudaSuccess) return e;
+    return cudaGetLastError();
+}
+
+}  // namespace yb

@@ -27,8 +27,9 @@ struct Op {
     int layer = 0;
     bool stem = false;
     ConvArgs a{};
-    bool use_tc = false;
+    bool use_tc = false, use_halo = false;
     TcPlan tc;
+    HaloPlan halo;
     StemTcPlan stem_tc;
 };
 
@@ -259,7 +260,13 @@ struct PlanBuilder {
         if (p->mode == YB_MODE_FP16) {
             if (!tc_supported(a)) { err = "plan: layer " + L.key + " not supported by the tensor-core kernel"; return false; }
             op.use_tc = true;
-            std::string e = tc_make_plan(op.tc, a, L.d_w16, L.cout_pad, L.ks * L.ks * L.cin, c->num_sms);
+            std::string e;
+            if (halo_supported(a)) {
+                op.use_halo = true;
+                e = halo_make_plan(op.halo, a, L.d_w16, L.cout_pad, L.ks * L.ks * L.cin, c->num_sms);
+            } else {
+                e = tc_make_plan(op.tc, a, L.d_w16, L.cout_pad, L.ks * L.ks * L.cin, c->num_sms);
+            }
             if (!e.empty()) { err = "plan: layer " + L.key + ": " + e; return false; }
         }
         p->ops.push_back(op);
@@ -385,6 +392,8 @@ int run_ops(yb_ctx* c, Plan* p, const float* x, int n_ops, cudaStream_t s) {
                 e = stem_tc_launch(op.stem_tc, x, p->B, p->H, p->W, L.d_w16, L.d_scale, L.d_bias, c->dbg, s);
             else
                 e = launch_stem<float>(x, static_cast<float*>(op.a.out), L.d_w32, L.d_scale, L.d_bias, p->B, p->H, p->W, s);
+        } else if (op.use_halo) {
+            e = halo_launch(op.halo, op.a, c->dbg, s);
         } else if (op.use_tc) {
             e = tc_launch(op.tc, op.a, c->dbg, s);
         } else {
@@ -1025,10 +1034,17 @@ int yb_run_layer(yb_ctx* c, int li, const void* in, int B, int H, int W, const v
     a.leaky = L.bn ? 1 : 0; a.upsample = 0; a.out_f32 = head ? 1 : 0;
     if (c->mode == YB_MODE_FP16) {
         if (!tc_supported(a)) return fail(c, YB_E_UNSUPPORTED, "yb_run_layer: layer not supported by the tensor-core kernel");
-        TcPlan tp;
-        std::string e = tc_make_plan(tp, a, L.d_w16, L.cout_pad, L.ks * L.ks * L.cin, c->num_sms);
-        if (!e.empty()) return fail(c, YB_E_CUDA, "yb_run_layer: " + e);
-        YB_CUDA(c, tc_launch(tp, a, c->dbg, s));
+        if (halo_supported(a)) {
+            HaloPlan hp;
+            std::string e = halo_make_plan(hp, a, L.d_w16, L.cout_pad, L.ks * L.ks * L.cin, c->num_sms);
+            if (!e.empty()) return fail(c, YB_E_CUDA, "yb_run_layer: " + e);
+            YB_CUDA(c, halo_launch(hp, a, c->dbg, s));
+        } else {
+            TcPlan tp;
+            std::string e = tc_make_plan(tp, a, L.d_w16, L.cout_pad, L.ks * L.ks * L.cin, c->num_sms);
+            if (!e.empty()) return fail(c, YB_E_CUDA, "yb_run_layer: " + e);
+            YB_CUDA(c, tc_launch(tp, a, c->dbg, s));
+        }
     } else {
         YB_CUDA(c, launch_conv_simt<float>(a, L.d_w32, L.cout_pad, s));
     }

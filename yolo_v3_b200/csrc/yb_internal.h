@@ -94,6 +94,17 @@ std::string stem_tc_make_plan(StemTcPlan& p, __half* out, long out_ld, int B, in
 cudaError_t stem_tc_launch(const StemTcPlan& p, const float* x, int B, int H, int W, const __half* w16, const float* scale,
                            const float* bias, int* dbg, cudaStream_t s);
 
+// conv_halo.cu  (3x3 stride-1 layers with Cin = 32 / 64 from a halo tile: every input pixel staged once)
+struct HaloPlan {
+    CUtensorMap tmIn, tmB, tmOut, tmRes;
+    int swz = 128, cout_pad = 0, tiles_x = 0, tiles_y = 0, n_tiles = 0, total_tiles = 0;
+    int ring = 0, tab_bytes = 0, slot_bytes = 0, stages = 0, grid = 0;
+    size_t smem = 0;
+};
+bool halo_supported(const ConvArgs& a);
+std::string halo_make_plan(HaloPlan& p, const ConvArgs& a, const __half* w16, int cout_pad, int K, int num_sms);
+cudaError_t halo_launch(const HaloPlan& p, const ConvArgs& a, int* dbg, cudaStream_t s);
+
 // decode.cu
 struct DecodeScale {
     const float* logits;  // NHWC [B,h,w,ld] (internal) or NCHW [B,3*(5+C),h,w] (API)
