@@ -90,6 +90,8 @@ CASES = [
     (3, 1, 5, 38, False),      # same without residual (two-deep staging ring), single column tile
     (6, 2, 7, 114, True),      # 64->128, Cin=64, two 64-channel halves per tile, residual
     (6, 1, 152, 152, True),    # the real stage-1 map
+    (1, 2, 20, 152, False),    # 32->64 stride 2 through four parity planes (output 10 x 76: partial last strip)
+    (1, 1, 14, 76, False),     # same, one column tile, odd number of output rows
 ]
 
 

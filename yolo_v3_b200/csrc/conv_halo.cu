@@ -1,4 +1,4 @@
-// K1h: 3x3 stride-1 convolution of the wide, shallow layers (Cin = 32 or 64 at 304x304 / 152x152) from a HALO TILE.
+// K1h: 3x3 convolution (stride 1, and stride 2 through parity planes) of the wide, shallow layers (Cin = 32 or 64 at 304x304 / 152x152) from a HALO TILE.
 //
 // conv_tc.cu fetches the A operand of a 3x3 layer with nine im2col TMA loads per tile, i.e. every input pixel travels
 // from L2 to shared memory nine times.  For the layers with few channels that traffic, not DRAM and not the tensor
@@ -31,6 +31,11 @@ constexpr int kHC = 38;                       // output columns per tile
 constexpr int kHR = 3;                        // output rows per tile
 constexpr int kHPatchPix = (kHR + 2) * kHP;   // 200 pixels per TMA load
 constexpr int kHSlotPix = 216;                // rows reserved per stage: the last tap reads up to row 2*40+2+127 = 209
+// stride 2: the input patch is staged as four parity planes (odd/even input rows x odd/even input columns, each 4 x 40
+// pixels, loaded with a traversal stride of 2), so that every tap is again a unit-pitch view: tap ky in {0,2} reads the
+// odd-row plane at row offset ky/2, ky = 1 the even-row plane, and likewise for kx.
+constexpr int kHPlanePix = 4 * kHP;           // 160 pixels per plane
+constexpr int kHSlotPix2 = 4 * kHPlanePix + 48;   // last view: plane 3 + (1*40+1) + 127 = 648 < 688
 constexpr int kHValid = kHR * kHC;            // 114 output pixels per tile
 constexpr int kHBN = 64;                      // output channels per tile
 constexpr int kHThreads = 768;                // warp 0 producer, 2 MMA, 3 TMEM alloc + store issuer, 4 residual, 8-23 epilogue
@@ -71,7 +76,7 @@ __device__ __forceinline__ TileXY tile_xy(const HaloArgs& a, int tile) {
     return t;
 }
 
-template <int SWZ>
+template <int SWZ, int STRIDE>
 __global__ void __launch_bounds__(kHThreads, 1)
 conv_halo_kernel(const __grid_constant__ CUtensorMap tmIn, const __grid_constant__ CUtensorMap tmB,
                  const __grid_constant__ CUtensorMap tmOut, const __grid_constant__ CUtensorMap tmRes, const HaloArgs a) {
@@ -133,8 +138,17 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmIn, const __grid_constant
             const TileXY t = tile_xy(a, tile);
             mbar_wait(empty0 + 8 * stage, phase ^ 1, a.dbg, 0, stage);
             if (elect_one()) {
-                mbar_arrive_expect_tx(full0 + 8 * stage, (uint32_t)kHPatchPix * SWZ);
-                tma_load_4d(&tmIn, stage0 + stage * a.slot_bytes, full0 + 8 * stage, 0, t.x0 - 1, t.y0 - 1, t.img);
+                const uint32_t slot = stage0 + stage * a.slot_bytes, fb = full0 + 8 * stage;
+                if (STRIDE == 1) {
+                    mbar_arrive_expect_tx(fb, (uint32_t)kHPatchPix * SWZ);
+                    tma_load_4d(&tmIn, slot, fb, 0, t.x0 - 1, t.y0 - 1, t.img);
+                } else {
+                    // planes: 0 = odd rows / odd cols, 1 = odd rows / even cols, 2 = even rows / odd cols, 3 = even / even
+                    mbar_arrive_expect_tx(fb, 4u * kHPlanePix * SWZ);
+#pragma unroll
+                    for (int pl = 0; pl < 4; ++pl)
+                        tma_load_4d(&tmIn, slot + pl * kHPlanePix * SWZ, fb, 0, 2 * t.x0 - 1 + (pl & 1), 2 * t.y0 - 1 + (pl >> 1), t.img);
+                }
             }
             __syncwarp();
             if (++stage == a.stages) { stage = 0; phase ^= 1; }
@@ -155,7 +169,11 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmIn, const __grid_constant
                 const uint64_t adesc0 = make_smem_desc<SWZ>(stage0 + stage * a.slot_bytes);
 #pragma unroll
                 for (int t = 0; t < 9; ++t) {
-                    const uint64_t ad = adesc0 + (uint64_t)(((t / 3) * kHP + (t % 3)) * SWZ >> 4);
+                    const int ky = t / 3, kx = t % 3;
+                    // stride 1: pixel (ky, kx) of the patch; stride 2: plane (ky odd?, kx odd?) at offset (ky/2, kx/2)
+                    const int pix = STRIDE == 1 ? ky * kHP + kx
+                                                : (((ky & 1) << 1) | (kx & 1)) * kHPlanePix + (ky >> 1) * kHP + (kx >> 1);
+                    const uint64_t ad = adesc0 + (uint64_t)((pix * SWZ) >> 4);
                     const uint64_t bd = bdesc0 + (uint64_t)(t * (B_SLOT >> 4));
 #pragma unroll
                     for (int k = 0; k < BKE / 16; ++k) umma_f16(d_tmem, ad + 2 * k, bd + 2 * k, idesc, (t | k) != 0);
@@ -287,9 +305,17 @@ std::string halo_err(const char* what, CUresult r) { return std::string(what) + 
 bool halo_supported(const ConvArgs& a) {
     static const bool enabled = !(getenv("YB_HALO") && atoi(getenv("YB_HALO")) == 0);
     if (!enabled) return false;
-    if (a.ks != 3 || a.stride != 1 || a.pad != 1 || a.upsample || a.out_f32) return false;
-    if (a.Cin != 32 && a.Cin != 64) return false;
-    if (a.W % kHC != 0 || a.Cout % kHBN != 0 || a.Cout > 128) return false;
+    if (a.ks != 3 || a.pad != 1 || a.upsample || a.out_f32) return false;
+    if (a.stride == 1) {
+        if (a.Cin != 32 && a.Cin != 64) return false;
+    } else if (a.stride == 2) {
+        // four parity planes per stage: fits next to the resident weights only for 64-byte pixels
+        static const bool s2 = !(getenv("YB_HALO_S2") && atoi(getenv("YB_HALO_S2")) == 0);
+        if (!s2 || a.Cin != 32 || a.H % 2 || a.W % 2) return false;
+    } else {
+        return false;
+    }
+    if (a.Wo % kHC != 0 || a.Cout % kHBN != 0 || a.Cout > 128) return false;
     // (the scheme trades 11 % of the tensor work -- 114 useful rows of 128 -- for ~5x less L2->SM traffic; with these
     // channel counts the im2col kernel is traffic-bound, so every eligible shape takes it)
     return !(a.in_ld % 8 || a.out_ld % 8 || (a.res && a.res_ld % 8));
@@ -305,13 +331,14 @@ std::string halo_make_plan(HaloPlan& p, const ConvArgs& a, const __half* w16, in
     }
     p.swz = a.Cin == 32 ? 64 : 128;
     p.cout_pad = cout_pad;
-    p.tiles_x = a.W / kHC;
-    p.tiles_y = (a.H + kHR - 1) / kHR;
+    p.stride = a.stride;
+    p.tiles_x = a.Wo / kHC;
+    p.tiles_y = (a.Ho + kHR - 1) / kHR;
     p.n_tiles = a.Cout / kHBN;
     p.total_tiles = a.B * p.tiles_x * p.tiles_y * p.n_tiles;
     p.ring = a.res ? 4 : 2;
     p.tab_bytes = (int)(((size_t)2 * cout_pad * sizeof(float) + 1023) & ~(size_t)1023);
-    p.slot_bytes = (int)(((size_t)kHSlotPix * p.swz + 1023) & ~(size_t)1023);
+    p.slot_bytes = (int)(((size_t)(a.stride == 1 ? kHSlotPix : kHSlotPix2) * p.swz + 1023) & ~(size_t)1023);
     const size_t fixed = 1024 + 1024 + p.tab_bytes + (size_t)p.ring * kHStgBytes + (size_t)9 * kHBN * p.swz;
     p.stages = (int)std::min<size_t>(kHMaxStages, (kHSmemBudget - fixed) / p.slot_bytes);
     if (p.stages < 2) return "not enough shared memory for two patch stages";
@@ -326,7 +353,12 @@ std::string halo_make_plan(HaloPlan& p, const ConvArgs& a, const __half* w16, in
         cuuint64_t dims[4] = {(cuuint64_t)a.Cin, (cuuint64_t)a.W, (cuuint64_t)a.H, (cuuint64_t)a.B};
         cuuint64_t st[3] = {(cuuint64_t)a.in_ld * 2, (cuuint64_t)a.W * a.in_ld * 2, (cuuint64_t)a.H * a.W * a.in_ld * 2};
         cuuint32_t box[4] = {(cuuint32_t)a.Cin, (cuuint32_t)kHP, (cuuint32_t)(kHR + 2), 1};
-        CUresult r = g_enc(&p.tmIn, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 4, const_cast<void*>(a.in), dims, st, box, es4,
+        cuuint32_t es_in[4] = {1, 1, 1, 1};
+        if (a.stride == 2) {        // one parity plane: 40 x 4 pixels traversed with stride 2 (box extent = 2x the count)
+            box[1] = 2 * kHP; box[2] = 2 * 4;
+            es_in[1] = 2; es_in[2] = 2;
+        }
+        CUresult r = g_enc(&p.tmIn, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 4, const_cast<void*>(a.in), dims, st, box, es_in,
                            CU_TENSOR_MAP_INTERLEAVE_NONE, swz, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
         if (r != CUDA_SUCCESS) return halo_err("cuTensorMapEncodeTiled(halo input)", r);
     }
@@ -339,14 +371,14 @@ std::string halo_make_plan(HaloPlan& p, const ConvArgs& a, const __half* w16, in
         if (r != CUDA_SUCCESS) return halo_err("cuTensorMapEncodeTiled(halo weights)", r);
     }
     {   // output / residual: box = 64 ch x 38 x 3 x 1, 128B swizzle (staging rows are 128 bytes)
-        cuuint64_t dims[4] = {(cuuint64_t)a.Cout, (cuuint64_t)a.W, (cuuint64_t)a.H, (cuuint64_t)a.B};
-        cuuint64_t st[3] = {(cuuint64_t)a.out_ld * 2, (cuuint64_t)a.W * a.out_ld * 2, (cuuint64_t)a.H * a.W * a.out_ld * 2};
+        cuuint64_t dims[4] = {(cuuint64_t)a.Cout, (cuuint64_t)a.Wo, (cuuint64_t)a.Ho, (cuuint64_t)a.B};
+        cuuint64_t st[3] = {(cuuint64_t)a.out_ld * 2, (cuuint64_t)a.Wo * a.out_ld * 2, (cuuint64_t)a.Ho * a.Wo * a.out_ld * 2};
         cuuint32_t box[4] = {(cuuint32_t)kHBN, (cuuint32_t)kHC, (cuuint32_t)kHR, 1};
         CUresult r = g_enc(&p.tmOut, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 4, a.out, dims, st, box, es4, CU_TENSOR_MAP_INTERLEAVE_NONE,
                            CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
         if (r != CUDA_SUCCESS) return halo_err("cuTensorMapEncodeTiled(halo output)", r);
         if (a.res) {
-            cuuint64_t rst[3] = {(cuuint64_t)a.res_ld * 2, (cuuint64_t)a.W * a.res_ld * 2, (cuuint64_t)a.H * a.W * a.res_ld * 2};
+            cuuint64_t rst[3] = {(cuuint64_t)a.res_ld * 2, (cuuint64_t)a.Wo * a.res_ld * 2, (cuuint64_t)a.Ho * a.Wo * a.res_ld * 2};
             r = g_enc(&p.tmRes, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 4, const_cast<void*>(a.res), dims, rst, box, es4,
                       CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
                       CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
@@ -368,9 +400,11 @@ cudaError_t halo_launch(const HaloPlan& p, const ConvArgs& a, int* dbg, cudaStre
     h.dbg = dbg;
     static bool attr_done = false;
     if (!attr_done) {
-        cudaError_t e = cudaFuncSetAttribute(conv_halo_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kHSmemBudget);
+        cudaError_t e = cudaFuncSetAttribute(conv_halo_kernel<128, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kHSmemBudget);
         if (e != cudaSuccess) return e;
-        e = cudaFuncSetAttribute(conv_halo_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kHSmemBudget);
+        e = cudaFuncSetAttribute(conv_halo_kernel<64, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kHSmemBudget);
+        if (e != cudaSuccess) return e;
+        e = cudaFuncSetAttribute(conv_halo_kernel<64, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kHSmemBudget);
         if (e != cudaSuccess) return e;
         attr_done = true;
     }
@@ -385,8 +419,10 @@ cudaError_t halo_launch(const HaloPlan& p, const ConvArgs& a, int* dbg, cudaStre
     attr[0].val.programmaticStreamSerializationAllowed = 1;
     cfg.attrs = attr;
     cfg.numAttrs = pdl ? 1 : 0;
-    cudaError_t e = p.swz == 128 ? cudaLaunchKernelEx(&cfg, conv_halo_kernel<128>, p.tmIn, p.tmB, p.tmOut, p.tmRes, h)
-                                 : cudaLaunchKernelEx(&cfg, conv_halo_kernel<64>, p.tmIn, p.tmB, p.tmOut, p.tmRes, h);
+    cudaError_t e;
+    if (p.stride == 2) e = cudaLaunchKernelEx(&cfg, conv_halo_kernel<64, 2>, p.tmIn, p.tmB, p.tmOut, p.tmRes, h);
+    else if (p.swz == 128) e = cudaLaunchKernelEx(&cfg, conv_halo_kernel<128, 1>, p.tmIn, p.tmB, p.tmOut, p.tmRes, h);
+    else e = cudaLaunchKernelEx(&cfg, conv_halo_kernel<64, 1>, p.tmIn, p.tmB, p.tmOut, p.tmRes, h);
     if (e != cudaSuccess) return e;
     return cudaGetLastError();
 }

@@ -97,7 +97,7 @@ cudaError_t stem_tc_launch(const StemTcPlan& p, const float* x, int B, int H, in
 // conv_halo.cu  (3x3 stride-1 layers with Cin = 32 / 64 from a halo tile: every input pixel staged once)
 struct HaloPlan {
     CUtensorMap tmIn, tmB, tmOut, tmRes;
-    int swz = 128, cout_pad = 0, tiles_x = 0, tiles_y = 0, n_tiles = 0, total_tiles = 0;
+    int swz = 128, stride = 1, cout_pad = 0, tiles_x = 0, tiles_y = 0, n_tiles = 0, total_tiles = 0;
     int ring = 0, tab_bytes = 0, slot_bytes = 0, stages = 0, grid = 0;
     size_t smem = 0;
 };
