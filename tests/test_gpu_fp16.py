@@ -120,10 +120,13 @@ def test_tc_layer_vs_torch(fp16_ctx, sd, li, B, H, W, with_res):
                            f"{tuple(int(v) for v in bad.nonzero()[0])}")
 
 
-@pytest.mark.parametrize("B,H,W", [(2, 40, 56), (1, 64, 32), (3, 17, 23)])
-def test_tc_stem_vs_torch(fp16_ctx, sd, B, H, W):
+# rows=True: the experimental pixel-row stem (stem_rows.cu, YB_STEM_ROWS=1, widths that are multiples of 38)
+@pytest.mark.parametrize("B,H,W,rows", [(2, 40, 56, False), (1, 64, 32, False), (3, 17, 23, False), (1, 64, 608, False),
+                                        (2, 10, 76, True), (1, 3, 38, True), (3, 7, 114, True), (1, 64, 608, True)])
+def test_tc_stem_vs_torch(fp16_ctx, sd, B, H, W, rows, monkeypatch):
     """Cin=3 stem on the tensor cores: NCHW fp32 image in, NHWC fp16 out (im2col rows built by producer warps)."""
     lib, ctx = fp16_ctx
+    monkeypatch.setenv("YB_STEM_ROWS", "1" if rows else "0")
     rs = np.random.RandomState(7)
     x = torch.from_numpy(rs.rand(B, 3, H, W).astype(np.float32))
     out = torch.full((B, H, W, 32), float("nan"), device="cuda", dtype=torch.float16)

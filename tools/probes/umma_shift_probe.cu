@@ -123,6 +123,114 @@ __global__ void __launch_bounds__(128, 1) probe(const __grid_constant__ CUtensor
     }
 }
 
+// ---- second question: un-swizzled 16-byte rows with a free leading-dimension offset ---------------------------
+// For a Cin = 3 stem the patch can be kept as [pixel][8 fp16] (16 bytes per pixel).  In the un-swizzled K-major
+// layout a K = 16 MMA reads, for row m, one 16-byte chunk at start + m*16 and a second one LBO bytes further: if LBO
+// may be ANY multiple of 16 bytes, the second chunk can be "the same pixel array seen from another filter tap", and
+// one MMA covers two taps.  out2[case][m][n]; cases: (row shift of chunk 0, pixel distance of chunk 1).
+__device__ __forceinline__ uint64_t make_desc_noswz(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+    return (uint64_t)((saddr >> 4) & 0x3FFF) | ((uint64_t)((lbo_bytes >> 4) & 0x3FFF) << 16) | ((uint64_t)((sbo_bytes >> 4) & 0x3FFF) << 32) |
+           (1ull << 46);
+}
+constexpr int kNsRows = 384, kNsCases = 6;
+__constant__ int c_ns_shift[kNsCases] = {0, 1, 3, 0, 5, 40};
+__constant__ int c_ns_dist[kNsCases] = {1, 1, 38, 40, 77, 82};
+
+__global__ void __launch_bounds__(128, 1) probe_noswz(const __half* __restrict__ A, const __half* __restrict__ B, float* out, int* status) {
+    extern __shared__ uint8_t raw[];
+    const uint32_t base = (smem_u32(raw) + 1023u) & ~1023u;
+    uint8_t* gen = raw + (base - smem_u32(raw));
+    const uint32_t bar_mma = base + 8;
+    volatile uint32_t* tmem_ptr = reinterpret_cast<volatile uint32_t*>(gen + 16);
+    const uint32_t sA = base + 1024;                                    // [384 rows][8 fp16]
+    const uint32_t sB = sA + 8 * 1024;                                  // [2 chunks][64 rows][8 fp16]: LBO = 1024, SBO = 128
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    for (int i = threadIdx.x; i < kNsRows; i += 128) reinterpret_cast<uint4*>(gen + 1024)[i] = reinterpret_cast<const uint4*>(A)[i];
+    for (int i = threadIdx.x; i < 2 * kN; i += 128) reinterpret_cast<uint4*>(gen + 1024 + 8 * 1024)[i] = reinterpret_cast<const uint4*>(B)[i];
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    if (threadIdx.x == 0) { mbar_init(bar_mma, 1); asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+    if (warp == 0) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(const_cast<uint32_t*>(tmem_ptr))), "r"(64u) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    const uint32_t tmem = *tmem_ptr;
+    const uint32_t idesc = (1u << 4) | ((uint32_t)(kN >> 3) << 17) | ((uint32_t)(kM >> 4) << 24);
+    bool ok = true;
+    uint32_t phase = 0;
+    for (int cs = 0; cs < kNsCases && ok; ++cs) {
+        if (threadIdx.x == 0) {
+            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+            const uint64_t ad = make_desc_noswz(sA + (uint32_t)c_ns_shift[cs] * 16u, (uint32_t)c_ns_dist[cs] * 16u, 128u);
+            const uint64_t bd = make_desc_noswz(sB, 1024u, 128u);
+            umma_f16(tmem, ad, bd, idesc, 0);
+            umma_commit(bar_mma);
+        }
+        ok = mbar_wait(bar_mma, phase);
+        phase ^= 1;
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        if (ok) {
+            const int m = warp * 32 + lane;
+            float* o = out + ((size_t)cs * kM + m) * kN;
+            for (int c0 = 0; c0 < kN; c0 += 16) {
+                uint32_t r[16];
+                tmem_ld16(tmem + ((uint32_t)(warp * 32) << 16) + c0, r);
+                asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+                for (int i = 0; i < 16; ++i) o[c0 + i] = __uint_as_float(r[i]);
+            }
+        }
+        asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+        __syncthreads();
+    }
+    if (!ok && threadIdx.x == 0) status[0] = 1;
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    if (warp == 0) {
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(64u) : "memory");
+    }
+}
+
+int run_noswz() {
+    std::vector<__half> hA((size_t)kNsRows * 8), hB((size_t)2 * kN * 8);
+    std::vector<int> iA(hA.size()), iB(hB.size());
+    srand(77);
+    for (size_t i = 0; i < hA.size(); ++i) { iA[i] = rand() % 7 - 3; hA[i] = __float2half((float)iA[i]); }
+    for (size_t i = 0; i < hB.size(); ++i) { iB[i] = rand() % 5 - 2; hB[i] = __float2half((float)iB[i]); }
+    __half *dA, *dB; float* dO; int* dS;
+    CK(cudaMalloc(&dA, hA.size() * 2)); CK(cudaMalloc(&dB, hB.size() * 2));
+    CK(cudaMalloc(&dO, sizeof(float) * kNsCases * kM * kN)); CK(cudaMalloc(&dS, 4));
+    CK(cudaMemcpy(dA, hA.data(), hA.size() * 2, cudaMemcpyHostToDevice));
+    CK(cudaMemcpy(dB, hB.data(), hB.size() * 2, cudaMemcpyHostToDevice));
+    CK(cudaMemset(dO, 0xFF, sizeof(float) * kNsCases * kM * kN)); CK(cudaMemset(dS, 0, 4));
+    CK(cudaFuncSetAttribute(probe_noswz, cudaFuncAttributeMaxDynamicSharedMemorySize, 32 * 1024));
+    probe_noswz<<<1, 128, 32 * 1024>>>(dA, dB, dO, dS);
+    cudaError_t e = cudaDeviceSynchronize();
+    if (e != cudaSuccess) { printf("no-swizzle probe: kernel failed: %s\n", cudaGetErrorString(e)); return 1; }
+    int st = 0; CK(cudaMemcpy(&st, dS, 4, cudaMemcpyDeviceToHost));
+    std::vector<float> hO((size_t)kNsCases * kM * kN);
+    CK(cudaMemcpy(hO.data(), dO, hO.size() * 4, cudaMemcpyDeviceToHost));
+    const int shift[kNsCases] = {0, 1, 3, 0, 5, 40}, dist[kNsCases] = {1, 1, 38, 40, 77, 82};
+    printf("un-swizzled 16-byte rows, K = 16 = [row m+shift | row m+shift+dist], barrier timeout: %d\n", st);
+    for (int cs = 0; cs < kNsCases; ++cs) {
+        long bad = 0;
+        for (int m = 0; m < kM; ++m)
+            for (int n = 0; n < kN; ++n) {
+                int ref = 0;
+                for (int c = 0; c < 8; ++c) {
+                    ref += iA[(size_t)(m + shift[cs]) * 8 + c] * iB[(size_t)(0 * kN + n) * 8 + c];
+                    ref += iA[(size_t)(m + shift[cs] + dist[cs]) * 8 + c] * iB[(size_t)(1 * kN + n) * 8 + c];
+                }
+                if (hO[((size_t)cs * kM + m) * kN + n] != (float)ref) ++bad;
+            }
+        printf("  start row %2d, LBO = %2d rows: %s (%ld / %d wrong)\n", shift[cs], dist[cs], bad ? "MISMATCH" : "exact", bad, kM * kN);
+    }
+    cudaFree(dA); cudaFree(dB); cudaFree(dO); cudaFree(dS);
+    return 0;
+}
+
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
                                   const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
                                   CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
@@ -184,5 +292,6 @@ int main() {
     EncodeTiledFn enc = reinterpret_cast<EncodeTiledFn>(f);
     int rc = run(128, enc);
     rc |= run(64, enc);
+    rc |= run_noswz();
     return rc;
 }

@@ -31,6 +31,8 @@ struct Op {
     TcPlan tc;
     HaloPlan halo;
     StemTcPlan stem_tc;
+    bool stem_rows = false;
+    StemRowsPlan stem_rows_plan;
 };
 
 struct Plan {
@@ -307,7 +309,9 @@ int build_plan(yb_ctx* c, int B, int H, int W, Plan** out) {
         op.layer = 0; op.stem = true;
         op.a.out = buf[0];
         if (p->mode == YB_MODE_FP16) {
-            std::string e = stem_tc_make_plan(op.stem_tc, static_cast<__half*>(buf[0]), 32, B, H, W, c->num_sms);
+            op.stem_rows = stem_rows_supported(B, H, W);
+            std::string e = op.stem_rows ? stem_rows_make_plan(op.stem_rows_plan, static_cast<__half*>(buf[0]), 32, B, H, W, c->num_sms)
+                                         : stem_tc_make_plan(op.stem_tc, static_cast<__half*>(buf[0]), 32, B, H, W, c->num_sms);
             if (!e.empty()) return bail("plan: stem: " + e);
         }
         p->ops.push_back(op);
@@ -388,7 +392,9 @@ int run_ops(yb_ctx* c, Plan* p, const float* x, int n_ops, cudaStream_t s) {
         const Layer& L = c->layers[op.layer];
         cudaError_t e;
         if (op.stem) {
-            if (p->mode == YB_MODE_FP16)
+            if (p->mode == YB_MODE_FP16 && op.stem_rows)
+                e = stem_rows_launch(op.stem_rows_plan, x, p->B, p->H, p->W, L.d_w16, L.d_scale, L.d_bias, c->dbg, s);
+            else if (p->mode == YB_MODE_FP16)
                 e = stem_tc_launch(op.stem_tc, x, p->B, p->H, p->W, L.d_w16, L.d_scale, L.d_bias, c->dbg, s);
             else
                 e = launch_stem<float>(x, static_cast<float*>(op.a.out), L.d_w32, L.d_scale, L.d_bias, p->B, p->H, p->W, s);
@@ -1008,7 +1014,12 @@ int yb_run_layer(yb_ctx* c, int li, const void* in, int B, int H, int W, const v
     const Layer& L = c->layers[li];
     if (li == 0) {
         cudaError_t e;
-        if (c->mode == YB_MODE_FP16) {
+        if (c->mode == YB_MODE_FP16 && stem_rows_supported(B, H, W)) {
+            StemRowsPlan sp;
+            std::string err = stem_rows_make_plan(sp, static_cast<__half*>(out), 32, B, H, W, c->num_sms);
+            if (!err.empty()) return fail(c, YB_E_CUDA, "yb_run_layer: " + err);
+            e = stem_rows_launch(sp, static_cast<const float*>(in), B, H, W, L.d_w16, L.d_scale, L.d_bias, c->dbg, s);
+        } else if (c->mode == YB_MODE_FP16) {
             StemTcPlan sp;
             std::string err = stem_tc_make_plan(sp, static_cast<__half*>(out), 32, B, H, W, c->num_sms);
             if (!err.empty()) return fail(c, YB_E_CUDA, "yb_run_layer: " + err);

@@ -94,6 +94,17 @@ std::string stem_tc_make_plan(StemTcPlan& p, __half* out, long out_ld, int B, in
 cudaError_t stem_tc_launch(const StemTcPlan& p, const float* x, int B, int H, int W, const __half* w16, const float* scale,
                            const float* bias, int* dbg, cudaStream_t s);
 
+// stem_rows.cu  (Cin = 3 stem from a [pixel][8 fp16] patch, tap pairs through the leading-dimension offset; W % 38 == 0)
+struct StemRowsPlan {
+    CUtensorMap tmOut;
+    int tiles_x = 0, tiles_y = 0, total_tiles = 0, grid = 0;
+    size_t smem = 0;
+};
+bool stem_rows_supported(int B, int H, int W);
+std::string stem_rows_make_plan(StemRowsPlan& p, __half* out, long out_ld, int B, int H, int W, int num_sms);
+cudaError_t stem_rows_launch(const StemRowsPlan& p, const float* x, int B, int H, int W, const __half* w16, const float* scale,
+                             const float* bias, int* dbg, cudaStream_t s);
+
 // conv_halo.cu  (3x3 stride-1 layers with Cin = 32 / 64 from a halo tile: every input pixel staged once)
 struct HaloPlan {
     CUtensorMap tmIn, tmB, tmOut, tmRes;
