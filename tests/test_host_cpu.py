@@ -164,3 +164,16 @@ def test_two_rank_gloo_plumbing():
     for p in procs:
         p.join(timeout=60)
     assert sorted(results) == [(0, True), (1, True)]
+
+
+def test_host_helpers_of_the_next_rows(oracle):
+    """Pure-host pieces of the pre-/post-path mirrors: letterbox geometry and the evaluate.py result entries."""
+    import json
+    from yolo_v3_b200.evaluate import create_results_entry, get_image_id_from_path
+    from yolo_v3_b200.utils import letterbox_transforms
+    for inner, outer in (((602, 452), (416, 416)), ((333, 500), (416, 416)), ((1280, 720), (608, 608)), ((64, 64), (96, 96))):
+        assert letterbox_transforms(inner, outer) == oracle.letterbox_transforms(inner, outer)
+    assert letterbox_transforms((602, 452), (416, 416))[:4] == (416, 312, 0, 52)           # SURVEY.md 8c fixture
+    assert get_image_id_from_path("coco/images/val2014/COCO_val2014_000000000139.jpg") == 139
+    e = create_results_entry(139, 17, [1.5, 2.0, 30.0, 40.25], 0.875)
+    assert json.dumps(e, separators=(",", ":")) == '{"image_id":139,"category_id":17,"bbox":[1.5,2.0,30.0,40.25],"score":0.875}'
