@@ -276,16 +276,18 @@ def run_ours(args):
 
     # ---- roofline: section times of the same step, CUDA events per section on the launch stream ----
     import ctypes
-    _lib.check(lib.yb_set_profiling(ctx, 1), ctx)          # events at the section boundaries only
-    conv_ms = dec_ms = post_ms = 0.0
-    reps = min(args.steps, 10)
+    # events at the section boundaries, recorded without synchronising so that the steps still run back to back as in
+    # the timed loop above; one query at the end averages them
+    _lib.check(lib.yb_set_profiling(ctx, 3), ctx)
+    reps = min(args.steps, 16)
+    for i in range(3):
+        net.detect_raw(xs[i & 1], CONF_THR, NMS_THR, False, True, cap)
+    a, b, c = ctypes.c_float(), ctypes.c_float(), ctypes.c_float()
+    lib.yb_get_section_ms(ctx, ctypes.byref(a), ctypes.byref(b), ctypes.byref(c))      # discard the warm-up sets
     for i in range(reps):
         net.detect_raw(xs[i & 1], CONF_THR, NMS_THR, False, True, cap)
-        a, b, c = ctypes.c_float(), ctypes.c_float(), ctypes.c_float()
-        lib.yb_get_section_ms(ctx, ctypes.byref(a), ctypes.byref(b), ctypes.byref(c))
-        conv_ms += a.value / reps
-        dec_ms += b.value / reps
-        post_ms += c.value / reps
+    lib.yb_get_section_ms(ctx, ctypes.byref(a), ctypes.byref(b), ctypes.byref(c))
+    conv_ms, dec_ms, post_ms = a.value, b.value, c.value
     layer_ms = []
     if args.layers:
         _lib.check(lib.yb_set_profiling(ctx, 2), ctx)      # + one event per convolution

@@ -184,7 +184,9 @@ long long yb_launch_count(const yb_ctx* ctx);
 /* Device time (ms) of the convolution stack / decode / post-process sections of the last
  * yb_forward/yb_detect call with profiling enabled.  yb_set_profiling level: 0 off, 1 = one CUDA event at
  * each section boundary (does not disturb the back-to-back launches inside the convolution stack),
- * 2 = additionally an event after every convolution (per-layer times, serialises the launches). */
+ * 2 = additionally an event after every convolution (per-layer times, serialises the launches), 3 = (yb_detect
+ * only) section events recorded without any synchronisation, so that calls still run back to back; yb_get_section_ms
+ * then synchronises once and returns the average over the (at most 16) calls made since the previous query. */
 int yb_set_profiling(yb_ctx* ctx, int enabled);
 int yb_get_section_ms(yb_ctx* ctx, float* conv_ms, float* decode_ms, float* post_ms);
 /* Per-layer timing of the last profiled call: ms[i] for the i-th convolution (75), returns count. */

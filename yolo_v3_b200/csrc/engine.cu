@@ -79,6 +79,11 @@ struct yb_ctx {
     long long launches = 0;
     bool profiling = false;
     bool profile_layers = false;      // profiling level 2: an event after every convolution (perturbs PDL overlap)
+    // profiling level 3 (yb_detect only): section events go to a rotating bank of kProfBank sets and nothing is
+    // synchronised per call; yb_get_section_ms averages the sets recorded since the last query
+    bool profile_deferred = false;
+    std::vector<cudaEvent_t> bank;    // [kProfBank][4]: start, after conv stack, after decode/score, after post-process
+    int bank_next = 0, bank_count = 0;
     std::vector<cudaEvent_t> ev;
     float sec_ms[3] = {0, 0, 0};
     std::vector<float> layer_ms;
@@ -377,8 +382,19 @@ int build_plan(yb_ctx* c, int B, int H, int W, Plan** out) {
     return YB_OK;
 }
 
+constexpr int kProfBank = 16;
+
 int run_ops(yb_ctx* c, Plan* p, const float* x, int n_ops, cudaStream_t s) {
-    const bool prof = c->profiling;
+    const bool deferred = c->profiling && c->profile_deferred;
+    const bool prof = c->profiling && !deferred;
+    if (deferred) {
+        while ((int)c->bank.size() < kProfBank * 4) {
+            cudaEvent_t e;
+            YB_CUDA(c, cudaEventCreate(&e));
+            c->bank.push_back(e);
+        }
+        YB_CUDA(c, cudaEventRecord(c->bank[c->bank_next * 4 + 0], s));
+    }
     if (prof) {
         while ((int)c->ev.size() < (int)p->ops.size() + 4) {
             cudaEvent_t e;
@@ -408,6 +424,7 @@ int run_ops(yb_ctx* c, Plan* p, const float* x, int n_ops, cudaStream_t s) {
         if (e != cudaSuccess) return fail(c, YB_E_CUDA, "launch of layer " + L.key + ": " + cudaGetErrorString(e));
         ++c->launches;
         if (prof && (c->profile_layers || i == n_ops - 1)) YB_CUDA(c, cudaEventRecord(c->ev[i + 1], s));
+        if (deferred && i == n_ops - 1) YB_CUDA(c, cudaEventRecord(c->bank[c->bank_next * 4 + 1], s));
     }
     return YB_OK;
 }
@@ -500,6 +517,7 @@ void yb_destroy(yb_ctx* c) {
     cudaFree(c->lb_params);
     cudaFreeHost(c->dbg_host);
     for (cudaEvent_t e : c->ev) cudaEventDestroy(e);
+    for (cudaEvent_t e : c->bank) cudaEventDestroy(e);
     if (c->nccl_comm) comm_destroy(c->nccl_comm);
     delete c;
 }
@@ -680,7 +698,7 @@ int yb_forward(yb_ctx* c, const float* x, int B, int H, int W, float* det, void*
     else
         YB_CUDA(c, launch_decode(sc, 0, B, c->attrs, total_rows(H, W), det, s));
     ++c->launches;
-    if (c->profiling) {
+    if (c->profiling && !c->profile_deferred) {
         YB_CUDA(c, cudaEventRecord(c->ev[p->ops.size() + 1], s));
         return record_sections(c, (int)p->ops.size(), true, false, s);
     }
@@ -702,7 +720,7 @@ int yb_forward_logits(yb_ctx* c, const float* x, int B, int H, int W, float* l32
         YB_CUDA(c, launch_nhwc_to_nchw_f32<float>(p->logits[i], cp, 3 * c->attrs, B, p->gh[i] * p->gw[i], outs[i], s));
         ++c->launches;
     }
-    if (c->profiling) {
+    if (c->profiling && !c->profile_deferred) {
         YB_CUDA(c, cudaEventRecord(c->ev[p->ops.size() + 1], s));
         return record_sections(c, (int)p->ops.size(), false, false, s);
     }
@@ -724,7 +742,7 @@ int yb_backbone(yb_ctx* c, const float* x, int B, int H, int W, float* feat, voi
     else
         YB_CUDA(c, launch_nhwc_to_nchw_f32<float>(static_cast<const float*>(v.p), v.ld, v.C, B, v.H * v.W, feat, s));
     ++c->launches;
-    if (c->profiling) {
+    if (c->profiling && !c->profile_deferred) {
         YB_CUDA(c, cudaEventRecord(c->ev[p->n_backbone_ops + 1], s));
         return record_sections(c, p->n_backbone_ops, false, false, s);
     }
@@ -808,11 +826,19 @@ int yb_detect(yb_ctx* c, const float* x, int B, int H, int W, float conf, float 
         YB_CUDA(c, launch_decode(sc, 0, B, c->attrs, N, c->det_scratch, s));
     }
     ++c->launches;
-    if (c->profiling) YB_CUDA(c, cudaEventRecord(c->ev[n_ops + 1], s));
+    const bool deferred = c->profiling && c->profile_deferred;
+    if (deferred) YB_CUDA(c, cudaEventRecord(c->bank[c->bank_next * 4 + 2], s));
+    else if (c->profiling) YB_CUDA(c, cudaEventRecord(c->ev[n_ops + 1], s));
     PostArgs a{fused ? nullptr : c->det_scratch, B, N, c->num_classes, conf, nms, is_eval, use_nms, rows7, counts, src_index,
                cand_counts, cap};
     a.pre_scored = fused ? 1 : 0;
     YB_CUDA(c, launch_postprocess(a, c->post, &c->launches, s));
+    if (deferred) {
+        YB_CUDA(c, cudaEventRecord(c->bank[c->bank_next * 4 + 3], s));
+        c->bank_next = (c->bank_next + 1) % kProfBank;
+        c->bank_count = std::min(c->bank_count + 1, kProfBank);
+        return YB_OK;
+    }
     if (c->profiling) {
         YB_CUDA(c, cudaEventRecord(c->ev[n_ops + 2], s));
         return record_sections(c, n_ops, true, true, s);
@@ -986,12 +1012,30 @@ int yb_debug_words(const yb_ctx* c, int* out, int n) {
 int yb_set_profiling(yb_ctx* c, int enabled) {
     if (!c) return fail(nullptr, YB_E_ARG, "null ctx");
     c->profiling = enabled != 0;
-    c->profile_layers = enabled >= 2;
+    c->profile_layers = enabled == 2;
+    c->profile_deferred = enabled == 3;
+    c->bank_next = c->bank_count = 0;
     return YB_OK;
 }
 
 int yb_get_section_ms(yb_ctx* c, float* conv_ms, float* decode_ms, float* post_ms) {
     if (!c) return fail(nullptr, YB_E_ARG, "null ctx");
+    if (c->profile_deferred && c->bank_count > 0) {
+        // average over the yb_detect calls recorded since the last query (at most kProfBank), one synchronisation here
+        const int last = (c->bank_next + kProfBank - 1) % kProfBank;
+        YB_CUDA(c, cudaEventSynchronize(c->bank[last * 4 + 3]));
+        float sum[3] = {0.f, 0.f, 0.f};
+        for (int k = 0; k < c->bank_count; ++k) {
+            const int set = (c->bank_next + kProfBank - 1 - k) % kProfBank;
+            for (int j = 0; j < 3; ++j) {
+                float ms = 0.f;
+                YB_CUDA(c, cudaEventElapsedTime(&ms, c->bank[set * 4 + j], c->bank[set * 4 + j + 1]));
+                sum[j] += ms;
+            }
+        }
+        for (int j = 0; j < 3; ++j) c->sec_ms[j] = sum[j] / c->bank_count;
+        c->bank_count = 0;
+    }
     if (conv_ms) *conv_ms = c->sec_ms[0];
     if (decode_ms) *decode_ms = c->sec_ms[1];
     if (post_ms) *post_ms = c->sec_ms[2];
