@@ -66,6 +66,7 @@ struct TcArgs {
     int pf_dist;             // L2 prefetch distance of the A operand, in tiles of this CTA (0 = off)
     int b_early;             // weights are touched (resident load / L2 prefetch) before griddepcontrol.wait
     int srel;                // store issuer: staging-buffer stores allowed to stay unread (0, 1 or 2)
+    int epi_sleep;           // nanoseconds the epilogue warps back off between probes of the accumulator barrier (0 = spin)
     int* dbg;
     long long* trace;        // optional [6 roles][64 tiles][4] clock64 stamps of CTA 0 (YB_TC_TRACE=1)
 };
@@ -522,7 +523,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             const int m_unit = tile / a.n_tiles, n_tile = tile - m_unit * a.n_tiles;
             const int m0 = (m_unit * NCTA + (int)rank) * kBM, n0 = n_tile * a.BN;
             if (issuer) YB_TRACE(2, ti, 0);
-            mbar_wait(tfull0 + 8 * acc, acc_phase, a.dbg, 2, 200 + (int)acc);
+            mbar_wait_relaxed(tfull0 + 8 * acc, acc_phase, a.dbg, 2, 200 + (int)acc, a.epi_sleep);
             tc_fence_after();
             if (issuer) YB_TRACE(2, ti, 1);
             const uint32_t taddr = tmem_base + acc * acc_stride + ((uint32_t)(q * 32) << 16);
@@ -1127,6 +1128,11 @@ cudaError_t tc_launch(const TcPlan& p, const ConvArgs& a, int* dbg, cudaStream_t
     t.pf_dist = p.pf_dist;
     t.b_early = p.b_early;
     t.srel = p.srel;
+    {
+        static const int epi_sleep = getenv("YB_TC_EPI_SLEEP") ? std::max(0, std::min(2000, atoi(getenv("YB_TC_EPI_SLEEP")))) : 0;
+        // only where the main loop of a tile is long enough for the back-off not to matter (>= 8 k-blocks)
+        t.epi_sleep = p.num_kblocks >= 8 ? epi_sleep : 0;
+    }
     t.exp_tiled = p.exp_tiled;
     t.dbg = dbg;
     static bool attr_done = false;

@@ -78,6 +78,29 @@ __device__ __noinline__ void mbar_wait_slow(uint32_t bar, uint32_t parity, int* 
 __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity, int* dbg, int role, int which) {
     if (!mbar_try_wait(bar, parity)) mbar_wait_slow(bar, parity, dbg, role, which);
 }
+// Same, for waits that are long by construction (the sixteen epilogue warps waiting for the next accumulator while the
+// main loop runs): back off between probes instead of spinning -- the step runs at the board's power cap, and warps
+// that poll cost issue slots and energy.
+__device__ __noinline__ void mbar_wait_relaxed_slow(uint32_t bar, uint32_t parity, int* dbg, int role, int which, unsigned sleep_ns) {
+    const long long t0 = clock64();
+    while (!mbar_try_wait(bar, parity)) {
+        __nanosleep(sleep_ns);
+        if (clock64() - t0 > kWatchdogCycles) {
+            if (dbg) {
+                dbg[1] = (int)blockIdx.x; dbg[2] = role; dbg[3] = which; dbg[4] = (int)parity;
+                __threadfence_system();
+                dbg[0] = 1;
+                __threadfence_system();
+            }
+            __trap();
+        }
+    }
+}
+__device__ __forceinline__ void mbar_wait_relaxed(uint32_t bar, uint32_t parity, int* dbg, int role, int which, int sleep_ns) {
+    if (mbar_try_wait(bar, parity)) return;
+    if (sleep_ns > 0) mbar_wait_relaxed_slow(bar, parity, dbg, role, which, (unsigned)sleep_ns);
+    else mbar_wait_slow(bar, parity, dbg, role, which);
+}
 
 __device__ __forceinline__ void tma_load_2d(const CUtensorMap* tm, uint32_t dst, uint32_t bar, int c0, int c1) {
     asm volatile(
