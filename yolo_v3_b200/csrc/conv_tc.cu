@@ -62,6 +62,7 @@ struct TcArgs {
     int n_sub;               // sub-tiles per tile (BN / cs)
     int has_res;
     int exp_tiled;           // timing experiment: fetch 3x3 A tiles with tiled-mode TMA (results are wrong)
+    int exp_nostore;         // timing experiment: the store issuer recycles buffers without issuing the TMA store (results are wrong)
     int b_resident;          // 1: the CTA's whole weight slab [BN][K] is loaded once and stays in smem
     int pf_dist;             // L2 prefetch distance of the A operand, in tiles of this CTA (0 = off)
     int b_early;             // weights are touched (resident load / L2 prefetch) before griddepcontrol.wait
@@ -487,7 +488,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                 for (int j = 0; j < a.n_sub; ++j, ++g) {
                     const uint32_t buf = g % (uint32_t)a.ring, ph = (g / (uint32_t)a.ring) & 1u;
                     mbar_wait(sready0 + 8 * buf, ph, a.dbg, 4, 700 + (int)buf);
-                    tma_store_2d(&tmOut, stg0 + buf * stg_bytes, n0 + j * a.cs, m0);
+                    if (!a.exp_nostore) tma_store_2d(&tmOut, stg0 + buf * stg_bytes, n0 + j * a.cs, m0);
                     tma_store_commit();
                     // Recycle buffers: keep at most `srel` stores unread.  srel = ring - 2 is the latest release that
                     // still lets the epilogue warps start sub-tile g+1 while sub-tile g is being finished; with the
@@ -1134,6 +1135,10 @@ cudaError_t tc_launch(const TcPlan& p, const ConvArgs& a, int* dbg, cudaStream_t
         t.epi_sleep = p.num_kblocks >= 8 ? epi_sleep : 0;
     }
     t.exp_tiled = p.exp_tiled;
+    {
+        static const int nostore = getenv("YB_TC_EXP_NOSTORE") ? atoi(getenv("YB_TC_EXP_NOSTORE")) : 0;
+        t.exp_nostore = nostore;
+    }
     t.dbg = dbg;
     static bool attr_done = false;
     if (!attr_done) {
