@@ -92,6 +92,10 @@ CASES = [
     (6, 1, 152, 152, True),    # the real stage-1 map
     (1, 2, 20, 152, False),    # 32->64 stride 2 through four parity planes (output 10 x 76: partial last strip)
     (1, 1, 14, 76, False),     # same, one column tile, odd number of output rows
+    # 64->128 stride 2 with enough tiles to run as CTA pairs with resident half weight slabs (BN = 128 pair mode)
+    (4, 4, 304, 304, False),   # M = 92 416 = 361 full 256-row units
+    (4, 7, 304, 152, False),   # M = 80 864: odd number of 128-row tiles and a partial last one
+    (6, 9, 104, 104, True),    # 64->128 stride 1 at a width the halo kernel does not take: pair mode + residual ring
 ]
 
 

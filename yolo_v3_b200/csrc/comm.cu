@@ -28,27 +28,28 @@ struct Nccl {
     std::string err;
 };
 
+// Bound once per process; the function-local static makes the first call thread-safe.
 Nccl* nccl() {
-    static Nccl n;
-    static bool tried = false;
-    if (tried) return &n;
-    tried = true;
-    const char* names[] = {"libnccl.so.2", "libnccl.so"};
-    for (const char* nm : names) {
-        n.h = dlopen(nm, RTLD_NOW | RTLD_GLOBAL);
-        if (n.h) break;
-    }
-    if (!n.h) { n.err = std::string("cannot dlopen libnccl.so.2: ") + dlerror(); return &n; }
+    static Nccl n = [] {
+        Nccl n;
+        const char* names[] = {"libnccl.so.2", "libnccl.so"};
+        for (const char* nm : names) {
+            n.h = dlopen(nm, RTLD_NOW | RTLD_GLOBAL);
+            if (n.h) break;
+        }
+        if (!n.h) { n.err = std::string("cannot dlopen libnccl.so.2: ") + dlerror(); return n; }
 #define YB_SYM(field, name)                                                         \
     *reinterpret_cast<void**>(&n.field) = dlsym(n.h, name);                          \
-    if (!n.field) { n.err = std::string("libnccl lacks ") + name; n.h = nullptr; return &n; }
-    YB_SYM(GetUniqueId, "ncclGetUniqueId")
-    YB_SYM(CommInitRank, "ncclCommInitRank")
-    YB_SYM(CommDestroy, "ncclCommDestroy")
-    YB_SYM(Broadcast, "ncclBroadcast")
-    YB_SYM(AllGather, "ncclAllGather")
-    YB_SYM(GetErrorString, "ncclGetErrorString")
+    if (!n.field) { n.err = std::string("libnccl lacks ") + name; n.h = nullptr; return n; }
+        YB_SYM(GetUniqueId, "ncclGetUniqueId")
+        YB_SYM(CommInitRank, "ncclCommInitRank")
+        YB_SYM(CommDestroy, "ncclCommDestroy")
+        YB_SYM(Broadcast, "ncclBroadcast")
+        YB_SYM(AllGather, "ncclAllGather")
+        YB_SYM(GetErrorString, "ncclGetErrorString")
 #undef YB_SYM
+        return n;
+    }();
     return &n;
 }
 

@@ -64,17 +64,38 @@ __device__ __forceinline__ void tma_store_4d(const CUtensorMap* tm, uint32_t src
                  ::"l"(tm), "r"(src), "r"(c0), "r"(c1), "r"(c2), "r"(c3) : "memory");
 }
 
-struct TileXY { int n_tile, x0, y0, img; };
-__device__ __forceinline__ TileXY tile_xy(const HaloArgs& a, int tile) {
-    TileXY t;
-    t.n_tile = tile % a.n_tiles;
-    const int mt = tile / a.n_tiles;
-    const int xt = mt % a.tiles_x, rest = mt / a.tiles_x;
-    t.x0 = xt * kHC;
-    t.y0 = (rest % a.tiles_y) * kHR;
-    t.img = rest / a.tiles_y;
-    return t;
-}
+// Position of the tiles a CTA visits -- tile = ((img * tiles_y + ty) * tiles_x + tx) * n_tiles + n_tile -- carried
+// without divisions: every role decodes its tile once per iteration, and for the epilogue warps that decode sits on
+// the per-tile dependent chain that paces these layers (a 32-bit division costs ~150-200 cycles of latency there).
+// The grid is a multiple of n_tiles (halo_make_plan), so a CTA's n-tile never changes.
+struct TileWalk {
+    int n_tile, tx, ty, img;
+    int dx, dy, dimg, tiles_x, tiles_y;
+    __device__ __forceinline__ TileWalk(const HaloArgs& a, int first, int step) : tiles_x(a.tiles_x), tiles_y(a.tiles_y) {
+        n_tile = first % a.n_tiles;
+        int mt = first / a.n_tiles;
+        tx = mt % tiles_x; mt /= tiles_x;
+        ty = mt % tiles_y; img = mt / tiles_y;
+        int dm = step / a.n_tiles;
+        dx = dm % tiles_x; dm /= tiles_x;
+        dy = dm % tiles_y; dimg = dm / tiles_y;
+    }
+    __device__ __forceinline__ void next() {
+        tx += dx;
+        int carry = 0;
+        if (tx >= tiles_x) { tx -= tiles_x; carry = 1; }
+        ty += dy + carry;
+        carry = 0;
+        if (ty >= tiles_y) { ty -= tiles_y; carry = 1; }
+        img += dimg + carry;
+    }
+    __device__ __forceinline__ int x0() const { return tx * kHC; }
+    __device__ __forceinline__ int y0() const { return ty * kHR; }
+};
+struct RingWalk {
+    uint32_t buf = 0, ph = 0;          // slot g % ring and parity (g / ring) & 1 of the g-th tile
+    __device__ __forceinline__ void next(uint32_t ring) { if (++buf == ring) { buf = 0; ph ^= 1u; } }
+};
 
 template <int SWZ, int STRIDE>
 __global__ void __launch_bounds__(kHThreads, 1)
@@ -134,20 +155,20 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmIn, const __grid_constant
         __syncwarp();
         int stage = 0;
         uint32_t phase = 0;
-        for (int tile = tile_first; tile < a.total_tiles; tile += tile_step) {
-            const TileXY t = tile_xy(a, tile);
+        TileWalk t(a, tile_first, tile_step);
+        for (int tile = tile_first; tile < a.total_tiles; tile += tile_step, t.next()) {
             mbar_wait(empty0 + 8 * stage, phase ^ 1, a.dbg, 0, stage);
             if (elect_one()) {
                 const uint32_t slot = stage0 + stage * a.slot_bytes, fb = full0 + 8 * stage;
                 if (STRIDE == 1) {
                     mbar_arrive_expect_tx(fb, (uint32_t)kHPatchPix * SWZ);
-                    tma_load_4d(&tmIn, slot, fb, 0, t.x0 - 1, t.y0 - 1, t.img);
+                    tma_load_4d(&tmIn, slot, fb, 0, t.x0() - 1, t.y0() - 1, t.img);
                 } else {
                     // planes: 0 = odd rows / odd cols, 1 = odd rows / even cols, 2 = even rows / odd cols, 3 = even / even
                     mbar_arrive_expect_tx(fb, 4u * kHPlanePix * SWZ);
 #pragma unroll
                     for (int pl = 0; pl < 4; ++pl)
-                        tma_load_4d(&tmIn, slot + pl * kHPlanePix * SWZ, fb, 0, 2 * t.x0 - 1 + (pl & 1), 2 * t.y0 - 1 + (pl >> 1), t.img);
+                        tma_load_4d(&tmIn, slot + pl * kHPlanePix * SWZ, fb, 0, 2 * t.x0() - 1 + (pl & 1), 2 * t.y0() - 1 + (pl >> 1), t.img);
                 }
             }
             __syncwarp();
@@ -189,30 +210,34 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmIn, const __grid_constant
     } else if (warp == 4) {
         // ===== residual prefetch into the staging ring (compact 3 x 38 pixel rows) =====
         if (lane == 0 && a.has_res) {
-            uint32_t g = 0;
-            for (int tile = tile_first; tile < a.total_tiles; tile += tile_step, ++g) {
-                const TileXY t = tile_xy(a, tile);
-                const uint32_t buf = g % (uint32_t)a.ring, ph = (g / (uint32_t)a.ring) & 1u;
+            TileWalk t(a, tile_first, tile_step);
+            RingWalk rw;
+            for (int tile = tile_first; tile < a.total_tiles; tile += tile_step, t.next(), rw.next((uint32_t)a.ring)) {
+                const uint32_t buf = rw.buf, ph = rw.ph;
                 mbar_wait(sempty0 + 8 * buf, ph ^ 1, a.dbg, 3, 300 + (int)buf);
                 mbar_arrive_expect_tx(sfull0 + 8 * buf, (uint32_t)kHValid * 128u);
-                tma_load_4d(&tmRes, stg0 + buf * kHStgBytes, sfull0 + 8 * buf, t.n_tile * kHBN, t.x0, t.y0, t.img);
+                tma_load_4d(&tmRes, stg0 + buf * kHStgBytes, sfull0 + 8 * buf, t.n_tile * kHBN, t.x0(), t.y0(), t.img);
             }
         }
         __syncwarp();
     } else if (warp == 3) {
         // ===== store issuer =====
         if (lane == 0) {
-            uint32_t g = 0;
-            for (int tile = tile_first; tile < a.total_tiles; tile += tile_step, ++g) {
-                const TileXY t = tile_xy(a, tile);
-                const uint32_t buf = g % (uint32_t)a.ring, ph = (g / (uint32_t)a.ring) & 1u;
+            TileWalk t(a, tile_first, tile_step);
+            RingWalk rw;
+            uint32_t prev = 0;
+            bool first = true;
+            for (int tile = tile_first; tile < a.total_tiles; tile += tile_step, t.next(), rw.next((uint32_t)a.ring)) {
+                const uint32_t buf = rw.buf, ph = rw.ph;
                 mbar_wait(sready0 + 8 * buf, ph, a.dbg, 4, 700 + (int)buf);
-                tma_store_4d(&tmOut, stg0 + buf * kHStgBytes, t.n_tile * kHBN, t.x0, t.y0, t.img);
+                tma_store_4d(&tmOut, stg0 + buf * kHStgBytes, t.n_tile * kHBN, t.x0(), t.y0(), t.img);
                 tma_store_commit();
-                if (g > 0) {                                  // the previous store has finished reading its buffer
+                if (!first) {                                 // the previous store has finished reading its buffer
                     tma_store_wait_read<1>();
-                    mbar_arrive(sempty0 + 8 * ((g - 1) % (uint32_t)a.ring));
+                    mbar_arrive(sempty0 + 8 * prev);
                 }
+                first = false;
+                prev = buf;
             }
             tma_store_wait_all();
         }
@@ -225,10 +250,19 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmIn, const __grid_constant
         const bool valid = r < kHR && c < kHC;
         const int mp = r * kHC + c;                             // compact row (only used when valid)
         const int xr = mp & 7;
-        uint32_t acc = 0, acc_phase = 0, g = 0;
-        for (int tile = tile_first; tile < a.total_tiles; tile += tile_step, ++g) {
-            const int n0 = (tile % a.n_tiles) * kHBN;
-            const uint32_t buf = g % (uint32_t)a.ring, ph = (g / (uint32_t)a.ring) & 1u;
+        uint32_t acc = 0, acc_phase = 0;
+        RingWalk rw;
+        const int n0 = (tile_first % a.n_tiles) * kHBN;        // the grid is a multiple of n_tiles: constant per CTA
+        // ... and so are this thread's sixteen channels: their scale / bias pairs live in registers for the whole kernel
+        float4 sc4[4], bi4[4];
+        {
+            const float4* sc = reinterpret_cast<const float4*>(tab + n0 + part * 16);
+            const float4* bi = reinterpret_cast<const float4*>(tab + a.cout_pad + n0 + part * 16);
+#pragma unroll
+            for (int i = 0; i < 4; ++i) { sc4[i] = sc[i]; bi4[i] = bi[i]; }
+        }
+        for (int tile = tile_first; tile < a.total_tiles; tile += tile_step, rw.next((uint32_t)a.ring)) {
+            const uint32_t buf = rw.buf, ph = rw.ph;
             mbar_wait(tfull0 + 8 * acc, acc_phase, a.dbg, 2, 200 + (int)acc);
             tc_fence_after();
             uint32_t r0[16];
@@ -241,13 +275,10 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmIn, const __grid_constant
             if (lane == 0) mbar_arrive(tempty0 + 8 * acc);      // accumulator drained into registers
             if (valid) {
                 uint8_t* srow = gen + (stg0 - base) + buf * kHStgBytes + (uint32_t)mp * 128u;
-                const int n = n0 + part * 16;
-                const float4* sc = reinterpret_cast<const float4*>(tab + n);
-                const float4* bi = reinterpret_cast<const float4*>(tab + a.cout_pad + n);
                 float v[16];
 #pragma unroll
                 for (int i = 0; i < 4; ++i) {
-                    const float4 s4 = sc[i], b4 = bi[i];
+                    const float4 s4 = sc4[i], b4 = bi4[i];
                     v[4 * i + 0] = fmaf(__uint_as_float(r0[4 * i + 0]), s4.x, b4.x);
                     v[4 * i + 1] = fmaf(__uint_as_float(r0[4 * i + 1]), s4.y, b4.y);
                     v[4 * i + 2] = fmaf(__uint_as_float(r0[4 * i + 2]), s4.z, b4.z);
@@ -398,15 +429,15 @@ cudaError_t halo_launch(const HaloPlan& p, const ConvArgs& a, int* dbg, cudaStre
     h.cout_pad = p.cout_pad; h.tab_bytes = p.tab_bytes;
     h.leaky = a.leaky; h.has_res = a.res != nullptr; h.ring = p.ring;
     h.dbg = dbg;
-    static bool attr_done = false;
-    if (!attr_done) {
-        cudaError_t e = cudaFuncSetAttribute(conv_halo_kernel<128, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kHSmemBudget);
+    static PerDeviceOnce attr_once;
+    {
+        cudaError_t e = attr_once.run([] {
+            cudaError_t r = cudaFuncSetAttribute(conv_halo_kernel<128, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kHSmemBudget);
+            if (r == cudaSuccess) r = cudaFuncSetAttribute(conv_halo_kernel<64, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kHSmemBudget);
+            if (r == cudaSuccess) r = cudaFuncSetAttribute(conv_halo_kernel<64, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kHSmemBudget);
+            return r;
+        });
         if (e != cudaSuccess) return e;
-        e = cudaFuncSetAttribute(conv_halo_kernel<64, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kHSmemBudget);
-        if (e != cudaSuccess) return e;
-        e = cudaFuncSetAttribute(conv_halo_kernel<64, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kHSmemBudget);
-        if (e != cudaSuccess) return e;
-        attr_done = true;
     }
     static const bool pdl = !(getenv("YB_TC_PDL") && atoi(getenv("YB_TC_PDL")) == 0);
     cudaLaunchConfig_t cfg{};

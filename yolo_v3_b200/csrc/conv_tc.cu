@@ -187,6 +187,43 @@ __device__ __forceinline__ void epilogue16_staged(const TcArgs& a, const uint32_
     }
 }
 
+// (m-unit, n-tile) of the tiles a CTA visits and the staging-ring slot of its sub-tiles, carried without divisions: these
+// loops run on one thread each or sit on the epilogue's per-tile dependent chain, which is what paces the layers with
+// small tiles (profiles/r01s_trace_layer2_ring*.txt) -- a 32-bit division there costs ~150-200 cycles of latency.
+struct TileWalk {
+    int m_unit, n_tile;
+    int dq, dr, n_tiles;
+    __device__ __forceinline__ TileWalk(int first, int step, int nt) : n_tiles(nt) {
+        m_unit = first / nt; n_tile = first - m_unit * nt;
+        dq = step / nt; dr = step - dq * nt;
+    }
+    __device__ __forceinline__ void next() {
+        m_unit += dq; n_tile += dr;
+        if (n_tile >= n_tiles) { n_tile -= n_tiles; ++m_unit; }
+    }
+};
+struct RingWalk {
+    uint32_t buf = 0, ph = 0;          // slot g % ring and parity (g / ring) & 1 of the g-th sub-tile
+    __device__ __forceinline__ void next(uint32_t ring) { if (++buf == ring) { buf = 0; ph ^= 1u; } }
+};
+
+// Resident weights: the CTA's slab [BN / NCTA rows][K] is loaded once (one elected thread) and stays in shared memory.
+// The plan makes the number of tiles in flight a multiple of n_tiles, so every tile of a CTA has the same n-tile.  In
+// pair mode each CTA keeps its half of the rows and both halves complete on the leader's barrier (the leader's MMA warp
+// is the only reader), which therefore expects the bytes of both.
+template <bool CTA2>
+__device__ __forceinline__ void load_resident_weights(const CUtensorMap* tmB, const TcArgs& a, uint32_t bres0, uint32_t b_slot,
+                                                      uint32_t b_bytes, uint32_t bres_bar, int bke, uint32_t rank) {
+    constexpr int NCTA = CTA2 ? 2 : 1;
+    const int n0 = (((int)blockIdx.x / NCTA) % a.n_tiles) * a.BN + (int)rank * (a.BN / NCTA);
+    if (rank == 0) mbar_arrive_expect_tx(bres_bar, (uint32_t)a.num_kblocks * b_bytes * NCTA);
+#pragma unroll 1
+    for (int kb = 0; kb < a.num_kblocks; ++kb) {
+        if constexpr (CTA2) tma_load_2d_pair(tmB, bres0 + kb * b_slot, bres_bar, kb * bke, n0);
+        else tma_load_2d(tmB, bres0 + kb * b_slot, bres_bar, kb * bke, n0);
+    }
+}
+
 template <int SWZ, bool CTA2>
 __global__ void __launch_bounds__(kThreads, 1)
 conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
@@ -255,10 +292,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     // slab (or, through an L2 prefetch, the first pipeline's worth of weight k-blocks) arrives under its tail.
     if (warp == 0 && a.b_early && tile_first < total_tiles && elect_one()) {
         if (a.b_resident) {
-            const int n0 = ((int)blockIdx.x % a.n_tiles) * a.BN;   // gridDim.x is a multiple of n_tiles
-            mbar_arrive_expect_tx(bres_bar, (uint32_t)a.num_kblocks * B_BYTES);
-#pragma unroll 1
-            for (int kb = 0; kb < a.num_kblocks; ++kb) tma_load_2d(&tmB, bres0 + kb * B_SLOT, bres_bar, kb * BKE, n0);
+            load_resident_weights<CTA2>(&tmB, a, bres0, B_SLOT, B_BYTES, bres_bar, BKE, rank);
         } else {
             const int n0 = (tile_first % a.n_tiles) * a.BN + (int)rank * (a.BN / NCTA);
             const int npf = min(a.num_kblocks, a.stages * a.kps);
@@ -278,12 +312,8 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             uint32_t itg = 0;                             // running stage counter across tiles
             int stage = 0;
             uint32_t phase = 0;
-            if (pw == 0 && a.b_resident && !a.b_early && tile_first < total_tiles && elect_one()) {
-                // gridDim.x is a multiple of n_tiles, so every tile of this CTA has the same n-tile
-                const int n0 = ((int)blockIdx.x % a.n_tiles) * a.BN;
-                mbar_arrive_expect_tx(bres_bar, (uint32_t)a.num_kblocks * B_BYTES);
-                for (int kb = 0; kb < a.num_kblocks; ++kb) tma_load_2d(&tmB, bres0 + kb * B_SLOT, bres_bar, kb * BKE, n0);
-            }
+            if (pw == 0 && a.b_resident && !a.b_early && tile_first < total_tiles && elect_one())
+                load_resident_weights<CTA2>(&tmB, a, bres0, B_SLOT, B_BYTES, bres_bar, BKE, rank);
             __syncwarp();
             // The loop below runs on one thread; everything that can be is carried incrementally
             // (no divisions, no address recomputation) because its latency paces the pipeline.
@@ -291,8 +321,9 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             const bool load_b = !a.b_resident;
             uint32_t sA = stage0, fb = full0, eb = empty0;
             int ti = 0;
-            for (int tile = tile_first; tile < total_tiles; tile += tile_step, ++ti) {
-                const int m_unit = tile / a.n_tiles, n_tile = tile - m_unit * a.n_tiles;
+            TileWalk tw(tile_first, tile_step, a.n_tiles);
+            for (int tile = tile_first; tile < total_tiles; tile += tile_step, ++ti, tw.next()) {
+                const int m_unit = tw.m_unit, n_tile = tw.n_tile;
                 const int m0 = (m_unit * NCTA + (int)rank) * kBM;
                 const int n0 = n_tile * a.BN + (int)rank * (a.BN / NCTA);   // this CTA's half of the weight rows
                 if (pw == 0) YB_TRACE(0, ti, 0);
@@ -342,7 +373,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                             if (el) {
                                 if constexpr (CTA2) {
                                     tma_load_2d_pair(&tmA, dst, fb, kc, m0);
-                                    tma_load_2d_pair(&tmB, dst + A_BYTES, fb, kc, n0);
+                                    if (load_b) tma_load_2d_pair(&tmB, dst + A_BYTES, fb, kc, n0);
                                 } else {
                                     tma_load_2d(&tmA, dst, fb, a.exp_tiled ? ka : kc, m0);
                                     if (load_b) tma_load_2d(&tmB, dst + A_BYTES, fb, kc, n0);
@@ -374,7 +405,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                             if (el) {
                                 if constexpr (CTA2) {
                                     tma_load_im2col_pair(&tmA, dst, fb, cc, cw, chh, cn, kw, kh);
-                                    tma_load_2d_pair(&tmB, dst + A_BYTES, fb, kc, n0);
+                                    if (load_b) tma_load_2d_pair(&tmB, dst + A_BYTES, fb, kc, n0);
                                 } else {
                                     tma_load_im2col(&tmA, dst, fb, cc, cw, chh, cn, kw, kh);
                                     if (load_b) tma_load_2d(&tmB, dst + A_BYTES, fb, kc, n0);
@@ -456,9 +487,10 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     } else if (warp == 4) {
         // ===== residual prefetch: TMA loads of the residual sub-tiles into the staging ring =====
         if (lane == 0 && a.epi_staged && a.has_res) {
-            uint32_t g = 0;
-            for (int tile = tile_first; tile < total_tiles; tile += tile_step) {
-                const int m_unit = tile / a.n_tiles, n_tile = tile - m_unit * a.n_tiles;
+            RingWalk rw;
+            TileWalk tw(tile_first, tile_step, a.n_tiles);
+            for (int tile = tile_first; tile < total_tiles; tile += tile_step, tw.next()) {
+                const int m_unit = tw.m_unit, n_tile = tw.n_tile;
                 const int m0 = (m_unit * NCTA + (int)rank) * kBM, n0 = n_tile * a.BN;
                 if (a.pf_dist) {                              // residual tile of a later round -> L2
                     const int tp = tile + a.pf_dist * tile_step;
@@ -468,8 +500,8 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                         for (int j = 0; j < a.n_sub; ++j) tma_prefetch_2d(&tmRes, nt * a.BN + j * a.cs, (mu * NCTA + (int)rank) * kBM);
                     }
                 }
-                for (int j = 0; j < a.n_sub; ++j, ++g) {
-                    const uint32_t buf = g % (uint32_t)a.ring, ph = (g / (uint32_t)a.ring) & 1u;
+                for (int j = 0; j < a.n_sub; ++j, rw.next((uint32_t)a.ring)) {
+                    const uint32_t buf = rw.buf, ph = rw.ph;
                     mbar_wait(sempty0 + 8 * buf, ph ^ 1, a.dbg, 3, 300 + (int)buf);
                     mbar_arrive_expect_tx(sfull0 + 8 * buf, stg_bytes);
                     tma_load_2d(&tmRes, stg0 + buf * stg_bytes, sfull0 + 8 * buf, n0 + j * a.cs, m0);
@@ -481,12 +513,14 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         // ===== store issuer: waits until the eight epilogue warps have filled a staging sub-tile, writes it
         // back with one TMA store and recycles the buffer once the store has drained it =====
         if (lane == 0 && a.epi_staged) {
-            uint32_t g = 0;
-            for (int tile = tile_first; tile < total_tiles; tile += tile_step) {
-                const int m_unit = tile / a.n_tiles, n_tile = tile - m_unit * a.n_tiles;
+            uint32_t g = 0, prev1 = 0, prev2 = 0;          // slots of sub-tiles g-1 and g-2
+            RingWalk rw;
+            TileWalk tw(tile_first, tile_step, a.n_tiles);
+            for (int tile = tile_first; tile < total_tiles; tile += tile_step, tw.next()) {
+                const int m_unit = tw.m_unit, n_tile = tw.n_tile;
                 const int m0 = (m_unit * NCTA + (int)rank) * kBM, n0 = n_tile * a.BN;
-                for (int j = 0; j < a.n_sub; ++j, ++g) {
-                    const uint32_t buf = g % (uint32_t)a.ring, ph = (g / (uint32_t)a.ring) & 1u;
+                for (int j = 0; j < a.n_sub; ++j, ++g, rw.next((uint32_t)a.ring)) {
+                    const uint32_t buf = rw.buf, ph = rw.ph;
                     mbar_wait(sready0 + 8 * buf, ph, a.dbg, 4, 700 + (int)buf);
                     if (!a.exp_nostore) tma_store_2d(&tmOut, stg0 + buf * stg_bytes, n0 + j * a.cs, m0);
                     tma_store_commit();
@@ -498,10 +532,11 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                         tma_store_wait_read<0>();
                         mbar_arrive(sempty0 + 8 * buf);
                     } else if (a.srel == 1) {
-                        if (g >= 1) { tma_store_wait_read<1>(); mbar_arrive(sempty0 + 8 * ((g - 1) % (uint32_t)a.ring)); }
+                        if (g >= 1) { tma_store_wait_read<1>(); mbar_arrive(sempty0 + 8 * prev1); }
                     } else {
-                        if (g >= 2) { tma_store_wait_read<2>(); mbar_arrive(sempty0 + 8 * ((g - 2) % (uint32_t)a.ring)); }
+                        if (g >= 2) { tma_store_wait_read<2>(); mbar_arrive(sempty0 + 8 * prev2); }
                     }
+                    prev2 = prev1; prev1 = buf;
                 }
             }
             tma_store_wait_all();
@@ -518,18 +553,21 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         const int ngrp = a.cs >> 4;                           // 16-column groups per sub-tile: 1, 2 or 4
         const bool active = part < ngrp;
         const bool issuer = (warp == 8 && lane == 0);
-        uint32_t acc = 0, acc_phase = 0, g = 0;
+        uint32_t acc = 0, acc_phase = 0;
         int ti = 0;
+        RingWalk rw;
+        // only the tile's first column is needed here: n0 = (tile % n_tiles) * BN, advanced modulo the padded width
+        const int n_wrap = a.n_tiles * a.BN;
+        int n0 = (tile_first % a.n_tiles) * a.BN;
+        const int dn0 = (tile_step % a.n_tiles) * a.BN;
         for (int tile = tile_first; tile < total_tiles; tile += tile_step, ++ti) {
-            const int m_unit = tile / a.n_tiles, n_tile = tile - m_unit * a.n_tiles;
-            const int m0 = (m_unit * NCTA + (int)rank) * kBM, n0 = n_tile * a.BN;
             if (issuer) YB_TRACE(2, ti, 0);
             mbar_wait_relaxed(tfull0 + 8 * acc, acc_phase, a.dbg, 2, 200 + (int)acc, a.epi_sleep);
             tc_fence_after();
             if (issuer) YB_TRACE(2, ti, 1);
             const uint32_t taddr = tmem_base + acc * acc_stride + ((uint32_t)(q * 32) << 16);
-            for (int j = 0; j < a.n_sub; ++j, ++g) {
-                const uint32_t buf = g % (uint32_t)a.ring, ph = (g / (uint32_t)a.ring) & 1u;
+            for (int j = 0; j < a.n_sub; ++j, rw.next((uint32_t)a.ring)) {
+                const uint32_t buf = rw.buf, ph = rw.ph;
                 uint32_t r0[16];
                 const uint32_t tcol = taddr + (uint32_t)(j * a.cs + part * 16);
                 if (active) tmem_ld16(tcol, r0);
@@ -559,14 +597,17 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             if (issuer) YB_TRACE(2, ti, 2);
             acc ^= 1;
             if (acc == 0) acc_phase ^= 1;
+            n0 += dn0;
+            if (n0 >= n_wrap) n0 -= n_wrap;
         }
     } else if (warp >= 8 && warp < 12) {
         // ===== epilogue (direct, warps 8-11 only): TMEM -> registers -> global, used by the nearest-upsample layers =====
         const int q = warp & 3;                               // TMEM lane quarter this warp may read
         const int row = q * 32 + lane;
         uint32_t acc = 0, acc_phase = 0;
-        for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
-            const int m_tile = tile / a.n_tiles, n_tile = tile - m_tile * a.n_tiles;
+        TileWalk tw((int)blockIdx.x, (int)gridDim.x, a.n_tiles);
+        for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, tw.next()) {
+            const int m_tile = tw.m_unit, n_tile = tw.n_tile;
             const long m = (long)m_tile * kBM + row;
             const int n0 = n_tile * a.BN;
             const bool valid = m < a.M;
@@ -921,7 +962,18 @@ std::string tc_make_plan(TcPlan& p, const ConvArgs& a, const __half* w16, int co
     p.n_tiles = cout_pad / p.BN;
     // CTA pairs (cta_group::2): 256-row UMMA tiles, each CTA stages only half of the weight rows, which
     // both halves the bytes every SM must ingest per FLOP and frees shared memory for deeper pipelines.
-    p.cta2 = p.swz == 128 && p.BN == 256 && !a.upsample && p.m_tiles >= 4 && num_sms % 2 == 0;
+    // BN = 128 3x3 layers whose weight slab (BN x K) is too large to stay resident in one CTA but whose half fits
+    // (64 -> 128 stride 2 at 152x152: 147 KB) also run as pairs, each CTA keeping its half resident: streamed, the slab
+    // is re-fetched for every tile and the layer is bound by L2 -> SM traffic (1.9 GB, 158 us at the ~6.3 KB/clk the
+    // L2 delivers, against 88 us of HBM time; profiles/README.md "L2 -> SM model").
+    bool pair128 = false;
+    {
+        const size_t slot_one = ((size_t)p.BN * p.swz + 1023) & ~(size_t)1023, slot_half = ((size_t)(p.BN / 2) * p.swz + 1023) & ~(size_t)1023;
+        pair128 = p.swz == 128 && p.BN == 128 && a.ks == 3 && slot_one * p.num_kblocks > 96 * 1024 &&
+                  slot_half * p.num_kblocks <= 96 * 1024 && p.m_tiles > 4 * num_sms;
+        if (const char* e = getenv("YB_TC_PAIR128")) pair128 = pair128 && atoi(e) != 0;
+    }
+    p.cta2 = p.swz == 128 && (p.BN == 256 || pair128) && !a.upsample && p.m_tiles >= 4 && num_sms % 2 == 0;
     if (const char* e = getenv("YB_TC_CTA2")) p.cta2 = p.cta2 && atoi(e) != 0;
     const int ncta = p.cta2 ? 2 : 1;
     if (p.cta2) p.m_tiles = (p.m_tiles + 1) / 2;            // 256-row units from here on
@@ -946,7 +998,8 @@ std::string tc_make_plan(TcPlan& p, const ConvArgs& a, const __half* w16, int co
     // small-K layers: keep the CTA's whole weight slab resident (halves the L2->SM traffic of 1x1 convs)
     const size_t b_slot = ((size_t)(p.BN / ncta) * p.swz + 1023) & ~(size_t)1023;
     const size_t bres_bytes = b_slot * p.num_kblocks;
-    p.b_resident = !p.cta2 && bres_bytes <= 96 * 1024 && p.grid % p.n_tiles == 0 && p.m_tiles > 2 * num_sms;
+    p.b_resident = (!p.cta2 || p.BN == 128) && bres_bytes <= 96 * 1024 && (p.grid / ncta) % p.n_tiles == 0 &&
+                   p.m_tiles > 2 * num_sms / ncta;
     if (const char* e = getenv("YB_TC_BRES")) p.b_resident = p.b_resident && atoi(e) != 0;
     // Experiments kept behind overrides (profiles/r01b_sweep_prefetch.txt): an L2 prefetch of the A operand
     // pf_dist tiles ahead makes the memory-bound layers SLOWER (32->64 s2: 0.25 -> 0.30 ms; the TMA request
@@ -973,6 +1026,12 @@ std::string tc_make_plan(TcPlan& p, const ConvArgs& a, const __half* w16, int co
         if (p.b_resident && !a.res && p.num_kblocks <= 9 && fixed + 2 * p.num_kblocks * kb_bytes <= kSmemBudget)
             p.kps = p.num_kblocks;
         if (const char* e = getenv("YB_TC_KPS")) { const int c = atoi(e); if (c >= 1 && p.num_kblocks % c == 0 && c * kb_bytes <= 96 * 1024) p.kps = c; }
+    }
+    // a resident slab next to a four-deep residual ring can leave room for fewer than two multi-k-block stages
+    while (p.kps > 1 && (kSmemBudget - fixed) / (kb_bytes * p.kps) < 2) {
+        int c = p.kps - 1;
+        while (c > 1 && p.num_kblocks % c) --c;
+        p.kps = c;
     }
     const size_t stage_bytes = kb_bytes * p.kps;
     p.stages = (int)std::min<size_t>(kMaxStages, (kSmemBudget - fixed) / stage_bytes);
@@ -1080,11 +1139,10 @@ cudaError_t stem_tc_launch(const StemTcPlan& p, const float* x, int B, int H, in
         a.pf_dist = pf;
     }
     a.epi.scale = scale; a.epi.bias = bias; a.epi.leaky = 1; a.epi.out_f32 = 0; a.epi.has_res = 0; a.epi.dbg = dbg;
-    static bool attr_done = false;
-    if (!attr_done) {
-        cudaError_t e = cudaFuncSetAttribute(stem_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 128 * 1024);
+    static PerDeviceOnce attr_once;
+    {
+        cudaError_t e = attr_once.run([] { return cudaFuncSetAttribute(stem_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 128 * 1024); });
         if (e != cudaSuccess) return e;
-        attr_done = true;
     }
     {
         static const bool pdl = !(getenv("YB_TC_PDL") && atoi(getenv("YB_TC_PDL")) == 0);
@@ -1140,15 +1198,15 @@ cudaError_t tc_launch(const TcPlan& p, const ConvArgs& a, int* dbg, cudaStream_t
         t.exp_nostore = nostore;
     }
     t.dbg = dbg;
-    static bool attr_done = false;
-    if (!attr_done) {
-        cudaError_t e = cudaFuncSetAttribute(conv_tc_kernel<128, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBudget);
+    static PerDeviceOnce attr_once;
+    {
+        cudaError_t e = attr_once.run([] {
+            cudaError_t r = cudaFuncSetAttribute(conv_tc_kernel<128, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBudget);
+            if (r == cudaSuccess) r = cudaFuncSetAttribute(conv_tc_kernel<64, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBudget);
+            if (r == cudaSuccess) r = cudaFuncSetAttribute(conv_tc_kernel<128, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBudget);
+            return r;
+        });
         if (e != cudaSuccess) return e;
-        e = cudaFuncSetAttribute(conv_tc_kernel<64, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBudget);
-        if (e != cudaSuccess) return e;
-        e = cudaFuncSetAttribute(conv_tc_kernel<128, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBudget);
-        if (e != cudaSuccess) return e;
-        attr_done = true;
     }
     {
         static const bool pdl = !(getenv("YB_TC_PDL") && atoi(getenv("YB_TC_PDL")) == 0);

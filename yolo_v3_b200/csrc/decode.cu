@@ -442,10 +442,10 @@ cudaError_t launch_decode(const DecodeScale sc[3], int nchw, int B, int attrs, i
         int nb[3];
         for (int i = 0; i < 3; ++i) nb[i] = B * ((sc[i].h * sc[i].w + 31) / 32);
         const size_t smem = (size_t)3 * attrs * 33 * sizeof(float);
-        static bool attr_set = false;
-        if (!attr_set && smem > 48 * 1024) {
-            cudaFuncSetAttribute(decode_nchw_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
-            attr_set = true;
+        static PerDeviceOnce attr_once;
+        if (smem > 48 * 1024) {
+            cudaError_t e = attr_once.run([] { return cudaFuncSetAttribute(decode_nchw_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024); });
+            if (e != cudaSuccess) return e;
         }
         decode_nchw_kernel<<<nb[0] + nb[1] + nb[2], 256, smem, s>>>(P, det, nb[0], nb[1]);
     }

@@ -975,6 +975,7 @@ int yb_comm_init(yb_ctx* c, const uint8_t id[128], int rank, int world) {
     if (!c || !id || world <= 0 || rank < 0 || rank >= world) return fail(c, YB_E_ARG, "yb_comm_init: bad arguments");
     YB_CUDA(c, cudaSetDevice(c->device));
     std::string err;
+    if (c->nccl_comm) { comm_destroy(c->nccl_comm); c->nccl_comm = nullptr; }   // re-initialisation replaces the communicator
     int rc = comm_init(&c->nccl_comm, id, rank, world, err);
     if (rc) return fail(c, rc, err);
     c->rank = rank; c->world = world;

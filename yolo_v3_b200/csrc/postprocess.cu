@@ -460,11 +460,14 @@ cudaError_t launch_correct_boxes(const float* boxes, int row_stride, const int* 
 cudaError_t launch_postprocess(const PostArgs& a, PostBuffers& buf, long long* launches, cudaStream_t s) {
     const long rows = (long)a.B * a.N;
     const int cand_cap = buf.cand_cap, sort_cap = buf.sort_cap;
-    static bool attrs_set = false;
-    if (!attrs_set) {
-        cudaFuncSetAttribute(pp_sort_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSortSmemKeys * 8);
-        cudaFuncSetAttribute(pp_nms_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kNmsSmemBoxes * 17);
-        attrs_set = true;
+    static PerDeviceOnce attr_once;
+    {
+        cudaError_t e = attr_once.run([] {
+            cudaError_t r = cudaFuncSetAttribute(pp_sort_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSortSmemKeys * 8);
+            if (r == cudaSuccess) r = cudaFuncSetAttribute(pp_nms_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kNmsSmemBoxes * 17);
+            return r;
+        });
+        if (e != cudaSuccess) return e;
     }
     if (a.pre_scored) {
         *launches -= 1;                 // the scoring ran inside the fused decode kernel (counted by the caller)

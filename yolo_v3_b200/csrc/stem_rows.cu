@@ -292,11 +292,10 @@ cudaError_t stem_rows_launch(const StemRowsPlan& p, const float* x, int B, int H
     a.x = x; a.B = B; a.H = H; a.W = W;
     a.tiles_x = p.tiles_x; a.tiles_y = p.tiles_y; a.total_tiles = p.total_tiles;
     a.w = w16; a.scale = scale; a.bias = bias; a.dbg = dbg;
-    static bool attr_done = false;
-    if (!attr_done) {
-        cudaError_t e = cudaFuncSetAttribute(stem_rows_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 128 * 1024);
+    static PerDeviceOnce attr_once;
+    {
+        cudaError_t e = attr_once.run([] { return cudaFuncSetAttribute(stem_rows_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 128 * 1024); });
         if (e != cudaSuccess) return e;
-        attr_done = true;
     }
     static const bool pdl = !(getenv("YB_TC_PDL") && atoi(getenv("YB_TC_PDL")) == 0);
     cudaLaunchConfig_t cfg{};

@@ -9,6 +9,7 @@
 #include <cstdint>
 #include <cstdio>
 #include <map>
+#include <mutex>
 #include <string>
 #include <vector>
 
@@ -34,6 +35,28 @@ struct Layer {
     float* d_bias = nullptr;                  // [cout_pad]  beta-mean*scale      (conv bias for heads)
     float* d_w32 = nullptr;                   // [ks*ks][cin][cout_pad] fp32      (YB_MODE_FP32)
     __half* d_w16 = nullptr;                  // [cout_pad][ks*ks*cin] fp16, K-major (YB_MODE_FP16)
+};
+
+// cudaFuncSetAttribute applies to the CURRENT device only, and a process may hold contexts on several devices
+// (one yb_ctx per device and host thread): run `set` once per device, serialised, before the first launch there.
+class PerDeviceOnce {
+public:
+    template <class F>
+    cudaError_t run(F&& set) {
+        int dev = 0;
+        cudaError_t e = cudaGetDevice(&dev);
+        if (e != cudaSuccess) return e;
+        const unsigned long long bit = 1ull << (dev & 63);
+        std::lock_guard<std::mutex> lock(mu_);
+        if (done_ & bit) return cudaSuccess;
+        e = set();
+        if (e == cudaSuccess) done_ |= bit;
+        return e;
+    }
+
+private:
+    std::mutex mu_;
+    unsigned long long done_ = 0;
 };
 
 // NHWC activation view: `p` already includes the channel offset of a concat slice.
