@@ -97,12 +97,30 @@ struct RingWalk {
     __device__ __forceinline__ void next(uint32_t ring) { if (++buf == ring) { buf = 0; ph ^= 1u; } }
 };
 
-template <int SWZ, int STRIDE>
+__device__ __forceinline__ void tma_load_4d_pair(const CUtensorMap* tm, uint32_t dst, uint32_t bar, int c0, int c1, int c2, int c3) {
+    asm volatile(
+        "cp.async.bulk.tensor.4d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint"
+        " [%0], [%1, {%3, %4, %5, %6}], [%2], %7;"
+        ::"r"(dst), "l"(tm), "r"(bar & kPeerBitMask), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "l"(kTmaCacheDefault) : "memory");
+}
+
+// PAIR (Cout = 128, Cin = 64, stride 1): two CTAs of a cluster run one cta_group::2 UMMA of M = 256 (two spatial tiles,
+// one patch per CTA) x N = 128 (each CTA keeps the 64 weight rows of its half resident).  A single CTA with N = 64 pays
+// ~76 cycles per M128 x N64 x K16 instruction against 32 of tensor work -- every instruction re-reads its 4 KB of A and
+// 2 KB of B from shared memory, 192 B/clk against the 128 B/clk a SM delivers -- and needs two passes over the patch;
+// the pair reads 6 KB per 64 tensor cycles.  Tile t of the pair's round is tile 2*p + rank, so the tile walk is the
+// same (first = blockIdx.x, step = gridDim.x); an odd tile count leaves rank 1 of the last pair a tile at image index
+// B, which TMA zero-fills on load and clips on store.
+template <int SWZ, int STRIDE, bool PAIR>
 __global__ void __launch_bounds__(kHThreads, 1)
 conv_halo_kernel(const __grid_constant__ CUtensorMap tmIn, const __grid_constant__ CUtensorMap tmB,
                  const __grid_constant__ CUtensorMap tmOut, const __grid_constant__ CUtensorMap tmRes, const HaloArgs a) {
+    static_assert(!PAIR || (SWZ == 128 && STRIDE == 1), "pair mode: 64-channel stride-1 layers only");
     constexpr int BKE = SWZ / 2;                                // fp16 per pixel = Cin
-    constexpr uint32_t B_SLOT = kHBN * SWZ;                     // one tap of the weight slab: 64 rows x Cin
+    constexpr uint32_t B_SLOT = kHBN * SWZ;                     // one tap of this CTA's weight rows: 64 rows x Cin
+    constexpr int NCTA = PAIR ? 2 : 1;
+    constexpr int NSUB = PAIR ? 2 : 1;                          // 64-channel sub-tiles per tile
+    constexpr uint32_t ACC_COLS = kHBN * NSUB;                  // TMEM columns per accumulator = UMMA N
     extern __shared__ uint8_t smem_raw[];
     const uint32_t raw = smem_u32(smem_raw);
     const uint32_t base = (raw + 1023u) & ~1023u;
@@ -118,7 +136,11 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmIn, const __grid_constant
     const uint32_t stage0 = bres0 + 9 * B_SLOT;
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const uint32_t rank = PAIR ? cluster_ctarank() : 0u;
+    const bool leader = rank == 0;
     const int tile_first = blockIdx.x, tile_step = gridDim.x;
+    // both CTAs of a pair run the same number of rounds: the bound is tested on the leader's tile
+    const int tile_end = a.total_tiles + (int)rank;
 
     for (int i = threadIdx.x; i < a.cout_pad; i += kHThreads) {
         float* t = reinterpret_cast<float*>(gen + 1024);
@@ -131,14 +153,17 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmIn, const __grid_constant
     }
     if (warp == 2 && lane == 0) {
         for (int s = 0; s < a.stages; ++s) { mbar_init(full0 + 8 * s, 1); mbar_init(empty0 + 8 * s, 1); }
-        for (int i = 0; i < 2; ++i) { mbar_init(tfull0 + 8 * i, 1); mbar_init(tempty0 + 8 * i, kHEpiWarps); }
+        for (int i = 0; i < 2; ++i) { mbar_init(tfull0 + 8 * i, 1); mbar_init(tempty0 + 8 * i, kHEpiWarps * NCTA); }
         for (int i = 0; i < kHMaxRing; ++i) { mbar_init(sfull0 + 8 * i, 1); mbar_init(sempty0 + 8 * i, 1); mbar_init(sready0 + 8 * i, kHEpiWarps); }
         mbar_init(bres_bar, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
-    if (warp == 3) tmem_alloc(smem_u32(const_cast<uint32_t*>(tmem_ptr)), 2 * kHBN);
+    if (warp == 3) {
+        if constexpr (PAIR) tmem_alloc_pair(smem_u32(const_cast<uint32_t*>(tmem_ptr)), 2 * ACC_COLS);
+        else tmem_alloc(smem_u32(const_cast<uint32_t*>(tmem_ptr)), 2 * ACC_COLS);
+    }
     tc_fence_before();
-    __syncthreads();
+    if constexpr (PAIR) cluster_sync_all(); else __syncthreads();   // peer barriers must exist before any remote signal
     tc_fence_after();
     const uint32_t tmem_base = *tmem_ptr;
     pdl_launch_dependents();
@@ -146,23 +171,28 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmIn, const __grid_constant
 
     if (warp == 0) {
         // ===== TMA producer: the resident weight slab once, then one patch per tile =====
-        if (tile_first < a.total_tiles && elect_one()) {
-            const int n0 = (tile_first % a.n_tiles) * kHBN;                // gridDim.x is a multiple of n_tiles
-            mbar_arrive_expect_tx(bres_bar, 9 * B_SLOT);
+        if (tile_first < tile_end && elect_one()) {
+            // the grid is a multiple of n_tiles: a CTA's n-tile never changes; pair mode: this CTA's half of the 128 rows
+            const int n0 = PAIR ? (int)rank * kHBN : (tile_first % a.n_tiles) * kHBN;
+            if (leader) mbar_arrive_expect_tx(bres_bar, 9 * B_SLOT * NCTA);
 #pragma unroll 1
-            for (int t = 0; t < 9; ++t) tma_load_2d(&tmB, bres0 + t * B_SLOT, bres_bar, t * BKE, n0);
+            for (int t = 0; t < 9; ++t) {
+                if constexpr (PAIR) tma_load_2d_pair(&tmB, bres0 + t * B_SLOT, bres_bar, t * BKE, n0);
+                else tma_load_2d(&tmB, bres0 + t * B_SLOT, bres_bar, t * BKE, n0);
+            }
         }
         __syncwarp();
         int stage = 0;
         uint32_t phase = 0;
         TileWalk t(a, tile_first, tile_step);
-        for (int tile = tile_first; tile < a.total_tiles; tile += tile_step, t.next()) {
+        for (int tile = tile_first; tile < tile_end; tile += tile_step, t.next()) {
             mbar_wait(empty0 + 8 * stage, phase ^ 1, a.dbg, 0, stage);
             if (elect_one()) {
                 const uint32_t slot = stage0 + stage * a.slot_bytes, fb = full0 + 8 * stage;
                 if (STRIDE == 1) {
-                    mbar_arrive_expect_tx(fb, (uint32_t)kHPatchPix * SWZ);
-                    tma_load_4d(&tmIn, slot, fb, 0, t.x0() - 1, t.y0() - 1, t.img);
+                    if (leader) mbar_arrive_expect_tx(fb, (uint32_t)kHPatchPix * SWZ * NCTA);
+                    if constexpr (PAIR) tma_load_4d_pair(&tmIn, slot, fb, 0, t.x0() - 1, t.y0() - 1, t.img);
+                    else tma_load_4d(&tmIn, slot, fb, 0, t.x0() - 1, t.y0() - 1, t.img);
                 } else {
                     // planes: 0 = odd rows / odd cols, 1 = odd rows / even cols, 2 = even rows / odd cols, 3 = even / even
                     mbar_arrive_expect_tx(fb, 4u * kHPlanePix * SWZ);
@@ -175,48 +205,57 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmIn, const __grid_constant
             if (++stage == a.stages) { stage = 0; phase ^= 1; }
         }
     } else if (warp == 2) {
-        // ===== MMA issuer: nine taps = nine shifted views of the patch =====
-        const uint32_t idesc = make_idesc(kHBN, 128);
-        int stage = 0;
-        uint32_t phase = 0, acc = 0, acc_phase = 0;
-        if (tile_first < a.total_tiles) mbar_wait(bres_bar, 0, a.dbg, 1, 600);
-        const uint64_t bdesc0 = make_smem_desc<SWZ>(bres0);
-        for (int tile = tile_first; tile < a.total_tiles; tile += tile_step) {
-            mbar_wait(tempty0 + 8 * acc, acc_phase ^ 1, a.dbg, 1, 100 + (int)acc);
-            mbar_wait(full0 + 8 * stage, phase, a.dbg, 1, stage);
-            tc_fence_after();
-            if (elect_one()) {
-                const uint32_t d_tmem = tmem_base + acc * kHBN;
-                const uint64_t adesc0 = make_smem_desc<SWZ>(stage0 + stage * a.slot_bytes);
+        // ===== MMA issuer (pair mode: the leader's warp issues for both CTAs): nine taps = nine shifted views of the patch =====
+        if (leader) {
+            const uint32_t idesc = make_idesc((int)ACC_COLS, 128 * NCTA);
+            int stage = 0;
+            uint32_t phase = 0, acc = 0, acc_phase = 0;
+            if (tile_first < tile_end) mbar_wait(bres_bar, 0, a.dbg, 1, 600);
+            const uint64_t bdesc0 = make_smem_desc<SWZ>(bres0);
+            for (int tile = tile_first; tile < tile_end; tile += tile_step) {
+                mbar_wait(tempty0 + 8 * acc, acc_phase ^ 1, a.dbg, 1, 100 + (int)acc);
+                mbar_wait(full0 + 8 * stage, phase, a.dbg, 1, stage);
+                tc_fence_after();
+                if (elect_one()) {
+                    const uint32_t d_tmem = tmem_base + acc * ACC_COLS;
+                    const uint64_t adesc0 = make_smem_desc<SWZ>(stage0 + stage * a.slot_bytes);
 #pragma unroll
-                for (int t = 0; t < 9; ++t) {
-                    const int ky = t / 3, kx = t % 3;
-                    // stride 1: pixel (ky, kx) of the patch; stride 2: plane (ky odd?, kx odd?) at offset (ky/2, kx/2)
-                    const int pix = STRIDE == 1 ? ky * kHP + kx
-                                                : (((ky & 1) << 1) | (kx & 1)) * kHPlanePix + (ky >> 1) * kHP + (kx >> 1);
-                    const uint64_t ad = adesc0 + (uint64_t)((pix * SWZ) >> 4);
-                    const uint64_t bd = bdesc0 + (uint64_t)(t * (B_SLOT >> 4));
+                    for (int t = 0; t < 9; ++t) {
+                        const int ky = t / 3, kx = t % 3;
+                        // stride 1: pixel (ky, kx) of the patch; stride 2: plane (ky odd?, kx odd?) at offset (ky/2, kx/2)
+                        const int pix = STRIDE == 1 ? ky * kHP + kx
+                                                    : (((ky & 1) << 1) | (kx & 1)) * kHPlanePix + (ky >> 1) * kHP + (kx >> 1);
+                        const uint64_t ad = adesc0 + (uint64_t)((pix * SWZ) >> 4);
+                        const uint64_t bd = bdesc0 + (uint64_t)(t * (B_SLOT >> 4));
 #pragma unroll
-                    for (int k = 0; k < BKE / 16; ++k) umma_f16(d_tmem, ad + 2 * k, bd + 2 * k, idesc, (t | k) != 0);
+                        for (int k = 0; k < BKE / 16; ++k) {
+                            if constexpr (PAIR) umma_f16_pair(d_tmem, ad + 2 * k, bd + 2 * k, idesc, (t | k) != 0);
+                            else umma_f16(d_tmem, ad + 2 * k, bd + 2 * k, idesc, (t | k) != 0);
+                        }
+                    }
+                    if constexpr (PAIR) { umma_commit_pair(empty0 + 8 * stage); umma_commit_pair(tfull0 + 8 * acc); }
+                    else { umma_commit(empty0 + 8 * stage); umma_commit(tfull0 + 8 * acc); }
                 }
-                umma_commit(empty0 + 8 * stage);
-                umma_commit(tfull0 + 8 * acc);
+                __syncwarp();
+                if (++stage == a.stages) { stage = 0; phase ^= 1; }
+                acc ^= 1;
+                if (acc == 0) acc_phase ^= 1;
             }
-            __syncwarp();
-            if (++stage == a.stages) { stage = 0; phase ^= 1; }
-            acc ^= 1;
-            if (acc == 0) acc_phase ^= 1;
         }
+        __syncwarp();
     } else if (warp == 4) {
-        // ===== residual prefetch into the staging ring (compact 3 x 38 pixel rows) =====
+        // ===== residual prefetch into the staging ring (compact 3 x 38 pixel rows, 64 channels per slot) =====
         if (lane == 0 && a.has_res) {
             TileWalk t(a, tile_first, tile_step);
             RingWalk rw;
-            for (int tile = tile_first; tile < a.total_tiles; tile += tile_step, t.next(), rw.next((uint32_t)a.ring)) {
-                const uint32_t buf = rw.buf, ph = rw.ph;
-                mbar_wait(sempty0 + 8 * buf, ph ^ 1, a.dbg, 3, 300 + (int)buf);
-                mbar_arrive_expect_tx(sfull0 + 8 * buf, (uint32_t)kHValid * 128u);
-                tma_load_4d(&tmRes, stg0 + buf * kHStgBytes, sfull0 + 8 * buf, t.n_tile * kHBN, t.x0(), t.y0(), t.img);
+            for (int tile = tile_first; tile < tile_end; tile += tile_step, t.next()) {
+#pragma unroll 1
+                for (int j = 0; j < NSUB; ++j, rw.next((uint32_t)a.ring)) {
+                    const uint32_t buf = rw.buf, ph = rw.ph;
+                    mbar_wait(sempty0 + 8 * buf, ph ^ 1, a.dbg, 3, 300 + (int)buf);
+                    mbar_arrive_expect_tx(sfull0 + 8 * buf, (uint32_t)kHValid * 128u);
+                    tma_load_4d(&tmRes, stg0 + buf * kHStgBytes, sfull0 + 8 * buf, (t.n_tile * NSUB + j) * kHBN, t.x0(), t.y0(), t.img);
+                }
             }
         }
         __syncwarp();
@@ -227,17 +266,20 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmIn, const __grid_constant
             RingWalk rw;
             uint32_t prev = 0;
             bool first = true;
-            for (int tile = tile_first; tile < a.total_tiles; tile += tile_step, t.next(), rw.next((uint32_t)a.ring)) {
-                const uint32_t buf = rw.buf, ph = rw.ph;
-                mbar_wait(sready0 + 8 * buf, ph, a.dbg, 4, 700 + (int)buf);
-                tma_store_4d(&tmOut, stg0 + buf * kHStgBytes, t.n_tile * kHBN, t.x0(), t.y0(), t.img);
-                tma_store_commit();
-                if (!first) {                                 // the previous store has finished reading its buffer
-                    tma_store_wait_read<1>();
-                    mbar_arrive(sempty0 + 8 * prev);
+            for (int tile = tile_first; tile < tile_end; tile += tile_step, t.next()) {
+#pragma unroll 1
+                for (int j = 0; j < NSUB; ++j, rw.next((uint32_t)a.ring)) {
+                    const uint32_t buf = rw.buf, ph = rw.ph;
+                    mbar_wait(sready0 + 8 * buf, ph, a.dbg, 4, 700 + (int)buf);
+                    tma_store_4d(&tmOut, stg0 + buf * kHStgBytes, (t.n_tile * NSUB + j) * kHBN, t.x0(), t.y0(), t.img);
+                    tma_store_commit();
+                    if (!first) {                             // the previous store has finished reading its buffer
+                        tma_store_wait_read<1>();
+                        mbar_arrive(sempty0 + 8 * prev);
+                    }
+                    first = false;
+                    prev = buf;
                 }
-                first = false;
-                prev = buf;
             }
             tma_store_wait_all();
         }
@@ -252,75 +294,90 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmIn, const __grid_constant
         const int xr = mp & 7;
         uint32_t acc = 0, acc_phase = 0;
         RingWalk rw;
-        const int n0 = (tile_first % a.n_tiles) * kHBN;        // the grid is a multiple of n_tiles: constant per CTA
-        // ... and so are this thread's sixteen channels: their scale / bias pairs live in registers for the whole kernel
+        const int n0 = PAIR ? 0 : (tile_first % a.n_tiles) * kHBN;   // the grid is a multiple of n_tiles: constant per CTA
+        // ... and so are this thread's sixteen channels (single-CTA mode): their scale / bias pairs live in registers for
+        // the whole kernel; pair mode (two sub-tiles = 32 channels per thread) reads the shared-memory table
         float4 sc4[4], bi4[4];
-        {
+        if constexpr (!PAIR) {
             const float4* sc = reinterpret_cast<const float4*>(tab + n0 + part * 16);
             const float4* bi = reinterpret_cast<const float4*>(tab + a.cout_pad + n0 + part * 16);
 #pragma unroll
             for (int i = 0; i < 4; ++i) { sc4[i] = sc[i]; bi4[i] = bi[i]; }
         }
-        for (int tile = tile_first; tile < a.total_tiles; tile += tile_step, rw.next((uint32_t)a.ring)) {
-            const uint32_t buf = rw.buf, ph = rw.ph;
+        for (int tile = tile_first; tile < tile_end; tile += tile_step) {
             mbar_wait(tfull0 + 8 * acc, acc_phase, a.dbg, 2, 200 + (int)acc);
             tc_fence_after();
-            uint32_t r0[16];
-            tmem_ld16(tmem_base + acc * kHBN + ((uint32_t)(q * 32) << 16) + (uint32_t)(part * 16), r0);
-            if (a.has_res) mbar_wait(sfull0 + 8 * buf, ph, a.dbg, 2, 400 + (int)buf);
-            else mbar_wait(sempty0 + 8 * buf, ph ^ 1, a.dbg, 2, 500 + (int)buf);
-            tmem_ld_wait();
-            tc_fence_before();
-            __syncwarp();
-            if (lane == 0) mbar_arrive(tempty0 + 8 * acc);      // accumulator drained into registers
-            if (valid) {
-                uint8_t* srow = gen + (stg0 - base) + buf * kHStgBytes + (uint32_t)mp * 128u;
-                float v[16];
-#pragma unroll
-                for (int i = 0; i < 4; ++i) {
-                    const float4 s4 = sc4[i], b4 = bi4[i];
-                    v[4 * i + 0] = fmaf(__uint_as_float(r0[4 * i + 0]), s4.x, b4.x);
-                    v[4 * i + 1] = fmaf(__uint_as_float(r0[4 * i + 1]), s4.y, b4.y);
-                    v[4 * i + 2] = fmaf(__uint_as_float(r0[4 * i + 2]), s4.z, b4.z);
-                    v[4 * i + 3] = fmaf(__uint_as_float(r0[4 * i + 3]), s4.w, b4.w);
-                }
-                if (a.leaky) {
-#pragma unroll
-                    for (int i = 0; i < 16; ++i) v[i] = leaky(v[i]);
-                }
-#pragma unroll
-                for (int h = 0; h < 2; ++h) {
-                    uint4* p = reinterpret_cast<uint4*>(srow + (((part * 2 + h) ^ xr) << 4));
-                    if (a.has_res) {
-                        const uint4 rr = *p;
-                        const __half2* hh = reinterpret_cast<const __half2*>(&rr);
-#pragma unroll
-                        for (int i = 0; i < 4; ++i) {
-                            const float2 f = __half22float2(hh[i]);
-                            v[8 * h + 2 * i] += f.x;
-                            v[8 * h + 2 * i + 1] += f.y;
-                        }
+#pragma unroll 1
+            for (int j = 0; j < NSUB; ++j, rw.next((uint32_t)a.ring)) {
+                const uint32_t buf = rw.buf, ph = rw.ph;
+                uint32_t r0[16];
+                tmem_ld16(tmem_base + acc * ACC_COLS + ((uint32_t)(q * 32) << 16) + (uint32_t)(j * kHBN + part * 16), r0);
+                if (a.has_res) mbar_wait(sfull0 + 8 * buf, ph, a.dbg, 2, 400 + (int)buf);
+                else mbar_wait(sempty0 + 8 * buf, ph ^ 1, a.dbg, 2, 500 + (int)buf);
+                tmem_ld_wait();
+                if (j == NSUB - 1) {                            // accumulator drained into registers
+                    tc_fence_before();
+                    __syncwarp();
+                    if (lane == 0) {
+                        if constexpr (PAIR) mbar_arrive_leader(tempty0 + 8 * acc); else mbar_arrive(tempty0 + 8 * acc);
                     }
-                    uint4 pk;
-                    __half2* ph2 = reinterpret_cast<__half2*>(&pk);
-#pragma unroll
-                    for (int i = 0; i < 4; ++i) ph2[i] = __floats2half2_rn(v[8 * h + 2 * i], v[8 * h + 2 * i + 1]);
-                    *p = pk;
                 }
+                if (valid) {
+                    uint8_t* srow = gen + (stg0 - base) + buf * kHStgBytes + (uint32_t)mp * 128u;
+                    float v[16];
+                    if constexpr (PAIR) {
+                        const float4* sc = reinterpret_cast<const float4*>(tab + j * kHBN + part * 16);
+                        const float4* bi = reinterpret_cast<const float4*>(tab + a.cout_pad + j * kHBN + part * 16);
+#pragma unroll
+                        for (int i = 0; i < 4; ++i) { sc4[i] = sc[i]; bi4[i] = bi[i]; }
+                    }
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) {
+                        const float4 s4 = sc4[i], b4 = bi4[i];
+                        v[4 * i + 0] = fmaf(__uint_as_float(r0[4 * i + 0]), s4.x, b4.x);
+                        v[4 * i + 1] = fmaf(__uint_as_float(r0[4 * i + 1]), s4.y, b4.y);
+                        v[4 * i + 2] = fmaf(__uint_as_float(r0[4 * i + 2]), s4.z, b4.z);
+                        v[4 * i + 3] = fmaf(__uint_as_float(r0[4 * i + 3]), s4.w, b4.w);
+                    }
+                    if (a.leaky) {
+#pragma unroll
+                        for (int i = 0; i < 16; ++i) v[i] = leaky(v[i]);
+                    }
+#pragma unroll
+                    for (int h = 0; h < 2; ++h) {
+                        uint4* p = reinterpret_cast<uint4*>(srow + (((part * 2 + h) ^ xr) << 4));
+                        if (a.has_res) {
+                            const uint4 rr = *p;
+                            const __half2* hh = reinterpret_cast<const __half2*>(&rr);
+#pragma unroll
+                            for (int i = 0; i < 4; ++i) {
+                                const float2 f = __half22float2(hh[i]);
+                                v[8 * h + 2 * i] += f.x;
+                                v[8 * h + 2 * i + 1] += f.y;
+                            }
+                        }
+                        uint4 pk;
+                        __half2* ph2 = reinterpret_cast<__half2*>(&pk);
+#pragma unroll
+                        for (int i = 0; i < 4; ++i) ph2[i] = __floats2half2_rn(v[8 * h + 2 * i], v[8 * h + 2 * i + 1]);
+                        *p = pk;
+                    }
+                }
+                fence_async_smem();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(sready0 + 8 * buf);
             }
-            fence_async_smem();
-            __syncwarp();
-            if (lane == 0) mbar_arrive(sready0 + 8 * buf);
             acc ^= 1;
             if (acc == 0) acc_phase ^= 1;
         }
     }
 
     tc_fence_before();
-    __syncthreads();
+    if constexpr (PAIR) cluster_sync_all(); else __syncthreads();   // the peer may still signal this CTA's barriers / read its smem
     if (warp == 3) {
         tc_fence_after();
-        tmem_dealloc(tmem_base, 2 * kHBN);
+        if constexpr (PAIR) tmem_dealloc_pair(tmem_base, 2 * ACC_COLS);
+        else tmem_dealloc(tmem_base, 2 * ACC_COLS);
     }
 }
 
@@ -365,17 +422,25 @@ std::string halo_make_plan(HaloPlan& p, const ConvArgs& a, const __half* w16, in
     p.stride = a.stride;
     p.tiles_x = a.Wo / kHC;
     p.tiles_y = (a.Ho + kHR - 1) / kHR;
-    p.n_tiles = a.Cout / kHBN;
+    // Cout = 128 with 128-byte pixels: CTA pairs, all 128 channels in one UMMA (see the kernel's header comment)
+    p.pair = p.swz == 128 && a.stride == 1 && a.Cout == 2 * kHBN && num_sms % 2 == 0;
+    if (const char* e = getenv("YB_HALO_PAIR")) p.pair = p.pair && atoi(e) != 0;
+    p.n_tiles = p.pair ? 1 : a.Cout / kHBN;
     p.total_tiles = a.B * p.tiles_x * p.tiles_y * p.n_tiles;
-    p.ring = a.res ? 4 : 2;
+    p.ring = (a.res || p.pair) ? 4 : 2;           // slots hold 64 channels: a pair-mode tile takes two
     p.tab_bytes = (int)(((size_t)2 * cout_pad * sizeof(float) + 1023) & ~(size_t)1023);
     p.slot_bytes = (int)(((size_t)(a.stride == 1 ? kHSlotPix : kHSlotPix2) * p.swz + 1023) & ~(size_t)1023);
     const size_t fixed = 1024 + 1024 + p.tab_bytes + (size_t)p.ring * kHStgBytes + (size_t)9 * kHBN * p.swz;
     p.stages = (int)std::min<size_t>(kHMaxStages, (kHSmemBudget - fixed) / p.slot_bytes);
     if (p.stages < 2) return "not enough shared memory for two patch stages";
     p.smem = fixed + (size_t)p.stages * p.slot_bytes;
-    p.grid = std::min(p.total_tiles, num_sms);
-    p.grid -= p.grid % p.n_tiles;
+    if (p.pair) {
+        p.grid = std::min(2 * ((p.total_tiles + 1) / 2), num_sms);
+        p.grid -= p.grid % 2;
+    } else {
+        p.grid = std::min(p.total_tiles, num_sms);
+        p.grid -= p.grid % p.n_tiles;
+    }
     if (p.grid <= 0) return "grid too small for the tile split";
     const CUtensorMapSwizzle swz = p.swz == 128 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B;
     const cuuint32_t es4[4] = {1, 1, 1, 1};
@@ -432,9 +497,10 @@ cudaError_t halo_launch(const HaloPlan& p, const ConvArgs& a, int* dbg, cudaStre
     static PerDeviceOnce attr_once;
     {
         cudaError_t e = attr_once.run([] {
-            cudaError_t r = cudaFuncSetAttribute(conv_halo_kernel<128, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kHSmemBudget);
-            if (r == cudaSuccess) r = cudaFuncSetAttribute(conv_halo_kernel<64, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kHSmemBudget);
-            if (r == cudaSuccess) r = cudaFuncSetAttribute(conv_halo_kernel<64, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kHSmemBudget);
+            cudaError_t r = cudaFuncSetAttribute(conv_halo_kernel<128, 1, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kHSmemBudget);
+            if (r == cudaSuccess) r = cudaFuncSetAttribute(conv_halo_kernel<128, 1, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kHSmemBudget);
+            if (r == cudaSuccess) r = cudaFuncSetAttribute(conv_halo_kernel<64, 1, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kHSmemBudget);
+            if (r == cudaSuccess) r = cudaFuncSetAttribute(conv_halo_kernel<64, 2, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kHSmemBudget);
             return r;
         });
         if (e != cudaSuccess) return e;
@@ -445,15 +511,27 @@ cudaError_t halo_launch(const HaloPlan& p, const ConvArgs& a, int* dbg, cudaStre
     cfg.blockDim = dim3(kHThreads);
     cfg.dynamicSmemBytes = p.smem;
     cfg.stream = s;
-    cudaLaunchAttribute attr[1];
-    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
-    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cudaLaunchAttribute attr[2];
+    int na = 0;
+    if (pdl) {
+        attr[na].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+        attr[na].val.programmaticStreamSerializationAllowed = 1;
+        ++na;
+    }
+    if (p.pair) {
+        attr[na].id = cudaLaunchAttributeClusterDimension;
+        attr[na].val.clusterDim.x = 2;
+        attr[na].val.clusterDim.y = 1;
+        attr[na].val.clusterDim.z = 1;
+        ++na;
+    }
     cfg.attrs = attr;
-    cfg.numAttrs = pdl ? 1 : 0;
+    cfg.numAttrs = na;
     cudaError_t e;
-    if (p.stride == 2) e = cudaLaunchKernelEx(&cfg, conv_halo_kernel<64, 2>, p.tmIn, p.tmB, p.tmOut, p.tmRes, h);
-    else if (p.swz == 128) e = cudaLaunchKernelEx(&cfg, conv_halo_kernel<128, 1>, p.tmIn, p.tmB, p.tmOut, p.tmRes, h);
-    else e = cudaLaunchKernelEx(&cfg, conv_halo_kernel<64, 1>, p.tmIn, p.tmB, p.tmOut, p.tmRes, h);
+    if (p.stride == 2) e = cudaLaunchKernelEx(&cfg, conv_halo_kernel<64, 2, false>, p.tmIn, p.tmB, p.tmOut, p.tmRes, h);
+    else if (p.pair) e = cudaLaunchKernelEx(&cfg, conv_halo_kernel<128, 1, true>, p.tmIn, p.tmB, p.tmOut, p.tmRes, h);
+    else if (p.swz == 128) e = cudaLaunchKernelEx(&cfg, conv_halo_kernel<128, 1, false>, p.tmIn, p.tmB, p.tmOut, p.tmRes, h);
+    else e = cudaLaunchKernelEx(&cfg, conv_halo_kernel<64, 1, false>, p.tmIn, p.tmB, p.tmOut, p.tmRes, h);
     if (e != cudaSuccess) return e;
     return cudaGetLastError();
 }

@@ -133,6 +133,7 @@ struct HaloPlan {
     CUtensorMap tmIn, tmB, tmOut, tmRes;
     int swz = 128, stride = 1, cout_pad = 0, tiles_x = 0, tiles_y = 0, n_tiles = 0, total_tiles = 0;
     int ring = 0, tab_bytes = 0, slot_bytes = 0, stages = 0, grid = 0;
+    int pair = 0;         // CTA pairs: M = 256 (two spatial tiles) x N = 128 per cta_group::2 UMMA (Cout = 128, Cin = 64, stride 1)
     size_t smem = 0;
 };
 bool halo_supported(const ConvArgs& a);
