@@ -14,8 +14,11 @@ Printed JSON (one line, rank 0):
             launch stream, max over ranks);
   e2e       the same through the public Python API with HOST buffers: every step copies its batch
             from pinned host memory and reads the detections back (copy engine overlapped with
-            compute by double buffering; both inside the timed region);
-  roofline  the convolution stack (dominant kernel conv_tc_kernel, 74 launches per step + the stem):
+            compute by double buffering; both inside the timed region).  The fp32 batch is 142 MB per
+            step, so the PCIe link (~26 GB/s on the test boxes) caps this figure near 6 000 img/s per GPU;
+  e2e_u8_frames  the same from uint8 camera frames ([B,480,640,3], 29.5 MB per step): H2D copy, letterbox
+            on the device (yb_letterbox), detect, detections back -- all inside the timed region;
+  roofline  the convolution stack (conv_tc_kernel / conv_halo_kernel, 74 launches per step + the stem):
             algorithmic 2*MAC FLOPs / CUDA-event time of the conv section, against the measured
             sustained bf16 tensor peak of MEASURED_PEAKS.json;
   cpu_baseline  the CPU oracle port (torch fp32 oneDNN convs + the reference's NMS algorithm) on a
@@ -237,9 +240,11 @@ def run_ours(args):
     h_rows = torch.empty(B * (world if comm else 1), cap, 7).pin_memory()
     h_counts = torch.empty(B * (world if comm else 1), dtype=torch.int32).pin_memory()
 
-    def e2e_loop(n):
+    def e2e_loop(n, host, devb, to_input):
+        """Double-buffered: the H2D copy of step i+1 (copy stream) overlaps the compute of step i; detections of every
+        step go back to pinned host memory.  to_input maps the device copy of the host batch to the network input."""
         with torch.cuda.stream(copy_stream):
-            dx[0].copy_(hx[0], non_blocking=True)
+            devb[0].copy_(host[0], non_blocking=True)
             ready[0].record(copy_stream)
         for i in range(n):
             cur, nxt = i & 1, (i + 1) & 1
@@ -247,10 +252,10 @@ def run_ours(args):
                 with torch.cuda.stream(copy_stream):
                     if i >= 1:
                         copy_stream.wait_event(free[nxt])
-                    dx[nxt].copy_(hx[nxt], non_blocking=True)
+                    devb[nxt].copy_(host[nxt], non_blocking=True)
                     ready[nxt].record(copy_stream)
             stream.wait_event(ready[cur])
-            rows, counts, _, _ = net.detect_raw(dx[cur], CONF_THR, NMS_THR, False, True, cap)
+            rows, counts, _, _ = net.detect_raw(to_input(devb[cur]), CONF_THR, NMS_THR, False, True, cap)
             free[cur].record(stream)
             if comm is not None:
                 rows, counts = comm.allgather(rows, counts)
@@ -258,21 +263,37 @@ def run_ours(args):
             h_counts.copy_(counts, non_blocking=True)
         stream.synchronize()
 
-    e2e_loop(max(2, args.warmup))
-    torch.cuda.synchronize()
-    if world > 1:
-        dist.barrier()
-    t0 = time.perf_counter()
-    e0.record(stream)
-    e2e_loop(args.steps)
-    e1.record(stream)
-    torch.cuda.synchronize()
-    wall = (time.perf_counter() - t0) * 1e3
-    e2e_ms = max(e0.elapsed_time(e1), wall)      # the first H2D precedes e0 on the compute stream: take the longer clock
-    t = torch.tensor([e2e_ms], device=dev, dtype=torch.float64)
-    if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    e2e_ms = float(t.item())
+    def time_e2e(host, devb, to_input):
+        e2e_loop(max(2, args.warmup), host, devb, to_input)
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        t0 = time.perf_counter()
+        e0.record(stream)
+        e2e_loop(args.steps, host, devb, to_input)
+        e1.record(stream)
+        torch.cuda.synchronize()
+        wall = (time.perf_counter() - t0) * 1e3
+        v = max(e0.elapsed_time(e1), wall)       # the first H2D precedes e0 on the compute stream: take the longer clock
+        t = torch.tensor([v], device=dev, dtype=torch.float64)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    e2e_ms = time_e2e(hx, dx, lambda x: x)
+    del hx, dx
+
+    # ---- the same from camera frames: pinned uint8 [B,480,640,3] in, letterbox on the device (yb_letterbox, the N1
+    # row), detect, detections out.  The fp32 batch above is 142 MB per step, i.e. the PCIe link (~26 GB/s measured)
+    # caps it near 6 000 img/s per GPU whatever the kernels do; frames are 29.5 MB per step. ----
+    import numpy as np
+    from yolo_v3_b200.utils import letterbox_batch
+    FH, FW = 480, 640
+    frames = np.stack([synth.make_photo(FH, FW, 90 + 17 * rank + i) for i in range(B)])
+    hu = [torch.from_numpy(frames).pin_memory(), torch.from_numpy(np.ascontiguousarray(frames[::-1])).pin_memory()]
+    du = [torch.empty(B, FH, FW, 3, dtype=torch.uint8, device=dev) for _ in range(2)]
+    e2e_u8_ms = time_e2e(hu, du, lambda u: letterbox_batch(list(u), (S, S))[0])
+    del hu, du
 
     # ---- roofline: section times of the same step, CUDA events per section on the launch stream ----
     import ctypes
@@ -357,10 +378,14 @@ def run_ours(args):
                    "l2": "inputs larger than L2 (two alternating 142 MB batches; activations 0.8 GB per layer)",
                    "parallelism": f"batch-sharded x{world}, weights broadcast once, detections all-gathered per step"},
         "e2e": {"value": total_imgs / (e2e_ms * 1e-3), "unit": "images/sec", "h2d_bytes_per_step": B * 3 * S * S * 4,
-                "d2h_bytes_per_step": int(h_rows.numel() * 4 + h_counts.numel() * 4), "ms_per_step": e2e_ms / args.steps},
+                "d2h_bytes_per_step": int(h_rows.numel() * 4 + h_counts.numel() * 4), "ms_per_step": e2e_ms / args.steps,
+                "input": "fp32 [B,3,608,608] in [0,1], what the reference's predict() moves with .cuda() (test.py:32)"},
+        "e2e_u8_frames": {"value": total_imgs / (e2e_u8_ms * 1e-3), "unit": "images/sec", "h2d_bytes_per_step": B * FH * FW * 3,
+                          "d2h_bytes_per_step": int(h_rows.numel() * 4 + h_counts.numel() * 4), "ms_per_step": e2e_u8_ms / args.steps,
+                          "input": f"uint8 [B,{FH},{FW},3] frames, letterboxed to {S}x{S} on the device (yb_letterbox) inside the timed region"},
         "gpu_launches": int(launches),
         "clocks": sampler.summary(),
-        "roofline": {"bound": "tensor", "kernel": "conv_tc_kernel (74 launches/step) + stem", "achieved": achieved,
+        "roofline": {"bound": "tensor", "kernel": "conv_tc_kernel + conv_halo_kernel (74 launches/step) + stem_tc_kernel", "achieved": achieved,
                      "peak": pk["tensor"], "unit": "TFLOP/s", "frac": achieved / pk["tensor"],
                      "traffic": ncu_conv_traffic() if (S == 608 and B == 32) else None,
                      "traffic_note": "DRAM read+write bytes of the 75 conv launches of one step (ncu, profiles/r01final_conv_metrics.csv); "
