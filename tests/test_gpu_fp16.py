@@ -96,6 +96,9 @@ CASES = [
     (4, 4, 304, 304, False),   # M = 92 416 = 361 full 256-row units
     (4, 7, 304, 152, False),   # M = 80 864: odd number of 128-row tiles and a partial last one
     (6, 9, 104, 104, True),    # 64->128 stride 1 at a width the halo kernel does not take: pair mode + residual ring
+    # 32-column sub-tiles: the two halves of the epilogue warps alternate over tiles (Cout = 32) / sub-tiles (fp32 heads)
+    (2, 4, 152, 152, False),   # 722 tiles: four or five per CTA, both parities
+    (74, 8, 76, 76, False),    # head at /8: 181 pair tiles, eight fp32 sub-tiles each
     # halo kernel in pair mode (Cout = 128: two spatial tiles per cta_group::2 UMMA)
     (6, 1, 9, 38, True),       # three tiles: rank 1 of the second pair gets the zero-filled / clipped tile past the batch
     (6, 3, 5, 76, False),      # no residual: the four-slot ring recycled by the stores alone; partial last row strip

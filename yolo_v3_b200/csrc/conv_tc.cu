@@ -67,6 +67,8 @@ struct TcArgs {
     int pf_dist;             // L2 prefetch distance of the A operand, in tiles of this CTA (0 = off)
     int b_early;             // weights are touched (resident load / L2 prefetch) before griddepcontrol.wait
     int srel;                // store issuer: staging-buffer stores allowed to stay unread (0, 1 or 2)
+    int epi_split;           // sub-tiles of 32 columns occupy only half of the sixteen epilogue warps: the halves take alternate
+                             // sub-tiles (n_sub even) or alternate tiles (n_sub == 1), two hand-over chains in flight
     int epi_sleep;           // nanoseconds the epilogue warps back off between probes of the accumulator barrier (0 = spin)
     int* dbg;
     long long* trace;        // optional [6 roles][64 tiles][4] clock64 stamps of CTA 0 (YB_TC_TRACE=1)
@@ -272,8 +274,11 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     }
     if (warp == 2 && lane == 0) {
         for (int s = 0; s < a.stages; ++s) { mbar_init(full0 + 8 * s, 1); mbar_init(empty0 + 8 * s, 1); }
-        for (int i = 0; i < 2; ++i) { mbar_init(tfull0 + 8 * i, 1); mbar_init(tempty0 + 8 * i, (a.epi_staged ? kEpiWarps : 4) * NCTA); }
-        for (int i = 0; i < kMaxRing; ++i) { mbar_init(sfull0 + 8 * i, 1); mbar_init(sempty0 + 8 * i, 1); mbar_init(sready0 + 8 * i, kEpiWarps); }
+        // arrivals per accumulator: every staged-epilogue warp that reads it (split by tiles: only one half of them does)
+        const int acc_readers = !a.epi_staged ? 4 : (a.epi_split && a.n_sub == 1) ? kEpiWarps / 2 : kEpiWarps;
+        const int sub_writers = a.epi_split ? kEpiWarps / 2 : kEpiWarps;
+        for (int i = 0; i < 2; ++i) { mbar_init(tfull0 + 8 * i, 1); mbar_init(tempty0 + 8 * i, acc_readers * NCTA); }
+        for (int i = 0; i < kMaxRing; ++i) { mbar_init(sfull0 + 8 * i, 1); mbar_init(sempty0 + 8 * i, 1); mbar_init(sready0 + 8 * i, sub_writers); }
         mbar_init(bres_bar, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
@@ -547,26 +552,38 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         // Sixteen warps: warp w reads TMEM lanes 32*(w%4).. (its rows); the four warps of a row quarter each
         // take one 16-column group of every sub-tile, so a thread's share is 16 values and four warps per
         // scheduler hide each other's instruction latency (the epilogue is issue-bound, not memory-bound).
-        const int q = warp & 3, part = (warp - 8) >> 2;
+        const int q = warp & 3, praw = (warp - 8) >> 2;
+        // split mode (32-column sub-tiles): warps with praw 0-1 form group 0, praw 2-3 group 1; the groups take the even /
+        // odd sub-tiles of the CTA's sub-tile sequence G = tile index * n_sub + j -- alternate sub-tiles of every tile when
+        // n_sub is even, alternate tiles when n_sub == 1 -- so two hand-over chains are in flight instead of one
+        const int egrp = a.epi_split ? (praw >> 1) : 0;
+        const int part = a.epi_split ? (praw & 1) : praw;
+        const bool split_tiles = a.epi_split && a.n_sub == 1;
+        const int jstep = (a.epi_split && !split_tiles) ? 2 : 1;
+        const int j_first = jstep == 2 ? egrp : 0;
+        const int j_last = a.n_sub - jstep + j_first;         // the last sub-tile of a tile this warp reads
+        const int tmul = split_tiles ? 2 : 1;                 // tiles advanced per iteration
         const int row = q * 32 + lane;
         const int xr = a.sub_bytes == 128 ? (row & 7) : ((row >> 1) & 3);
         const int ngrp = a.cs >> 4;                           // 16-column groups per sub-tile: 1, 2 or 4
         const bool active = part < ngrp;
         const bool issuer = (warp == 8 && lane == 0);
-        uint32_t acc = 0, acc_phase = 0;
-        int ti = 0;
+        uint32_t acc = split_tiles ? (uint32_t)egrp : 0u, acc_phase = 0;
+        int ti = split_tiles ? egrp : 0;
         RingWalk rw;
+        if (a.epi_split && egrp) rw.next((uint32_t)a.ring);   // group 1 starts at G = 1
         // only the tile's first column is needed here: n0 = (tile % n_tiles) * BN, advanced modulo the padded width
         const int n_wrap = a.n_tiles * a.BN;
-        int n0 = (tile_first % a.n_tiles) * a.BN;
-        const int dn0 = (tile_step % a.n_tiles) * a.BN;
-        for (int tile = tile_first; tile < total_tiles; tile += tile_step, ++ti) {
+        const int tile_begin = tile_first + (split_tiles ? egrp * tile_step : 0);
+        int n0 = (tile_begin % a.n_tiles) * a.BN;
+        const int dn0 = ((tmul * tile_step) % a.n_tiles) * a.BN;
+        for (int tile = tile_begin; tile < total_tiles; tile += tmul * tile_step, ti += tmul) {
             if (issuer) YB_TRACE(2, ti, 0);
             mbar_wait_relaxed(tfull0 + 8 * acc, acc_phase, a.dbg, 2, 200 + (int)acc, a.epi_sleep);
             tc_fence_after();
             if (issuer) YB_TRACE(2, ti, 1);
             const uint32_t taddr = tmem_base + acc * acc_stride + ((uint32_t)(q * 32) << 16);
-            for (int j = 0; j < a.n_sub; ++j, rw.next((uint32_t)a.ring)) {
+            for (int j = j_first; j < a.n_sub; j += jstep) {
                 const uint32_t buf = rw.buf, ph = rw.ph;
                 uint32_t r0[16];
                 const uint32_t tcol = taddr + (uint32_t)(j * a.cs + part * 16);
@@ -577,7 +594,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                 if (issuer && j == 0) YB_TRACE(3, ti, 0);
                 tmem_ld_wait();
                 if (issuer && j == 0) YB_TRACE(3, ti, 1);
-                if (j == a.n_sub - 1) {                       // accumulator fully read: hand it back to the MMA warp
+                if (j == j_last) {                            // accumulator fully read by this warp: hand it back to the MMA warp
                     tc_fence_before();
                     __syncwarp();
                     if (lane == 0) {
@@ -593,10 +610,16 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                 __syncwarp();
                 if (lane == 0) mbar_arrive(sready0 + 8 * buf);   // no block-wide barrier: warps run ahead independently
                 if (issuer && j == 0) YB_TRACE(4, ti, 0);
+                rw.next((uint32_t)a.ring);
+                if (a.epi_split) rw.next((uint32_t)a.ring);   // the other group's sub-tile
             }
             if (issuer) YB_TRACE(2, ti, 2);
-            acc ^= 1;
-            if (acc == 0) acc_phase ^= 1;
+            if (split_tiles) {
+                acc_phase ^= 1;                               // this group always reads accumulator `egrp`
+            } else {
+                acc ^= 1;
+                if (acc == 0) acc_phase ^= 1;
+            }
             n0 += dn0;
             if (n0 >= n_wrap) n0 -= n_wrap;
         }
@@ -657,7 +680,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 // (one tcgen05.mma pair per tile: M=128, N=32, K=32).  Four TMEM accumulators of 32 columns keep the
 // producers, the tensor core and the epilogue warps (same staged TMA-store epilogue) overlapped.
 constexpr int kStemGroups = 3;            // producer groups of 128 threads
-constexpr int kStemThreads = 704;          // warps 0-11 producers (three groups), 12-19 epilogue, 20 MMA + TMEM alloc, 21 store issuer
+constexpr int kStemThreads = 704;          // warps 0-11 producers (three groups), 12-19 epilogue (two groups), 20 MMA + TMEM alloc, 21 store issuer
                                            // (22 warps)
 constexpr int kStemStages = 8;
 constexpr int kStemAcc = 4;
@@ -692,8 +715,8 @@ stem_tc_kernel(const __grid_constant__ CUtensorMap tmOut, const StemArgs a_in) {
     if (warp == 0 && lane == 0) prefetch_tmap(&tmOut);
     if (warp == 20 && lane == 0) {
         for (int s = 0; s < kStemStages; ++s) { mbar_init(full0 + 8 * s, 128); mbar_init(empty0 + 8 * s, 1); }
-        for (int i = 0; i < kStemAcc; ++i) { mbar_init(tfull0 + 8 * i, 1); mbar_init(tempty0 + 8 * i, 8); }
-        for (int i = 0; i < kStemRing; ++i) { mbar_init(sempty0 + 8 * i, 1); mbar_init(sready0 + 8 * i, 8); }
+        for (int i = 0; i < kStemAcc; ++i) { mbar_init(tfull0 + 8 * i, 1); mbar_init(tempty0 + 8 * i, 4); }     // four epilogue
+        for (int i = 0; i < kStemRing; ++i) { mbar_init(sempty0 + 8 * i, 1); mbar_init(sready0 + 8 * i, 4); }   // warps per tile
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 20) tmem_alloc(smem_u32(const_cast<uint32_t*>(tmem_ptr)), 32 * kStemAcc);
@@ -846,22 +869,25 @@ stem_tc_kernel(const __grid_constant__ CUtensorMap tmOut, const StemArgs a_in) {
         }
         __syncwarp();
     } else if (warp >= 12 && warp < 20) {
-        // ===== epilogue (8 warps, 16 columns per thread): TMEM -> scale/bias/LeakyReLU -> fp16 -> swizzled smem.
-        // A thread owns the same 16 channels in every tile, so their scale/bias live in registers. =====
-        const int q = warp & 3, part = (warp - 12) >> 2;
+        // ===== epilogue: TMEM -> scale/bias/LeakyReLU -> fp16 -> swizzled smem.  Two groups of four warps take ALTERNATE
+        // tiles (a warp owns the 32 rows of TMEM lane quarter warp % 4 and all 32 channels): the per-tile chain
+        // accumulator-ready -> tcgen05.ld -> math -> staged write -> hand-over is ~800 cycles of dependent latency however
+        // many warps share a tile, and with one group it paced the kernel (624 tiles per CTA x 822 cycles = the 0.27 ms). =====
+        const int q = warp & 3, grp = (warp - 12) >> 2;
         const int row = q * 32 + lane;
         const int xr = (row >> 1) & 3;
-        float sc[16], bi[16];
-#pragma unroll
-        for (int j = 0; j < 16; ++j) { sc[j] = a.epi.tab[part * 16 + j]; bi[j] = a.epi.tab[32 + part * 16 + j]; }
-        uint32_t acc = 0, acc_phase = 0, g = 0;
-        for (int tile = blockIdx.x; tile < a.tiles; tile += gridDim.x, ++g) {
+        const float4* sc4 = reinterpret_cast<const float4*>(a.epi.tab);     // scale[32] | bias[32] (shared memory, broadcast reads)
+        const float4* bi4 = sc4 + 8;
+        uint32_t g = (uint32_t)grp;                                          // index of the tile among this CTA's tiles
+        for (int tile = (int)blockIdx.x + grp * (int)gridDim.x; tile < a.tiles; tile += 2 * (int)gridDim.x, g += 2) {
+            const uint32_t acc = g % kStemAcc, acc_phase = (g / kStemAcc) & 1u;
             const uint32_t buf = g % kStemRing, ph = (g / kStemRing) & 1u;
             mbar_wait(tfull0 + 8 * acc, acc_phase, a.epi.dbg, 2, 200 + (int)acc);
             tc_fence_after();
-            uint32_t r0[16];
+            uint32_t r0[16], r1[16];
             const uint32_t taddr = tmem_base + acc * 32 + ((uint32_t)(q * 32) << 16);
-            tmem_ld16(taddr + part * 16, r0);
+            tmem_ld16(taddr, r0);
+            tmem_ld16(taddr + 16, r1);
             mbar_wait(sempty0 + 8 * buf, ph ^ 1, a.epi.dbg, 2, 500 + (int)buf);
             tmem_ld_wait();
             tc_fence_before();
@@ -869,22 +895,21 @@ stem_tc_kernel(const __grid_constant__ CUtensorMap tmOut, const StemArgs a_in) {
             if (lane == 0) mbar_arrive(tempty0 + 8 * acc);   // accumulator drained into registers
             uint8_t* srow = gen + (stg0 - base) + buf * STG_BYTES + row * 64;
 #pragma unroll
-            for (int h = 0; h < 2; ++h) {
+            for (int c = 0; c < 4; ++c) {                     // 16-byte chunk c = channels 8c .. 8c+7
+                const uint32_t* rr = c < 2 ? r0 : r1;
+                const int j0 = 8 * (c & 1);
+                const float4 s0 = sc4[2 * c], s1 = sc4[2 * c + 1], b0 = bi4[2 * c], b1 = bi4[2 * c + 1];
                 uint4 pk;
                 __half2* ph2 = reinterpret_cast<__half2*>(&pk);
-#pragma unroll
-                for (int e = 0; e < 4; ++e) {
-                    const int j = 8 * h + 2 * e;
-                    const float v0 = leaky(fmaf(__uint_as_float(r0[j]), sc[j], bi[j]));
-                    const float v1 = leaky(fmaf(__uint_as_float(r0[j + 1]), sc[j + 1], bi[j + 1]));
-                    ph2[e] = __floats2half2_rn(v0, v1);
-                }
-                *reinterpret_cast<uint4*>(srow + (((part * 2 + h) ^ xr) << 4)) = pk;
+                ph2[0] = __floats2half2_rn(leaky(fmaf(__uint_as_float(rr[j0 + 0]), s0.x, b0.x)), leaky(fmaf(__uint_as_float(rr[j0 + 1]), s0.y, b0.y)));
+                ph2[1] = __floats2half2_rn(leaky(fmaf(__uint_as_float(rr[j0 + 2]), s0.z, b0.z)), leaky(fmaf(__uint_as_float(rr[j0 + 3]), s0.w, b0.w)));
+                ph2[2] = __floats2half2_rn(leaky(fmaf(__uint_as_float(rr[j0 + 4]), s1.x, b1.x)), leaky(fmaf(__uint_as_float(rr[j0 + 5]), s1.y, b1.y)));
+                ph2[3] = __floats2half2_rn(leaky(fmaf(__uint_as_float(rr[j0 + 6]), s1.z, b1.z)), leaky(fmaf(__uint_as_float(rr[j0 + 7]), s1.w, b1.w)));
+                *reinterpret_cast<uint4*>(srow + ((c ^ xr) << 4)) = pk;
             }
             fence_async_smem();
             __syncwarp();
             if (lane == 0) mbar_arrive(sready0 + 8 * buf);
-            if (++acc == kStemAcc) { acc = 0; acc_phase ^= 1; }
         }
     }
     tc_fence_before();
@@ -991,6 +1016,11 @@ std::string tc_make_plan(TcPlan& p, const ConvArgs& a, const __half* w16, int co
     p.n_sub = p.epi_staged ? p.BN / p.cs : 0;
     if (p.epi_staged) p.ring = a.res ? 4 : 2;
     if (const char* e = getenv("YB_TC_RING")) if (p.epi_staged) p.ring = std::max(2, std::min(kMaxRing, atoi(e)));
+    // 32-column sub-tiles (Cout = 32 in fp16, the fp32 head maps) keep only eight of the sixteen epilogue warps busy:
+    // the two halves then work on alternate sub-tiles, each with its own slot of a four-deep ring
+    p.epi_split = p.epi_staged && p.cs == 32 && (p.n_sub == 1 || p.n_sub % 2 == 0);
+    if (const char* e = getenv("YB_TC_EPISPLIT")) p.epi_split = p.epi_split && atoi(e) != 0;
+    if (p.epi_split) p.ring = 4;
     const size_t stg_bytes = ((size_t)kBM * p.sub_bytes + 1023) & ~(size_t)1023;
     const size_t ring_bytes = p.epi_staged ? p.ring * stg_bytes : 0;
     p.grid = p.cta2 ? 2 * (int)std::min<long>((long)p.m_tiles * p.n_tiles, num_sms / 2)
@@ -1193,6 +1223,7 @@ cudaError_t tc_launch(const TcPlan& p, const ConvArgs& a, int* dbg, cudaStream_t
         t.epi_sleep = p.num_kblocks >= 8 ? epi_sleep : 0;
     }
     t.exp_tiled = p.exp_tiled;
+    t.epi_split = p.epi_split;
     {
         static const int nostore = getenv("YB_TC_EXP_NOSTORE") ? atoi(getenv("YB_TC_EXP_NOSTORE")) : 0;
         t.exp_nostore = nostore;

@@ -98,6 +98,7 @@ struct TcPlan {
     int BN = 0, n_tiles = 0, m_tiles = 0, stages = 0, tmem_cols = 0;
     int num_kblocks = 0, cin_blocks = 0, kps = 1, cta2 = 0, cout_pad = 0, tab_bytes = 0;
     int pf_dist = 0, b_early = 0, srel = 0;
+    int epi_split = 0;    // 32-column sub-tiles: the two halves of the epilogue warps take alternate sub-tiles
     int grid = 0;
     size_t smem = 0;
     long M = 0;
