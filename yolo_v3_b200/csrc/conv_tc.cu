@@ -624,7 +624,9 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             if (n0 >= n_wrap) n0 -= n_wrap;
         }
     } else if (warp >= 8 && warp < 12) {
-        // ===== epilogue (direct, warps 8-11 only): TMEM -> registers -> global, used by the nearest-upsample layers =====
+        // ===== epilogue (direct, warps 8-11 only): TMEM -> registers -> global, used by the nearest-upsample layers.
+        // (Spreading the columns over all sixteen warps changes nothing -- profiles/README.md r01x: the 2x2-replicated
+        // 32-byte stores, one 768-byte pixel pitch apart per lane, are what these two layers wait for.) =====
         const int q = warp & 3;                               // TMEM lane quarter this warp may read
         const int row = q * 32 + lane;
         uint32_t acc = 0, acc_phase = 0;
@@ -808,6 +810,19 @@ stem_tc_kernel(const __grid_constant__ CUtensorMap tmOut, const StemArgs a_in) {
                 for (int k = 0; k < 27; ++k) v[k] = 0.f;
             }
         };
+        // L2 prefetch of this thread's pixel pf_dist rounds ahead (its three channel values of the centre row; the rows
+        // above / below are the centre rows of tiles that other CTAs gather at about the same time).  With one tile of
+        // loads in flight per producer group the gather waits out a DRAM round trip per tile (~2 300 cycles: 142 MB in
+        // 0.25 ms is what 148 SMs x 3 groups x 1.5 KB per ~1.2 us amounts to); prefetched, it waits for L2.
+        long m2 = m;
+        int pb2 = pb, py2 = py, px2 = px;
+        auto advance2 = [&]() {
+            m2 += dm;
+            px2 += dx; if (px2 >= a.W) { px2 -= a.W; ++py2; }
+            py2 += dy; if (py2 >= a.H) { py2 -= a.H; ++pb2; }
+            pb2 += db;
+        };
+        for (int k = 0; k < a.pf_dist; ++k) advance2();
         float v[27];
         if (tile < a.tiles) gather(v);
         while (tile < a.tiles) {
@@ -819,6 +834,15 @@ stem_tc_kernel(const __grid_constant__ CUtensorMap tmOut, const StemArgs a_in) {
             h[14] = __floats2half2_rn(0.f, 0.f);
             h[15] = h[14];
             advance();
+            if (a.pf_dist) {
+                advance2();
+                if (m2 < a.M) {
+                    const float* p2 = a.x + (long)pb2 * img_stride + py2 * a.W + px2;
+                    asm volatile("prefetch.global.L2 [%0];" ::"l"(p2));
+                    asm volatile("prefetch.global.L2 [%0];" ::"l"(p2 + HW));
+                    asm volatile("prefetch.global.L2 [%0];" ::"l"(p2 + 2 * HW));
+                }
+            }
             gather(v);                                     // next tile's loads in flight (zeros past the end)
             const int stage = i % kStemStages;
             const uint32_t phase = (uint32_t)(i / kStemStages) & 1u;
