@@ -379,7 +379,7 @@ def run_ours(args):
                    "parallelism": f"batch-sharded x{world}, weights broadcast once, detections all-gathered per step"},
         "e2e": {"value": total_imgs / (e2e_ms * 1e-3), "unit": "images/sec", "h2d_bytes_per_step": B * 3 * S * S * 4,
                 "d2h_bytes_per_step": int(h_rows.numel() * 4 + h_counts.numel() * 4), "ms_per_step": e2e_ms / args.steps,
-                "input": "fp32 [B,3,608,608] in [0,1], what the reference's predict() moves with .cuda() (test.py:32)"},
+                "input": f"fp32 [B,3,{S},{S}] in [0,1], what the reference's predict() moves with .cuda() (test.py:32)"},
         "e2e_u8_frames": {"value": total_imgs / (e2e_u8_ms * 1e-3), "unit": "images/sec", "h2d_bytes_per_step": B * FH * FW * 3,
                           "d2h_bytes_per_step": int(h_rows.numel() * 4 + h_counts.numel() * 4), "ms_per_step": e2e_u8_ms / args.steps,
                           "input": f"uint8 [B,{FH},{FW},3] frames, letterboxed to {S}x{S} on the device (yb_letterbox) inside the timed region"},

@@ -51,6 +51,7 @@ struct HaloArgs {
     const float* scale; const float* bias;
     int cout_pad, tab_bytes;
     int leaky, has_res, ring;
+    int b_early;                  // request the weight slab before griddepcontrol.wait
     int* dbg;
 };
 
@@ -167,20 +168,27 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmIn, const __grid_constant
     tc_fence_after();
     const uint32_t tmem_base = *tmem_ptr;
     pdl_launch_dependents();
+    // the resident weight slab (one elected thread of warp 0).  The weights do not depend on the previous layer, so with
+    // b_early they are requested before waiting for it and arrive under its tail.
+    auto load_slab = [&]() {
+        // the grid is a multiple of n_tiles: a CTA's n-tile never changes; pair mode: this CTA's half of the 128 rows
+        const int n0 = PAIR ? (int)rank * kHBN : (tile_first % a.n_tiles) * kHBN;
+        if (leader) mbar_arrive_expect_tx(bres_bar, 9 * B_SLOT * NCTA);
+#pragma unroll 1
+        for (int t = 0; t < 9; ++t) {
+            if constexpr (PAIR) tma_load_2d_pair(&tmB, bres0 + t * B_SLOT, bres_bar, t * BKE, n0);
+            else tma_load_2d(&tmB, bres0 + t * B_SLOT, bres_bar, t * BKE, n0);
+        }
+    };
+    if (warp == 0 && a.b_early) {
+        if (tile_first < tile_end && elect_one()) load_slab();
+        __syncwarp();
+    }
     pdl_wait_prior();
 
     if (warp == 0) {
         // ===== TMA producer: the resident weight slab once, then one patch per tile =====
-        if (tile_first < tile_end && elect_one()) {
-            // the grid is a multiple of n_tiles: a CTA's n-tile never changes; pair mode: this CTA's half of the 128 rows
-            const int n0 = PAIR ? (int)rank * kHBN : (tile_first % a.n_tiles) * kHBN;
-            if (leader) mbar_arrive_expect_tx(bres_bar, 9 * B_SLOT * NCTA);
-#pragma unroll 1
-            for (int t = 0; t < 9; ++t) {
-                if constexpr (PAIR) tma_load_2d_pair(&tmB, bres0 + t * B_SLOT, bres_bar, t * BKE, n0);
-                else tma_load_2d(&tmB, bres0 + t * B_SLOT, bres_bar, t * BKE, n0);
-            }
-        }
+        if (!a.b_early && tile_first < tile_end && elect_one()) load_slab();
         __syncwarp();
         int stage = 0;
         uint32_t phase = 0;
@@ -494,6 +502,10 @@ cudaError_t halo_launch(const HaloPlan& p, const ConvArgs& a, int* dbg, cudaStre
     h.cout_pad = p.cout_pad; h.tab_bytes = p.tab_bytes;
     h.leaky = a.leaky; h.has_res = a.res != nullptr; h.ring = p.ring;
     h.dbg = dbg;
+    {
+        static const int b_early = getenv("YB_TC_BEARLY") ? atoi(getenv("YB_TC_BEARLY")) != 0 : 0;
+        h.b_early = b_early;
+    }
     static PerDeviceOnce attr_once;
     {
         cudaError_t e = attr_once.run([] {
