@@ -1106,6 +1106,11 @@ std::string tc_make_plan(TcPlan& p, const ConvArgs& a, const __half* w16, int co
         if (r != CUDA_SUCCESS) return cu_err("cuTensorMapEncodeTiled(weights)", r);
     }
     p.exp_tiled = a.ks == 3 && getenv("YB_TC_EXP_TILED") && atoi(getenv("YB_TC_EXP_TILED")) != 0;
+    if (p.exp_tiled) {
+        static bool warned = false;
+        if (!warned) fprintf(stderr, "[yolo_b200] YB_TC_EXP_TILED is a TIMING experiment: 3x3 convolution results are WRONG\n");
+        warned = true;
+    }
     if (a.ks == 1 || p.exp_tiled) {
         // A: [M][Cin] with pixel pitch in_ld; rows past M are zero-filled
         cuuint64_t dims[2] = {(cuuint64_t)a.Cin, (cuuint64_t)p.M};
@@ -1249,7 +1254,11 @@ cudaError_t tc_launch(const TcPlan& p, const ConvArgs& a, int* dbg, cudaStream_t
     t.exp_tiled = p.exp_tiled;
     t.epi_split = p.epi_split;
     {
-        static const int nostore = getenv("YB_TC_EXP_NOSTORE") ? atoi(getenv("YB_TC_EXP_NOSTORE")) : 0;
+        static const int nostore = [] {
+            const int v = getenv("YB_TC_EXP_NOSTORE") ? atoi(getenv("YB_TC_EXP_NOSTORE")) : 0;
+            if (v) fprintf(stderr, "[yolo_b200] YB_TC_EXP_NOSTORE is a TIMING experiment: convolution outputs are NOT written\n");
+            return v;
+        }();
         t.exp_nostore = nostore;
     }
     t.dbg = dbg;
