@@ -295,6 +295,15 @@ def run_ours(args):
     e2e_u8_ms = time_e2e(hu, du, lambda u: letterbox_batch(list(u), (S, S))[0])
     del hu, du
 
+    # ---- and from fp16 images read by the stem directly (yb_set_input_dtype; same detections as the fp32 batches, half
+    # the PCIe bytes).  Opt-in with the library path it exercises (YB_INPUT_F16=1) until validated on the GPU box. ----
+    e2e_f16_ms = None
+    if os.environ.get("YB_INPUT_F16") == "1" and args.precision == "fp16":
+        hh = [synth.make_images(B, S, S, seed=7 + i).half().pin_memory() for i in range(2)]
+        dh = [torch.empty(B, 3, S, S, dtype=torch.float16, device=dev) for _ in range(2)]
+        e2e_f16_ms = time_e2e(hh, dh, lambda x: x)
+        del hh, dh
+
     # ---- roofline: section times of the same step, CUDA events per section on the launch stream ----
     import ctypes
     # events at the section boundaries, recorded without synchronising so that the steps still run back to back as in
@@ -405,6 +414,10 @@ def run_ours(args):
         "cpu_baseline": cpu,
         "detections_last_step": int(counts_h.sum()),
     }
+    if e2e_f16_ms is not None:
+        line["e2e_f16_input"] = {"value": total_imgs / (e2e_f16_ms * 1e-3), "unit": "images/sec", "h2d_bytes_per_step": B * 3 * S * S * 2,
+                                 "d2h_bytes_per_step": int(h_rows.numel() * 4 + h_counts.numel() * 4), "ms_per_step": e2e_f16_ms / args.steps,
+                                 "input": f"fp16 [B,3,{S},{S}] read by the stem directly (bit-identical detections)"}
     emit(line)
     if args.layers:
         specs = topology.layer_specs(80)

@@ -79,6 +79,15 @@ int yb_save_darknet_blob(const yb_ctx* ctx, float* host_out, size_t capacity, in
  * mode and uploads them.  Must be called after the weights change and before forward.  Synchronous. */
 int yb_finalize(yb_ctx* ctx, int precision_mode);
 
+/* Element type of the images handed to yb_forward / yb_forward_logits / yb_backbone / yb_detect (x_nchw is then read as
+ * that type).  The reference's callers hold fp32 tensors (imgs.cuda(), test.py:32): YB_INPUT_F32, the default.  With
+ * YB_INPUT_F16 (YB_MODE_FP16 only) the stem reads fp16 [B,3,H,W] and produces the SAME bits -- the fp32 path rounds every
+ * pixel to fp16 (round to nearest even, what Tensor.half() does on the host) before the tensor core sees it -- for half
+ * the host-to-device bytes. */
+#define YB_INPUT_F32 0
+#define YB_INPUT_F16 1
+int yb_set_input_dtype(yb_ctx* ctx, int dtype);
+
 /* ---- the hot path ---------------------------------------------------------------------------- */
 
 /* Replaces YoloNet.forward(x, target=None) + torch.cat((det1,det2,det3),1) (darknet.py:198-231,

@@ -15,6 +15,8 @@ LIB_PATH = os.path.join(HERE, "lib", "libyolo_b200.so")
 
 YB_MODE_FP32 = 0
 YB_MODE_FP16 = 1
+YB_INPUT_F32 = 0
+YB_INPUT_F16 = 1
 YB_E_CAP = -6
 
 # name -> (restype, argtypes); every entry point declared in include/yolo_b200.h
@@ -29,6 +31,7 @@ PROTOTYPES = {
     "yb_load_darknet_blob": (c_int, [c_void_p, c_void_p, c_size_t, c_int, POINTER(c_size_t)]),
     "yb_save_darknet_blob": (c_int, [c_void_p, c_void_p, c_size_t, c_int, POINTER(c_size_t)]),
     "yb_finalize": (c_int, [c_void_p, c_int]),
+    "yb_set_input_dtype": (c_int, [c_void_p, c_int]),
     "yb_forward": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_void_p, c_void_p]),
     "yb_forward_logits": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p]),
     "yb_backbone": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_void_p, c_void_p]),

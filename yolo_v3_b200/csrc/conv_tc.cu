@@ -689,7 +689,7 @@ constexpr int kStemAcc = 4;
 constexpr int kStemRing = 4;              // epilogue staging buffers (a two-deep ring chained the tiles one after another)
 
 struct StemArgs {
-    const float* x;
+    const void* x;                          // NCHW image, fp32 or fp16 (kernel template parameter)
     int B, H, W;
     long M;
     int tiles;
@@ -698,6 +698,13 @@ struct StemArgs {
     const __half* w;                        // [32][32] fp16, k = (ky*3+kx)*3 + c, zero padded
 };
 
+// TIn: element type of the caller's image.  fp32 is what the reference's callers hold; the fp16 instantiation reads half
+// the bytes and produces the same bits, because the fp32 path rounds every pixel to fp16 (round to nearest even, what
+// Tensor.half() does on the host) before it reaches the tensor core anyway.
+__device__ __forceinline__ float stem_ld(const float* p) { return __ldg(p); }
+__device__ __forceinline__ float stem_ld(const __half* p) { return __half2float(__ldg(p)); }
+
+template <typename TIn>
 __global__ void __launch_bounds__(kStemThreads, 1)
 stem_tc_kernel(const __grid_constant__ CUtensorMap tmOut, const StemArgs a_in) {
     StemArgs a = a_in;
@@ -778,16 +785,16 @@ stem_tc_kernel(const __grid_constant__ CUtensorMap tmOut, const StemArgs a_in) {
         };
         auto gather = [&](float (&v)[27]) {
             if (m < a.M) {
-                const float* p = a.x + (long)pb * img_stride + py * a.W + px;
+                const TIn* p = static_cast<const TIn*>(a.x) + (long)pb * img_stride + py * a.W + px;
                 if (py >= 1 && py < a.H - 1 && px >= 1 && px < a.W - 1) {
 #pragma unroll
                     for (int c = 0; c < 3; ++c) {
 #pragma unroll
                         for (int ky = 0; ky < 3; ++ky) {
-                            const float* q = p + c * HW + (ky - 1) * a.W;
-                            v[(ky * 3 + 0) * 3 + c] = __ldg(q - 1);
-                            v[(ky * 3 + 1) * 3 + c] = __ldg(q);
-                            v[(ky * 3 + 2) * 3 + c] = __ldg(q + 1);
+                            const TIn* q = p + c * HW + (ky - 1) * a.W;
+                            v[(ky * 3 + 0) * 3 + c] = stem_ld(q - 1);
+                            v[(ky * 3 + 1) * 3 + c] = stem_ld(q);
+                            v[(ky * 3 + 2) * 3 + c] = stem_ld(q + 1);
                         }
                     }
                 } else {
@@ -801,7 +808,7 @@ stem_tc_kernel(const __grid_constant__ CUtensorMap tmOut, const StemArgs a_in) {
                             const bool ok = oky && ix >= 0 && ix < a.W;
 #pragma unroll
                             for (int c = 0; c < 3; ++c)
-                                v[(ky * 3 + kx) * 3 + c] = ok ? __ldg(p + c * HW + (ky - 1) * a.W + (kx - 1)) : 0.f;
+                                v[(ky * 3 + kx) * 3 + c] = ok ? stem_ld(p + c * HW + (ky - 1) * a.W + (kx - 1)) : 0.f;
                         }
                     }
                 }
@@ -837,7 +844,7 @@ stem_tc_kernel(const __grid_constant__ CUtensorMap tmOut, const StemArgs a_in) {
             if (a.pf_dist) {
                 advance2();
                 if (m2 < a.M) {
-                    const float* p2 = a.x + (long)pb2 * img_stride + py2 * a.W + px2;
+                    const TIn* p2 = static_cast<const TIn*>(a.x) + (long)pb2 * img_stride + py2 * a.W + px2;
                     asm volatile("prefetch.global.L2 [%0];" ::"l"(p2));
                     asm volatile("prefetch.global.L2 [%0];" ::"l"(p2 + HW));
                     asm volatile("prefetch.global.L2 [%0];" ::"l"(p2 + 2 * HW));
@@ -1189,7 +1196,7 @@ std::string stem_tc_make_plan(StemTcPlan& p, __half* out, long out_ld, int B, in
     return "";
 }
 
-cudaError_t stem_tc_launch(const StemTcPlan& p, const float* x, int B, int H, int W, const __half* w16, const float* scale,
+cudaError_t stem_tc_launch(const StemTcPlan& p, const void* x, int in_f16, int B, int H, int W, const __half* w16, const float* scale,
                            const float* bias, int* dbg, cudaStream_t s) {
     StemArgs a{};
     a.x = x; a.B = B; a.H = H; a.W = W; a.M = p.M; a.tiles = p.tiles; a.w = w16;
@@ -1200,7 +1207,11 @@ cudaError_t stem_tc_launch(const StemTcPlan& p, const float* x, int B, int H, in
     a.epi.scale = scale; a.epi.bias = bias; a.epi.leaky = 1; a.epi.out_f32 = 0; a.epi.has_res = 0; a.epi.dbg = dbg;
     static PerDeviceOnce attr_once;
     {
-        cudaError_t e = attr_once.run([] { return cudaFuncSetAttribute(stem_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 128 * 1024); });
+        cudaError_t e = attr_once.run([] {
+            cudaError_t r = cudaFuncSetAttribute(stem_tc_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, 128 * 1024);
+            if (r == cudaSuccess) r = cudaFuncSetAttribute(stem_tc_kernel<__half>, cudaFuncAttributeMaxDynamicSharedMemorySize, 128 * 1024);
+            return r;
+        });
         if (e != cudaSuccess) return e;
     }
     {
@@ -1215,7 +1226,8 @@ cudaError_t stem_tc_launch(const StemTcPlan& p, const float* x, int B, int H, in
         attr[0].val.programmaticStreamSerializationAllowed = 1;
         cfg.attrs = attr;
         cfg.numAttrs = pdl ? 1 : 0;
-        cudaError_t e = cudaLaunchKernelEx(&cfg, stem_tc_kernel, p.tmOut, a);
+        cudaError_t e = in_f16 ? cudaLaunchKernelEx(&cfg, stem_tc_kernel<__half>, p.tmOut, a)
+                               : cudaLaunchKernelEx(&cfg, stem_tc_kernel<float>, p.tmOut, a);
         if (e != cudaSuccess) return e;
     }
     return cudaGetLastError();

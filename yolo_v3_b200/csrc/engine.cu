@@ -62,6 +62,7 @@ struct yb_ctx {
     std::vector<std::pair<std::string, Slot>> keys;         // registration order
     std::map<std::string, int> key_index;
     int mode = -1;
+    int input_f16 = 0;                // element type of the images handed to yb_forward / yb_detect / ... (yb_set_input_dtype)
     bool finalized = false;
     unsigned char* d_blob = nullptr;
     size_t blob_bytes = 0;
@@ -408,10 +409,12 @@ int run_ops(yb_ctx* c, Plan* p, const float* x, int n_ops, cudaStream_t s) {
         const Layer& L = c->layers[op.layer];
         cudaError_t e;
         if (op.stem) {
+            if (c->input_f16 && (p->mode != YB_MODE_FP16 || op.stem_rows))
+                return fail(c, YB_E_UNSUPPORTED, "fp16 input images need YB_MODE_FP16 and the default stem kernel");
             if (p->mode == YB_MODE_FP16 && op.stem_rows)
                 e = stem_rows_launch(op.stem_rows_plan, x, p->B, p->H, p->W, L.d_w16, L.d_scale, L.d_bias, c->dbg, s);
             else if (p->mode == YB_MODE_FP16)
-                e = stem_tc_launch(op.stem_tc, x, p->B, p->H, p->W, L.d_w16, L.d_scale, L.d_bias, c->dbg, s);
+                e = stem_tc_launch(op.stem_tc, x, c->input_f16, p->B, p->H, p->W, L.d_w16, L.d_scale, L.d_bias, c->dbg, s);
             else
                 e = launch_stem<float>(x, static_cast<float*>(op.a.out), L.d_w32, L.d_scale, L.d_bias, p->B, p->H, p->W, s);
         } else if (op.use_halo) {
@@ -1001,6 +1004,13 @@ int yb_allgather_dets(yb_ctx* c, const float* rows7, const int* counts, int B_lo
     return rc ? fail(c, rc, err) : YB_OK;
 }
 
+int yb_set_input_dtype(yb_ctx* c, int dtype) {
+    if (!c) return fail(nullptr, YB_E_ARG, "null ctx");
+    if (dtype != YB_INPUT_F32 && dtype != YB_INPUT_F16) return fail(c, YB_E_ARG, "yb_set_input_dtype: unknown element type");
+    c->input_f16 = dtype == YB_INPUT_F16;
+    return YB_OK;
+}
+
 long long yb_launch_count(const yb_ctx* c) { return c ? c->launches : 0; }
 
 int yb_debug_words(const yb_ctx* c, int* out, int n) {
@@ -1059,6 +1069,8 @@ int yb_run_layer(yb_ctx* c, int li, const void* in, int B, int H, int W, const v
     const Layer& L = c->layers[li];
     if (li == 0) {
         cudaError_t e;
+        if (c->input_f16 && (c->mode != YB_MODE_FP16 || stem_rows_supported(B, H, W)))
+            return fail(c, YB_E_UNSUPPORTED, "fp16 input images need YB_MODE_FP16 and the default stem kernel");
         if (c->mode == YB_MODE_FP16 && stem_rows_supported(B, H, W)) {
             StemRowsPlan sp;
             std::string err = stem_rows_make_plan(sp, static_cast<__half*>(out), 32, B, H, W, c->num_sms);
@@ -1068,7 +1080,7 @@ int yb_run_layer(yb_ctx* c, int li, const void* in, int B, int H, int W, const v
             StemTcPlan sp;
             std::string err = stem_tc_make_plan(sp, static_cast<__half*>(out), 32, B, H, W, c->num_sms);
             if (!err.empty()) return fail(c, YB_E_CUDA, "yb_run_layer: " + err);
-            e = stem_tc_launch(sp, static_cast<const float*>(in), B, H, W, L.d_w16, L.d_scale, L.d_bias, c->dbg, s);
+            e = stem_tc_launch(sp, in, c->input_f16, B, H, W, L.d_w16, L.d_scale, L.d_bias, c->dbg, s);
         } else {
             e = launch_stem<float>(static_cast<const float*>(in), static_cast<float*>(out), L.d_w32, L.d_scale, L.d_bias, B, H, W, s);
         }

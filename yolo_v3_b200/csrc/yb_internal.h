@@ -115,7 +115,8 @@ struct StemTcPlan {
     size_t smem = 0;
 };
 std::string stem_tc_make_plan(StemTcPlan& p, __half* out, long out_ld, int B, int H, int W, int num_sms);
-cudaError_t stem_tc_launch(const StemTcPlan& p, const float* x, int B, int H, int W, const __half* w16, const float* scale,
+// x: the caller's NCHW image, fp32 (in_f16 = 0) or fp16 (in_f16 = 1)
+cudaError_t stem_tc_launch(const StemTcPlan& p, const void* x, int in_f16, int B, int H, int W, const __half* w16, const float* scale,
                            const float* bias, int* dbg, cudaStream_t s);
 
 // stem_rows.cu  (Cin = 3 stem from a [pixel][8 fp16] patch, tap pairs through the leading-dimension offset; W % 38 == 0)

@@ -162,6 +162,7 @@ class YoloNet(nn.Module):
         self._ctx = None
         self._ctx_device = None
         self._sig = None
+        self._in_dtype = _lib.YB_INPUT_F32
         self.header = torch.tensor([0, 2, 0, 0, 0], dtype=torch.int32)
         self.seen = self.header[3]
 
@@ -185,6 +186,7 @@ class YoloNet(nn.Module):
             self._ctx = _lib.create_ctx(index, self.numClass, self.anchors)
             self._ctx_device = index
             self._sig = None
+            self._in_dtype = _lib.YB_INPUT_F32          # a new context reads fp32 images
         sig = self._signature(device)
         if sig != self._sig:
             for k, v in self._named_tensors():
@@ -213,17 +215,30 @@ class YoloNet(nn.Module):
         except Exception:
             pass
 
-    @staticmethod
-    def _check_input(x):
+    def _check_input(self, x):
         if not isinstance(x, torch.Tensor) or x.dim() != 4 or x.shape[1] != 3:
             raise ValueError("expected a [B,3,H,W] tensor")
         if not x.is_cuda:
             raise RuntimeError("yolo_v3_b200 runs on CUDA devices only (no CPU fallback): got a CPU tensor")
         if x.shape[2] % 32 or x.shape[3] % 32:
             raise ValueError("H and W must be multiples of 32")
-        if x.dtype != torch.float32:
+        # fp16 images can be read by the stem directly (yb_set_input_dtype): same bits as the fp32 path, which rounds
+        # every pixel to fp16 itself, for half the host-to-device bytes.  Opt-in (YB_INPUT_F16=1) until it has been
+        # validated on the GPU box; otherwise any other dtype is widened to fp32, as the reference's callers pass it.
+        direct_f16 = (x.dtype == torch.float16 and self.precision == "fp16" and os.environ.get("YB_INPUT_F16") == "1")
+        if not direct_f16 and x.dtype != torch.float32:
             x = x.float()
         return x.contiguous()
+
+    def _prepare(self, x):
+        """Validated input + (lib, ctx) with the context's input element type matching x."""
+        x = self._check_input(x)
+        lib, ctx = self._engine(x.device)
+        want = _lib.YB_INPUT_F16 if x.dtype == torch.float16 else _lib.YB_INPUT_F32
+        if self._in_dtype != want:
+            _lib.check(lib.yb_set_input_dtype(ctx, want), ctx)
+            self._in_dtype = want
+        return x, lib, ctx
 
     def _stream(self, device):
         return ctypes.c_void_p(torch.cuda.current_stream(device).cuda_stream)
@@ -236,8 +251,7 @@ class YoloNet(nn.Module):
             raise NotImplementedError("training (target is not None) is outside the scope of the B200 inference path")
         if self.training:
             raise RuntimeError("inference path only: call .eval() first (BatchNorm uses running statistics)")
-        x = self._check_input(x)
-        lib, ctx = self._engine(x.device)
+        x, lib, ctx = self._prepare(x)
         B, _, H, W = x.shape
         n = num_boxes(H, W)
         det = torch.empty(B, n, 5 + self.numClass, device=x.device, dtype=torch.float32)
@@ -251,8 +265,7 @@ class YoloNet(nn.Module):
 
     def head_logits(self, x):
         """The three raw head maps (pre_detN.mlist[6] outputs), NCHW fp32 -- parity/debug aid."""
-        x = self._check_input(x)
-        lib, ctx = self._engine(x.device)
+        x, lib, ctx = self._prepare(x)
         B, _, H, W = x.shape
         ch = 3 * (5 + self.numClass)
         outs = [torch.empty(B, ch, H // s, W // s, device=x.device, dtype=torch.float32) for s in (32, 16, 8)]
@@ -263,8 +276,7 @@ class YoloNet(nn.Module):
 
     def backbone(self, x):
         """Darknet.forward (darknet.py:83-88): [B,1024,H/32,W/32] fp32."""
-        x = self._check_input(x)
-        lib, ctx = self._engine(x.device)
+        x, lib, ctx = self._prepare(x)
         B, _, H, W = x.shape
         out = torch.empty(B, 1024, H // 32, W // 32, device=x.device, dtype=torch.float32)
         with torch.cuda.device(x.device):
@@ -275,8 +287,7 @@ class YoloNet(nn.Module):
     def detect_raw(self, x, obj_conf_thr=0.5, nms_thr=0.4, is_eval=False, use_nms=True, cap=None):
         """forward + postprocessing fused on the device (yb_detect). Returns CUDA tensors
         (rows7 [B,cap,7], counts [B], src_index [B,cap], cand_counts [B]); nothing is synchronised."""
-        x = self._check_input(x)
-        lib, ctx = self._engine(x.device)
+        x, lib, ctx = self._prepare(x)
         B, _, H, W = x.shape
         n = num_boxes(H, W)
         if cap is None:
