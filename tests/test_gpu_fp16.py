@@ -226,15 +226,7 @@ def test_fp16_plan_cache_two_shapes(sd):
     assert torch.equal(a1, a2) and torch.equal(b1, b2)
 
 
-# ---- fp16 input images (yb_set_input_dtype): written without access to a GPU box, so the tests run only on request
-# (YB_INPUT_F16=1 python -m pytest tests -m gpu) until the path has been validated there -------------------------------
-import os  # noqa: E402
-
-needs_f16_input = pytest.mark.skipif(os.environ.get("YB_INPUT_F16") != "1",
-                                     reason="fp16 input path is opt-in until validated on the GPU box (set YB_INPUT_F16=1)")
-
-
-@needs_f16_input
+# ---- fp16 input images (yb_set_input_dtype) ---------------------------------------------------------------------------
 @pytest.mark.parametrize("B,H,W", [(2, 40, 56), (3, 17, 23), (1, 64, 608)])
 def test_stem_fp16_input_same_bits_as_fp32(fp16_ctx, B, H, W, monkeypatch):
     """The stem rounds every fp32 pixel to fp16 (round to nearest even) before the tensor core sees it, so reading the
@@ -257,7 +249,6 @@ def test_stem_fp16_input_same_bits_as_fp32(fp16_ctx, B, H, W, monkeypatch):
     assert torch.equal(out32.view(torch.int16), out16.view(torch.int16))
 
 
-@needs_f16_input
 def test_detect_fp16_input_same_detections(sd):
     from yolo_v3_b200 import YoloNet
     net = YoloNet((224, 160), precision="fp16")
@@ -265,7 +256,7 @@ def test_detect_fp16_input_same_detections(sd):
     net = net.cuda().eval()
     x = synth.make_images(2, 160, 224, seed=5).cuda()
     a = net.detect(x, 0.05, 0.4)
-    b = net.detect(x.half(), 0.05, 0.4)          # read by the stem as fp16 (YB_INPUT_F16=1)
+    b = net.detect(x.half(), 0.05, 0.4)          # read by the stem as fp16
     c = net.detect(x, 0.05, 0.4)                 # and back to fp32 input on the same context
     assert len(a) == len(b) == len(c)
     for ra, rb, rc in zip(a, b, c):
