@@ -177,3 +177,31 @@ def test_host_helpers_of_the_next_rows(oracle):
     assert get_image_id_from_path("coco/images/val2014/COCO_val2014_000000000139.jpg") == 139
     e = create_results_entry(139, 17, [1.5, 2.0, 30.0, 40.25], 0.875)
     assert json.dumps(e, separators=(",", ":")) == '{"image_id":139,"category_id":17,"bbox":[1.5,2.0,30.0,40.25],"score":0.875}'
+
+
+def test_named_tensors_follow_the_live_state_dict():
+    """YoloNet._named_tensors feeds the change signature checked before every forward; it reads the modules' own
+    parameter / buffer tables through slots resolved once, and must always yield exactly the live state_dict tensors."""
+    from yolo_v3_b200 import YoloNet
+
+    def same(net):
+        a = list(net._named_tensors())
+        b = list(net.state_dict(keep_vars=True).items())
+        return len(a) == len(b) == 438 and all(k1 == k2 and t1 is t2 for (k1, t1), (k2, t2) in zip(a, b))
+
+    net = YoloNet((416, 416))
+    dev = torch.device("cpu")
+    assert same(net)
+    s0 = net._signature(dev)
+    assert net._signature(dev) == s0                      # nothing changed
+    sd = {k: v.clone() + 1 for k, v in net.state_dict().items()}
+    net.load_state_dict(sd)                               # in-place copies: same tensors, new versions
+    s1 = net._signature(dev)
+    assert same(net) and s1 != s0
+    net.double()                                          # Module._apply replaces buffers and parameter data
+    assert same(net) and net._signature(dev) != s1
+    net.feature.float()                                   # ... also when applied to a sub-module only
+    assert same(net)
+    with torch.no_grad():
+        net.pre_det1.mlist[6].bias.add_(1.0)              # a direct in-place edit of one tensor
+    assert net._signature(dev) != s1 and same(net)

@@ -168,8 +168,23 @@ class YoloNet(nn.Module):
 
     # ---- engine plumbing ----------------------------------------------------------------------
     def _named_tensors(self):
-        for k, v in self.state_dict(keep_vars=True).items():
-            yield k, v
+        """(state_dict key, current tensor) in state_dict order.  Runs before every forward (the signature below), so it
+        does not build a state_dict each time: the (module, slot) of every key is resolved once -- the module tree of
+        this class never changes -- and the tensors are read from the modules' own tables, which is where .cuda(),
+        load_state_dict() or an assignment put their current versions."""
+        slots = self.__dict__.get("_tensor_slots")
+        if slots is None:
+            where = {}
+            for prefix, mod in self.named_modules():
+                dot = prefix + "." if prefix else ""
+                for name in mod._parameters:
+                    where[dot + name] = (mod._parameters, name)
+                for name in mod._buffers:
+                    where[dot + name] = (mod._buffers, name)
+            slots = [(k, *where[k]) for k in self.state_dict(keep_vars=True)]
+            self.__dict__["_tensor_slots"] = slots
+        for k, table, name in slots:
+            yield k, table[name]
 
     def _signature(self, device):
         return (str(device), self.precision) + tuple((v.data_ptr(), v._version) for _, v in self._named_tensors())
