@@ -18,6 +18,9 @@ for i in 1 2 3 4; do for be in 0 1; do
   python -c "
 import json; d=json.load(open('/tmp/ab.json')); print('BEARLY=$be run $i:', round(d['value'],1), 'img/s', round(d['ms_per_step'],4), 'ms/step  conv', round(d['roofline']['conv_ms_per_step'],4), 'clocks', d['clocks']['sm_mhz'])"
 done; done 2>&1 | tee gpurun_out/${T}_bearly_ab.txt
+echo "== blocked-layout access pattern on the 1x1 layers (timing experiment, results wrong)"
+{ echo "### NHWC (default)"; timeout 200 python tools/layer_bench.py --layers 5,10,27,44,68
+  echo "### YB_TC_EXP_BLOCKED=1"; YB_TC_EXP_BLOCKED=1 timeout 200 python tools/layer_bench.py --layers 5,10,27,44,68; } 2>&1 | tee gpurun_out/${T}_blocked_layout.txt
 echo "== ncu: launch list, per-launch conv metrics, full sets of the changed kernels"
 ncu --metrics gpu__time_duration.sum --clock-control none -s 246 -c 82 --csv --log-file gpurun_out/${T}_launches.csv \
     python tools/one_step.py --steps 1 --warmup 3 --recipe calibrated > gpurun_out/${T}_launches.log 2>&1

@@ -226,7 +226,10 @@ __device__ __forceinline__ void load_resident_weights(const CUtensorMap* tmB, co
     }
 }
 
-template <int SWZ, bool CTA2>
+// EXPB: timing experiment (YB_TC_EXP_BLOCKED=1, 1x1 layers, results are WRONG): the A operand is fetched as if the
+// activations were stored channel-blocked, [Cin/64][M][64] -- every k-block box one contiguous 16 KB run instead of 128
+// rows strided by the pixel pitch -- through a 2-D map over the same memory and coordinates (0, kb*M + m0).
+template <int SWZ, bool CTA2, bool EXPB = false>
 __global__ void __launch_bounds__(kThreads, 1)
 conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                const __grid_constant__ CUtensorMap tmOut, const __grid_constant__ CUtensorMap tmRes, const TcArgs a_in) {
@@ -368,6 +371,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                 }
                 if (a.ks == 1 || a.exp_tiled) {
                     int kc = 0, ka = 0;
+                    [[maybe_unused]] int mb = m0;              // EXPB: row of this k-block's box in the blocked view
                     for (int it = 0; it < a.num_iters; ++it, ++itg) {
                         const bool mine = (itg & 1u) == pw;
                         if (mine) mbar_wait(eb, phase ^ 1, a.dbg, 0, stage);
@@ -377,13 +381,16 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                         for (int j = 0; j < a.kps; ++j) {
                             if (el) {
                                 if constexpr (CTA2) {
-                                    tma_load_2d_pair(&tmA, dst, fb, kc, m0);
+                                    if constexpr (EXPB) tma_load_2d_pair(&tmA, dst, fb, 0, mb);
+                                    else tma_load_2d_pair(&tmA, dst, fb, kc, m0);
                                     if (load_b) tma_load_2d_pair(&tmB, dst + A_BYTES, fb, kc, n0);
                                 } else {
-                                    tma_load_2d(&tmA, dst, fb, a.exp_tiled ? ka : kc, m0);
+                                    if constexpr (EXPB) tma_load_2d(&tmA, dst, fb, 0, mb);
+                                    else tma_load_2d(&tmA, dst, fb, a.exp_tiled ? ka : kc, m0);
                                     if (load_b) tma_load_2d(&tmB, dst + A_BYTES, fb, kc, n0);
                                 }
                             }
+                            if constexpr (EXPB) mb += (int)a.M;
                             kc += BKE;
                             ka += BKE;
                             if (ka == a.cin_blocks * BKE) ka = 0;
@@ -1118,10 +1125,20 @@ std::string tc_make_plan(TcPlan& p, const ConvArgs& a, const __half* w16, int co
         if (!warned) fprintf(stderr, "[yolo_b200] YB_TC_EXP_TILED is a TIMING experiment: 3x3 convolution results are WRONG\n");
         warned = true;
     }
+    p.exp_blocked = a.ks == 1 && p.swz == 128 && a.in_ld == a.Cin && getenv("YB_TC_EXP_BLOCKED") && atoi(getenv("YB_TC_EXP_BLOCKED")) != 0;
+    if (p.exp_blocked) {
+        static bool warned = false;
+        if (!warned) fprintf(stderr, "[yolo_b200] YB_TC_EXP_BLOCKED is a TIMING experiment: 1x1 convolution results are WRONG\n");
+        warned = true;
+    }
     if (a.ks == 1 || p.exp_tiled) {
         // A: [M][Cin] with pixel pitch in_ld; rows past M are zero-filled
         cuuint64_t dims[2] = {(cuuint64_t)a.Cin, (cuuint64_t)p.M};
         cuuint64_t strides[1] = {(cuuint64_t)a.in_ld * sizeof(__half)};
+        if (p.exp_blocked) {        // the same bytes read as [Cin/64][M][64]: rows of 128 bytes, Cin/64 * M of them
+            dims[0] = 64; dims[1] = (cuuint64_t)p.M * (a.Cin / 64);
+            strides[0] = 128;
+        }
         cuuint32_t box[2] = {(cuuint32_t)bke, (cuuint32_t)kBM};
         cuuint32_t es[2] = {1, 1};
         CUresult r = g_encode_tiled(&p.tmA, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, const_cast<void*>(a.in), dims, strides, box, es,
@@ -1280,6 +1297,8 @@ cudaError_t tc_launch(const TcPlan& p, const ConvArgs& a, int* dbg, cudaStream_t
             cudaError_t r = cudaFuncSetAttribute(conv_tc_kernel<128, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBudget);
             if (r == cudaSuccess) r = cudaFuncSetAttribute(conv_tc_kernel<64, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBudget);
             if (r == cudaSuccess) r = cudaFuncSetAttribute(conv_tc_kernel<128, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBudget);
+            if (r == cudaSuccess) r = cudaFuncSetAttribute(conv_tc_kernel<128, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBudget);
+            if (r == cudaSuccess) r = cudaFuncSetAttribute(conv_tc_kernel<128, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBudget);
             return r;
         });
         if (e != cudaSuccess) return e;
@@ -1308,7 +1327,9 @@ cudaError_t tc_launch(const TcPlan& p, const ConvArgs& a, int* dbg, cudaStream_t
         cfg.attrs = attr;
         cfg.numAttrs = na;
         cudaError_t e;
-        if (p.cta2) e = cudaLaunchKernelEx(&cfg, conv_tc_kernel<128, true>, p.tmA, p.tmB, p.tmOut, p.tmRes, t);
+        if (p.exp_blocked && p.cta2) e = cudaLaunchKernelEx(&cfg, conv_tc_kernel<128, true, true>, p.tmA, p.tmB, p.tmOut, p.tmRes, t);
+        else if (p.exp_blocked) e = cudaLaunchKernelEx(&cfg, conv_tc_kernel<128, false, true>, p.tmA, p.tmB, p.tmOut, p.tmRes, t);
+        else if (p.cta2) e = cudaLaunchKernelEx(&cfg, conv_tc_kernel<128, true>, p.tmA, p.tmB, p.tmOut, p.tmRes, t);
         else if (p.swz == 128) e = cudaLaunchKernelEx(&cfg, conv_tc_kernel<128, false>, p.tmA, p.tmB, p.tmOut, p.tmRes, t);
         else e = cudaLaunchKernelEx(&cfg, conv_tc_kernel<64, false>, p.tmA, p.tmB, p.tmOut, p.tmRes, t);
         if (e != cudaSuccess) return e;

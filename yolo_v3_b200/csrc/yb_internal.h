@@ -93,7 +93,7 @@ cudaError_t launch_f32_to_f16(const float* in, __half* out, size_t n, cudaStream
 // conv_tc.cu  (tcgen05 + TMA implicit GEMM)
 struct TcPlan {
     CUtensorMap tmA, tmB, tmOut, tmRes;
-    int epi_staged = 0, ring = 0, sub_bytes = 128, cs = 0, n_sub = 0, b_resident = 0, exp_tiled = 0;
+    int epi_staged = 0, ring = 0, sub_bytes = 128, cs = 0, n_sub = 0, b_resident = 0, exp_tiled = 0, exp_blocked = 0;
     int swz = 128;        // 128: 64-channel k-blocks, 64: 32-channel k-blocks (Cin == 32)
     int BN = 0, n_tiles = 0, m_tiles = 0, stages = 0, tmem_cols = 0;
     int num_kblocks = 0, cin_blocks = 0, kps = 1, cta2 = 0, cout_pad = 0, tab_bytes = 0;
