@@ -205,3 +205,20 @@ def test_named_tensors_follow_the_live_state_dict():
     with torch.no_grad():
         net.pre_det1.mlist[6].bias.add_(1.0)              # a direct in-place edit of one tensor
     assert net._signature(dev) != s1 and same(net)
+
+
+def test_bench_reference_arm_prints_one_contract_line():
+    """bench.py --impl reference runs on the host cores only (the CPU port of the reference path): one JSON line on
+    stdout with the keys the driver reads, whatever else the libraries print."""
+    import json
+    out = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--steps", "1", "--warmup", "0",
+                          "--ref-batch", "1", "--size", "416"], capture_output=True, text=True, timeout=600)
+    assert out.returncode == 0, out.stderr[-2000:]
+    lines = [l for l in out.stdout.splitlines() if l.strip()]
+    assert len(lines) == 1, lines
+    d = json.loads(lines[0])
+    assert d["impl"] == "reference" and d["unit"] == "images/sec" and d["higher_is_better"] is True
+    assert d["value"] > 0 and d["steps"] == 1 and d["n_gpus"] == 1
+    assert d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["cores"] >= 1 and d["cpu_baseline"]["value"] == d["value"]
+    assert d["e2e"] == {"value": d["value"], "unit": "images/sec", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
+    assert d["config"]["workload"].startswith("yolov3_416x416")
