@@ -12,6 +12,10 @@ import json; d=json.load(open('gpurun_out/${T}_bench.json'))
 print('value', round(d['value'],1), 'ms/step', round(d['ms_per_step'],4), 'e2e', round(d['e2e']['value'],1),
       'e2e_u8', round(d['e2e_u8_frames']['value'],1), 'e2e_f16', round(d.get('e2e_f16_input',{}).get('value',0),1), 'frac', round(d['roofline']['frac'],4))
 PY
+echo "== pinned parameter staging: letterbox / resize / box-correction tests and the uint8-frames e2e with it"
+YB_PINNED_PARAMS=1 timeout 600 python -m pytest tests/test_gpu_parity.py -x -q -k "letterbox or resize or correct_yolo_boxes or eval_json" 2>&1 | tail -3 | tee gpurun_out/${T}_pinned_pytest.log
+YB_PINNED_PARAMS=1 timeout 600 python bench.py > /tmp/pin.json 2>/dev/null; python -c "
+import json; d=json.load(open('/tmp/pin.json')); print('YB_PINNED_PARAMS=1: e2e_u8', round(d['e2e_u8_frames']['value'],1), 'e2e', round(d['e2e']['value'],1), 'value', round(d['value'],1))" | tee gpurun_out/${T}_pinned_bench.txt
 echo "== early weights inside the step, 4 x A/B at 100 steps"
 for i in 1 2 3 4; do for be in 0 1; do
   YB_TC_BEARLY=$be timeout 300 python bench.py --steps 100 --warmup 10 > /tmp/ab.json 2>/dev/null

@@ -72,6 +72,12 @@ struct yb_ctx {
     int box_params_cap = 0;
     LbImage* lb_params = nullptr;     // [B] per-image parameters of yb_letterbox
     int lb_params_cap = 0;
+    // pinned staging ring for the small per-call parameter blocks (see stage_params)
+    unsigned char* stage_host = nullptr;
+    size_t stage_slot_bytes = 0;
+    int stage_next = 0;
+    std::vector<cudaEvent_t> stage_ev;
+    std::vector<char> stage_used;
     float* det_scratch = nullptr;     // for yb_detect
     size_t det_scratch_bytes = 0;
     int* dbg = nullptr;               // device alias of dbg_host (mapped pinned memory): watchdog words of the
@@ -114,6 +120,47 @@ int fail(const yb_ctx* c, int code, const std::string& msg) {
         if (e_ != cudaSuccess)                                                                        \
             return fail(c, YB_E_CUDA, std::string(#expr) + ": " + cudaGetErrorString(e_));            \
     } while (0)
+
+// Per-call parameter blocks (per-image letterbox / box-correction parameters, a few KB) go to the device with
+// cudaMemcpyAsync.  From PAGEABLE memory that call first synchronises the stream (CUDA runtime API, "API synchronization
+// behavior"), which serialises host and device for every yb_letterbox / yb_resize / yb_correct_boxes call.  With
+// YB_PINNED_PARAMS=1 the block is staged in a ring of pinned slots instead, so the copy is truly asynchronous; a slot is
+// reused only after the copy that last read it has executed (event per slot).  Opt-in until validated on the GPU box.
+constexpr int kStageSlots = 8;
+
+int stage_params(yb_ctx* c, const void* src, size_t bytes, void* dst, cudaStream_t s) {
+    static const bool pinned = getenv("YB_PINNED_PARAMS") && atoi(getenv("YB_PINNED_PARAMS")) != 0;
+    if (!pinned) {
+        YB_CUDA(c, cudaMemcpyAsync(dst, src, bytes, cudaMemcpyHostToDevice, s));
+        return YB_OK;
+    }
+    if (bytes > c->stage_slot_bytes) {
+        for (size_t i = 0; i < c->stage_ev.size(); ++i)
+            if (c->stage_used[i]) YB_CUDA(c, cudaEventSynchronize(c->stage_ev[i]));
+        cudaFreeHost(c->stage_host);
+        c->stage_host = nullptr;
+        c->stage_slot_bytes = 0;
+        const size_t slot = (std::max<size_t>(bytes, 4096) + 255) / 256 * 256;
+        YB_CUDA(c, cudaHostAlloc(reinterpret_cast<void**>(&c->stage_host), slot * kStageSlots, cudaHostAllocDefault));
+        c->stage_slot_bytes = slot;
+        while ((int)c->stage_ev.size() < kStageSlots) {
+            cudaEvent_t e;
+            YB_CUDA(c, cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+            c->stage_ev.push_back(e);
+        }
+        c->stage_used.assign(kStageSlots, 0);
+        c->stage_next = 0;
+    }
+    const int i = c->stage_next;
+    c->stage_next = (i + 1) % kStageSlots;
+    if (c->stage_used[i]) YB_CUDA(c, cudaEventSynchronize(c->stage_ev[i]));
+    unsigned char* slot = c->stage_host + (size_t)i * c->stage_slot_bytes;
+    std::memcpy(slot, src, bytes);
+    YB_CUDA(c, cudaMemcpyAsync(dst, slot, bytes, cudaMemcpyHostToDevice, s));
+    YB_CUDA(c, cudaEventRecord(c->stage_ev[i], s));
+    c->stage_used[i] = 1;
+    return YB_OK;
+}
 
 const float kDefaultAnchors[18] = {10, 13, 16, 30, 33, 23, 30, 61, 62, 45, 59, 119, 116, 90, 156, 198, 373, 326};
 const int kBlocks[5] = {1, 2, 8, 8, 4};
@@ -519,6 +566,8 @@ void yb_destroy(yb_ctx* c) {
     cudaFree(c->box_params);
     cudaFree(c->lb_params);
     cudaFreeHost(c->dbg_host);
+    cudaFreeHost(c->stage_host);
+    for (cudaEvent_t e : c->stage_ev) cudaEventDestroy(e);
     for (cudaEvent_t e : c->ev) cudaEventDestroy(e);
     for (cudaEvent_t e : c->bank) cudaEventDestroy(e);
     if (c->nccl_comm) comm_destroy(c->nccl_comm);
@@ -883,7 +932,7 @@ int yb_correct_boxes(yb_ctx* c, const float* boxes, int row_stride, const int* c
         p[0] = (float)rx; p[1] = (float)ry; p[2] = (float)xpad; p[3] = (float)ypad; p[4] = (float)ow; p[5] = (float)oh;
     }
     cudaStream_t s = static_cast<cudaStream_t>(stream);
-    YB_CUDA(c, cudaMemcpyAsync(c->box_params, prm.data(), prm.size() * sizeof(float), cudaMemcpyHostToDevice, s));
+    if (int rc = stage_params(c, prm.data(), prm.size() * sizeof(float), c->box_params, s)) return rc;
     YB_CUDA(c, launch_correct_boxes(boxes, row_stride, counts, B, cap, c->box_params, out_xywh, s));
     ++c->launches;
     return YB_OK;
@@ -913,7 +962,7 @@ int yb_resize(yb_ctx* c, const uint8_t* const* imgs_dev, const int* hw_host, int
         q.interp = 1;
     }
     cudaStream_t s = static_cast<cudaStream_t>(stream);
-    YB_CUDA(c, cudaMemcpyAsync(c->lb_params, prm.data(), prm.size() * sizeof(LbImage), cudaMemcpyHostToDevice, s));
+    if (int rc = stage_params(c, prm.data(), prm.size() * sizeof(LbImage), c->lb_params, s)) return rc;
     YB_CUDA(c, launch_letterbox(c->lb_params, B, dim_h, dim_w, out_nchw, out_hwc, s));
     ++c->launches;
     return YB_OK;
@@ -962,7 +1011,7 @@ int yb_letterbox(yb_ctx* c, const uint8_t* const* imgs_dev, const int* hw_host, 
         }
     }
     cudaStream_t s = static_cast<cudaStream_t>(stream);
-    YB_CUDA(c, cudaMemcpyAsync(c->lb_params, prm.data(), prm.size() * sizeof(LbImage), cudaMemcpyHostToDevice, s));
+    if (int rc = stage_params(c, prm.data(), prm.size() * sizeof(LbImage), c->lb_params, s)) return rc;
     YB_CUDA(c, launch_letterbox(c->lb_params, B, canvas_h, canvas_w, out_nchw, canvas_hwc, s));
     ++c->launches;
     return YB_OK;
