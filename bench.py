@@ -62,12 +62,50 @@ def ncu_conv_traffic():
     return total or None
 
 
+def _flatten(d, prefix=""):
+    if isinstance(d, dict):
+        for k, v in d.items():
+            yield from _flatten(v, f"{prefix}.{k}".lower() if prefix else str(k).lower())
+    elif isinstance(d, (list, tuple)):
+        for i, v in enumerate(d):
+            yield from _flatten(v, f"{prefix}[{i}]")
+    elif isinstance(d, (int, float)) and not isinstance(d, bool):
+        yield prefix, float(d)
+
+
+def parse_peaks(d):
+    """Sustained dense bf16 TFLOP/s and HBM copy GB/s out of the driver-written MEASURED_PEAKS.json, whose exact key
+    names this repository does not control: known names first, then any numeric leaf whose path says what it is (a
+    sustained tensor figure is preferred over a burst one -- the conv stack is timed inside a long step).  Returns
+    (tensor, hbm), either may be None."""
+    flat = list(_flatten(d))
+    by = dict(flat)
+    tensor = by.get("bf16_tflops_sustained")
+    hbm = by.get("hbm_gbs")
+    if tensor is None:
+        cand = [(k, v) for k, v in flat if any(t in k for t in ("bf16", "tflop", "tf/s", "tensor")) and 100.0 <= v <= 5000.0]
+        sus = [v for k, v in cand if "sustain" in k]
+        other = [v for k, v in cand if "burst" not in k and "peak" not in k]
+        tensor = sus[0] if sus else (other[0] if other else (min(v for _, v in cand) if cand else None))
+    if hbm is None:
+        cand = [v for k, v in flat if any(t in k for t in ("hbm", "dram", "copy", "gb/s", "gbs", "gbps", "bandwidth")) and 500.0 <= v <= 20000.0]
+        hbm = cand[0] if cand else None
+    return tensor, hbm
+
+
 def peaks():
+    """Roofline denominators: MEASURED_PEAKS.json when the driver has written it, else the profiling recipe's fallback."""
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    tensor = hbm = None
     if os.path.exists(p):
-        d = json.load(open(p))
-        return dict(tensor=d.get("bf16_tflops_sustained", 1386.8), hbm=d.get("hbm_gbs", 6445.3), src="measured")
-    return dict(tensor=1400.0, hbm=6650.0, src="fallback")
+        try:
+            tensor, hbm = parse_peaks(json.load(open(p)))
+        except Exception as e:  # noqa: BLE001 -- a malformed file must not take the bench down
+            print(f"[bench] MEASURED_PEAKS.json unreadable ({e}); using the fallback peaks", file=sys.stderr)
+    if tensor is None and hbm is None:
+        return dict(tensor=1400.0, hbm=6650.0, src="fallback")
+    src = "measured" if tensor is not None and hbm is not None else "measured+fallback"
+    return dict(tensor=tensor if tensor is not None else 1400.0, hbm=hbm if hbm is not None else 6650.0, src=src)
 
 
 class ClockSampler(threading.Thread):
