@@ -22,6 +22,12 @@ for i in 1 2 3 4; do for be in 0 1; do
   python -c "
 import json; d=json.load(open('/tmp/ab.json')); print('BEARLY=$be run $i:', round(d['value'],1), 'img/s', round(d['ms_per_step'],4), 'ms/step  conv', round(d['roofline']['conv_ms_per_step'],4), 'clocks', d['clocks']['sm_mhz'])"
 done; done 2>&1 | tee gpurun_out/${T}_bearly_ab.txt
+echo "== L2 persistence of layer outputs (host-side launch attribute), A/B at 100 steps"
+for i in 1 2; do for mb in 0 48 80; do
+  YB_L2_PERSIST=$mb timeout 300 python bench.py --steps 100 --warmup 10 > /tmp/l2.json 2>/dev/null
+  python -c "
+import json; d=json.load(open('/tmp/l2.json')); print('YB_L2_PERSIST=$mb run $i:', round(d['value'],1), 'img/s', round(d['ms_per_step'],4), 'ms/step  conv', round(d['roofline']['conv_ms_per_step'],4), 'dets', d['detections_last_step'])"
+done; done 2>&1 | tee gpurun_out/${T}_l2_persist_ab.txt
 echo "== blocked-layout access pattern on the 1x1 layers (timing experiment, results wrong)"
 { echo "### NHWC (default)"; timeout 200 python tools/layer_bench.py --layers 5,10,27,44,68
   echo "### YB_TC_EXP_BLOCKED=1"; YB_TC_EXP_BLOCKED=1 timeout 200 python tools/layer_bench.py --layers 5,10,27,44,68; } 2>&1 | tee gpurun_out/${T}_blocked_layout.txt

@@ -1310,7 +1310,7 @@ cudaError_t tc_launch(const TcPlan& p, const ConvArgs& a, int* dbg, cudaStream_t
         cfg.blockDim = dim3(kThreads);
         cfg.dynamicSmemBytes = p.smem;
         cfg.stream = s;
-        cudaLaunchAttribute attr[2];
+        cudaLaunchAttribute attr[3];
         int na = 0;
         if (pdl) {
             attr[na].id = cudaLaunchAttributeProgrammaticStreamSerialization;
@@ -1324,6 +1324,8 @@ cudaError_t tc_launch(const TcPlan& p, const ConvArgs& a, int* dbg, cudaStream_t
             attr[na].val.clusterDim.z = 1;
             ++na;
         }
+        // experiment (off unless YB_L2_PERSIST is set): keep this layer's output in L2 for its consumer
+        if (l2_persist_window(a.out, (size_t)p.M * (a.upsample ? 4 : 1) * (size_t)a.out_ld * (a.out_f32 ? 4 : 2), &attr[na])) ++na;
         cfg.attrs = attr;
         cfg.numAttrs = na;
         cudaError_t e;

@@ -46,6 +46,34 @@ struct Plan {
     size_t bytes = 0;
 };
 
+bool l2_persist_window(const void* base, size_t bytes, cudaLaunchAttribute* attr) {
+    struct State { size_t set_aside = 0, max_window = 0; };
+    static PerDeviceOnce once;
+    static State st;                     // one configuration per process (the experiment targets one-GPU-per-process runs)
+    static const long mb = getenv("YB_L2_PERSIST") ? atol(getenv("YB_L2_PERSIST")) : 0;
+    if (mb <= 0 || !base || bytes == 0) return false;
+    const cudaError_t e = once.run([] {
+        int dev = 0, max_persist = 0, max_window = 0;
+        cudaError_t r = cudaGetDevice(&dev);
+        if (r == cudaSuccess) r = cudaDeviceGetAttribute(&max_persist, cudaDevAttrMaxPersistingL2CacheSize, dev);
+        if (r == cudaSuccess) r = cudaDeviceGetAttribute(&max_window, cudaDevAttrMaxAccessPolicyWindowSize, dev);
+        if (r != cudaSuccess) return r;
+        const size_t want = std::min<size_t>((size_t)mb << 20, (size_t)max_persist);
+        r = cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, want);
+        if (r == cudaSuccess) { st.set_aside = want; st.max_window = (size_t)max_window; }
+        return r;
+    });
+    if (e != cudaSuccess) { cudaGetLastError(); return false; }
+    if (bytes > st.set_aside || bytes > st.max_window) return false;
+    attr->id = cudaLaunchAttributeAccessPolicyWindow;
+    attr->val.accessPolicyWindow.base_ptr = const_cast<void*>(base);
+    attr->val.accessPolicyWindow.num_bytes = bytes;
+    attr->val.accessPolicyWindow.hitRatio = 1.0f;
+    attr->val.accessPolicyWindow.hitProp = cudaAccessPropertyPersisting;
+    attr->val.accessPolicyWindow.missProp = cudaAccessPropertyNormal;
+    return true;
+}
+
 }  // namespace yb
 
 using namespace yb;

@@ -59,6 +59,14 @@ private:
     unsigned long long done_ = 0;
 };
 
+// L2 persistence experiment (YB_L2_PERSIST=<MB of L2 set aside>; unset or 0 = off, the validated behaviour): a layer whose
+// output fits writes it with the persisting access property (launch attribute cudaLaunchAttributeAccessPolicyWindow over
+// the output span), so that the next layer -- which reads it as A operand and as residual -- finds it in L2.  The 1x1
+// layers at 38x38 / 19x19 run at "cold" HBM speed inside the step although their 47 / 24 MB inputs were written by the
+// previous kernel.  Host-side only; written at the end of round 1, not yet run on a GPU.
+// Returns true and fills *attr when the window applies.
+bool l2_persist_window(const void* base, size_t bytes, cudaLaunchAttribute* attr);
+
 // NHWC activation view: `p` already includes the channel offset of a concat slice.
 struct TView {
     void* p = nullptr;
