@@ -321,26 +321,44 @@ def run_ours(args):
     e2e_ms = time_e2e(hx, dx, lambda x: x)
     del hx, dx
 
-    # ---- the same from camera frames: pinned uint8 [B,480,640,3] in, letterbox on the device (yb_letterbox, the N1
-    # row), detect, detections out.  The fp32 batch above is 142 MB per step, i.e. the PCIe link (~26 GB/s measured)
-    # caps it near 6 000 img/s per GPU whatever the kernels do; frames are 29.5 MB per step. ----
-    import numpy as np
-    from yolo_v3_b200.utils import letterbox_batch
+    # ---- optional legs (one GPU only, and never allowed to take the contract line down) ----
+    # (a) from camera frames: pinned uint8 [B,480,640,3] in, letterbox on the device (yb_letterbox, the N1 row), detect,
+    #     detections out.  The fp32 batch above is 142 MB per step, i.e. the PCIe link (~26 GB/s measured) caps it near
+    #     6 000 img/s per GPU whatever the kernels do; frames are 29.5 MB per step.
+    # (b) from fp16 images read by the stem directly (yb_set_input_dtype): bit-identical detections, half the PCIe bytes.
     FH, FW = 480, 640
-    frames = np.stack([synth.make_photo(FH, FW, 90 + 17 * rank + i) for i in range(B)])
-    hu = [torch.from_numpy(frames).pin_memory(), torch.from_numpy(np.ascontiguousarray(frames[::-1])).pin_memory()]
-    du = [torch.empty(B, FH, FW, 3, dtype=torch.uint8, device=dev) for _ in range(2)]
-    e2e_u8_ms = time_e2e(hu, du, lambda u: letterbox_batch(list(u), (S, S))[0])
-    del hu, du
-
-    # ---- and from fp16 images read by the stem directly (yb_set_input_dtype; same detections as the fp32 batches, half
-    # the PCIe bytes).  Opt-in with the library path it exercises (YB_INPUT_F16=1) until validated on the GPU box. ----
-    e2e_f16_ms = None
-    if os.environ.get("YB_INPUT_F16") == "1" and args.precision == "fp16":
-        hh = [synth.make_images(B, S, S, seed=7 + i).half().pin_memory() for i in range(2)]
-        dh = [torch.empty(B, 3, S, S, dtype=torch.float16, device=dev) for _ in range(2)]
-        e2e_f16_ms = time_e2e(hh, dh, lambda x: x)
-        del hh, dh
+    extra = {}
+    if world == 1:
+        d2h = int(h_rows.numel() * 4 + h_counts.numel() * 4)
+        try:
+            import numpy as np
+            from yolo_v3_b200.utils import letterbox_batch
+            frames = np.stack([synth.make_photo(FH, FW, 90 + i) for i in range(B)])
+            hu = [torch.from_numpy(frames).pin_memory(), torch.from_numpy(np.ascontiguousarray(frames[::-1])).pin_memory()]
+            du = [torch.empty(B, FH, FW, 3, dtype=torch.uint8, device=dev) for _ in range(2)]
+            t_ms = time_e2e(hu, du, lambda u: letterbox_batch(list(u), (S, S))[0])
+            del hu, du
+            extra["e2e_u8_frames"] = {
+                "value": B * args.steps / (t_ms * 1e-3), "unit": "images/sec", "h2d_bytes_per_step": B * FH * FW * 3,
+                "d2h_bytes_per_step": d2h, "ms_per_step": t_ms / args.steps,
+                "input": f"uint8 [B,{FH},{FW},3] frames, letterboxed to {S}x{S} on the device (yb_letterbox) inside the timed region"}
+        except Exception as e:  # noqa: BLE001
+            extra["e2e_u8_frames"] = {"error": f"{type(e).__name__}: {e}"}
+            torch.cuda.synchronize()
+        # (b) is timed on request (YB_INPUT_F16=1) until this leg itself has run on a GPU box at the full batch size
+        if args.precision == "fp16" and os.environ.get("YB_INPUT_F16") == "1":
+            try:
+                hh = [synth.make_images(B, S, S, seed=7 + i).half().pin_memory() for i in range(2)]
+                dh = [torch.empty(B, 3, S, S, dtype=torch.float16, device=dev) for _ in range(2)]
+                t_ms = time_e2e(hh, dh, lambda x: x)
+                del hh, dh
+                extra["e2e_f16_input"] = {
+                    "value": B * args.steps / (t_ms * 1e-3), "unit": "images/sec", "h2d_bytes_per_step": B * 3 * S * S * 2,
+                    "d2h_bytes_per_step": d2h, "ms_per_step": t_ms / args.steps,
+                    "input": f"fp16 [B,3,{S},{S}] read by the stem directly (yb_set_input_dtype; bit-identical detections)"}
+            except Exception as e:  # noqa: BLE001
+                extra["e2e_f16_input"] = {"error": f"{type(e).__name__}: {e}"}
+                torch.cuda.synchronize()
 
     # ---- roofline: section times of the same step, CUDA events per section on the launch stream ----
     import ctypes
@@ -427,9 +445,6 @@ def run_ours(args):
         "e2e": {"value": total_imgs / (e2e_ms * 1e-3), "unit": "images/sec", "h2d_bytes_per_step": B * 3 * S * S * 4,
                 "d2h_bytes_per_step": int(h_rows.numel() * 4 + h_counts.numel() * 4), "ms_per_step": e2e_ms / args.steps,
                 "input": f"fp32 [B,3,{S},{S}] in [0,1], what the reference's predict() moves with .cuda() (test.py:32)"},
-        "e2e_u8_frames": {"value": total_imgs / (e2e_u8_ms * 1e-3), "unit": "images/sec", "h2d_bytes_per_step": B * FH * FW * 3,
-                          "d2h_bytes_per_step": int(h_rows.numel() * 4 + h_counts.numel() * 4), "ms_per_step": e2e_u8_ms / args.steps,
-                          "input": f"uint8 [B,{FH},{FW},3] frames, letterboxed to {S}x{S} on the device (yb_letterbox) inside the timed region"},
         "gpu_launches": int(launches),
         "clocks": sampler.summary(),
         "roofline": {"bound": "tensor", "kernel": "conv_tc_kernel + conv_halo_kernel (74 launches/step) + stem_tc_kernel", "achieved": achieved,
@@ -452,10 +467,7 @@ def run_ours(args):
         "cpu_baseline": cpu,
         "detections_last_step": int(counts_h.sum()),
     }
-    if e2e_f16_ms is not None:
-        line["e2e_f16_input"] = {"value": total_imgs / (e2e_f16_ms * 1e-3), "unit": "images/sec", "h2d_bytes_per_step": B * 3 * S * S * 2,
-                                 "d2h_bytes_per_step": int(h_rows.numel() * 4 + h_counts.numel() * 4), "ms_per_step": e2e_f16_ms / args.steps,
-                                 "input": f"fp16 [B,3,{S},{S}] read by the stem directly (bit-identical detections)"}
+    line.update(extra)
     emit(line)
     if args.layers:
         specs = topology.layer_specs(80)
