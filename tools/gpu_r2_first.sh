@@ -12,6 +12,15 @@ import json; d=json.load(open('gpurun_out/${T}_bench.json'))
 print('value', round(d['value'],1), 'ms/step', round(d['ms_per_step'],4), 'e2e', round(d['e2e']['value'],1),
       'e2e_u8', round(d['e2e_u8_frames']['value'],1), 'e2e_f16', round(d.get('e2e_f16_input',{}).get('value',0),1), 'frac', round(d['roofline']['frac'],4))
 PY
+echo "== uniform role dispatch (YB_TC_UW) and the leaner stem (YB_STEM_V2): the whole GPU suite with both, then an A/B of the step"
+YB_TC_UW=1 YB_STEM_V2=1 timeout 900 python -m pytest tests -x -q -m gpu 2>&1 | tail -4 | tee gpurun_out/${T}_uw_pytest.log
+{ echo "### default"; timeout 200 python tools/layer_bench.py --layers 0,1,2,3,6,10,27,74
+  echo "### YB_TC_UW=1 YB_STEM_V2=1"; YB_TC_UW=1 YB_STEM_V2=1 timeout 200 python tools/layer_bench.py --layers 0,1,2,3,6,10,27,74; } 2>&1 | tee gpurun_out/${T}_uw_layers.txt
+for i in 1 2; do for uw in 0 1; do
+  YB_TC_UW=$uw YB_STEM_V2=$uw timeout 300 python bench.py --steps 100 --warmup 10 > /tmp/uw.json 2>/dev/null
+  python -c "
+import json; d=json.load(open('/tmp/uw.json')); print('UW/V2=$uw run $i:', round(d['value'],1), 'img/s', round(d['ms_per_step'],4), 'ms/step  conv', round(d['roofline']['conv_ms_per_step'],4), 'dets', d['detections_last_step'])"
+done; done 2>&1 | tee gpurun_out/${T}_uw_ab.txt
 echo "== pinned parameter staging: letterbox / resize / box-correction tests and the uint8-frames e2e with it"
 YB_PINNED_PARAMS=1 timeout 600 python -m pytest tests/test_gpu_parity.py -x -q -k "letterbox or resize or correct_yolo_boxes or eval_json" 2>&1 | tail -3 | tee gpurun_out/${T}_pinned_pytest.log
 YB_PINNED_PARAMS=1 timeout 600 python bench.py > /tmp/pin.json 2>/dev/null; python -c "

@@ -112,7 +112,8 @@ __device__ __forceinline__ void tma_load_4d_pair(const CUtensorMap* tm, uint32_t
 // the pair reads 6 KB per 64 tensor cycles.  Tile t of the pair's round is tile 2*p + rank, so the tile walk is the
 // same (first = blockIdx.x, step = gridDim.x); an odd tile count leaves rank 1 of the last pair a tile at image index
 // B, which TMA zero-fills on load and clips on store.
-template <int SWZ, int STRIDE, bool PAIR>
+// UW (YB_TC_UW=1, as in conv_tc.cu; not yet run on a GPU): warp index through a shuffle broadcast = uniform role dispatch.
+template <int SWZ, int STRIDE, bool PAIR, bool UW = false>
 __global__ void __launch_bounds__(kHThreads, 1)
 conv_halo_kernel(const __grid_constant__ CUtensorMap tmIn, const __grid_constant__ CUtensorMap tmB,
                  const __grid_constant__ CUtensorMap tmOut, const __grid_constant__ CUtensorMap tmRes, const HaloArgs a) {
@@ -136,7 +137,8 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmIn, const __grid_constant
     const uint32_t bres0 = stg0 + (uint32_t)a.ring * kHStgBytes;
     const uint32_t stage0 = bres0 + 9 * B_SLOT;
 
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int warp = UW ? __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0) : (int)(threadIdx.x >> 5);
+    const int lane = threadIdx.x & 31;
     const uint32_t rank = PAIR ? cluster_ctarank() : 0u;
     const bool leader = rank == 0;
     const int tile_first = blockIdx.x, tile_step = gridDim.x;
@@ -513,6 +515,10 @@ cudaError_t halo_launch(const HaloPlan& p, const ConvArgs& a, int* dbg, cudaStre
             if (r == cudaSuccess) r = cudaFuncSetAttribute(conv_halo_kernel<128, 1, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kHSmemBudget);
             if (r == cudaSuccess) r = cudaFuncSetAttribute(conv_halo_kernel<64, 1, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kHSmemBudget);
             if (r == cudaSuccess) r = cudaFuncSetAttribute(conv_halo_kernel<64, 2, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kHSmemBudget);
+            if (r == cudaSuccess) r = cudaFuncSetAttribute(conv_halo_kernel<128, 1, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kHSmemBudget);
+            if (r == cudaSuccess) r = cudaFuncSetAttribute(conv_halo_kernel<128, 1, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kHSmemBudget);
+            if (r == cudaSuccess) r = cudaFuncSetAttribute(conv_halo_kernel<64, 1, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kHSmemBudget);
+            if (r == cudaSuccess) r = cudaFuncSetAttribute(conv_halo_kernel<64, 2, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kHSmemBudget);
             return r;
         });
         if (e != cudaSuccess) return e;
@@ -540,6 +546,13 @@ cudaError_t halo_launch(const HaloPlan& p, const ConvArgs& a, int* dbg, cudaStre
     cfg.attrs = attr;
     cfg.numAttrs = na;
     cudaError_t e;
+    static const bool uw = getenv("YB_TC_UW") && atoi(getenv("YB_TC_UW")) != 0;
+    if (uw) {
+        if (p.stride == 2) e = cudaLaunchKernelEx(&cfg, conv_halo_kernel<64, 2, false, true>, p.tmIn, p.tmB, p.tmOut, p.tmRes, h);
+        else if (p.pair) e = cudaLaunchKernelEx(&cfg, conv_halo_kernel<128, 1, true, true>, p.tmIn, p.tmB, p.tmOut, p.tmRes, h);
+        else if (p.swz == 128) e = cudaLaunchKernelEx(&cfg, conv_halo_kernel<128, 1, false, true>, p.tmIn, p.tmB, p.tmOut, p.tmRes, h);
+        else e = cudaLaunchKernelEx(&cfg, conv_halo_kernel<64, 1, false, true>, p.tmIn, p.tmB, p.tmOut, p.tmRes, h);
+    } else
     if (p.stride == 2) e = cudaLaunchKernelEx(&cfg, conv_halo_kernel<64, 2, false>, p.tmIn, p.tmB, p.tmOut, p.tmRes, h);
     else if (p.pair) e = cudaLaunchKernelEx(&cfg, conv_halo_kernel<128, 1, true>, p.tmIn, p.tmB, p.tmOut, p.tmRes, h);
     else if (p.swz == 128) e = cudaLaunchKernelEx(&cfg, conv_halo_kernel<128, 1, false>, p.tmIn, p.tmB, p.tmOut, p.tmRes, h);

@@ -229,7 +229,11 @@ __device__ __forceinline__ void load_resident_weights(const CUtensorMap* tmB, co
 // EXPB: timing experiment (YB_TC_EXP_BLOCKED=1, 1x1 layers, results are WRONG): the A operand is fetched as if the
 // activations were stored channel-blocked, [Cin/64][M][64] -- every k-block box one contiguous 16 KB run instead of 128
 // rows strided by the pixel pitch -- through a 2-D map over the same memory and coordinates (0, kb*M + m0).
-template <int SWZ, bool CTA2, bool EXPB = false>
+// UW (YB_TC_UW=1; written at the end of round 1 from the SASS, not yet run on a GPU): the warp index is read through a
+// shuffle broadcast, which the compiler knows to be warp-uniform (cutlass::canonical_warp_idx_sync does the same), so the
+// role dispatch becomes a uniform branch and uniform registers stay usable inside the roles -- without it every role is a
+// "divergent" region to the compiler and the single-thread issue loops and the epilogue are littered with R2UR copies.
+template <int SWZ, bool CTA2, bool EXPB = false, bool UW = false>
 __global__ void __launch_bounds__(kThreads, 1)
 conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                const __grid_constant__ CUtensorMap tmOut, const __grid_constant__ CUtensorMap tmRes, const TcArgs a_in) {
@@ -260,7 +264,8 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     const uint32_t bres0 = stg0 + (a.epi_staged ? (uint32_t)a.ring * ((stg_bytes + 1023u) & ~1023u) : 0u);
     const uint32_t stage0 = bres0 + (a.b_resident ? (uint32_t)a.num_kblocks * B_SLOT : 0u);
 
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int warp = UW ? __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0) : (int)(threadIdx.x >> 5);
+    const int lane = threadIdx.x & 31;
     const int total_tiles = a.m_tiles * a.n_tiles;          // m_tiles counts 256-row units in pair mode
     const int tile_first = blockIdx.x / NCTA, tile_step = gridDim.x / NCTA;
 
@@ -711,7 +716,25 @@ struct StemArgs {
 __device__ __forceinline__ float stem_ld(const float* p) { return __ldg(p); }
 __device__ __forceinline__ float stem_ld(const __half* p) { return __half2float(__ldg(p)); }
 
-template <typename TIn>
+// V2 (YB_STEM_V2=1, written at the end of round 1 from the SASS of the V1 loops, not yet run on a GPU): same results bit
+// for bit with fewer instructions -- the interior / border decision of the gather is taken per WARP (a vote), so the fast
+// path is a uniform branch and the compiler keeps the memory descriptor in uniform registers instead of re-copying it for
+// every load; the epilogue uses packed fp32 arithmetic (fma.rn.f32x2, mul.f32x2) and LeakyReLU as max(v, 0.1 v).
+__device__ __forceinline__ float2 ffma2(float2 a, float2 b, float2 c) {
+    unsigned long long ra;
+    asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(ra)
+        : "l"(*reinterpret_cast<unsigned long long*>(&a)), "l"(*reinterpret_cast<unsigned long long*>(&b)),
+          "l"(*reinterpret_cast<unsigned long long*>(&c)));
+    return *reinterpret_cast<float2*>(&ra);
+}
+__device__ __forceinline__ float2 fmul2(float2 a, float2 b) {
+    unsigned long long ra;
+    asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(ra)
+        : "l"(*reinterpret_cast<unsigned long long*>(&a)), "l"(*reinterpret_cast<unsigned long long*>(&b)));
+    return *reinterpret_cast<float2*>(&ra);
+}
+
+template <typename TIn, bool V2 = false>
 __global__ void __launch_bounds__(kStemThreads, 1)
 stem_tc_kernel(const __grid_constant__ CUtensorMap tmOut, const StemArgs a_in) {
     StemArgs a = a_in;
@@ -726,7 +749,10 @@ stem_tc_kernel(const __grid_constant__ CUtensorMap tmOut, const StemArgs a_in) {
     const uint32_t wsm = base + 1024;                      // weights 32 x 64 B (2 KB), swizzled
     const uint32_t stg0 = base + 4096;                     // kStemRing staging buffers
     const uint32_t stage0 = stg0 + kStemRing * STG_BYTES;
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    // V2: the warp index read through a shuffle is warp-uniform for the compiler (what cutlass::canonical_warp_idx_sync does),
+    // so the role dispatch below is a uniform branch and uniform registers stay usable inside the roles
+    const int warp = V2 ? __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0) : (int)(threadIdx.x >> 5);
+    const int lane = threadIdx.x & 31;
 
     if (warp == 0 && lane == 0) prefetch_tmap(&tmOut);
     if (warp == 20 && lane == 0) {
@@ -791,6 +817,38 @@ stem_tc_kernel(const __grid_constant__ CUtensorMap tmOut, const StemArgs a_in) {
             pb += db;
         };
         auto gather = [&](float (&v)[27]) {
+            if constexpr (V2) {
+                const bool inside = m < a.M;
+                const bool interior = inside && py >= 1 && py < a.H - 1 && px >= 1 && px < a.W - 1;
+                const TIn* p = static_cast<const TIn*>(a.x) + (long)pb * img_stride + py * a.W + px;
+                if (__all_sync(0xffffffffu, interior)) {       // warp-uniform: 32 consecutive pixels of one image row
+#pragma unroll
+                    for (int c = 0; c < 3; ++c) {
+#pragma unroll
+                        for (int ky = 0; ky < 3; ++ky) {
+                            const TIn* q = p + c * HW + (ky - 1) * a.W;
+                            v[(ky * 3 + 0) * 3 + c] = stem_ld(q - 1);
+                            v[(ky * 3 + 1) * 3 + c] = stem_ld(q);
+                            v[(ky * 3 + 2) * 3 + c] = stem_ld(q + 1);
+                        }
+                    }
+                } else {
+#pragma unroll
+                    for (int ky = 0; ky < 3; ++ky) {
+                        const int iy = py + ky - 1;
+                        const bool oky = inside && iy >= 0 && iy < a.H;
+#pragma unroll
+                        for (int kx = 0; kx < 3; ++kx) {
+                            const int ix = px + kx - 1;
+                            const bool ok = oky && ix >= 0 && ix < a.W;
+#pragma unroll
+                            for (int c = 0; c < 3; ++c)
+                                v[(ky * 3 + kx) * 3 + c] = ok ? stem_ld(p + c * HW + (ky - 1) * a.W + (kx - 1)) : 0.f;
+                        }
+                    }
+                }
+                return;
+            }
             if (m < a.M) {
                 const TIn* p = static_cast<const TIn*>(a.x) + (long)pb * img_stride + py * a.W + px;
                 if (py >= 1 && py < a.H - 1 && px >= 1 && px < a.W - 1) {
@@ -939,6 +997,20 @@ stem_tc_kernel(const __grid_constant__ CUtensorMap tmOut, const StemArgs a_in) {
                 const float4 s0 = sc4[2 * c], s1 = sc4[2 * c + 1], b0 = bi4[2 * c], b1 = bi4[2 * c + 1];
                 uint4 pk;
                 __half2* ph2 = reinterpret_cast<__half2*>(&pk);
+                if constexpr (V2) {
+                    const float2 tenth = make_float2(kLeaky, kLeaky);
+                    const float2 sc[4] = {make_float2(s0.x, s0.y), make_float2(s0.z, s0.w), make_float2(s1.x, s1.y), make_float2(s1.z, s1.w)};
+                    const float2 bi[4] = {make_float2(b0.x, b0.y), make_float2(b0.z, b0.w), make_float2(b1.x, b1.y), make_float2(b1.z, b1.w)};
+#pragma unroll
+                    for (int e = 0; e < 4; ++e) {
+                        const float2 acc = make_float2(__uint_as_float(rr[j0 + 2 * e]), __uint_as_float(rr[j0 + 2 * e + 1]));
+                        const float2 y = ffma2(acc, sc[e], bi[e]);
+                        const float2 t = fmul2(y, tenth);
+                        ph2[e] = __floats2half2_rn(fmaxf(y.x, t.x), fmaxf(y.y, t.y));     // LeakyReLU(0.1) = max(v, 0.1 v)
+                    }
+                    *reinterpret_cast<uint4*>(srow + ((c ^ xr) << 4)) = pk;
+                    continue;
+                }
                 ph2[0] = __floats2half2_rn(leaky(fmaf(__uint_as_float(rr[j0 + 0]), s0.x, b0.x)), leaky(fmaf(__uint_as_float(rr[j0 + 1]), s0.y, b0.y)));
                 ph2[1] = __floats2half2_rn(leaky(fmaf(__uint_as_float(rr[j0 + 2]), s0.z, b0.z)), leaky(fmaf(__uint_as_float(rr[j0 + 3]), s0.w, b0.w)));
                 ph2[2] = __floats2half2_rn(leaky(fmaf(__uint_as_float(rr[j0 + 4]), s1.x, b1.x)), leaky(fmaf(__uint_as_float(rr[j0 + 5]), s1.y, b1.y)));
@@ -1227,6 +1299,8 @@ cudaError_t stem_tc_launch(const StemTcPlan& p, const void* x, int in_f16, int B
         cudaError_t e = attr_once.run([] {
             cudaError_t r = cudaFuncSetAttribute(stem_tc_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, 128 * 1024);
             if (r == cudaSuccess) r = cudaFuncSetAttribute(stem_tc_kernel<__half>, cudaFuncAttributeMaxDynamicSharedMemorySize, 128 * 1024);
+            if (r == cudaSuccess) r = cudaFuncSetAttribute(stem_tc_kernel<float, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 128 * 1024);
+            if (r == cudaSuccess) r = cudaFuncSetAttribute(stem_tc_kernel<__half, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 128 * 1024);
             return r;
         });
         if (e != cudaSuccess) return e;
@@ -1243,8 +1317,12 @@ cudaError_t stem_tc_launch(const StemTcPlan& p, const void* x, int in_f16, int B
         attr[0].val.programmaticStreamSerializationAllowed = 1;
         cfg.attrs = attr;
         cfg.numAttrs = pdl ? 1 : 0;
-        cudaError_t e = in_f16 ? cudaLaunchKernelEx(&cfg, stem_tc_kernel<__half>, p.tmOut, a)
-                               : cudaLaunchKernelEx(&cfg, stem_tc_kernel<float>, p.tmOut, a);
+        static const bool v2 = getenv("YB_STEM_V2") && atoi(getenv("YB_STEM_V2")) != 0;
+        cudaError_t e;
+        if (v2) e = in_f16 ? cudaLaunchKernelEx(&cfg, stem_tc_kernel<__half, true>, p.tmOut, a)
+                           : cudaLaunchKernelEx(&cfg, stem_tc_kernel<float, true>, p.tmOut, a);
+        else e = in_f16 ? cudaLaunchKernelEx(&cfg, stem_tc_kernel<__half>, p.tmOut, a)
+                        : cudaLaunchKernelEx(&cfg, stem_tc_kernel<float>, p.tmOut, a);
         if (e != cudaSuccess) return e;
     }
     return cudaGetLastError();
@@ -1299,6 +1377,9 @@ cudaError_t tc_launch(const TcPlan& p, const ConvArgs& a, int* dbg, cudaStream_t
             if (r == cudaSuccess) r = cudaFuncSetAttribute(conv_tc_kernel<128, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBudget);
             if (r == cudaSuccess) r = cudaFuncSetAttribute(conv_tc_kernel<128, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBudget);
             if (r == cudaSuccess) r = cudaFuncSetAttribute(conv_tc_kernel<128, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBudget);
+            if (r == cudaSuccess) r = cudaFuncSetAttribute(conv_tc_kernel<128, false, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBudget);
+            if (r == cudaSuccess) r = cudaFuncSetAttribute(conv_tc_kernel<64, false, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBudget);
+            if (r == cudaSuccess) r = cudaFuncSetAttribute(conv_tc_kernel<128, true, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBudget);
             return r;
         });
         if (e != cudaSuccess) return e;
@@ -1329,6 +1410,12 @@ cudaError_t tc_launch(const TcPlan& p, const ConvArgs& a, int* dbg, cudaStream_t
         cfg.attrs = attr;
         cfg.numAttrs = na;
         cudaError_t e;
+        static const bool uw = getenv("YB_TC_UW") && atoi(getenv("YB_TC_UW")) != 0;
+        if (uw && !p.exp_blocked) {
+            if (p.cta2) e = cudaLaunchKernelEx(&cfg, conv_tc_kernel<128, true, false, true>, p.tmA, p.tmB, p.tmOut, p.tmRes, t);
+            else if (p.swz == 128) e = cudaLaunchKernelEx(&cfg, conv_tc_kernel<128, false, false, true>, p.tmA, p.tmB, p.tmOut, p.tmRes, t);
+            else e = cudaLaunchKernelEx(&cfg, conv_tc_kernel<64, false, false, true>, p.tmA, p.tmB, p.tmOut, p.tmRes, t);
+        } else
         if (p.exp_blocked && p.cta2) e = cudaLaunchKernelEx(&cfg, conv_tc_kernel<128, true, true>, p.tmA, p.tmB, p.tmOut, p.tmRes, t);
         else if (p.exp_blocked) e = cudaLaunchKernelEx(&cfg, conv_tc_kernel<128, false, true>, p.tmA, p.tmB, p.tmOut, p.tmRes, t);
         else if (p.cta2) e = cudaLaunchKernelEx(&cfg, conv_tc_kernel<128, true>, p.tmA, p.tmB, p.tmOut, p.tmRes, t);
