@@ -515,10 +515,13 @@ cudaError_t halo_launch(const HaloPlan& p, const ConvArgs& a, int* dbg, cudaStre
             if (r == cudaSuccess) r = cudaFuncSetAttribute(conv_halo_kernel<128, 1, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kHSmemBudget);
             if (r == cudaSuccess) r = cudaFuncSetAttribute(conv_halo_kernel<64, 1, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kHSmemBudget);
             if (r == cudaSuccess) r = cudaFuncSetAttribute(conv_halo_kernel<64, 2, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kHSmemBudget);
-            if (r == cudaSuccess) r = cudaFuncSetAttribute(conv_halo_kernel<128, 1, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kHSmemBudget);
-            if (r == cudaSuccess) r = cudaFuncSetAttribute(conv_halo_kernel<128, 1, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kHSmemBudget);
-            if (r == cudaSuccess) r = cudaFuncSetAttribute(conv_halo_kernel<64, 1, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kHSmemBudget);
-            if (r == cudaSuccess) r = cudaFuncSetAttribute(conv_halo_kernel<64, 2, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kHSmemBudget);
+            if (r == cudaSuccess) {     // opt-in instantiations: best effort, must not take the validated path down
+                cudaFuncSetAttribute(conv_halo_kernel<128, 1, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kHSmemBudget);
+                cudaFuncSetAttribute(conv_halo_kernel<128, 1, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kHSmemBudget);
+                cudaFuncSetAttribute(conv_halo_kernel<64, 1, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kHSmemBudget);
+                cudaFuncSetAttribute(conv_halo_kernel<64, 2, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kHSmemBudget);
+                cudaGetLastError();
+            }
             return r;
         });
         if (e != cudaSuccess) return e;

@@ -1299,8 +1299,11 @@ cudaError_t stem_tc_launch(const StemTcPlan& p, const void* x, int in_f16, int B
         cudaError_t e = attr_once.run([] {
             cudaError_t r = cudaFuncSetAttribute(stem_tc_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, 128 * 1024);
             if (r == cudaSuccess) r = cudaFuncSetAttribute(stem_tc_kernel<__half>, cudaFuncAttributeMaxDynamicSharedMemorySize, 128 * 1024);
-            if (r == cudaSuccess) r = cudaFuncSetAttribute(stem_tc_kernel<float, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 128 * 1024);
-            if (r == cudaSuccess) r = cudaFuncSetAttribute(stem_tc_kernel<__half, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 128 * 1024);
+            if (r == cudaSuccess) {     // opt-in instantiations: best effort, a failure here must not take the validated path down
+                cudaFuncSetAttribute(stem_tc_kernel<float, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 128 * 1024);
+                cudaFuncSetAttribute(stem_tc_kernel<__half, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 128 * 1024);
+                cudaGetLastError();
+            }
             return r;
         });
         if (e != cudaSuccess) return e;
@@ -1375,11 +1378,14 @@ cudaError_t tc_launch(const TcPlan& p, const ConvArgs& a, int* dbg, cudaStream_t
             cudaError_t r = cudaFuncSetAttribute(conv_tc_kernel<128, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBudget);
             if (r == cudaSuccess) r = cudaFuncSetAttribute(conv_tc_kernel<64, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBudget);
             if (r == cudaSuccess) r = cudaFuncSetAttribute(conv_tc_kernel<128, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBudget);
-            if (r == cudaSuccess) r = cudaFuncSetAttribute(conv_tc_kernel<128, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBudget);
-            if (r == cudaSuccess) r = cudaFuncSetAttribute(conv_tc_kernel<128, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBudget);
-            if (r == cudaSuccess) r = cudaFuncSetAttribute(conv_tc_kernel<128, false, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBudget);
-            if (r == cudaSuccess) r = cudaFuncSetAttribute(conv_tc_kernel<64, false, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBudget);
-            if (r == cudaSuccess) r = cudaFuncSetAttribute(conv_tc_kernel<128, true, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBudget);
+            if (r == cudaSuccess) {     // experiment / opt-in instantiations: best effort, must not take the validated path down
+                cudaFuncSetAttribute(conv_tc_kernel<128, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBudget);
+                cudaFuncSetAttribute(conv_tc_kernel<128, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBudget);
+                cudaFuncSetAttribute(conv_tc_kernel<128, false, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBudget);
+                cudaFuncSetAttribute(conv_tc_kernel<64, false, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBudget);
+                cudaFuncSetAttribute(conv_tc_kernel<128, true, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBudget);
+                cudaGetLastError();
+            }
             return r;
         });
         if (e != cudaSuccess) return e;
