@@ -74,9 +74,10 @@ struct TcArgs {
     long long* trace;        // optional [6 roles][64 tiles][4] clock64 stamps of CTA 0 (YB_TC_TRACE=1)
 };
 
+// (kTraceOn is a compile-time constant of the enclosing kernel: the opt-in UW instantiations are built without the trace points)
 #define YB_TRACE(role, idx, slot)                                                                   \
     do {                                                                                            \
-        if (a.trace && blockIdx.x == 0 && (idx) < 64) a.trace[((role) * 64 + (idx)) * 4 + (slot)] = clock64(); \
+        if (kTraceOn && a.trace && blockIdx.x == 0 && (idx) < 64) a.trace[((role) * 64 + (idx)) * 4 + (slot)] = clock64(); \
     } while (0)
 
 // Epilogue for 16 consecutive channels of one output pixel.
@@ -238,6 +239,7 @@ __global__ void __launch_bounds__(kThreads, 1)
 conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                const __grid_constant__ CUtensorMap tmOut, const __grid_constant__ CUtensorMap tmRes, const TcArgs a_in) {
     constexpr int BKE = SWZ / 2;                  // fp16 elements per k-block row
+    constexpr bool kTraceOn = !UW;
     TcArgs a = a_in;
     constexpr uint32_t A_BYTES = kBM * SWZ;
     extern __shared__ uint8_t smem_raw[];
