@@ -43,8 +43,11 @@ typedef enum {
 } yb_status;
 
 /* precision_mode for yb_finalize */
-#define YB_MODE_FP32 0  /* fp32 activations + fp32 CUDA-core implicit GEMM: fp32-grade parity with the reference */
-#define YB_MODE_FP16 1  /* fp16 activations/weights, fp32 accumulate in TMEM on tcgen05 tensor cores (perf path) */
+#define YB_MODE_FP32 0    /* fp32 activations + fp32 CUDA-core implicit GEMM (debugging aid: slow, fixed summation order) */
+#define YB_MODE_FP16 1    /* fp16 activations/weights, fp32 accumulate in TMEM on tcgen05 tensor cores (perf path) */
+#define YB_MODE_FP32_TC 2 /* fp32-grade parity with the reference ON the tensor cores: every activation and weight is an
+                           * fp16 pair hi + lo (22 mantissa bits), three tcgen05 kind::f16 partial products per k-step
+                           * (hi*hi + hi*lo + lo*hi) accumulated in fp32 in TMEM, fp32 epilogue.  What precision='fp32' runs. */
 
 /* ---- lifetime -------------------------------------------------------------------------------- */
 

@@ -15,6 +15,7 @@ LIB_PATH = os.path.join(HERE, "lib", "libyolo_b200.so")
 
 YB_MODE_FP32 = 0
 YB_MODE_FP16 = 1
+YB_MODE_FP32_TC = 2
 YB_INPUT_F32 = 0
 YB_INPUT_F16 = 1
 YB_E_CAP = -6

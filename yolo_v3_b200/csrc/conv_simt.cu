@@ -122,13 +122,16 @@ __global__ void __launch_bounds__(256) conv_simt_kernel(ConvArgs a, const float*
 // Stem: conv 3->32, 3x3, stride 1, pad 1 straight from the caller's NCHW fp32 image to NHWC.
 // One thread per output pixel, 32 fp32 accumulators; the 32x32 tile a warp produces is contiguous
 // in NHWC memory, so it is staged in shared memory and written with 16-byte coalesced stores.
-template <typename T>
+// SPLIT (YB_MODE_FP32_TC): T = __half and every pixel is written as 64 values, hi[32] | lo[32] with hi = RN16(v),
+// lo = RN16(v - hi) -- the activation format of the split-mode tensor-core convolutions (conv_tc.cu).
+template <typename T, bool SPLIT = false>
 __global__ void __launch_bounds__(128) stem_kernel(const float* __restrict__ x, T* __restrict__ out,
                                                    const float* __restrict__ w, const float* __restrict__ scale,
                                                    const float* __restrict__ bias, int B, int H, int W) {
+    constexpr int CH = SPLIT ? 64 : 32;             // values stored per pixel
     __shared__ float ws[27 * 32];
     __shared__ float ss[32], sb[32];
-    __shared__ __align__(16) T stage[4][32][32 + 8];
+    __shared__ __align__(16) T stage[4][32][CH + 8];
     for (int i = threadIdx.x; i < 27 * 32; i += blockDim.x) ws[i] = w[i];
     if (threadIdx.x < 32) { ss[threadIdx.x] = scale[threadIdx.x]; sb[threadIdx.x] = bias[threadIdx.x]; }
     __syncthreads();
@@ -163,19 +166,21 @@ __global__ void __launch_bounds__(128) stem_kernel(const float* __restrict__ x, 
     for (int n = 0; n < 32; ++n) {
         float v = fmaf(acc[n], ss[n], sb[n]);
         v = v > 0.f ? v : v * kLeaky;
-        stage[warp][lane][n] = from_f32<T>(v);
+        const T hi = from_f32<T>(v);
+        stage[warp][lane][n] = hi;
+        if constexpr (SPLIT) stage[warp][lane][32 + n] = from_f32<T>(v - to_f32(hi));
     }
     __syncwarp();
-    // the warp's 32 pixels x 32 channels are one contiguous run of 32*32*sizeof(T) bytes
+    // the warp's 32 pixels x CH values are one contiguous run of 32*CH*sizeof(T) bytes
     const long warp_pix0 = (long)blockIdx.x * blockDim.x + warp * 32;
     constexpr int VEC = 16 / sizeof(T);              // elements per 16-byte store
-    constexpr int CHUNKS = 32 * 32 / VEC;            // per warp
+    constexpr int CHUNKS = 32 * CH / VEC;            // per warp
     for (int ch = lane; ch < CHUNKS; ch += 32) {
         const int e = ch * VEC;
-        const int p = e / 32, c = e % 32;
+        const int p = e / CH, c = e % CH;
         if (warp_pix0 + p < total) {
             const uint4 v = *reinterpret_cast<const uint4*>(&stage[warp][p][c]);
-            *reinterpret_cast<uint4*>(out + (warp_pix0 + p) * 32 + c) = v;
+            *reinterpret_cast<uint4*>(out + (warp_pix0 + p) * CH + c) = v;
         }
     }
 }
@@ -195,6 +200,51 @@ __global__ void nhwc_to_nchw_kernel(const T* __restrict__ in, long in_ld, int C,
     for (int i = ty; i < 32; i += 8) {
         const int c = c0 + i, p = p0 + tx;
         if (p < HW && c < C) out[((long)b * C + c) * HW + p] = tile[tx][i];
+    }
+}
+
+// split activations [pixel][.. hi at 0, lo at `lo` ..] (pitch in_ld, first C channels) -> dense NCHW fp32
+__global__ void split_to_nchw_kernel(const __half* __restrict__ in, long in_ld, long lo, int C, int HW, float* __restrict__ out) {
+    __shared__ float tile[32][33];
+    const int b = blockIdx.z;
+    const int p0 = blockIdx.x * 32, c0 = blockIdx.y * 32;
+    const int tx = threadIdx.x, ty = threadIdx.y;   // 32 x 8
+    for (int i = ty; i < 32; i += 8) {
+        const int p = p0 + i, c = c0 + tx;
+        float v = 0.f;
+        if (p < HW && c < C) {
+            const __half* q = in + ((long)b * HW + p) * in_ld + c;
+            v = __half2float(q[0]) + __half2float(q[lo]);
+        }
+        tile[i][tx] = v;
+    }
+    __syncthreads();
+    for (int i = ty; i < 32; i += 8) {
+        const int c = c0 + i, p = p0 + tx;
+        if (p < HW && c < C) out[((long)b * C + c) * HW + p] = tile[tx][i];
+    }
+}
+
+// fp32 [M][C] <-> split fp16 [M][2C] (hi | lo); test / API-boundary converters of yb_run_layer in YB_MODE_FP32_TC
+__global__ void f32_to_split_kernel(const float* __restrict__ in, __half* __restrict__ out, size_t M, int C) {
+    const size_t n = M * (size_t)C;
+    const size_t stride = (size_t)gridDim.x * blockDim.x;
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+        const size_t m = i / C;
+        const int c = (int)(i - m * C);
+        const float v = in[i];
+        const __half hi = __float2half_rn(v);
+        out[m * 2 * C + c] = hi;
+        out[m * 2 * C + C + c] = __float2half_rn(v - __half2float(hi));
+    }
+}
+__global__ void split_to_f32_kernel(const __half* __restrict__ in, float* __restrict__ out, size_t M, int C) {
+    const size_t n = M * (size_t)C;
+    const size_t stride = (size_t)gridDim.x * blockDim.x;
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+        const size_t m = i / C;
+        const int c = (int)(i - m * C);
+        out[i] = __half2float(in[m * 2 * C + c]) + __half2float(in[m * 2 * C + C + c]);
     }
 }
 
@@ -225,6 +275,26 @@ cudaError_t launch_stem(const float* x, T* out, const float* w32, const float* s
 }
 template cudaError_t launch_stem<float>(const float*, float*, const float*, const float*, const float*, int, int, int, cudaStream_t);
 template cudaError_t launch_stem<__half>(const float*, __half*, const float*, const float*, const float*, int, int, int, cudaStream_t);
+
+cudaError_t launch_stem_split(const float* x, __half* out, const float* w32, const float* scale, const float* bias,
+                              int B, int H, int W, cudaStream_t s) {
+    const long total = (long)B * H * W;
+    stem_kernel<__half, true><<<(unsigned)((total + 127) / 128), 128, 0, s>>>(x, out, w32, scale, bias, B, H, W);
+    return cudaGetLastError();
+}
+cudaError_t launch_split_to_nchw_f32(const __half* in, long in_ld, long lo, int C, int B, int HW, float* out, cudaStream_t s) {
+    dim3 grid((HW + 31) / 32, (C + 31) / 32, B), block(32, 8);
+    split_to_nchw_kernel<<<grid, block, 0, s>>>(in, in_ld, lo, C, HW, out);
+    return cudaGetLastError();
+}
+cudaError_t launch_f32_to_split(const float* in, __half* out, size_t M, int C, cudaStream_t s) {
+    f32_to_split_kernel<<<1184, 256, 0, s>>>(in, out, M, C);
+    return cudaGetLastError();
+}
+cudaError_t launch_split_to_f32(const __half* in, float* out, size_t M, int C, cudaStream_t s) {
+    split_to_f32_kernel<<<1184, 256, 0, s>>>(in, out, M, C);
+    return cudaGetLastError();
+}
 
 template <typename T>
 cudaError_t launch_nhwc_to_nchw_f32(const T* in, long in_ld, int C, int B, int HW, float* out, cudaStream_t s) {

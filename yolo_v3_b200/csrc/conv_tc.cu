@@ -70,6 +70,10 @@ struct TcArgs {
     int epi_split;           // sub-tiles of 32 columns occupy only half of the sixteen epilogue warps: the halves take alternate
                              // sub-tiles (n_sub even) or alternate tiles (n_sub == 1), two hand-over chains in flight
     int epi_sleep;           // nanoseconds the epilogue warps back off between probes of the accumulator barrier (0 = spin)
+    // split mode (SPLIT instantiations, YB_MODE_FP32_TC): every activation is a pair of fp16 tensors hi + lo sharing one
+    // pixel pitch; a_lo / out_lo / res_lo = channel offset of the lo half relative to the hi pointer; split_out = the
+    // output is written as such a pair (everything but the fp32 head maps)
+    int a_lo, out_lo, res_lo, split_out;
     int* dbg;
     long long* trace;        // optional [6 roles][64 tiles][4] clock64 stamps of CTA 0 (YB_TC_TRACE=1)
 };
@@ -190,6 +194,126 @@ __device__ __forceinline__ void epilogue16_staged(const TcArgs& a, const uint32_
     }
 }
 
+// ---- split mode (YB_MODE_FP32_TC): fp32-grade convolutions on the fp16 tensor pipe ----------------------------------
+// Every activation x is stored as two fp16 tensors, hi = RN16(x) and lo = RN16(x - hi) (x - hi is exact in fp32, so
+// hi + lo carries 22 bits of x), and every weight w -- pre-scaled per output channel by a power of two so that its lo part
+// stays a normal fp16 number, the scale is undone in the fp32 epilogue -- as wh + wl.  The GEMM accumulates the three
+// significant partial products xh*wh + xh*wl + xl*wh (exact in the fp32 accumulator's product stage; the dropped xl*wl
+// term is 2^-22 relative) by running the unchanged main loop over a K axis three times as long: k-blocks are ordered
+// (tap, section, channel block), sections 0/1 fetch the hi half of A, section 2 the lo half; the weight rows are packed
+// [tap][wh | wl | wh][Cin] to match.  tools/split_numerics.py (profiles/r02_split_numerics_cpu.txt): the operand
+// representation error of this scheme through all 75 layers is 3e-6 of max|logit| -- below the fp32 oracle's own 5e-6.
+__device__ __forceinline__ void split2(float a, float b, __half2& hi, __half2& lo) {
+    hi = __floats2half2_rn(a, b);
+    const float2 f = __half22float2(hi);
+    lo = __floats2half2_rn(a - f.x, b - f.y);
+}
+
+// Direct (non-staged) split epilogue for 16 consecutive channels of one output pixel: used by the two nearest-upsample layers.
+__device__ __forceinline__ void epilogue16_split(const TcArgs& a, const uint32_t (&acc)[16], int n, bool valid, long m,
+                                                 long o00, long W2ld) {
+    float v[16];
+    const float4* sc = reinterpret_cast<const float4*>(a.tab + n);
+    const float4* bi = reinterpret_cast<const float4*>(a.tab + a.cout_pad + n);
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+        const float4 s4 = sc[q], b4 = bi[q];
+        v[4 * q + 0] = fmaf(__uint_as_float(acc[4 * q + 0]), s4.x, b4.x);
+        v[4 * q + 1] = fmaf(__uint_as_float(acc[4 * q + 1]), s4.y, b4.y);
+        v[4 * q + 2] = fmaf(__uint_as_float(acc[4 * q + 2]), s4.z, b4.z);
+        v[4 * q + 3] = fmaf(__uint_as_float(acc[4 * q + 3]), s4.w, b4.w);
+    }
+    if (a.leaky) {
+#pragma unroll
+        for (int i = 0; i < 16; ++i) v[i] = leaky(v[i]);
+    }
+    if (!valid) return;
+    __half* ob = reinterpret_cast<__half*>(a.out);
+    if (a.res) {
+        const uint4* rh = reinterpret_cast<const uint4*>(a.res + m * a.res_ld + n);
+        const uint4* rl = reinterpret_cast<const uint4*>(a.res + m * a.res_ld + a.res_lo + n);
+#pragma unroll
+        for (int q = 0; q < 2; ++q) {
+            const uint4 h4 = rh[q], l4 = rl[q];
+            const __half2* hh = reinterpret_cast<const __half2*>(&h4);
+            const __half2* ll = reinterpret_cast<const __half2*>(&l4);
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                const float2 fh = __half22float2(hh[i]), fl = __half22float2(ll[i]);
+                v[8 * q + 2 * i] += fh.x + fl.x;          // hi + lo is exact in fp32: one rounding, like the reference's x + f(x)
+                v[8 * q + 2 * i + 1] += fh.y + fl.y;
+            }
+        }
+    }
+    uint4 ph[2], pl[2];
+#pragma unroll
+    for (int q = 0; q < 2; ++q) {
+        __half2* h = reinterpret_cast<__half2*>(&ph[q]);
+        __half2* l = reinterpret_cast<__half2*>(&pl[q]);
+#pragma unroll
+        for (int i = 0; i < 4; ++i) split2(v[8 * q + 2 * i], v[8 * q + 2 * i + 1], h[i], l[i]);
+    }
+    if (!a.upsample) {
+        uint4* o = reinterpret_cast<uint4*>(ob + m * a.out_ld + n);
+        uint4* ol = reinterpret_cast<uint4*>(ob + m * a.out_ld + a.out_lo + n);
+        o[0] = ph[0]; o[1] = ph[1];
+        ol[0] = pl[0]; ol[1] = pl[1];
+    } else {
+#pragma unroll
+        for (int d = 0; d < 4; ++d) {
+            __half* px = ob + o00 + (d >> 1) * W2ld + (d & 1) * a.out_ld + n;
+            uint4* o = reinterpret_cast<uint4*>(px);
+            uint4* ol = reinterpret_cast<uint4*>(px + a.out_lo);
+            o[0] = ph[0]; o[1] = ph[1];
+            ol[0] = pl[0]; ol[1] = pl[1];
+        }
+    }
+}
+
+// Staged split epilogue: the staging slot holds the hi sub-tile followed (lo_delta bytes later) by the lo sub-tile, both
+// 128B- (or 64B-) swizzled like the single sub-tile of the fp16 mode; the residual arrives the same way.
+__device__ __forceinline__ void epilogue16_staged_split(const TcArgs& a, const uint32_t (&acc)[16], int n, uint8_t* srow,
+                                                        uint32_t lo_delta, int grp, int xr) {
+    float v[16];
+    const float4* sc = reinterpret_cast<const float4*>(a.tab + n);
+    const float4* bi = reinterpret_cast<const float4*>(a.tab + a.cout_pad + n);
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+        const float4 s4 = sc[q], b4 = bi[q];
+        v[4 * q + 0] = fmaf(__uint_as_float(acc[4 * q + 0]), s4.x, b4.x);
+        v[4 * q + 1] = fmaf(__uint_as_float(acc[4 * q + 1]), s4.y, b4.y);
+        v[4 * q + 2] = fmaf(__uint_as_float(acc[4 * q + 2]), s4.z, b4.z);
+        v[4 * q + 3] = fmaf(__uint_as_float(acc[4 * q + 3]), s4.w, b4.w);
+    }
+    if (a.leaky) {
+#pragma unroll
+        for (int i = 0; i < 16; ++i) v[i] = leaky(v[i]);
+    }
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+        uint4* p = reinterpret_cast<uint4*>(srow + (((grp * 2 + h) ^ xr) << 4));
+        uint4* pl = reinterpret_cast<uint4*>(reinterpret_cast<uint8_t*>(p) + lo_delta);
+        if (a.has_res) {
+            const uint4 r = *p, rl = *pl;
+            const __half2* hh = reinterpret_cast<const __half2*>(&r);
+            const __half2* ll = reinterpret_cast<const __half2*>(&rl);
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                const float2 fh = __half22float2(hh[i]), fl = __half22float2(ll[i]);
+                v[8 * h + 2 * i] += fh.x + fl.x;
+                v[8 * h + 2 * i + 1] += fh.y + fl.y;
+            }
+        }
+        uint4 pk, pkl;
+        __half2* ph = reinterpret_cast<__half2*>(&pk);
+        __half2* pq = reinterpret_cast<__half2*>(&pkl);
+#pragma unroll
+        for (int i = 0; i < 4; ++i) split2(v[8 * h + 2 * i], v[8 * h + 2 * i + 1], ph[i], pq[i]);
+        *p = pk;
+        *pl = pkl;
+    }
+}
+
 // (m-unit, n-tile) of the tiles a CTA visits and the staging-ring slot of its sub-tiles, carried without divisions: these
 // loops run on one thread each or sit on the epilogue's per-tile dependent chain, which is what paces the layers with
 // small tiles (profiles/r01s_trace_layer2_ring*.txt) -- a 32-bit division there costs ~150-200 cycles of latency.
@@ -234,7 +358,7 @@ __device__ __forceinline__ void load_resident_weights(const CUtensorMap* tmB, co
 // shuffle broadcast, which the compiler knows to be warp-uniform (cutlass::canonical_warp_idx_sync does the same), so the
 // role dispatch becomes a uniform branch and uniform registers stay usable inside the roles -- without it every role is a
 // "divergent" region to the compiler and the single-thread issue loops and the epilogue are littered with R2UR copies.
-template <int SWZ, bool CTA2, bool EXPB = false, bool UW = false>
+template <int SWZ, bool CTA2, bool EXPB = false, bool UW = false, bool SPLIT = false>
 __global__ void __launch_bounds__(kThreads, 1)
 conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                const __grid_constant__ CUtensorMap tmOut, const __grid_constant__ CUtensorMap tmRes, const TcArgs a_in) {
@@ -259,7 +383,9 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     volatile uint32_t* tmem_ptr = reinterpret_cast<volatile uint32_t*>(gen + 16 * kMaxStages + 32);
     const uint32_t sfull0 = base + 16 * kMaxStages + 64, sempty0 = sfull0 + 32, bres_bar = sempty0 + 32, sready0 = bres_bar + 16;
     // staging ring (epilogue), resident weight slab, then the operand pipeline stages; all 1024-byte aligned
-    const uint32_t stg_bytes = (uint32_t)kBM * (uint32_t)a.sub_bytes;
+    const uint32_t stg_half = (uint32_t)kBM * (uint32_t)a.sub_bytes;
+    const bool split_out = SPLIT && a.split_out;                       // staging slots hold a hi and a lo sub-tile
+    const uint32_t stg_bytes = split_out ? 2u * stg_half : stg_half;
     a.tab = reinterpret_cast<const float*>(gen + kSmemHeader);          // scale | bias table
     const uint32_t stg0 = base + (uint32_t)kSmemHeader + (uint32_t)a.tab_bytes;
     const uint32_t B_SLOT = (B_BYTES + 1023u) & ~1023u;
@@ -378,6 +504,8 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                 }
                 if (a.ks == 1 || a.exp_tiled) {
                     int kc = 0, ka = 0;
+                    [[maybe_unused]] int cc = 0, sec = 0;      // SPLIT: channel of the A box inside its half, section 0..2
+                    [[maybe_unused]] const int cend = a.cin_blocks * BKE;
                     [[maybe_unused]] int mb = m0;              // EXPB: row of this k-block's box in the blocked view
                     for (int it = 0; it < a.num_iters; ++it, ++itg) {
                         const bool mine = (itg & 1u) == pw;
@@ -387,17 +515,22 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                         uint32_t dst = sA;
                         for (int j = 0; j < a.kps; ++j) {
                             if (el) {
+                                const int ac = SPLIT ? cc + (sec == 2 ? a.a_lo : 0) : kc;
                                 if constexpr (CTA2) {
                                     if constexpr (EXPB) tma_load_2d_pair(&tmA, dst, fb, 0, mb);
-                                    else tma_load_2d_pair(&tmA, dst, fb, kc, m0);
+                                    else tma_load_2d_pair(&tmA, dst, fb, ac, m0);
                                     if (load_b) tma_load_2d_pair(&tmB, dst + A_BYTES, fb, kc, n0);
                                 } else {
                                     if constexpr (EXPB) tma_load_2d(&tmA, dst, fb, 0, mb);
-                                    else tma_load_2d(&tmA, dst, fb, a.exp_tiled ? ka : kc, m0);
+                                    else tma_load_2d(&tmA, dst, fb, a.exp_tiled ? ka : ac, m0);
                                     if (load_b) tma_load_2d(&tmB, dst + A_BYTES, fb, kc, n0);
                                 }
                             }
                             if constexpr (EXPB) mb += (int)a.M;
+                            if constexpr (SPLIT) {
+                                cc += BKE;
+                                if (cc == cend) { cc = 0; if (++sec == 3) sec = 0; }
+                            }
                             kc += BKE;
                             ka += BKE;
                             if (ka == a.cin_blocks * BKE) ka = 0;
@@ -412,6 +545,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                     const int p = r / a.Wo, q = r - p * a.Wo;
                     const int cw = q * a.stride - a.pad, chh = p * a.stride - a.pad;
                     int kc = 0, cc = 0;                      // k coordinate of the weights, channel coordinate of A
+                    [[maybe_unused]] int sec = 0;            // SPLIT: section 0..2 of the current tap
                     uint16_t kw = 0, kh = 0;
                     const int cend = a.cin_blocks * BKE;
                     for (int it = 0; it < a.num_iters; ++it, ++itg) {
@@ -422,17 +556,23 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                         uint32_t dst = sA;
                         for (int j = 0; j < a.kps; ++j) {
                             if (el) {
+                                const int ac = SPLIT ? cc + (sec == 2 ? a.a_lo : 0) : cc;
                                 if constexpr (CTA2) {
-                                    tma_load_im2col_pair(&tmA, dst, fb, cc, cw, chh, cn, kw, kh);
+                                    tma_load_im2col_pair(&tmA, dst, fb, ac, cw, chh, cn, kw, kh);
                                     if (load_b) tma_load_2d_pair(&tmB, dst + A_BYTES, fb, kc, n0);
                                 } else {
-                                    tma_load_im2col(&tmA, dst, fb, cc, cw, chh, cn, kw, kh);
+                                    tma_load_im2col(&tmA, dst, fb, ac, cw, chh, cn, kw, kh);
                                     if (load_b) tma_load_2d(&tmB, dst + A_BYTES, fb, kc, n0);
                                 }
                             }
                             kc += BKE;
                             cc += BKE;
-                            if (cc == cend) { cc = 0; if (++kw == 3) { kw = 0; ++kh; } }
+                            if (cc == cend) {
+                                cc = 0;
+                                bool next_tap = true;
+                                if constexpr (SPLIT) { if (++sec < 3) next_tap = false; else sec = 0; }
+                                if (next_tap && ++kw == 3) { kw = 0; ++kh; }
+                            }
                             dst += kb_bytes;
                         }
                         sA += stage_bytes; fb += 8; eb += 8;
@@ -524,6 +664,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                     mbar_wait(sempty0 + 8 * buf, ph ^ 1, a.dbg, 3, 300 + (int)buf);
                     mbar_arrive_expect_tx(sfull0 + 8 * buf, stg_bytes);
                     tma_load_2d(&tmRes, stg0 + buf * stg_bytes, sfull0 + 8 * buf, n0 + j * a.cs, m0);
+                    if (split_out) tma_load_2d(&tmRes, stg0 + buf * stg_bytes + stg_half, sfull0 + 8 * buf, a.res_lo + n0 + j * a.cs, m0);
                 }
             }
         }
@@ -542,6 +683,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                     const uint32_t buf = rw.buf, ph = rw.ph;
                     mbar_wait(sready0 + 8 * buf, ph, a.dbg, 4, 700 + (int)buf);
                     if (!a.exp_nostore) tma_store_2d(&tmOut, stg0 + buf * stg_bytes, n0 + j * a.cs, m0);
+                    if (split_out) tma_store_2d(&tmOut, stg0 + buf * stg_bytes + stg_half, a.out_lo + n0 + j * a.cs, m0);
                     tma_store_commit();
                     // Recycle buffers: keep at most `srel` stores unread.  srel = ring - 2 is the latest release that
                     // still lets the epilogue warps start sub-tile g+1 while sub-tile g is being finished; with the
@@ -617,7 +759,10 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                 }
                 uint8_t* srow = gen + (stg0 - base) + buf * stg_bytes + (uint32_t)row * (uint32_t)a.sub_bytes;
                 const int nb = n0 + j * a.cs;
-                if (active) epilogue16_staged(a, r0, nb + part * 16, srow, part, xr);
+                if (active) {
+                    if (split_out) epilogue16_staged_split(a, r0, nb + part * 16, srow, stg_half, part, xr);
+                    else epilogue16_staged(a, r0, nb + part * 16, srow, part, xr);
+                }
                 if (issuer && j == 0) YB_TRACE(3, ti, 2);
                 fence_async_smem();                           // generic-proxy smem writes -> visible to the TMA engine
                 if (issuer && j == 0) YB_TRACE(3, ti, 3);
@@ -667,8 +812,13 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                 tmem_ld16(taddr + c0, r0);
                 if (two) tmem_ld16(taddr + c0 + 16, r1);
                 tmem_ld_wait();
-                epilogue16(a, r0, n0 + c0, valid, m, o00, W2ld);
-                if (two) epilogue16(a, r1, n0 + c0 + 16, valid, m, o00, W2ld);
+                if (split_out) {
+                    epilogue16_split(a, r0, n0 + c0, valid, m, o00, W2ld);
+                    if (two) epilogue16_split(a, r1, n0 + c0 + 16, valid, m, o00, W2ld);
+                } else {
+                    epilogue16(a, r0, n0 + c0, valid, m, o00, W2ld);
+                    if (two) epilogue16(a, r1, n0 + c0 + 16, valid, m, o00, W2ld);
+                }
             }
             tc_fence_before();
             __syncwarp();
@@ -1075,7 +1225,10 @@ std::string tc_make_plan(TcPlan& p, const ConvArgs& a, const __half* w16, int co
     p.cout_pad = cout_pad;
     const int bke = p.swz / 2;
     p.cin_blocks = a.Cin / bke;
-    p.num_kblocks = a.ks * a.ks * p.cin_blocks;
+    p.split = a.split;
+    p.num_kblocks = a.ks * a.ks * p.cin_blocks * (a.split ? 3 : 1);   // split mode: three sections per tap (conv_tc_kernel)
+    if (a.split && K != 3 * a.ks * a.ks * a.Cin) return "split mode expects the [tap][wh|wl|wh][Cin] weight packing";
+    const bool split_out = a.split && !a.out_f32;
     p.M = (long)a.B * a.Ho * a.Wo;
     p.m_tiles = (int)((p.M + kBM - 1) / kBM);
     // tile N: the kernel is bound by bytes brought into the SM (A: 128 rows, B: BN rows per k-block), so
@@ -1126,14 +1279,14 @@ std::string tc_make_plan(TcPlan& p, const ConvArgs& a, const __half* w16, int co
     }
     p.cs = p.sub_bytes / esz;
     p.n_sub = p.epi_staged ? p.BN / p.cs : 0;
-    if (p.epi_staged) p.ring = a.res ? 4 : 2;
+    if (p.epi_staged) p.ring = a.res && !split_out ? 4 : 2;        // split mode: a slot holds a hi and a lo sub-tile
     if (const char* e = getenv("YB_TC_RING")) if (p.epi_staged) p.ring = std::max(2, std::min(kMaxRing, atoi(e)));
     // 32-column sub-tiles (Cout = 32 in fp16, the fp32 head maps) keep only eight of the sixteen epilogue warps busy:
     // the two halves then work on alternate sub-tiles, each with its own slot of a four-deep ring
-    p.epi_split = p.epi_staged && p.cs == 32 && (p.n_sub == 1 || p.n_sub % 2 == 0);
+    p.epi_split = p.epi_staged && p.cs == 32 && (p.n_sub == 1 || p.n_sub % 2 == 0) && !split_out;
     if (const char* e = getenv("YB_TC_EPISPLIT")) p.epi_split = p.epi_split && atoi(e) != 0;
     if (p.epi_split) p.ring = 4;
-    const size_t stg_bytes = ((size_t)kBM * p.sub_bytes + 1023) & ~(size_t)1023;
+    const size_t stg_bytes = ((size_t)kBM * p.sub_bytes * (split_out ? 2 : 1) + 1023) & ~(size_t)1023;
     const size_t ring_bytes = p.epi_staged ? p.ring * stg_bytes : 0;
     p.grid = p.cta2 ? 2 * (int)std::min<long>((long)p.m_tiles * p.n_tiles, num_sms / 2)
                     : (int)std::min<long>((long)p.m_tiles * p.n_tiles, num_sms);
@@ -1193,13 +1346,13 @@ std::string tc_make_plan(TcPlan& p, const ConvArgs& a, const __half* w16, int co
                                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
         if (r != CUDA_SUCCESS) return cu_err("cuTensorMapEncodeTiled(weights)", r);
     }
-    p.exp_tiled = a.ks == 3 && getenv("YB_TC_EXP_TILED") && atoi(getenv("YB_TC_EXP_TILED")) != 0;
+    p.exp_tiled = !a.split && a.ks == 3 && getenv("YB_TC_EXP_TILED") && atoi(getenv("YB_TC_EXP_TILED")) != 0;
     if (p.exp_tiled) {
         static bool warned = false;
         if (!warned) fprintf(stderr, "[yolo_b200] YB_TC_EXP_TILED is a TIMING experiment: 3x3 convolution results are WRONG\n");
         warned = true;
     }
-    p.exp_blocked = a.ks == 1 && p.swz == 128 && a.in_ld == a.Cin && getenv("YB_TC_EXP_BLOCKED") && atoi(getenv("YB_TC_EXP_BLOCKED")) != 0;
+    p.exp_blocked = !a.split && a.ks == 1 && p.swz == 128 && a.in_ld == a.Cin && getenv("YB_TC_EXP_BLOCKED") && atoi(getenv("YB_TC_EXP_BLOCKED")) != 0;
     if (p.exp_blocked) {
         static bool warned = false;
         if (!warned) fprintf(stderr, "[yolo_b200] YB_TC_EXP_BLOCKED is a TIMING experiment: 1x1 convolution results are WRONG\n");
@@ -1207,7 +1360,7 @@ std::string tc_make_plan(TcPlan& p, const ConvArgs& a, const __half* w16, int co
     }
     if (a.ks == 1 || p.exp_tiled) {
         // A: [M][Cin] with pixel pitch in_ld; rows past M are zero-filled
-        cuuint64_t dims[2] = {(cuuint64_t)a.Cin, (cuuint64_t)p.M};
+        cuuint64_t dims[2] = {(cuuint64_t)(a.split ? a.in_lo + a.Cin : a.Cin), (cuuint64_t)p.M};
         cuuint64_t strides[1] = {(cuuint64_t)a.in_ld * sizeof(__half)};
         if (p.exp_blocked) {        // the same bytes read as [Cin/64][M][64]: rows of 128 bytes, Cin/64 * M of them
             dims[0] = 64; dims[1] = (cuuint64_t)p.M * (a.Cin / 64);
@@ -1223,7 +1376,7 @@ std::string tc_make_plan(TcPlan& p, const ConvArgs& a, const __half* w16, int co
         // A: NHWC as (C, W, H, N); im2col box of 128 output pixels x one k-block of channels.  The
         // bounding box of filter-window origins is [-pad, dim-1+upper] with upper = pad-(ks-1); the
         // traversal stride is the conv stride; the (kx, ky) tap arrives as the instruction's offsets.
-        cuuint64_t dims[4] = {(cuuint64_t)a.Cin, (cuuint64_t)a.W, (cuuint64_t)a.H, (cuuint64_t)a.B};
+        cuuint64_t dims[4] = {(cuuint64_t)(a.split ? a.in_lo + a.Cin : a.Cin), (cuuint64_t)a.W, (cuuint64_t)a.H, (cuuint64_t)a.B};
         cuuint64_t strides[3] = {(cuuint64_t)a.in_ld * sizeof(__half), (cuuint64_t)a.W * a.in_ld * sizeof(__half),
                                  (cuuint64_t)a.H * a.W * a.in_ld * sizeof(__half)};
         int lower[2] = {-a.pad, -a.pad};
@@ -1246,7 +1399,7 @@ std::string tc_make_plan(TcPlan& p, const ConvArgs& a, const __half* w16, int co
     if (p.epi_staged) {
         const CUtensorMapSwizzle eswz = p.sub_bytes == 128 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B;
         const CUtensorMapDataType dt = a.out_f32 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_FLOAT16;
-        cuuint64_t dims[2] = {(cuuint64_t)a.Cout, (cuuint64_t)p.M};
+        cuuint64_t dims[2] = {(cuuint64_t)(split_out ? a.out_lo + a.Cout : a.Cout), (cuuint64_t)p.M};
         cuuint64_t strides[1] = {(cuuint64_t)a.out_ld * esz};
         cuuint32_t box[2] = {(cuuint32_t)p.cs, (cuuint32_t)kBM};
         cuuint32_t es[2] = {1, 1};
@@ -1255,7 +1408,8 @@ std::string tc_make_plan(TcPlan& p, const ConvArgs& a, const __half* w16, int co
         if (r != CUDA_SUCCESS) return cu_err("cuTensorMapEncodeTiled(output)", r);
         if (a.res) {
             cuuint64_t rstrides[1] = {(cuuint64_t)a.res_ld * sizeof(__half)};
-            r = g_encode_tiled(&p.tmRes, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, const_cast<void*>(a.res), dims, rstrides, box, es,
+            cuuint64_t rdims[2] = {(cuuint64_t)(split_out ? a.res_lo + a.Cout : a.Cout), (cuuint64_t)p.M};
+            r = g_encode_tiled(&p.tmRes, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, const_cast<void*>(a.res), rdims, rstrides, box, es,
                                CU_TENSOR_MAP_INTERLEAVE_NONE, eswz, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
                                CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
             if (r != CUDA_SUCCESS) return cu_err("cuTensorMapEncodeTiled(residual)", r);
@@ -1365,6 +1519,8 @@ cudaError_t tc_launch(const TcPlan& p, const ConvArgs& a, int* dbg, cudaStream_t
     }
     t.exp_tiled = p.exp_tiled;
     t.epi_split = p.epi_split;
+    t.a_lo = (int)a.in_lo; t.out_lo = (int)a.out_lo; t.res_lo = (int)a.res_lo;
+    t.split_out = p.split && !a.out_f32;
     {
         static const int nostore = [] {
             const int v = getenv("YB_TC_EXP_NOSTORE") ? atoi(getenv("YB_TC_EXP_NOSTORE")) : 0;
@@ -1387,6 +1543,11 @@ cudaError_t tc_launch(const TcPlan& p, const ConvArgs& a, int* dbg, cudaStream_t
                 cudaFuncSetAttribute(conv_tc_kernel<64, false, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBudget);
                 cudaFuncSetAttribute(conv_tc_kernel<128, true, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBudget);
                 cudaGetLastError();
+            }
+            if (r == cudaSuccess) {     // split mode (YB_MODE_FP32_TC)
+                r = cudaFuncSetAttribute(conv_tc_kernel<128, false, false, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBudget);
+                if (r == cudaSuccess) r = cudaFuncSetAttribute(conv_tc_kernel<64, false, false, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBudget);
+                if (r == cudaSuccess) r = cudaFuncSetAttribute(conv_tc_kernel<128, true, false, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBudget);
             }
             return r;
         });
@@ -1419,6 +1580,11 @@ cudaError_t tc_launch(const TcPlan& p, const ConvArgs& a, int* dbg, cudaStream_t
         cfg.numAttrs = na;
         cudaError_t e;
         static const bool uw = getenv("YB_TC_UW") && atoi(getenv("YB_TC_UW")) != 0;
+        if (p.split) {
+            if (p.cta2) e = cudaLaunchKernelEx(&cfg, conv_tc_kernel<128, true, false, false, true>, p.tmA, p.tmB, p.tmOut, p.tmRes, t);
+            else if (p.swz == 128) e = cudaLaunchKernelEx(&cfg, conv_tc_kernel<128, false, false, false, true>, p.tmA, p.tmB, p.tmOut, p.tmRes, t);
+            else e = cudaLaunchKernelEx(&cfg, conv_tc_kernel<64, false, false, false, true>, p.tmA, p.tmB, p.tmOut, p.tmRes, t);
+        } else
         if (uw && !p.exp_blocked) {
             if (p.cta2) e = cudaLaunchKernelEx(&cfg, conv_tc_kernel<128, true, false, true>, p.tmA, p.tmB, p.tmOut, p.tmRes, t);
             else if (p.swz == 128) e = cudaLaunchKernelEx(&cfg, conv_tc_kernel<128, false, false, true>, p.tmA, p.tmB, p.tmOut, p.tmRes, t);

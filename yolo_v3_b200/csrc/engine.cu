@@ -307,6 +307,7 @@ struct PlanBuilder {
     Plan* p;
     size_t elem;
     std::string err;
+    bool split = false;   // YB_MODE_FP32_TC
 
     void* alloc(size_t bytes) {
         void* q = nullptr;
@@ -316,10 +317,14 @@ struct PlanBuilder {
         p->bytes += bytes;
         return q;
     }
+    // `ld` = channels of the whole buffer (C for a plain tensor, 768 / 384 for the concat buffers).  Split mode stores
+    // hi[ld] | lo[ld] per pixel: the pitch doubles and the lo half of any channel slice sits `ld` elements after its hi half.
     TView view(void* base, int B, int H, int W, int C, long ld, int ch_off = 0) const {
         TView v;
         v.p = static_cast<unsigned char*>(base) + (size_t)ch_off * elem;
-        v.B = B; v.H = H; v.W = W; v.C = C; v.ld = ld;
+        v.B = B; v.H = H; v.W = W; v.C = C;
+        v.ld = split ? 2 * ld : ld;
+        v.lo = split ? ld : 0;
         return v;
     }
     // conv `li`: in -> out (+res), returns false on error
@@ -339,8 +344,15 @@ struct PlanBuilder {
         a.leaky = L.bn ? 1 : 0;
         a.upsample = upsample ? 1 : 0;
         a.out_f32 = head ? 1 : 0;
+        a.split = split ? 1 : 0;
+        a.in_lo = in.lo; a.out_lo = head ? 0 : out.lo; a.res_lo = res ? res->lo : 0;
         if (in.C != L.cin) { err = "plan: channel mismatch at layer " + L.key; return false; }
-        if (p->mode == YB_MODE_FP16) {
+        if (p->mode == YB_MODE_FP32_TC) {
+            if (!tc_supported(a)) { err = "plan: layer " + L.key + " not supported by the tensor-core kernel"; return false; }
+            op.use_tc = true;
+            std::string e = tc_make_plan(op.tc, a, L.d_w16, L.cout_pad, 3 * L.ks * L.ks * L.cin, c->num_sms);
+            if (!e.empty()) { err = "plan: layer " + L.key + ": " + e; return false; }
+        } else if (p->mode == YB_MODE_FP16) {
             if (!tc_supported(a)) { err = "plan: layer " + L.key + " not supported by the tensor-core kernel"; return false; }
             op.use_tc = true;
             std::string e;
@@ -364,8 +376,9 @@ int build_plan(yb_ctx* c, int B, int H, int W, Plan** out) {
     std::unique_ptr<Plan> plan(new Plan());
     Plan* p = plan.get();
     p->B = B; p->H = H; p->W = W; p->mode = c->mode;
-    PlanBuilder pb{c, p, c->mode == YB_MODE_FP16 ? sizeof(__half) : sizeof(float), ""};
-    const size_t elem = pb.elem;
+    const bool split = c->mode == YB_MODE_FP32_TC;
+    PlanBuilder pb{c, p, c->mode == YB_MODE_FP32 ? sizeof(float) : sizeof(__half), "", split};
+    const size_t elem = pb.elem * (split ? 2 : 1);      // bytes per stored channel (hi + lo in split mode)
     auto bail = [&](const std::string& m) {
         for (void* q : p->allocs) cudaFree(q);
         return fail(c, m.find("cudaMalloc") != std::string::npos ? YB_E_NOMEM : YB_E_CUDA, m);
@@ -433,9 +446,9 @@ int build_plan(yb_ctx* c, int B, int H, int W, Plan** out) {
             if (i == 4) *route = o;
         }
         const int cp = c->layers[li].cout_pad;
-        TView lo;
-        lo.p = p->logits[scale_i]; lo.B = B; lo.H = x.H; lo.W = x.W; lo.C = cp; lo.ld = cp;
-        return pb.conv(li++, x, lo, nullptr, false, true);
+        TView lg;
+        lg.p = p->logits[scale_i]; lg.B = B; lg.H = x.H; lg.W = x.W; lg.C = cp; lg.ld = cp;
+        return pb.conv(li++, x, lg, nullptr, false, true);
     };
     TView route;
     if (!predet(cur, curb, 512, 0, &route)) return bail(pb.err);
@@ -490,6 +503,8 @@ int run_ops(yb_ctx* c, Plan* p, const float* x, int n_ops, cudaStream_t s) {
                 e = stem_rows_launch(op.stem_rows_plan, x, p->B, p->H, p->W, L.d_w16, L.d_scale, L.d_bias, c->dbg, s);
             else if (p->mode == YB_MODE_FP16)
                 e = stem_tc_launch(op.stem_tc, x, c->input_f16, p->B, p->H, p->W, L.d_w16, L.d_scale, L.d_bias, c->dbg, s);
+            else if (p->mode == YB_MODE_FP32_TC)     // Cin = 3: exact fp32 FMAs on the CUDA cores, output written as hi | lo
+                e = launch_stem_split(x, static_cast<__half*>(op.a.out), L.d_w32, L.d_scale, L.d_bias, p->B, p->H, p->W, s);
             else
                 e = launch_stem<float>(x, static_cast<float*>(op.a.out), L.d_w32, L.d_scale, L.d_bias, p->B, p->H, p->W, s);
         } else if (op.use_halo) {
@@ -687,10 +702,11 @@ int yb_save_darknet_blob(const yb_ctx* c, float* host_out, size_t capacity, int 
 
 int yb_finalize(yb_ctx* c, int mode) {
     if (!c) return fail(nullptr, YB_E_ARG, "null ctx");
-    if (mode != YB_MODE_FP32 && mode != YB_MODE_FP16) return fail(c, YB_E_ARG, "yb_finalize: unknown precision mode");
+    if (mode != YB_MODE_FP32 && mode != YB_MODE_FP16 && mode != YB_MODE_FP32_TC) return fail(c, YB_E_ARG, "yb_finalize: unknown precision mode");
     YB_CUDA(c, cudaSetDevice(c->device));
-    if (mode == YB_MODE_FP16 && c->cc_major != 10)
-        return fail(c, YB_E_UNSUPPORTED, "YB_MODE_FP16 needs an sm_100 (B200) device: the tcgen05/TMA kernels have no fallback");
+    if (mode != YB_MODE_FP32 && c->cc_major != 10)
+        return fail(c, YB_E_UNSUPPORTED, "the tensor-core modes need an sm_100 (B200) device: the tcgen05/TMA kernels have no fallback");
+    const bool split = mode == YB_MODE_FP32_TC;
     if (mode != c->mode) free_plans(c);
     // one contiguous device blob (so multi-GPU replication is a single broadcast): per layer
     // scale[cout_pad], bias[cout_pad], then the packed weights of the mode (the stem always keeps fp32)
@@ -706,7 +722,8 @@ int yb_finalize(yb_ctx* c, int mode) {
         const bool need32 = mode == YB_MODE_FP32 || i == 0;
         offs[i].w32 = need32 ? place(sizeof(float) * K * L.cout_pad) : (size_t)-1;
         // the stem's fp16 weights are [32][K padded to 32] for the tensor-core stem kernel
-        offs[i].w16 = mode == YB_MODE_FP16 ? place(sizeof(__half) * (i == 0 ? 32 : K) * L.cout_pad) : (size_t)-1;
+        offs[i].w16 = mode == YB_MODE_FP16 ? place(sizeof(__half) * (i == 0 ? 32 : K) * L.cout_pad)
+                      : (split && i != 0) ? place(sizeof(__half) * 3 * K * L.cout_pad) : (size_t)-1;
     }
     if (off != c->blob_bytes || !c->d_blob) {
         cudaFree(c->d_blob);
@@ -740,7 +757,31 @@ int yb_finalize(yb_ctx* c, int mode) {
                     for (int t = 0; t < taps; ++t)
                         w[((size_t)t * L.cin + ci) * L.cout_pad + n] = L.w[((size_t)n * L.cin + ci) * taps + t];
         }
-        if (offs[i].w16 != (size_t)-1) {
+        if (offs[i].w16 != (size_t)-1 && split) {
+            // [cout_pad][tap][wh | wl | wh][cin]: row n is scaled by 2^s(n) so that max|w'| lies in [2048, 4096) -- the lo part
+            // of every weight down to 2^-23 of the row maximum is then a NORMAL fp16 number -- and the epilogue scale undoes
+            // it exactly (a power of two).  wh = RN16(w'), wl = RN16(w' - wh).
+            __half* w = reinterpret_cast<__half*>(host.data() + offs[i].w16);
+            for (int n = 0; n < L.cout; ++n) {
+                float mx = 0.f;
+                for (size_t k = 0; k < (size_t)L.cin * taps; ++k) mx = std::max(mx, std::fabs(L.w[(size_t)n * L.cin * taps + k]));
+                int sh = 0;
+                if (mx > 0.f && std::isfinite(mx)) {
+                    int e2 = 0;
+                    std::frexp(mx, &e2);                         // mx = f * 2^e2, f in [0.5, 1)
+                    sh = std::max(-24, std::min(40, 12 - e2));
+                }
+                sc[n] = std::ldexp(sc[n], -sh);
+                for (int ci = 0; ci < L.cin; ++ci)
+                    for (int t = 0; t < taps; ++t) {
+                        const float ws = std::ldexp(L.w[((size_t)n * L.cin + ci) * taps + t], sh);
+                        const __half wh = __float2half_rn(ws);
+                        const __half wl = __float2half_rn(ws - __half2float(wh));
+                        __half* row = w + (size_t)n * 3 * K + (size_t)t * 3 * L.cin + ci;
+                        row[0] = wh; row[L.cin] = wl; row[2 * L.cin] = wh;
+                    }
+            }
+        } else if (offs[i].w16 != (size_t)-1) {
             __half* w = reinterpret_cast<__half*>(host.data() + offs[i].w16);  // [cout_pad][tap][cin]
             const int Kp = i == 0 ? 32 : K;
             for (int n = 0; n < L.cout; ++n)
@@ -817,7 +858,9 @@ int yb_backbone(yb_ctx* c, const float* x, int B, int H, int W, float* feat, voi
     if ((rc = build_plan(c, B, H, W, &p))) return rc;
     if ((rc = run_ops(c, p, x, p->n_backbone_ops, s))) return rc;
     const TView& v = p->backbone_out;
-    if (p->mode == YB_MODE_FP16)
+    if (p->mode == YB_MODE_FP32_TC)
+        YB_CUDA(c, launch_split_to_nchw_f32(static_cast<const __half*>(v.p), v.ld, v.lo, v.C, B, v.H * v.W, feat, s));
+    else if (p->mode == YB_MODE_FP16)
         YB_CUDA(c, launch_nhwc_to_nchw_f32<__half>(static_cast<const __half*>(v.p), v.ld, v.C, B, v.H * v.W, feat, s));
     else
         YB_CUDA(c, launch_nhwc_to_nchw_f32<float>(static_cast<const float*>(v.p), v.ld, v.C, B, v.H * v.W, feat, s));
@@ -1144,6 +1187,48 @@ int yb_run_layer(yb_ctx* c, int li, const void* in, int B, int H, int W, const v
     YB_CUDA(c, cudaSetDevice(c->device));
     cudaStream_t s = static_cast<cudaStream_t>(stream);
     const Layer& L = c->layers[li];
+    if (c->mode == YB_MODE_FP32_TC) {
+        // Unit-test entry of the split mode: fp32 NHWC tensors at the boundary (what the mode stands in for), converted to /
+        // from the hi | lo fp16 pairs the kernels work on.  Scratch is allocated per call -- this is not a hot path.
+        const bool head = !L.bn;
+        const int Ho = H / L.stride, Wo = W / L.stride;
+        if (li != 0 && (H % L.stride || W % L.stride)) return fail(c, YB_E_ARG, "yb_run_layer: H, W must be multiples of the stride");
+        const size_t Min = (size_t)B * H * W, Mout = (size_t)B * Ho * Wo;
+        __half *xin = nullptr, *xout = nullptr, *xres = nullptr;
+        auto cleanup = [&]() { cudaFree(xin); cudaFree(xout); cudaFree(xres); };
+        if (li != 0) YB_CUDA(c, cudaMalloc(&xin, Min * 2 * L.cin * sizeof(__half)));
+        if (!head && cudaMalloc(&xout, Mout * 2 * L.cout * sizeof(__half)) != cudaSuccess) { cleanup(); return fail(c, YB_E_NOMEM, "yb_run_layer: scratch"); }
+        if (res && cudaMalloc(&xres, Mout * 2 * L.cout * sizeof(__half)) != cudaSuccess) { cleanup(); return fail(c, YB_E_NOMEM, "yb_run_layer: scratch"); }
+        cudaError_t e = cudaSuccess;
+        if (li == 0) {
+            e = launch_stem_split(static_cast<const float*>(in), xout, L.d_w32, L.d_scale, L.d_bias, B, H, W, s);
+        } else {
+            e = launch_f32_to_split(static_cast<const float*>(in), xin, Min, L.cin, s);
+            if (e == cudaSuccess && res) e = launch_f32_to_split(static_cast<const float*>(res), xres, Mout, L.cout, s);
+            ConvArgs a{};
+            a.in = xin; a.in_ld = 2 * L.cin; a.in_lo = L.cin;
+            a.out = head ? out : xout; a.out_ld = head ? L.cout_pad : 2 * L.cout; a.out_lo = head ? 0 : L.cout;
+            a.res = xres; a.res_ld = 2 * L.cout; a.res_lo = res ? L.cout : 0;
+            a.scale = L.d_scale; a.bias = L.d_bias;
+            a.B = B; a.H = H; a.W = W; a.Cin = L.cin;
+            a.Ho = Ho; a.Wo = Wo; a.Cout = head ? L.cout_pad : L.cout;
+            a.ks = L.ks; a.stride = L.stride; a.pad = (L.ks - 1) / 2;
+            a.leaky = L.bn ? 1 : 0; a.upsample = 0; a.out_f32 = head ? 1 : 0; a.split = 1;
+            if (e == cudaSuccess) {
+                if (!tc_supported(a)) { cleanup(); return fail(c, YB_E_UNSUPPORTED, "yb_run_layer: layer not supported by the tensor-core kernel"); }
+                TcPlan tp;
+                std::string err = tc_make_plan(tp, a, L.d_w16, L.cout_pad, 3 * L.ks * L.ks * L.cin, c->num_sms);
+                if (!err.empty()) { cleanup(); return fail(c, YB_E_CUDA, "yb_run_layer: " + err); }
+                e = tc_launch(tp, a, c->dbg, s);
+            }
+        }
+        if (e == cudaSuccess && !head) e = launch_split_to_f32(xout, static_cast<float*>(out), Mout, L.cout, s);
+        if (e == cudaSuccess) e = cudaStreamSynchronize(s);
+        cleanup();
+        ++c->launches;
+        YB_CUDA(c, e);
+        return YB_OK;
+    }
     if (li == 0) {
         cudaError_t e;
         if (c->input_f16 && (c->mode != YB_MODE_FP16 || stem_rows_supported(B, H, W)))

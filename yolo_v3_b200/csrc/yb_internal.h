@@ -34,7 +34,8 @@ struct Layer {
     float* d_scale = nullptr;                 // [cout_pad]  gamma/sqrt(var+eps)  (1 for heads)
     float* d_bias = nullptr;                  // [cout_pad]  beta-mean*scale      (conv bias for heads)
     float* d_w32 = nullptr;                   // [ks*ks][cin][cout_pad] fp32      (YB_MODE_FP32)
-    __half* d_w16 = nullptr;                  // [cout_pad][ks*ks*cin] fp16, K-major (YB_MODE_FP16)
+    __half* d_w16 = nullptr;                  // [cout_pad][ks*ks*cin] fp16, K-major (YB_MODE_FP16);
+                                              // YB_MODE_FP32_TC: [cout_pad][ks*ks][wh | wl | wh][cin], rows pre-scaled by 2^s
 };
 
 // cudaFuncSetAttribute applies to the CURRENT device only, and a process may hold contexts on several devices
@@ -72,6 +73,7 @@ struct TView {
     void* p = nullptr;
     int B = 0, H = 0, W = 0, C = 0;
     long ld = 0;          // elements between consecutive pixels
+    long lo = 0;          // YB_MODE_FP32_TC: channel offset of the lo half (0 in the other modes)
 };
 
 // Arguments common to both convolution kernels.
@@ -86,6 +88,10 @@ struct ConvArgs {
     int leaky;                        // LeakyReLU(0.1) after scale/bias
     int upsample;                     // nearest x2: every output pixel is written to a 2x2 block of a [B,2Ho,2Wo] tensor
     int out_f32;                      // output element is fp32 regardless of the activation type (head maps)
+    // YB_MODE_FP32_TC ("split"): activations are fp16 pairs hi + lo sharing the pixel pitch; *_lo = channel offset of the
+    // lo half relative to the hi pointer (in / out / res point at the hi half)
+    int split;
+    long in_lo, out_lo, res_lo;
 };
 
 // conv_simt.cu
@@ -97,6 +103,12 @@ cudaError_t launch_stem(const float* x_nchw, T* out_nhwc, const float* w32, cons
 template <typename T>
 cudaError_t launch_nhwc_to_nchw_f32(const T* in, long in_ld, int C, int B, int HW, float* out, cudaStream_t s);
 cudaError_t launch_f32_to_f16(const float* in, __half* out, size_t n, cudaStream_t s);
+// YB_MODE_FP32_TC ("split" activations: fp16 hi | lo per pixel)
+cudaError_t launch_stem_split(const float* x_nchw, __half* out_nhwc64, const float* w32, const float* scale, const float* bias,
+                              int B, int H, int W, cudaStream_t s);
+cudaError_t launch_split_to_nchw_f32(const __half* in, long in_ld, long lo, int C, int B, int HW, float* out, cudaStream_t s);
+cudaError_t launch_f32_to_split(const float* in, __half* out, size_t M, int C, cudaStream_t s);
+cudaError_t launch_split_to_f32(const __half* in, float* out, size_t M, int C, cudaStream_t s);
 
 // conv_tc.cu  (tcgen05 + TMA implicit GEMM)
 struct TcPlan {
@@ -107,6 +119,7 @@ struct TcPlan {
     int num_kblocks = 0, cin_blocks = 0, kps = 1, cta2 = 0, cout_pad = 0, tab_bytes = 0;
     int pf_dist = 0, b_early = 0, srel = 0;
     int epi_split = 0;    // 32-column sub-tiles: the two halves of the epilogue warps take alternate sub-tiles
+    int split = 0;        // YB_MODE_FP32_TC: hi/lo operands, three k sections per tap (conv_tc.cu)
     int grid = 0;
     size_t smem = 0;
     long M = 0;

@@ -15,7 +15,16 @@ Differences from the reference, all deliberate:
     still works and yields the same values);
   * ``saveWeight(format='darknet')`` is implemented (the reference raises NotImplementedError,
     darknet.py:237-238);
-  * extra keyword ``precision`` ('fp16' = tcgen05 tensor-core path, 'fp32' = CUDA-core parity path).
+  * extra keyword ``precision``: 'fp16' = the tcgen05 tensor-core path the benchmark measures; 'fp32' = fp32-grade
+    parity with the reference, also on the tensor cores (YB_MODE_FP32_TC: fp16 hi/lo operand pairs, three partial
+    products per k-step, fp32 accumulation in TMEM); 'fp32_simt' = the CUDA-core fp32 debugging path.
+
+Weight changes are picked up automatically when they go through ``load_state_dict``, ``loadWeight``, ``.cuda()`` /
+``.to()`` / ``.half()``, an optimizer-style in-place op on the parameter itself, or re-assignment.  An in-place write
+through ``param.data`` (``p.data.copy_(...)``, what the reference's WeightManager does internally, darknet.py:275) does
+NOT bump the tensor's version counter and cannot be seen without reading the weights back: call
+``net.refresh_weights()`` after such a write (or construct with ``check_weights=True`` to compare a device-side
+checksum of every tensor on each forward, at the cost of one synchronisation per call).
 """
 from __future__ import annotations
 
@@ -93,6 +102,11 @@ class Darknet(nn.Module):
         self.mlist = nn.ModuleList(mods)
         self._owner = None
 
+    def __getstate__(self):                     # the back-reference is a weakref: not picklable, rebound by YoloNet.__setstate__
+        st = self.__dict__.copy()
+        st["_owner"] = None
+        return st
+
     def loadWeight(self, weights_path):
         """Backbone-only darknet stream, e.g. darknet53.conv.74 (darknet.py:102-104)."""
         owner = self._owner() if self._owner is not None else None
@@ -132,8 +146,10 @@ class UpsampleGroup(nn.Module):
 class YoloNet(nn.Module):
     """Drop-in for the reference's YoloNet (darknet.py:167-246), inference path only."""
 
+    _MODES = {"fp16": _lib.YB_MODE_FP16, "fp32": _lib.YB_MODE_FP32_TC, "fp32_simt": _lib.YB_MODE_FP32}
+
     def __init__(self, img_dim=None, anchors: Sequence[float] = tuple(DEFAULT_ANCHORS), numClass=80,
-                 precision: Optional[str] = None):
+                 precision: Optional[str] = None, check_weights: bool = False):
         super().__init__()
         import weakref
         self.numClass = numClass
@@ -145,8 +161,10 @@ class YoloNet(nn.Module):
             raise ValueError("anchors must hold 9 (w,h) pairs")
         pairs = [(self.anchors[i], self.anchors[i + 1]) for i in range(0, 18, 2)]
         self.precision = (precision or os.environ.get("YOLO_B200_PRECISION", "fp16")).lower()
-        if self.precision not in ("fp16", "fp32"):
-            raise ValueError("precision must be 'fp16' or 'fp32'")
+        if self.precision not in self._MODES:
+            raise ValueError("precision must be 'fp16', 'fp32' or 'fp32_simt'")
+        self.check_weights = bool(check_weights)
+        self._frozen = False
 
         self.feature = Darknet(BLOCKS)
         self.feature._owner = weakref.ref(self)
@@ -187,7 +205,39 @@ class YoloNet(nn.Module):
             yield k, table[name]
 
     def _signature(self, device):
-        return (str(device), self.precision) + tuple((v.data_ptr(), v._version) for _, v in self._named_tensors())
+        sig = (str(device), self.precision) + tuple((v.data_ptr(), v._version) for _, v in self._named_tensors())
+        if self.check_weights:
+            # content check for writes that bypass the version counter (param.data.copy_()): one multi-tensor reduction
+            # and one device-to-host read per forward
+            ts = [v.detach().float() for k, v in self._named_tensors() if not k.endswith("num_batches_tracked")]
+            sums = torch.stack(torch._foreach_norm(ts)).double()
+            w = torch.arange(1, len(ts) + 1, dtype=torch.float64, device=sums.device)
+            sig += (float((sums * w).sum()), float(torch.stack([t.reshape(-1)[0] for t in ts]).double().sum()))
+        return sig
+
+    def refresh_weights(self):
+        """Forget the uploaded weights: the next forward re-reads every tensor, folds BN and re-packs.  Needed after an
+        in-place write through ``param.data`` / ``buffer.data`` (e.g. ``p.data.copy_(w)``), which PyTorch does not
+        version -- every other way of changing the weights is detected automatically."""
+        self._sig = None
+        self._frozen = False
+        return self
+
+    def freeze_weights(self, frozen: bool = True):
+        """Skip the per-forward change detection (a walk over the 438 tensors, ~0.1 ms of host time -- visible at batch 1)
+        until refresh_weights() / load_state_dict() / loadWeight() is called."""
+        self._frozen = bool(frozen)
+        return self
+
+    def load_state_dict(self, *args, **kwargs):
+        self._sig = None
+        self._frozen = False
+        return super().load_state_dict(*args, **kwargs)
+
+    def _apply(self, fn, *args, **kwargs):            # .cuda() / .to() / .half() / .float()
+        self._sig = None
+        self._frozen = False
+        return super()._apply(fn, *args, **kwargs)
 
     def _engine(self, device: torch.device):
         """Create the context on `device` if needed and (re)upload + finalize when any tensor changed."""
@@ -202,6 +252,8 @@ class YoloNet(nn.Module):
             self._ctx_device = index
             self._sig = None
             self._in_dtype = _lib.YB_INPUT_F32          # a new context reads fp32 images
+        if self._frozen and self._sig is not None:
+            return lib, self._ctx
         sig = self._signature(device)
         if sig != self._sig:
             for k, v in self._named_tensors():
@@ -214,10 +266,26 @@ class YoloNet(nn.Module):
                 on_host = 0 if t.is_cuda else 1
                 _lib.check(lib.yb_set_tensor(self._ctx, k.encode(), ctypes.c_void_p(t.data_ptr()), t.numel(), on_host),
                            self._ctx)
-            mode = _lib.YB_MODE_FP16 if self.precision == "fp16" else _lib.YB_MODE_FP32
-            _lib.check(lib.yb_finalize(self._ctx, mode), self._ctx)
+            _lib.check(lib.yb_finalize(self._ctx, self._MODES[self.precision]), self._ctx)
             self._sig = sig
         return lib, self._ctx
+
+    # copy.deepcopy / pickle / torch.save(net): the engine context is a raw pointer and belongs to THIS object; a copy
+    # starts without one (it is created on its first forward) and its backbone points back at the copy
+    def __getstate__(self):
+        st = self.__dict__.copy()
+        st["_ctx"] = None
+        st["_ctx_device"] = None
+        st["_sig"] = None
+        st["_in_dtype"] = _lib.YB_INPUT_F32
+        st.pop("_tensor_slots", None)
+        st.pop("_last_det", None)
+        return st
+
+    def __setstate__(self, st):
+        import weakref
+        self.__dict__.update(st)
+        self.feature._owner = weakref.ref(self)
 
     def _release(self):
         if self._ctx is not None:
@@ -373,6 +441,7 @@ class YoloNet(nn.Module):
                     raise ValueError(f"darknet weight stream ends inside {k}")
                 sd[k].copy_(torch.from_numpy(weights[ptr:ptr + n].copy()).view(*shape))
                 ptr += n
+        self.refresh_weights()
         return ptr
 
 
