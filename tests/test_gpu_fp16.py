@@ -102,6 +102,9 @@ CASES = [
     # halo kernel in pair mode (Cout = 128: two spatial tiles per cta_group::2 UMMA)
     (6, 1, 9, 38, True),       # three tiles: rank 1 of the second pair gets the zero-filled / clipped tile past the batch
     (6, 3, 5, 76, False),      # no residual: the four-slot ring recycled by the stores alone; partial last row strip
+    # the benched batch: 608x608 batch 32 shapes of the last stage (2.49 waves of pair tiles: the tail wave is partial)
+    (45, 32, 19, 19, True),    # 512->1024 3x3 + residual, M = 11 552
+    (27, 32, 38, 38, False),   # 512->256 1x1 at 38^2, M = 46 208
 ]
 
 
@@ -130,13 +133,10 @@ def test_tc_layer_vs_torch(fp16_ctx, sd, li, B, H, W, with_res):
                            f"{tuple(int(v) for v in bad.nonzero()[0])}")
 
 
-# rows=True: the experimental pixel-row stem (stem_rows.cu, YB_STEM_ROWS=1, widths that are multiples of 38)
-@pytest.mark.parametrize("B,H,W,rows", [(2, 40, 56, False), (1, 64, 32, False), (3, 17, 23, False), (1, 64, 608, False),
-                                        (2, 10, 76, True), (1, 3, 38, True), (3, 7, 114, True), (1, 64, 608, True)])
-def test_tc_stem_vs_torch(fp16_ctx, sd, B, H, W, rows, monkeypatch):
+@pytest.mark.parametrize("B,H,W", [(2, 40, 56), (1, 64, 32), (3, 17, 23), (1, 64, 608), (2, 10, 76), (1, 3, 38), (3, 7, 114)])
+def test_tc_stem_vs_torch(fp16_ctx, sd, B, H, W):
     """Cin=3 stem on the tensor cores: NCHW fp32 image in, NHWC fp16 out (im2col rows built by producer warps)."""
     lib, ctx = fp16_ctx
-    monkeypatch.setenv("YB_STEM_ROWS", "1" if rows else "0")
     rs = np.random.RandomState(7)
     x = torch.from_numpy(rs.rand(B, 3, H, W).astype(np.float32))
     out = torch.full((B, H, W, 32), float("nan"), device="cuda", dtype=torch.float16)
@@ -153,8 +153,9 @@ def test_tc_stem_vs_torch(fp16_ctx, sd, B, H, W, rows, monkeypatch):
 
 
 def test_fp16_net_deviation_report(oracle, sd):
-    """End to end at 416 (one image) and 608 (two images): report the deviation of the fp16
-    tensor-core path from the fp32 CPU oracle; assert only coarse sanity bounds."""
+    """End to end at 416 (one image) and 608 (two images): the deviation of the fp16 tensor-core path from the fp32 CPU
+    oracle is reported and bounded at about twice what is measured (rounds 1-2: logits max 0.07-0.15, xy 0.26-0.47 px,
+    conf/cls 0.022-0.035), so that a real regression of the benched path fails here."""
     from yolo_v3_b200 import YoloNet
     net = YoloNet((416, 416), precision="fp16")
     net.load_state_dict(sd)
@@ -167,13 +168,43 @@ def test_fp16_net_deviation_report(oracle, sd):
             d = (l.cpu() - r).abs()
             print(f"[fp16 deviation] {hw}px head{i}: logits max|d|={float(d.max()):.4f} mean|d|={float(d.mean()):.5f} "
                   f"(logit std {float(r.std()):.3f})")
-            assert float(d.max()) < 1.0 and float(d.mean()) < 0.05
+            assert float(d.max()) < 0.3 and float(d.mean()) < 0.02
         det = torch.cat(net(x.cuda(), None), 1).cpu()
         ref = torch.cat(oracle.forward(sd, x), 1)
         dxy = (det[..., :2] - ref[..., :2]).abs().max()
         dconf = (det[..., 4:] - ref[..., 4:]).abs().max()
         print(f"[fp16 deviation] {hw}px boxes: max|d xy|={float(dxy):.3f}px  max|d conf/cls|={float(dconf):.4f}")
-        assert float(dxy) < 4.0 and float(dconf) < 0.15
+        assert float(dxy) < 0.75 and float(dconf) < 0.06
+
+
+def test_fp16_final_detections_vs_oracle_at_bench_thresholds(oracle, sd):
+    """the FINAL detections of the benched fp16 path against the fp32 oracle's own end-to-end result
+    (oracle.forward + oracle.postprocessing) on 8 images of the bench workload at conf 0.5 / nms 0.4: boxes are matched
+    one to one (same class, IOU > 0.5); the sets may differ only where a score sits at the threshold or an IOU at the
+    NMS threshold.  bench.py reports the same figures in its `parity` block."""
+    import importlib.util
+    import os
+    from yolo_v3_b200 import YoloNet
+    spec = importlib.util.spec_from_file_location("bench_mod", os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "bench.py"))
+    bench = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(bench)
+    net = YoloNet((608, 608), precision="fp16")
+    net.load_state_dict(sd)
+    net = net.cuda().eval()
+    x = synth.make_images(8, 608, 608, seed=100)           # the first resident batch of bench.py, first 8 images
+    got = net.detect(x.cuda(), 0.5, 0.4)
+    ref = oracle.postprocessing(torch.cat(oracle.forward(sd, x), 1), 80, 0.5, 0.4)
+    assert len(got) == len(ref) == 8
+    m = g = r = 0
+    ious = []
+    for a, b in zip(got, ref):
+        mm, ng, nr, mi, _ = bench.match_detections(a.cpu(), b)
+        m += mm; g += ng; r += nr
+        if mm:
+            ious.append(mi)
+    set_iou = m / max(1, g + r - m)
+    print(f"[fp16 vs oracle, conf 0.5] ours {g}, oracle {r}, matched {m}, set IOU {set_iou:.4f}, mean box IOU {sum(ious) / len(ious):.4f}")
+    assert r > 500 and set_iou > 0.95 and sum(ious) / len(ious) > 0.97
 
 
 def test_fp16_detect_matches_own_postprocess(sd):
@@ -204,7 +235,8 @@ def test_fp16_other_shapes_and_class_counts(oracle):
         ref = torch.cat(oracle.forward(sd, x, num_classes=nc), 1)
         assert det.shape == ref.shape == (B, topology.num_boxes(h, w), 5 + nc)
         d = (det.cpu() - ref).abs()
-        assert float(d[..., :2].max()) < 4.0 and float(d[..., 4:].max()) < 0.15
+        print(f"[fp16 deviation] {nc} classes {h}x{w}: max|d xy|={float(d[..., :2].max()):.3f}px max|d conf/cls|={float(d[..., 4:].max()):.4f}")
+        assert float(d[..., :2].max()) < 1.0 and float(d[..., 4:].max()) < 0.08
         res, idx = postprocessing(det, nc, 0.05, 0.4, return_index=True)
         ref_res, ref_idx = oracle.postprocessing_c(det.cpu(), nc, 0.05, 0.4)
         for r, e, i, ei in zip(res, ref_res, idx, ref_idx):
@@ -228,11 +260,10 @@ def test_fp16_plan_cache_two_shapes(sd):
 
 # ---- fp16 input images (yb_set_input_dtype) ---------------------------------------------------------------------------
 @pytest.mark.parametrize("B,H,W", [(2, 40, 56), (3, 17, 23), (1, 64, 608)])
-def test_stem_fp16_input_same_bits_as_fp32(fp16_ctx, B, H, W, monkeypatch):
+def test_stem_fp16_input_same_bits_as_fp32(fp16_ctx, B, H, W):
     """The stem rounds every fp32 pixel to fp16 (round to nearest even) before the tensor core sees it, so reading the
     host-rounded fp16 image must give bit-identical output."""
     lib, ctx = fp16_ctx
-    monkeypatch.setenv("YB_STEM_ROWS", "0")
     rs = np.random.RandomState(11)
     x = torch.from_numpy(rs.rand(B, 3, H, W).astype(np.float32)).cuda()
     xh = x.half()

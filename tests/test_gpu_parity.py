@@ -5,15 +5,16 @@ Tolerances (stated where used):
   * post-process: bit-exact rows and identical survivor indices (integer/index work);
   * decode given identical fp32 logits: allclose(atol=1e-4, rtol=1e-6)  (1 fp32 ulp at
     608 px is 6.1e-5; exp(tw)*anchor reaches thousands of px, hence the rtol term);
-  * fp32 convolution stack: head logits within 1e-4 * max|logit| (75 layers of fp32 re-association
-    against oneDNN; measured 2e-5 of max|logit|, i.e. ~1.7e-4 absolute).  The decode turns that logit
-    error d into: conf/cls 0.25*d (< 1e-4 absolute), xy 0.25*stride*d (<= 8*d: measured 5e-4 px, bound
-    2e-3 px), w/h a RELATIVE error d (measured 1.7e-4, bound 1e-3).  So end to end the checks are
-    conf/cls atol 1e-4, xy atol 2e-3 px, w/h rtol 1e-3 -- the fp32 noise floor of two different
-    75-layer fp32 convolution stacks, not a loosened kernel tolerance (decode alone holds 1e-4, above);
+  * fp32-grade convolution stack (precision='fp32' = YB_MODE_FP32_TC: the tensor-core split mode, csrc/conv_tc.cu): head
+    logits within 1e-4 * max|logit| (measured 1.1e-5 at 608x608 batch 4 -- the fp32 CPU oracle is itself 5e-6 away from
+    a float64 evaluation).  The decode turns a logit error d into: conf/cls 0.25*d, xy 0.25*stride*d (<= 8*d), w/h a
+    RELATIVE error d.  End to end: conf/cls allclose(atol=1e-4, rtol=1e-6) -- the north-star bar (measured 3.8e-5) --
+    xy atol 1e-3 px (measured 4.6e-4), w/h rtol 5e-4 (measured 1.4e-4): the noise floor between two fp32-grade
+    75-layer stacks, not a loosened kernel tolerance (decode alone holds 1e-4, above);
   * fp16 tensor-core stack: every layer against a torch conv on the same fp16-rounded operands
     (atol 3e-3*max|y| + rtol 2e-3 = fp16 output rounding); end-to-end deviation vs the fp32 oracle is
-    REPORTED and only sanity-bounded, as BASELINE/SURVEY state (it cannot meet 1e-4).
+    REPORTED and bounded at twice the measured figures (tests/test_gpu_fp16.py), as BASELINE/SURVEY state (fp16 cannot
+    meet 1e-4); the final detections are compared with the oracle's at the bench thresholds.
 """
 import ctypes
 
@@ -273,7 +274,7 @@ def test_fp32_net_vs_reference_golden(golden, sd_analytic):
         np.testing.assert_allclose(l.cpu().numpy(), ref, rtol=0, atol=1e-4 * np.abs(ref).max())
     dets = net(x.cuda(), None)
     for i, d in enumerate(dets):
-        np.testing.assert_allclose(d.cpu().numpy(), g[f"det{i}"], rtol=1e-3, atol=1e-4)
+        np.testing.assert_allclose(d.cpu().numpy(), g[f"det{i}"], rtol=5e-4, atol=1e-4)
     bb = net.backbone(x.cuda())
     np.testing.assert_allclose(bb.cpu().numpy(), g["backbone"], rtol=0, atol=1e-4 * np.abs(g["backbone"]).max())
 
@@ -287,8 +288,8 @@ def test_fp32_net_416_plumbing_config(oracle, sd_calibrated):
     assert d1.shape == (1, 507, 85) and d2.shape == (1, 2028, 85) and d3.shape == (1, 8112, 85)   # yolo_detect.ipynb:643
     det = torch.cat((d1, d2, d3), 1)
     ref = torch.cat(oracle.forward(sd_calibrated, x), 1)
-    np.testing.assert_allclose(det.cpu().numpy(), ref.numpy(), rtol=1e-3, atol=1e-4)
-    np.testing.assert_allclose(det[..., :2].cpu().numpy(), ref[..., :2].numpy(), rtol=0, atol=2e-3)
+    np.testing.assert_allclose(det.cpu().numpy(), ref.numpy(), rtol=5e-4, atol=1e-4)
+    np.testing.assert_allclose(det[..., :2].cpu().numpy(), ref[..., :2].numpy(), rtol=0, atol=1e-3)
     np.testing.assert_allclose(det[..., 4:].cpu().numpy(), ref[..., 4:].numpy(), rtol=0, atol=1e-4)
     # identical candidates -> identical survivors: run both post-processes on the SAME tensor
     res, idx = postprocessing(det, 80, 0.1, 0.4, return_index=True)
@@ -305,8 +306,8 @@ def test_fp32_net_608_batch(oracle, sd_calibrated):
     det = torch.cat(net(x.cuda(), None), 1)
     assert det.shape == (2, 22743, 85)
     ref = torch.cat(oracle.forward(sd_calibrated, x), 1)
-    np.testing.assert_allclose(det.cpu().numpy(), ref.numpy(), rtol=1e-3, atol=1e-4)
-    np.testing.assert_allclose(det[..., :2].cpu().numpy(), ref[..., :2].numpy(), rtol=0, atol=2e-3)
+    np.testing.assert_allclose(det.cpu().numpy(), ref.numpy(), rtol=5e-4, atol=1e-4)
+    np.testing.assert_allclose(det[..., :2].cpu().numpy(), ref[..., :2].numpy(), rtol=0, atol=1e-3)
     np.testing.assert_allclose(det[..., 4:].cpu().numpy(), ref[..., 4:].numpy(), rtol=0, atol=1e-4)
 
 

@@ -176,7 +176,9 @@ def test_split_detections_equal_oracle_detections(sd):
         assert abs(len(g) - len(r)) <= 1
         if len(g) == len(r) and len(g):
             assert torch.equal(g[:, 6], r[:, 6])                                        # same classes in the same order
-            np.testing.assert_allclose(g[:, :4].numpy(), r[:, :4].numpy(), rtol=0, atol=2e-3)
+            # corners of boxes thousands of pixels wide (random weights): w/h carry the logit noise as a RELATIVE error
+            wh = (r[:, 2:4] - r[:, 0:2]).abs().repeat(1, 2).numpy()
+            assert (np.abs(g[:, :4].numpy() - r[:, :4].numpy()) <= 2e-3 + 5e-4 * wh).all()
             np.testing.assert_allclose(g[:, 4:6].numpy(), r[:, 4:6].numpy(), rtol=0, atol=1e-4)
 
 

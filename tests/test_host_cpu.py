@@ -207,34 +207,122 @@ def test_named_tensors_follow_the_live_state_dict():
     assert net._signature(dev) != s1 and same(net)
 
 
+def test_data_writes_need_refresh_weights_or_check_weights():
+    """`param.data.copy_()` (the idiom of the reference's WeightManager, darknet.py:275) does not bump the tensor's version
+    counter: the default signature cannot see it (documented), refresh_weights() forgets the upload, and
+    check_weights=True sees the new contents."""
+    from yolo_v3_b200 import YoloNet
+    dev = torch.device("cpu")
+    net = YoloNet((416, 416))
+    s0 = net._signature(dev)
+    net._sig = s0                                          # as after a forward
+    p = net.feature.mlist[0].conv.weight
+    p.data.mul_(2.0)
+    net.feature.mlist[0].bn.running_mean.data.copy_(torch.ones(32))
+    assert net._signature(dev) == s0                      # the limitation
+    net.refresh_weights()
+    assert net._sig is None                                # next forward re-uploads
+    chk = YoloNet((416, 416), check_weights=True)
+    c0 = chk._signature(dev)
+    assert chk._signature(dev) == c0
+    chk.feature.mlist[0].conv.weight.data.mul_(2.0)
+    c1 = chk._signature(dev)
+    assert c1 != c0
+    chk.pre_det3.mlist[6].bias.data.copy_(torch.full((255,), 0.25))
+    assert chk._signature(dev) != c1
+    # load_state_dict / _apply / the darknet loader invalidate explicitly, whatever the version counters say
+    net._sig = s0
+    net.load_state_dict(net.state_dict())
+    assert net._sig is None
+    net._sig = s0
+    net.float()
+    assert net._sig is None
+
+
+def test_copy_and_pickle_drop_the_engine_and_rebind_the_backbone():
+    """copy.deepcopy / pickle of a YoloNet: the copy has no engine context of its own yet, and its `feature` points back at
+    the COPY (loadWeight / forward on copy.feature must not act on the original)."""
+    import copy
+    import io
+    import pickle
+    from yolo_v3_b200 import YoloNet
+    net = YoloNet((416, 416), numClass=20)
+    net._ctx = ctypes.c_void_p(12345)                      # stands for a live engine (never dereferenced here)
+    net._sig = ("x",)
+    try:
+        cp = copy.deepcopy(net)
+        assert cp._ctx is None and cp._sig is None and cp.feature._owner() is cp and net.feature._owner() is net
+        assert cp.numClass == 20 and all(torch.equal(a, b) for a, b in zip(cp.state_dict().values(), net.state_dict().values()))
+        rt = pickle.loads(pickle.dumps(net))
+        assert rt._ctx is None and rt.feature._owner() is rt
+        buf = io.BytesIO()
+        torch.save(net, buf)
+        buf.seek(0)
+        back = torch.load(buf, weights_only=False)
+        assert back._ctx is None and back.feature._owner() is back
+    finally:
+        net._ctx = None                                    # nothing to destroy
+
+
 def test_bench_reference_arm_prints_one_contract_line():
-    """bench.py --impl reference runs on the host cores only (the CPU port of the reference path): one JSON line on
-    stdout with the keys the driver reads, whatever else the libraries print."""
+    """bench.py --impl reference runs on the host cores only -- the reference's own modules from oracle/_ref where that
+    directory exists (`make -C oracle ref`), else the oracle port: one JSON line on stdout with the keys the driver reads,
+    whatever else the libraries print."""
     import json
     out = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--steps", "1", "--warmup", "0",
-                          "--ref-batch", "1", "--size", "416"], capture_output=True, text=True, timeout=600)
+                          "--size", "416"], capture_output=True, text=True, timeout=600)
     assert out.returncode == 0, out.stderr[-2000:]
     lines = [l for l in out.stdout.splitlines() if l.strip()]
     assert len(lines) == 1, lines
     d = json.loads(lines[0])
     assert d["impl"] == "reference" and d["unit"] == "images/sec" and d["higher_is_better"] is True
     assert d["value"] > 0 and d["steps"] == 1 and d["n_gpus"] == 1
-    assert d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["cores"] >= 1 and d["cpu_baseline"]["value"] == d["value"]
+    have_ref = os.path.exists(os.path.join(ROOT, "oracle", "_ref", "darknet.py"))
+    assert d["cpu_baseline"]["kind"] == ("reference" if have_ref else "port")
+    assert d["cpu_baseline"]["cores"] >= 1 and d["cpu_baseline"]["value"] == d["value"]
     assert d["e2e"] == {"value": d["value"], "unit": "images/sec", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
     assert d["config"]["workload"].startswith("yolov3_416x416")
 
 
+def test_reference_in_oracle_ref_is_what_the_oracle_restates():
+    """Where oracle/_ref exists (build container: copied from /root/reference by `make -C oracle ref`; GPU box: shipped with
+    the snapshot), the reference's own forward + postprocessing and the oracle port agree on a seeded input: logits to
+    fp32 round-off of the same torch build, detections identical."""
+    from oracle import ref_loader
+    if not ref_loader.available():
+        pytest.skip("oracle/_ref not present")
+    import oracle.yolo_oracle as O
+    from yolo_v3_b200 import synth
+    darknet, utils = ref_loader.load()
+    assert "utils" not in sys.modules or not getattr(sys.modules["utils"], "__file__", "").startswith(ref_loader.REF_DIR)
+    sd = synth.make_state_dict(seed=1234, recipe="calibrated")
+    net = darknet.YoloNet((160, 96))
+    net.load_state_dict(sd)
+    net.eval()
+    x = synth.make_images(2, 96, 160, seed=4)
+    with ref_loader.cpu_only(), torch.no_grad():
+        det = torch.cat(net(x, None), 1)
+        res = utils.postprocessing(det.clone(), 80, 0.3, 0.4)
+    ref = torch.cat(O.forward(sd, x), 1)
+    assert torch.allclose(det, ref, rtol=1e-5, atol=1e-6)
+    mine = O.postprocessing(ref, 80, 0.3, 0.4)
+    assert len(res) == len(mine) and all(torch.equal(a, b) for a, b in zip(res, mine))
+
+
 def test_bench_reads_measured_peaks_whatever_the_key_names():
-    """MEASURED_PEAKS.json is written by the driver; bench.py must find the sustained bf16 figure and the HBM copy figure
-    under any reasonable naming, and must never crash on the file."""
+    """MEASURED_PEAKS.json is written by the driver; bench.py must find the sustained and burst bf16 figures and the HBM
+    copy figure under any reasonable naming, and must never crash on the file."""
     import importlib.util
     spec = importlib.util.spec_from_file_location("bench_mod", os.path.join(ROOT, "bench.py"))
     b = importlib.util.module_from_spec(spec)
     spec.loader.exec_module(b)
-    assert b.parse_peaks({"bf16_tflops_sustained": 1386.8, "hbm_gbs": 6445.3}) == (1386.8, 6445.3)
+    assert b.parse_peaks({"bf16_tflops": 1632.4, "bf16_tflops_sustained": 1360.4, "hbm_gbs": 6557.8}) == (1360.4, 6557.8, 1632.4)
+    assert b.parse_peaks({"bf16_tflops_sustained": 1386.8, "hbm_gbs": 6445.3}) == (1386.8, 6445.3, 1386.8)
     nested = {"hbm": {"copy_GBps": 6445.3}, "tensor": {"bf16_dense_tflops": {"burst": 1642.7, "sustained": 1386.8}},
               "sm_clock_mhz": {"median": 1342, "max": 1965}}
-    assert b.parse_peaks(nested) == (1386.8, 6445.3)
-    assert b.parse_peaks({"hbm_gb_s": 6445.3, "bf16_tflops_burst": 1642.7, "bf16_tflops": 1386.8}) == (1386.8, 6445.3)
-    assert b.parse_peaks({"peaks": [{"name": "hbm_copy", "GB/s": 6445.3}, {"name": "bf16", "TFLOP/s": 1642.7}]}) == (1642.7, 6445.3)
-    assert b.parse_peaks([]) == (None, None) and b.parse_peaks({"x": "y"}) == (None, None)
+    assert b.parse_peaks(nested) == (1386.8, 6445.3, 1642.7)
+    assert b.parse_peaks({"hbm_gb_s": 6445.3, "bf16_tflops_burst": 1642.7, "bf16_tflops": 1386.8}) == (1386.8, 6445.3, 1642.7)
+    assert b.parse_peaks({"peaks": [{"name": "hbm_copy", "GB/s": 6445.3}, {"name": "bf16", "TFLOP/s": 1642.7}]}) == (1642.7, 6445.3, 1642.7)
+    assert b.parse_peaks([]) == (None, None, None) and b.parse_peaks({"x": "y"}) == (None, None, None)
+    pk = b.peaks()
+    assert pk["burst"] >= pk["tensor"] > 0 and pk["hbm"] > 0

@@ -14,9 +14,10 @@ ap.add_argument("--warmup", type=int, default=3)
 ap.add_argument("--batch", type=int, default=32)
 ap.add_argument("--size", type=int, default=608)
 ap.add_argument("--recipe", default="analytic")
+ap.add_argument("--precision", default="fp16")
 a = ap.parse_args()
 sd = synth.make_state_dict(seed=1234, recipe=a.recipe)
-net = YoloNet((a.size, a.size), precision="fp16")
+net = YoloNet((a.size, a.size), precision=a.precision)
 net.load_state_dict(sd)
 net = net.cuda().eval()
 x = synth.make_images(a.batch, a.size, a.size, seed=0).cuda()

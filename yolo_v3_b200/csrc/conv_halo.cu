@@ -51,7 +51,6 @@ struct HaloArgs {
     const float* scale; const float* bias;
     int cout_pad, tab_bytes;
     int leaky, has_res, ring;
-    int b_early;                  // request the weight slab before griddepcontrol.wait
     int* dbg;
 };
 
@@ -112,8 +111,8 @@ __device__ __forceinline__ void tma_load_4d_pair(const CUtensorMap* tm, uint32_t
 // the pair reads 6 KB per 64 tensor cycles.  Tile t of the pair's round is tile 2*p + rank, so the tile walk is the
 // same (first = blockIdx.x, step = gridDim.x); an odd tile count leaves rank 1 of the last pair a tile at image index
 // B, which TMA zero-fills on load and clips on store.
-// UW (YB_TC_UW=1, as in conv_tc.cu; not yet run on a GPU): warp index through a shuffle broadcast = uniform role dispatch.
-template <int SWZ, int STRIDE, bool PAIR, bool UW = false>
+// (warp index through a shuffle broadcast = uniform role dispatch, as in conv_tc.cu)
+template <int SWZ, int STRIDE, bool PAIR>
 __global__ void __launch_bounds__(kHThreads, 1)
 conv_halo_kernel(const __grid_constant__ CUtensorMap tmIn, const __grid_constant__ CUtensorMap tmB,
                  const __grid_constant__ CUtensorMap tmOut, const __grid_constant__ CUtensorMap tmRes, const HaloArgs a) {
@@ -137,7 +136,7 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmIn, const __grid_constant
     const uint32_t bres0 = stg0 + (uint32_t)a.ring * kHStgBytes;
     const uint32_t stage0 = bres0 + 9 * B_SLOT;
 
-    const int warp = UW ? __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0) : (int)(threadIdx.x >> 5);
+    const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0);
     const int lane = threadIdx.x & 31;
     const uint32_t rank = PAIR ? cluster_ctarank() : 0u;
     const bool leader = rank == 0;
@@ -170,8 +169,7 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmIn, const __grid_constant
     tc_fence_after();
     const uint32_t tmem_base = *tmem_ptr;
     pdl_launch_dependents();
-    // the resident weight slab (one elected thread of warp 0).  The weights do not depend on the previous layer, so with
-    // b_early they are requested before waiting for it and arrive under its tail.
+    // the resident weight slab (one elected thread of warp 0)
     auto load_slab = [&]() {
         // the grid is a multiple of n_tiles: a CTA's n-tile never changes; pair mode: this CTA's half of the 128 rows
         const int n0 = PAIR ? (int)rank * kHBN : (tile_first % a.n_tiles) * kHBN;
@@ -182,15 +180,11 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmIn, const __grid_constant
             else tma_load_2d(&tmB, bres0 + t * B_SLOT, bres_bar, t * BKE, n0);
         }
     };
-    if (warp == 0 && a.b_early) {
-        if (tile_first < tile_end && elect_one()) load_slab();
-        __syncwarp();
-    }
     pdl_wait_prior();
 
     if (warp == 0) {
         // ===== TMA producer: the resident weight slab once, then one patch per tile =====
-        if (!a.b_early && tile_first < tile_end && elect_one()) load_slab();
+        if (tile_first < tile_end && elect_one()) load_slab();
         __syncwarp();
         int stage = 0;
         uint32_t phase = 0;
@@ -401,14 +395,14 @@ std::string halo_err(const char* what, CUresult r) { return std::string(what) + 
 }  // namespace
 
 bool halo_supported(const ConvArgs& a) {
-    static const bool enabled = !(getenv("YB_HALO") && atoi(getenv("YB_HALO")) == 0);
+    static const bool enabled = !(tune_env("YB_HALO") && atoi(tune_env("YB_HALO")) == 0);
     if (!enabled) return false;
     if (a.ks != 3 || a.pad != 1 || a.upsample || a.out_f32) return false;
     if (a.stride == 1) {
         if (a.Cin != 32 && a.Cin != 64) return false;
     } else if (a.stride == 2) {
         // four parity planes per stage: fits next to the resident weights only for 64-byte pixels
-        static const bool s2 = !(getenv("YB_HALO_S2") && atoi(getenv("YB_HALO_S2")) == 0);
+        static const bool s2 = !(tune_env("YB_HALO_S2") && atoi(tune_env("YB_HALO_S2")) == 0);
         if (!s2 || a.Cin != 32 || a.H % 2 || a.W % 2) return false;
     } else {
         return false;
@@ -434,7 +428,7 @@ std::string halo_make_plan(HaloPlan& p, const ConvArgs& a, const __half* w16, in
     p.tiles_y = (a.Ho + kHR - 1) / kHR;
     // Cout = 128 with 128-byte pixels: CTA pairs, all 128 channels in one UMMA (see the kernel's header comment)
     p.pair = p.swz == 128 && a.stride == 1 && a.Cout == 2 * kHBN && num_sms % 2 == 0;
-    if (const char* e = getenv("YB_HALO_PAIR")) p.pair = p.pair && atoi(e) != 0;
+    if (const char* e = tune_env("YB_HALO_PAIR")) p.pair = p.pair && atoi(e) != 0;
     p.n_tiles = p.pair ? 1 : a.Cout / kHBN;
     p.total_tiles = a.B * p.tiles_x * p.tiles_y * p.n_tiles;
     p.ring = (a.res || p.pair) ? 4 : 2;           // slots hold 64 channels: a pair-mode tile takes two
@@ -504,10 +498,6 @@ cudaError_t halo_launch(const HaloPlan& p, const ConvArgs& a, int* dbg, cudaStre
     h.cout_pad = p.cout_pad; h.tab_bytes = p.tab_bytes;
     h.leaky = a.leaky; h.has_res = a.res != nullptr; h.ring = p.ring;
     h.dbg = dbg;
-    {
-        static const int b_early = getenv("YB_TC_BEARLY") ? atoi(getenv("YB_TC_BEARLY")) != 0 : 0;
-        h.b_early = b_early;
-    }
     static PerDeviceOnce attr_once;
     {
         cudaError_t e = attr_once.run([] {
@@ -515,18 +505,11 @@ cudaError_t halo_launch(const HaloPlan& p, const ConvArgs& a, int* dbg, cudaStre
             if (r == cudaSuccess) r = cudaFuncSetAttribute(conv_halo_kernel<128, 1, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kHSmemBudget);
             if (r == cudaSuccess) r = cudaFuncSetAttribute(conv_halo_kernel<64, 1, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kHSmemBudget);
             if (r == cudaSuccess) r = cudaFuncSetAttribute(conv_halo_kernel<64, 2, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kHSmemBudget);
-            if (r == cudaSuccess) {     // opt-in instantiations: best effort, must not take the validated path down
-                cudaFuncSetAttribute(conv_halo_kernel<128, 1, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kHSmemBudget);
-                cudaFuncSetAttribute(conv_halo_kernel<128, 1, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kHSmemBudget);
-                cudaFuncSetAttribute(conv_halo_kernel<64, 1, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kHSmemBudget);
-                cudaFuncSetAttribute(conv_halo_kernel<64, 2, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kHSmemBudget);
-                cudaGetLastError();
-            }
             return r;
         });
         if (e != cudaSuccess) return e;
     }
-    static const bool pdl = !(getenv("YB_TC_PDL") && atoi(getenv("YB_TC_PDL")) == 0);
+    static const bool pdl = !(tune_env("YB_TC_PDL") && atoi(tune_env("YB_TC_PDL")) == 0);
     cudaLaunchConfig_t cfg{};
     cfg.gridDim = dim3(p.grid);
     cfg.blockDim = dim3(kHThreads);
@@ -549,13 +532,6 @@ cudaError_t halo_launch(const HaloPlan& p, const ConvArgs& a, int* dbg, cudaStre
     cfg.attrs = attr;
     cfg.numAttrs = na;
     cudaError_t e;
-    static const bool uw = getenv("YB_TC_UW") && atoi(getenv("YB_TC_UW")) != 0;
-    if (uw) {
-        if (p.stride == 2) e = cudaLaunchKernelEx(&cfg, conv_halo_kernel<64, 2, false, true>, p.tmIn, p.tmB, p.tmOut, p.tmRes, h);
-        else if (p.pair) e = cudaLaunchKernelEx(&cfg, conv_halo_kernel<128, 1, true, true>, p.tmIn, p.tmB, p.tmOut, p.tmRes, h);
-        else if (p.swz == 128) e = cudaLaunchKernelEx(&cfg, conv_halo_kernel<128, 1, false, true>, p.tmIn, p.tmB, p.tmOut, p.tmRes, h);
-        else e = cudaLaunchKernelEx(&cfg, conv_halo_kernel<64, 1, false, true>, p.tmIn, p.tmB, p.tmOut, p.tmRes, h);
-    } else
     if (p.stride == 2) e = cudaLaunchKernelEx(&cfg, conv_halo_kernel<64, 2, false>, p.tmIn, p.tmB, p.tmOut, p.tmRes, h);
     else if (p.pair) e = cudaLaunchKernelEx(&cfg, conv_halo_kernel<128, 1, true>, p.tmIn, p.tmB, p.tmOut, p.tmRes, h);
     else if (p.swz == 128) e = cudaLaunchKernelEx(&cfg, conv_halo_kernel<128, 1, false>, p.tmIn, p.tmB, p.tmOut, p.tmRes, h);

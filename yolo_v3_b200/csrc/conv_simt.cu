@@ -6,6 +6,8 @@
 // NHWC implicit GEMM with fp32 FMA accumulation in a fixed (tap, channel) order, so results are
 // fp32-grade against the reference's CPU path.  It is the correctness anchor, not the fast path:
 // the tensor-core kernel in conv_tc.cu is what YB_MODE_FP16 runs.
+#include <algorithm>
+
 #include "yb_internal.h"
 
 namespace yb {
@@ -248,6 +250,27 @@ __global__ void split_to_f32_kernel(const __half* __restrict__ in, float* __rest
     }
 }
 
+// nearest-neighbour x2 of a split tensor into a channel slice of the concat buffer (UpsampleGroup, darknet.py:161-162, in
+// YB_MODE_FP32_TC, where the 1x1 "up" convolution writes a plain tensor): one thread per 16-byte chunk of an input pixel
+__global__ void upsample2x_split_kernel(const __half* __restrict__ in, long in_ld, long in_lo, __half* __restrict__ out, long out_ld,
+                                        long out_lo, int C, int H, int W, long total) {
+    const int cpp = C / 8;                                 // chunks per half of a pixel
+    const long stride = (long)gridDim.x * blockDim.x;
+    for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += stride) {
+        const int ch = (int)(i % (2 * cpp));
+        const long pix = i / (2 * cpp);
+        const int half_i = ch / cpp, c = (ch - half_i * cpp) * 8;
+        const int x = (int)(pix % W);
+        const long by = pix / W;                           // b * H + y
+        const uint4 v = *reinterpret_cast<const uint4*>(in + pix * in_ld + (half_i ? in_lo : 0) + c);
+        __half* o = out + ((by * 2) * (2L * W) + 2 * x) * out_ld + (half_i ? out_lo : 0) + c;
+        *reinterpret_cast<uint4*>(o) = v;
+        *reinterpret_cast<uint4*>(o + out_ld) = v;
+        *reinterpret_cast<uint4*>(o + 2L * W * out_ld) = v;
+        *reinterpret_cast<uint4*>(o + 2L * W * out_ld + out_ld) = v;
+    }
+}
+
 __global__ void f32_to_f16_kernel(const float* __restrict__ in, __half* __restrict__ out, size_t n) {
     size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     const size_t stride = (size_t)gridDim.x * blockDim.x;
@@ -285,6 +308,13 @@ cudaError_t launch_stem_split(const float* x, __half* out, const float* w32, con
 cudaError_t launch_split_to_nchw_f32(const __half* in, long in_ld, long lo, int C, int B, int HW, float* out, cudaStream_t s) {
     dim3 grid((HW + 31) / 32, (C + 31) / 32, B), block(32, 8);
     split_to_nchw_kernel<<<grid, block, 0, s>>>(in, in_ld, lo, C, HW, out);
+    return cudaGetLastError();
+}
+cudaError_t launch_upsample2x_split(const __half* in, long in_ld, long in_lo, __half* out, long out_ld, long out_lo, int C,
+                                    int B, int H, int W, cudaStream_t s) {
+    const long total = (long)B * H * W * 2 * (C / 8);
+    const int blocks = (int)std::min<long>((total + 255) / 256, 148 * 8);
+    upsample2x_split_kernel<<<blocks, 256, 0, s>>>(in, in_ld, in_lo, out, out_ld, out_lo, C, H, W, total);
     return cudaGetLastError();
 }
 cudaError_t launch_f32_to_split(const float* in, __half* out, size_t M, int C, cudaStream_t s) {

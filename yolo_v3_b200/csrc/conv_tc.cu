@@ -22,7 +22,15 @@
 //   * persistent CTAs (one per SM), static round-robin over the (m-tile, n-tile) grid.
 //
 // Layers with Cin == 32 use 32-channel k-blocks with the 64B swizzle; everything else 64-channel
-// k-blocks with the 128B swizzle.  The Cin == 3 stem runs on CUDA cores (conv_simt.cu).
+// k-blocks with the 128B swizzle.  The Cin == 3 stem is stem_tc_kernel below (producer warps build the im2col rows).
+//
+// Every role reads its warp index through a shuffle broadcast, which the compiler knows to be warp-uniform (what
+// cutlass::canonical_warp_idx_sync does): the role dispatch is then a uniform branch and the single-thread issue loops and
+// the epilogue run on the uniform datapath instead of being littered with R2UR copies (validated in round 2:
+// profiles/r02a_uw_ab.txt, +5 % on the whole step).
+//
+// Build flavours: the release library reads no environment variable.  -DYB_EXPERIMENTS (make EXPERIMENTS=1) adds the
+// tuning overrides used by tools/layer_bench.py sweeps (tune_env) and the in-kernel clock64 time line (YB_TC_TRACE).
 #include <algorithm>
 #include <cstdlib>
 
@@ -35,6 +43,8 @@ namespace {
 constexpr int kBM = 128;
 constexpr int kMaxStages = 16;
 constexpr int kThreads = 768;            // warps 0-1 TMA producers, 2 MMA, 3 TMEM alloc + store issuer, 4 residual TMA, 8-23 epilogue
+constexpr int kThreadsSplit = 640;       // split mode: warp 0 TMA producer, 1 residual TMA, 2 MMA, 3 TMEM alloc + store issuer, 4-19 epilogue
+                                         // (five warpgroups: 96 registers per thread -- the epilogue keeps 32 fp32 accumulators)
 constexpr int kEpiWarps = 16;
 constexpr int kMaxRing = 4;              // epilogue staging ring depth
 constexpr size_t kSmemBudget = 227 * 1024;
@@ -61,28 +71,28 @@ struct TcArgs {
     int cs;                  // columns per sub-tile
     int n_sub;               // sub-tiles per tile (BN / cs)
     int has_res;
-    int exp_tiled;           // timing experiment: fetch 3x3 A tiles with tiled-mode TMA (results are wrong)
-    int exp_nostore;         // timing experiment: the store issuer recycles buffers without issuing the TMA store (results are wrong)
     int b_resident;          // 1: the CTA's whole weight slab [BN][K] is loaded once and stays in smem
-    int pf_dist;             // L2 prefetch distance of the A operand, in tiles of this CTA (0 = off)
-    int b_early;             // weights are touched (resident load / L2 prefetch) before griddepcontrol.wait
     int srel;                // store issuer: staging-buffer stores allowed to stay unread (0, 1 or 2)
     int epi_split;           // sub-tiles of 32 columns occupy only half of the sixteen epilogue warps: the halves take alternate
                              // sub-tiles (n_sub even) or alternate tiles (n_sub == 1), two hand-over chains in flight
-    int epi_sleep;           // nanoseconds the epilogue warps back off between probes of the accumulator barrier (0 = spin)
     // split mode (SPLIT instantiations, YB_MODE_FP32_TC): every activation is a pair of fp16 tensors hi + lo sharing one
     // pixel pitch; a_lo / out_lo / res_lo = channel offset of the lo half relative to the hi pointer; split_out = the
     // output is written as such a pair (everything but the fp32 head maps)
     int a_lo, out_lo, res_lo, split_out;
+    int chunk_iters, n_chunks;   // two-level accumulation: pipeline stages per TMEM chunk, chunks per tile
     int* dbg;
     long long* trace;        // optional [6 roles][64 tiles][4] clock64 stamps of CTA 0 (YB_TC_TRACE=1)
 };
 
-// (kTraceOn is a compile-time constant of the enclosing kernel: the opt-in UW instantiations are built without the trace points)
+// clock64 time line of CTA 0 (YB_TC_TRACE=1): only in -DYB_EXPERIMENTS builds, the release kernels carry no trace points
+#ifdef YB_EXPERIMENTS
 #define YB_TRACE(role, idx, slot)                                                                   \
     do {                                                                                            \
-        if (kTraceOn && a.trace && blockIdx.x == 0 && (idx) < 64) a.trace[((role) * 64 + (idx)) * 4 + (slot)] = clock64(); \
+        if (a.trace && blockIdx.x == 0 && (idx) < 64) a.trace[((role) * 64 + (idx)) * 4 + (slot)] = clock64(); \
     } while (0)
+#else
+#define YB_TRACE(role, idx, slot) do { } while (0)
+#endif
 
 // Epilogue for 16 consecutive channels of one output pixel.
 __device__ __forceinline__ void epilogue16(const TcArgs& a, const uint32_t (&acc)[16], int n, bool valid, long m,
@@ -199,80 +209,29 @@ __device__ __forceinline__ void epilogue16_staged(const TcArgs& a, const uint32_
 // hi + lo carries 22 bits of x), and every weight w -- pre-scaled per output channel by a power of two so that its lo part
 // stays a normal fp16 number, the scale is undone in the fp32 epilogue -- as wh + wl.  The GEMM accumulates the three
 // significant partial products xh*wh + xh*wl + xl*wh (exact in the fp32 accumulator's product stage; the dropped xl*wl
-// term is 2^-22 relative) by running the unchanged main loop over a K axis three times as long: k-blocks are ordered
-// (tap, section, channel block), sections 0/1 fetch the hi half of A, section 2 the lo half; the weight rows are packed
-// [tap][wh | wl | wh][Cin] to match.  tools/split_numerics.py (profiles/r02_split_numerics_cpu.txt): the operand
-// representation error of this scheme through all 75 layers is 3e-6 of max|logit| -- below the fp32 oracle's own 5e-6.
+// term is 2^-22 relative) by running the main loop over a K axis three times as long: k-blocks are ordered (tap, channel
+// block, section); section 0 = xl*wh, 1 = xh*wl (the two corrections first, while the accumulator is small), 2 = xh*wh;
+// the weight rows are packed [tap][channel block][wh | wl | wh][64] to match.  tools/split_numerics.py
+// (profiles/r02_split_numerics_cpu.txt): the operand representation error of this scheme through all 75 layers is 3e-6 of
+// max|logit| -- below the fp32 oracle's own 5e-6.
+//
+// TWO-LEVEL ACCUMULATION.  The tcgen05 fp32 accumulator does not round to nearest: every MMA truncates the running sum
+// (profiles/r02a_tc_accum_probe.txt, r02c_split_error_vs_chain_length.txt: the result shrinks toward zero by 1.7e-8 per
+// MMA in the chain -- 1.4e-5 for the 864 MMAs of a 512->1024 3x3 layer, against 1e-6 for an fp32 GEMM on the CPU), so
+// a long K loop into one TMEM accumulator cannot be fp32-grade.  The SPLIT kernels therefore accumulate in TMEM only over
+// a CHUNK of one (tap, channel block) triple -- 12 MMAs, of which only the last four carry the main term -- and the
+// epilogue warps add every finished chunk into fp32 REGISTER accumulators with round-to-nearest adds while the tensor
+// core works on the next chunk in the other TMEM buffer.  A thread owns at most 32 accumulators (two 16-column groups),
+// which caps the tile width at 128 columns (64 for the fp32 head maps).
 __device__ __forceinline__ void split2(float a, float b, __half2& hi, __half2& lo) {
     hi = __floats2half2_rn(a, b);
     const float2 f = __half22float2(hi);
     lo = __floats2half2_rn(a - f.x, b - f.y);
 }
 
-// Direct (non-staged) split epilogue for 16 consecutive channels of one output pixel: used by the two nearest-upsample layers.
-__device__ __forceinline__ void epilogue16_split(const TcArgs& a, const uint32_t (&acc)[16], int n, bool valid, long m,
-                                                 long o00, long W2ld) {
-    float v[16];
-    const float4* sc = reinterpret_cast<const float4*>(a.tab + n);
-    const float4* bi = reinterpret_cast<const float4*>(a.tab + a.cout_pad + n);
-#pragma unroll
-    for (int q = 0; q < 4; ++q) {
-        const float4 s4 = sc[q], b4 = bi[q];
-        v[4 * q + 0] = fmaf(__uint_as_float(acc[4 * q + 0]), s4.x, b4.x);
-        v[4 * q + 1] = fmaf(__uint_as_float(acc[4 * q + 1]), s4.y, b4.y);
-        v[4 * q + 2] = fmaf(__uint_as_float(acc[4 * q + 2]), s4.z, b4.z);
-        v[4 * q + 3] = fmaf(__uint_as_float(acc[4 * q + 3]), s4.w, b4.w);
-    }
-    if (a.leaky) {
-#pragma unroll
-        for (int i = 0; i < 16; ++i) v[i] = leaky(v[i]);
-    }
-    if (!valid) return;
-    __half* ob = reinterpret_cast<__half*>(a.out);
-    if (a.res) {
-        const uint4* rh = reinterpret_cast<const uint4*>(a.res + m * a.res_ld + n);
-        const uint4* rl = reinterpret_cast<const uint4*>(a.res + m * a.res_ld + a.res_lo + n);
-#pragma unroll
-        for (int q = 0; q < 2; ++q) {
-            const uint4 h4 = rh[q], l4 = rl[q];
-            const __half2* hh = reinterpret_cast<const __half2*>(&h4);
-            const __half2* ll = reinterpret_cast<const __half2*>(&l4);
-#pragma unroll
-            for (int i = 0; i < 4; ++i) {
-                const float2 fh = __half22float2(hh[i]), fl = __half22float2(ll[i]);
-                v[8 * q + 2 * i] += fh.x + fl.x;          // hi + lo is exact in fp32: one rounding, like the reference's x + f(x)
-                v[8 * q + 2 * i + 1] += fh.y + fl.y;
-            }
-        }
-    }
-    uint4 ph[2], pl[2];
-#pragma unroll
-    for (int q = 0; q < 2; ++q) {
-        __half2* h = reinterpret_cast<__half2*>(&ph[q]);
-        __half2* l = reinterpret_cast<__half2*>(&pl[q]);
-#pragma unroll
-        for (int i = 0; i < 4; ++i) split2(v[8 * q + 2 * i], v[8 * q + 2 * i + 1], h[i], l[i]);
-    }
-    if (!a.upsample) {
-        uint4* o = reinterpret_cast<uint4*>(ob + m * a.out_ld + n);
-        uint4* ol = reinterpret_cast<uint4*>(ob + m * a.out_ld + a.out_lo + n);
-        o[0] = ph[0]; o[1] = ph[1];
-        ol[0] = pl[0]; ol[1] = pl[1];
-    } else {
-#pragma unroll
-        for (int d = 0; d < 4; ++d) {
-            __half* px = ob + o00 + (d >> 1) * W2ld + (d & 1) * a.out_ld + n;
-            uint4* o = reinterpret_cast<uint4*>(px);
-            uint4* ol = reinterpret_cast<uint4*>(px + a.out_lo);
-            o[0] = ph[0]; o[1] = ph[1];
-            ol[0] = pl[0]; ol[1] = pl[1];
-        }
-    }
-}
-
 // Staged split epilogue: the staging slot holds the hi sub-tile followed (lo_delta bytes later) by the lo sub-tile, both
 // 128B- (or 64B-) swizzled like the single sub-tile of the fp16 mode; the residual arrives the same way.
-__device__ __forceinline__ void epilogue16_staged_split(const TcArgs& a, const uint32_t (&acc)[16], int n, uint8_t* srow,
+__device__ __forceinline__ void epilogue16_staged_split(const TcArgs& a, const float (&acc)[16], int n, uint8_t* srow,
                                                         uint32_t lo_delta, int grp, int xr) {
     float v[16];
     const float4* sc = reinterpret_cast<const float4*>(a.tab + n);
@@ -280,10 +239,10 @@ __device__ __forceinline__ void epilogue16_staged_split(const TcArgs& a, const u
 #pragma unroll
     for (int q = 0; q < 4; ++q) {
         const float4 s4 = sc[q], b4 = bi[q];
-        v[4 * q + 0] = fmaf(__uint_as_float(acc[4 * q + 0]), s4.x, b4.x);
-        v[4 * q + 1] = fmaf(__uint_as_float(acc[4 * q + 1]), s4.y, b4.y);
-        v[4 * q + 2] = fmaf(__uint_as_float(acc[4 * q + 2]), s4.z, b4.z);
-        v[4 * q + 3] = fmaf(__uint_as_float(acc[4 * q + 3]), s4.w, b4.w);
+        v[4 * q + 0] = fmaf(acc[4 * q + 0], s4.x, b4.x);
+        v[4 * q + 1] = fmaf(acc[4 * q + 1], s4.y, b4.y);
+        v[4 * q + 2] = fmaf(acc[4 * q + 2], s4.z, b4.z);
+        v[4 * q + 3] = fmaf(acc[4 * q + 3], s4.w, b4.w);
     }
     if (a.leaky) {
 #pragma unroll
@@ -351,19 +310,11 @@ __device__ __forceinline__ void load_resident_weights(const CUtensorMap* tmB, co
     }
 }
 
-// EXPB: timing experiment (YB_TC_EXP_BLOCKED=1, 1x1 layers, results are WRONG): the A operand is fetched as if the
-// activations were stored channel-blocked, [Cin/64][M][64] -- every k-block box one contiguous 16 KB run instead of 128
-// rows strided by the pixel pitch -- through a 2-D map over the same memory and coordinates (0, kb*M + m0).
-// UW (YB_TC_UW=1; written at the end of round 1 from the SASS, not yet run on a GPU): the warp index is read through a
-// shuffle broadcast, which the compiler knows to be warp-uniform (cutlass::canonical_warp_idx_sync does the same), so the
-// role dispatch becomes a uniform branch and uniform registers stay usable inside the roles -- without it every role is a
-// "divergent" region to the compiler and the single-thread issue loops and the epilogue are littered with R2UR copies.
-template <int SWZ, bool CTA2, bool EXPB = false, bool UW = false, bool SPLIT = false>
-__global__ void __launch_bounds__(kThreads, 1)
+template <int SWZ, bool CTA2, bool SPLIT = false>
+__global__ void __launch_bounds__(SPLIT ? kThreadsSplit : kThreads, 1)
 conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                const __grid_constant__ CUtensorMap tmOut, const __grid_constant__ CUtensorMap tmRes, const TcArgs a_in) {
     constexpr int BKE = SWZ / 2;                  // fp16 elements per k-block row
-    constexpr bool kTraceOn = !UW;
     TcArgs a = a_in;
     constexpr uint32_t A_BYTES = kBM * SWZ;
     extern __shared__ uint8_t smem_raw[];
@@ -392,12 +343,13 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     const uint32_t bres0 = stg0 + (a.epi_staged ? (uint32_t)a.ring * ((stg_bytes + 1023u) & ~1023u) : 0u);
     const uint32_t stage0 = bres0 + (a.b_resident ? (uint32_t)a.num_kblocks * B_SLOT : 0u);
 
-    const int warp = UW ? __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0) : (int)(threadIdx.x >> 5);
+    const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0);     // warp-uniform for the compiler
     const int lane = threadIdx.x & 31;
     const int total_tiles = a.m_tiles * a.n_tiles;          // m_tiles counts 256-row units in pair mode
     const int tile_first = blockIdx.x / NCTA, tile_step = gridDim.x / NCTA;
 
-    for (int i = threadIdx.x; i < a.cout_pad; i += kThreads) {
+    constexpr int NT = SPLIT ? kThreadsSplit : kThreads;
+    for (int i = threadIdx.x; i < a.cout_pad; i += NT) {
         float* tab = reinterpret_cast<float*>(gen + kSmemHeader);
         tab[i] = __ldg(a.scale + i);
         tab[a.cout_pad + i] = __ldg(a.bias + i);
@@ -429,31 +381,19 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     const uint32_t acc_stride = (uint32_t)a.tmem_cols >> 1;
     if (threadIdx.x == 0) YB_TRACE(5, 0, 1);
     pdl_launch_dependents();      // everything above (barriers, TMEM, table) overlaps the previous layer's tail
-    // The weights do not depend on the previous layer: touch them before waiting for it, so that the resident
-    // slab (or, through an L2 prefetch, the first pipeline's worth of weight k-blocks) arrives under its tail.
-    if (warp == 0 && a.b_early && tile_first < total_tiles && elect_one()) {
-        if (a.b_resident) {
-            load_resident_weights<CTA2>(&tmB, a, bres0, B_SLOT, B_BYTES, bres_bar, BKE, rank);
-        } else {
-            const int n0 = (tile_first % a.n_tiles) * a.BN + (int)rank * (a.BN / NCTA);
-            const int npf = min(a.num_kblocks, a.stages * a.kps);
-#pragma unroll 1
-            for (int kb = 0; kb < npf; ++kb) tma_prefetch_2d(&tmB, kb * BKE, n0);
-        }
-    }
     __syncwarp();
     pdl_wait_prior();             // activations written by the previous layer are complete and visible
     if (threadIdx.x == 0) YB_TRACE(5, 0, 2);
 
-    if (warp < 2) {
-        // ===== TMA producers (two warps take alternate pipeline stages; whole warp runs the loop, one
+    if (warp < (SPLIT ? 1 : 2)) {
+        // ===== TMA producers (two warps take alternate pipeline stages -- one warp takes all of them in split mode; whole warp runs the loop, one
         // elected lane issues).  Both walk the same stage/coordinate sequence and act on their own parity. =====
         {
             const uint32_t pw = (uint32_t)warp;
             uint32_t itg = 0;                             // running stage counter across tiles
             int stage = 0;
             uint32_t phase = 0;
-            if (pw == 0 && a.b_resident && !a.b_early && tile_first < total_tiles && elect_one())
+            if (pw == 0 && a.b_resident && tile_first < total_tiles && elect_one())
                 load_resident_weights<CTA2>(&tmB, a, bres0, B_SLOT, B_BYTES, bres_bar, BKE, rank);
             __syncwarp();
             // The loop below runs on one thread; everything that can be is carried incrementally
@@ -468,72 +408,30 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                 const int m0 = (m_unit * NCTA + (int)rank) * kBM;
                 const int n0 = n_tile * a.BN + (int)rank * (a.BN / NCTA);   // this CTA's half of the weight rows
                 if (pw == 0) YB_TRACE(0, ti, 0);
-                if (a.pf_dist && pw == 1 && !a.exp_tiled) {
-                    // L2 prefetch of the A operand of this CTA's tile pf_dist rounds ahead: the memory-bound layers
-                    // keep only one or two tiles in flight in shared memory, which leaves them DRAM-latency-bound;
-                    // the prefetch moves the DRAM round trip out of the pipeline (one CTA per m-tile issues it).
-                    const int tp = tile + a.pf_dist * tile_step;
-                    if (tp < total_tiles) {
-                        const int mu = tp / a.n_tiles;
-                        if (tp - mu * a.n_tiles == 0 && elect_one()) {
-                            const int m0p = (mu * NCTA + (int)rank) * kBM;
-                            if (a.ks == 1) {
-#pragma unroll 1
-                                for (int kb = 0; kb < a.num_kblocks; ++kb) tma_prefetch_2d(&tmA, kb * BKE, m0p);
-                            } else {
-                                const int cn = m0p / a.HoWo;
-                                const int r = m0p - cn * a.HoWo;
-                                const int p = r / a.Wo, q = r - p * a.Wo;
-                                const int cw = q * a.stride - a.pad, chh = p * a.stride - a.pad;
-                                // stride 1: the centre tap is the tile's own pixels (the rows above / below belong to
-                                // neighbouring tiles, prefetched by their CTAs at the same time); stride 2: the four
-                                // taps (1..2, 1..2) tile the input without overlap
-#pragma unroll 1
-                                for (int cb = 0; cb < a.cin_blocks; ++cb) {
-                                    tma_prefetch_im2col(&tmA, cb * BKE, cw, chh, cn, 1, 1);
-                                    if (a.stride == 2) {
-                                        tma_prefetch_im2col(&tmA, cb * BKE, cw, chh, cn, 2, 1);
-                                        tma_prefetch_im2col(&tmA, cb * BKE, cw, chh, cn, 1, 2);
-                                        tma_prefetch_im2col(&tmA, cb * BKE, cw, chh, cn, 2, 2);
-                                    }
-                                }
-                            }
-                        }
-                    }
-                    __syncwarp();
-                }
-                if (a.ks == 1 || a.exp_tiled) {
-                    int kc = 0, ka = 0;
+                if (a.ks == 1) {
+                    int kc = 0;
                     [[maybe_unused]] int cc = 0, sec = 0;      // SPLIT: channel of the A box inside its half, section 0..2
-                    [[maybe_unused]] const int cend = a.cin_blocks * BKE;
-                    [[maybe_unused]] int mb = m0;              // EXPB: row of this k-block's box in the blocked view
                     for (int it = 0; it < a.num_iters; ++it, ++itg) {
-                        const bool mine = (itg & 1u) == pw;
+                        const bool mine = SPLIT || (itg & 1u) == pw;
                         if (mine) mbar_wait(eb, phase ^ 1, a.dbg, 0, stage);
                         const bool el = mine && elect_one();
                         if (leader && el) mbar_arrive_expect_tx(fb, tx_bytes);
                         uint32_t dst = sA;
                         for (int j = 0; j < a.kps; ++j) {
                             if (el) {
-                                const int ac = SPLIT ? cc + (sec == 2 ? a.a_lo : 0) : kc;
+                                const int ac = SPLIT ? cc + (sec == 0 ? a.a_lo : 0) : kc;
                                 if constexpr (CTA2) {
-                                    if constexpr (EXPB) tma_load_2d_pair(&tmA, dst, fb, 0, mb);
-                                    else tma_load_2d_pair(&tmA, dst, fb, ac, m0);
+                                    tma_load_2d_pair(&tmA, dst, fb, ac, m0);
                                     if (load_b) tma_load_2d_pair(&tmB, dst + A_BYTES, fb, kc, n0);
                                 } else {
-                                    if constexpr (EXPB) tma_load_2d(&tmA, dst, fb, 0, mb);
-                                    else tma_load_2d(&tmA, dst, fb, a.exp_tiled ? ka : ac, m0);
+                                    tma_load_2d(&tmA, dst, fb, ac, m0);
                                     if (load_b) tma_load_2d(&tmB, dst + A_BYTES, fb, kc, n0);
                                 }
                             }
-                            if constexpr (EXPB) mb += (int)a.M;
                             if constexpr (SPLIT) {
-                                cc += BKE;
-                                if (cc == cend) { cc = 0; if (++sec == 3) sec = 0; }
+                                if (++sec == 3) { sec = 0; cc += BKE; }
                             }
                             kc += BKE;
-                            ka += BKE;
-                            if (ka == a.cin_blocks * BKE) ka = 0;
                             dst += kb_bytes;
                         }
                         sA += stage_bytes; fb += 8; eb += 8;
@@ -549,14 +447,14 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                     uint16_t kw = 0, kh = 0;
                     const int cend = a.cin_blocks * BKE;
                     for (int it = 0; it < a.num_iters; ++it, ++itg) {
-                        const bool mine = (itg & 1u) == pw;
+                        const bool mine = SPLIT || (itg & 1u) == pw;
                         if (mine) mbar_wait(eb, phase ^ 1, a.dbg, 0, stage);
                         const bool el = mine && elect_one();
                         if (leader && el) mbar_arrive_expect_tx(fb, tx_bytes);
                         uint32_t dst = sA;
                         for (int j = 0; j < a.kps; ++j) {
                             if (el) {
-                                const int ac = SPLIT ? cc + (sec == 2 ? a.a_lo : 0) : cc;
+                                const int ac = SPLIT ? cc + (sec == 0 ? a.a_lo : 0) : cc;
                                 if constexpr (CTA2) {
                                     tma_load_im2col_pair(&tmA, dst, fb, ac, cw, chh, cn, kw, kh);
                                     if (load_b) tma_load_2d_pair(&tmB, dst + A_BYTES, fb, kc, n0);
@@ -566,12 +464,11 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                                 }
                             }
                             kc += BKE;
-                            cc += BKE;
-                            if (cc == cend) {
-                                cc = 0;
-                                bool next_tap = true;
-                                if constexpr (SPLIT) { if (++sec < 3) next_tap = false; else sec = 0; }
-                                if (next_tap && ++kw == 3) { kw = 0; ++kh; }
+                            bool next_cb = true;
+                            if constexpr (SPLIT) { if (++sec < 3) next_cb = false; else sec = 0; }
+                            if (next_cb) {
+                                cc += BKE;
+                                if (cc == cend) { cc = 0; if (++kw == 3) { kw = 0; ++kh; } }
                             }
                             dst += kb_bytes;
                         }
@@ -603,9 +500,25 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                 mbar_wait(tempty0 + 8 * acc, acc_phase ^ 1, a.dbg, 1, 100 + (int)acc);
                 tc_fence_after();
                 YB_TRACE(1, ti, 1);
-                const uint32_t d_tmem = tmem_base + acc * acc_stride;
+                uint32_t d_tmem = tmem_base + acc * acc_stride;
                 int kb = 0;
+                [[maybe_unused]] int kbc = 0, it_chunk = 0;   // SPLIT: k-block / stage index inside the current TMEM chunk
                 for (int it = 0; it < a.num_iters; ++it) {
+                    if constexpr (SPLIT) {
+                        if (it_chunk == a.chunk_iters) {
+                            // chunk complete: publish it to the epilogue warps and continue in the other TMEM buffer
+                            if (elect_one()) {
+                                if constexpr (CTA2) umma_commit_pair(tfull0 + 8 * acc); else umma_commit(tfull0 + 8 * acc);
+                            }
+                            acc ^= 1;
+                            if (acc == 0) acc_phase ^= 1;
+                            mbar_wait(tempty0 + 8 * acc, acc_phase ^ 1, a.dbg, 1, 100 + (int)acc);
+                            tc_fence_after();
+                            d_tmem = tmem_base + acc * acc_stride;
+                            kbc = 0; it_chunk = 0;
+                        }
+                        ++it_chunk;
+                    }
                     if (!ready) mbar_wait(fbar, phase, a.dbg, 1, stage);
                     tc_fence_after();
                     // probe the NEXT stage's barrier now: its latency overlaps the MMA issue below
@@ -616,17 +529,19 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                     for (int j = 0; j < a.kps; ++j, ++kb) {
                         const uint64_t bd = a.b_resident ? bres_desc + (uint64_t)kb * bres_inc : ad + b_off;
                         if (el) {
+                            const int first = SPLIT ? kbc : kb;       // 0: the MMA overwrites the accumulator
                             if constexpr (CTA2) {
 #pragma unroll
-                                for (int k = 0; k < BKE / 16; ++k) umma_f16_pair(d_tmem, ad + 2 * k, bd + 2 * k, idesc, (kb | k) != 0);
+                                for (int k = 0; k < BKE / 16; ++k) umma_f16_pair(d_tmem, ad + 2 * k, bd + 2 * k, idesc, (first | k) != 0);
                             } else {
-                                umma_f16(d_tmem, ad, bd, idesc, kb != 0);
+                                umma_f16(d_tmem, ad, bd, idesc, first != 0);
 #pragma unroll
                                 for (int k = 1; k < BKE / 16; ++k)   // 16 fp16 = 32 bytes per MMA: descriptor address += 2
                                     umma_f16_imm<1>(d_tmem, ad + 2 * k, bd + 2 * k, idesc);
                             }
                         }
                         ad += kb_inc;
+                        if constexpr (SPLIT) ++kbc;
                     }
                     if (el) {
                         if constexpr (CTA2) umma_commit_pair(ebar); else umma_commit(ebar);   // frees the stage (in both CTAs)
@@ -643,7 +558,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             }
         }
         __syncwarp();
-    } else if (warp == 4) {
+    } else if (warp == (SPLIT ? 1 : 4)) {
         // ===== residual prefetch: TMA loads of the residual sub-tiles into the staging ring =====
         if (lane == 0 && a.epi_staged && a.has_res) {
             RingWalk rw;
@@ -651,14 +566,6 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             for (int tile = tile_first; tile < total_tiles; tile += tile_step, tw.next()) {
                 const int m_unit = tw.m_unit, n_tile = tw.n_tile;
                 const int m0 = (m_unit * NCTA + (int)rank) * kBM, n0 = n_tile * a.BN;
-                if (a.pf_dist) {                              // residual tile of a later round -> L2
-                    const int tp = tile + a.pf_dist * tile_step;
-                    if (tp < total_tiles) {
-                        const int mu = tp / a.n_tiles, nt = tp - mu * a.n_tiles;
-#pragma unroll 1
-                        for (int j = 0; j < a.n_sub; ++j) tma_prefetch_2d(&tmRes, nt * a.BN + j * a.cs, (mu * NCTA + (int)rank) * kBM);
-                    }
-                }
                 for (int j = 0; j < a.n_sub; ++j, rw.next((uint32_t)a.ring)) {
                     const uint32_t buf = rw.buf, ph = rw.ph;
                     mbar_wait(sempty0 + 8 * buf, ph ^ 1, a.dbg, 3, 300 + (int)buf);
@@ -682,7 +589,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                 for (int j = 0; j < a.n_sub; ++j, ++g, rw.next((uint32_t)a.ring)) {
                     const uint32_t buf = rw.buf, ph = rw.ph;
                     mbar_wait(sready0 + 8 * buf, ph, a.dbg, 4, 700 + (int)buf);
-                    if (!a.exp_nostore) tma_store_2d(&tmOut, stg0 + buf * stg_bytes, n0 + j * a.cs, m0);
+                    tma_store_2d(&tmOut, stg0 + buf * stg_bytes, n0 + j * a.cs, m0);
                     if (split_out) tma_store_2d(&tmOut, stg0 + buf * stg_bytes + stg_half, a.out_lo + n0 + j * a.cs, m0);
                     tma_store_commit();
                     // Recycle buffers: keep at most `srel` stores unread.  srel = ring - 2 is the latest release that
@@ -703,6 +610,78 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             tma_store_wait_all();
         }
         __syncwarp();
+    } else if (SPLIT && warp >= 4 && warp < 20) {
+        // ===== epilogue of the split mode: every finished TMEM chunk is added into fp32 register accumulators (round to
+        // nearest -- the second level of the accumulation, see the comment on split2), then the usual staged hand-over:
+        // scale/bias, LeakyReLU, residual, hi/lo split, swizzled smem sub-tile, TMA store.  Warp w owns TMEM lanes
+        // 32*(w%4).. and the 16-column group (w-8)/4 of each of the (at most two) sub-tiles =====
+        const int q = warp & 3, part = (warp - 4) >> 2;
+        const int row = q * 32 + lane;
+        const int xr = a.sub_bytes == 128 ? (row & 7) : ((row >> 1) & 3);
+        const bool active = part < (a.cs >> 4);
+        const bool two = a.n_sub > 1;
+        uint32_t accb = 0, acc_phase = 0;
+        RingWalk rw;
+        const int n_wrap = a.n_tiles * a.BN;
+        int n0 = (tile_first % a.n_tiles) * a.BN;
+        const int dn0 = (tile_step % a.n_tiles) * a.BN;
+        for (int tile = tile_first; tile < total_tiles; tile += tile_step) {
+            float s0[16], s1[16];
+#pragma unroll
+            for (int i = 0; i < 16; ++i) { s0[i] = 0.f; s1[i] = 0.f; }
+            for (int ch = 0; ch < a.n_chunks; ++ch) {
+                mbar_wait(tfull0 + 8 * accb, acc_phase, a.dbg, 2, 200 + (int)accb);
+                tc_fence_after();
+                const uint32_t tcol = tmem_base + accb * acc_stride + ((uint32_t)(q * 32) << 16) + (uint32_t)(part * 16);
+                uint32_t r0[16], r1[16];
+                if (active) {
+                    tmem_ld16(tcol, r0);
+                    if (two) tmem_ld16(tcol + (uint32_t)a.cs, r1);
+                }
+                tmem_ld_wait();
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) {                               // chunk drained into registers: the buffer goes back to the MMA warp
+                    if constexpr (CTA2) mbar_arrive_leader(tempty0 + 8 * accb); else mbar_arrive(tempty0 + 8 * accb);
+                }
+                if (active) {
+#pragma unroll
+                    for (int i = 0; i < 16; ++i) s0[i] = __fadd_rn(s0[i], __uint_as_float(r0[i]));
+                    if (two) {
+#pragma unroll
+                        for (int i = 0; i < 16; ++i) s1[i] = __fadd_rn(s1[i], __uint_as_float(r1[i]));
+                    }
+                }
+                accb ^= 1;
+                if (accb == 0) acc_phase ^= 1;
+            }
+#pragma unroll
+            for (int j = 0; j < 2; ++j) {
+                if (j < a.n_sub) {
+                    const uint32_t buf = rw.buf, ph = rw.ph;
+                    if (a.has_res) mbar_wait(sfull0 + 8 * buf, ph, a.dbg, 2, 400 + (int)buf);
+                    else mbar_wait(sempty0 + 8 * buf, ph ^ 1, a.dbg, 2, 500 + (int)buf);
+                    uint8_t* srow = gen + (stg0 - base) + buf * stg_bytes + (uint32_t)row * (uint32_t)a.sub_bytes;
+                    const int nb = n0 + j * a.cs + part * 16;
+                    if (active) {
+                        if (split_out) {
+                            epilogue16_staged_split(a, j == 0 ? s0 : s1, nb, srow, stg_half, part, xr);
+                        } else {                               // fp32 head maps: the plain staged epilogue on the summed values
+                            uint32_t rr[16];
+#pragma unroll
+                            for (int i = 0; i < 16; ++i) rr[i] = __float_as_uint(j == 0 ? s0[i] : s1[i]);
+                            epilogue16_staged(a, rr, nb, srow, part, xr);
+                        }
+                    }
+                    fence_async_smem();
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(sready0 + 8 * buf);
+                    rw.next((uint32_t)a.ring);
+                }
+            }
+            n0 += dn0;
+            if (n0 >= n_wrap) n0 -= n_wrap;
+        }
     } else if (warp >= 8 && a.epi_staged) {
         // ===== epilogue (staged): TMEM -> registers -> swizzled smem sub-tile -> TMA store =====
         // Sixteen warps: warp w reads TMEM lanes 32*(w%4).. (its rows); the four warps of a row quarter each
@@ -735,7 +714,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         const int dn0 = ((tmul * tile_step) % a.n_tiles) * a.BN;
         for (int tile = tile_begin; tile < total_tiles; tile += tmul * tile_step, ti += tmul) {
             if (issuer) YB_TRACE(2, ti, 0);
-            mbar_wait_relaxed(tfull0 + 8 * acc, acc_phase, a.dbg, 2, 200 + (int)acc, a.epi_sleep);
+            mbar_wait(tfull0 + 8 * acc, acc_phase, a.dbg, 2, 200 + (int)acc);
             tc_fence_after();
             if (issuer) YB_TRACE(2, ti, 1);
             const uint32_t taddr = tmem_base + acc * acc_stride + ((uint32_t)(q * 32) << 16);
@@ -759,10 +738,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                 }
                 uint8_t* srow = gen + (stg0 - base) + buf * stg_bytes + (uint32_t)row * (uint32_t)a.sub_bytes;
                 const int nb = n0 + j * a.cs;
-                if (active) {
-                    if (split_out) epilogue16_staged_split(a, r0, nb + part * 16, srow, stg_half, part, xr);
-                    else epilogue16_staged(a, r0, nb + part * 16, srow, part, xr);
-                }
+                if (active) epilogue16_staged(a, r0, nb + part * 16, srow, part, xr);
                 if (issuer && j == 0) YB_TRACE(3, ti, 2);
                 fence_async_smem();                           // generic-proxy smem writes -> visible to the TMA engine
                 if (issuer && j == 0) YB_TRACE(3, ti, 3);
@@ -812,13 +788,8 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                 tmem_ld16(taddr + c0, r0);
                 if (two) tmem_ld16(taddr + c0 + 16, r1);
                 tmem_ld_wait();
-                if (split_out) {
-                    epilogue16_split(a, r0, n0 + c0, valid, m, o00, W2ld);
-                    if (two) epilogue16_split(a, r1, n0 + c0 + 16, valid, m, o00, W2ld);
-                } else {
-                    epilogue16(a, r0, n0 + c0, valid, m, o00, W2ld);
-                    if (two) epilogue16(a, r1, n0 + c0 + 16, valid, m, o00, W2ld);
-                }
+                epilogue16(a, r0, n0 + c0, valid, m, o00, W2ld);
+                if (two) epilogue16(a, r1, n0 + c0 + 16, valid, m, o00, W2ld);
             }
             tc_fence_before();
             __syncwarp();
@@ -858,7 +829,6 @@ struct StemArgs {
     long M;
     int tiles;
     TcArgs epi;                             // scale, bias, leaky; staged-epilogue fields
-    int pf_dist;                            // L2 prefetch distance of the input image, in rounds of a producer group (0 = off)
     const __half* w;                        // [32][32] fp16, k = (ky*3+kx)*3 + c, zero padded
 };
 
@@ -868,10 +838,10 @@ struct StemArgs {
 __device__ __forceinline__ float stem_ld(const float* p) { return __ldg(p); }
 __device__ __forceinline__ float stem_ld(const __half* p) { return __half2float(__ldg(p)); }
 
-// V2 (YB_STEM_V2=1, written at the end of round 1 from the SASS of the V1 loops, not yet run on a GPU): same results bit
-// for bit with fewer instructions -- the interior / border decision of the gather is taken per WARP (a vote), so the fast
-// path is a uniform branch and the compiler keeps the memory descriptor in uniform registers instead of re-copying it for
-// every load; the epilogue uses packed fp32 arithmetic (fma.rn.f32x2, mul.f32x2) and LeakyReLU as max(v, 0.1 v).
+// The kernel is instruction-issue-bound, so the loops are written for instruction count: the interior / border decision of
+// the gather is taken per WARP (a vote), so the fast path is a uniform branch and the compiler keeps the memory descriptor
+// in uniform registers instead of re-copying it for every load; the epilogue uses packed fp32 arithmetic (fma.rn.f32x2,
+// mul.f32x2) and LeakyReLU as max(v, 0.1 v).  (Round 1's per-thread version: 0.266 ms at 608x608 batch 32; this one 0.231.)
 __device__ __forceinline__ float2 ffma2(float2 a, float2 b, float2 c) {
     unsigned long long ra;
     asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(ra)
@@ -886,7 +856,7 @@ __device__ __forceinline__ float2 fmul2(float2 a, float2 b) {
     return *reinterpret_cast<float2*>(&ra);
 }
 
-template <typename TIn, bool V2 = false>
+template <typename TIn>
 __global__ void __launch_bounds__(kStemThreads, 1)
 stem_tc_kernel(const __grid_constant__ CUtensorMap tmOut, const StemArgs a_in) {
     StemArgs a = a_in;
@@ -901,9 +871,9 @@ stem_tc_kernel(const __grid_constant__ CUtensorMap tmOut, const StemArgs a_in) {
     const uint32_t wsm = base + 1024;                      // weights 32 x 64 B (2 KB), swizzled
     const uint32_t stg0 = base + 4096;                     // kStemRing staging buffers
     const uint32_t stage0 = stg0 + kStemRing * STG_BYTES;
-    // V2: the warp index read through a shuffle is warp-uniform for the compiler (what cutlass::canonical_warp_idx_sync does),
+    // the warp index read through a shuffle is warp-uniform for the compiler (what cutlass::canonical_warp_idx_sync does),
     // so the role dispatch below is a uniform branch and uniform registers stay usable inside the roles
-    const int warp = V2 ? __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0) : (int)(threadIdx.x >> 5);
+    const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0);
     const int lane = threadIdx.x & 31;
 
     if (warp == 0 && lane == 0) prefetch_tmap(&tmOut);
@@ -969,84 +939,36 @@ stem_tc_kernel(const __grid_constant__ CUtensorMap tmOut, const StemArgs a_in) {
             pb += db;
         };
         auto gather = [&](float (&v)[27]) {
-            if constexpr (V2) {
-                const bool inside = m < a.M;
-                const bool interior = inside && py >= 1 && py < a.H - 1 && px >= 1 && px < a.W - 1;
-                const TIn* p = static_cast<const TIn*>(a.x) + (long)pb * img_stride + py * a.W + px;
-                if (__all_sync(0xffffffffu, interior)) {       // warp-uniform: 32 consecutive pixels of one image row
+            const bool inside = m < a.M;
+            const bool interior = inside && py >= 1 && py < a.H - 1 && px >= 1 && px < a.W - 1;
+            const TIn* p = static_cast<const TIn*>(a.x) + (long)pb * img_stride + py * a.W + px;
+            if (__all_sync(0xffffffffu, interior)) {       // warp-uniform: 32 consecutive pixels of one image row
 #pragma unroll
-                    for (int c = 0; c < 3; ++c) {
-#pragma unroll
-                        for (int ky = 0; ky < 3; ++ky) {
-                            const TIn* q = p + c * HW + (ky - 1) * a.W;
-                            v[(ky * 3 + 0) * 3 + c] = stem_ld(q - 1);
-                            v[(ky * 3 + 1) * 3 + c] = stem_ld(q);
-                            v[(ky * 3 + 2) * 3 + c] = stem_ld(q + 1);
-                        }
-                    }
-                } else {
+                for (int c = 0; c < 3; ++c) {
 #pragma unroll
                     for (int ky = 0; ky < 3; ++ky) {
-                        const int iy = py + ky - 1;
-                        const bool oky = inside && iy >= 0 && iy < a.H;
-#pragma unroll
-                        for (int kx = 0; kx < 3; ++kx) {
-                            const int ix = px + kx - 1;
-                            const bool ok = oky && ix >= 0 && ix < a.W;
-#pragma unroll
-                            for (int c = 0; c < 3; ++c)
-                                v[(ky * 3 + kx) * 3 + c] = ok ? stem_ld(p + c * HW + (ky - 1) * a.W + (kx - 1)) : 0.f;
-                        }
-                    }
-                }
-                return;
-            }
-            if (m < a.M) {
-                const TIn* p = static_cast<const TIn*>(a.x) + (long)pb * img_stride + py * a.W + px;
-                if (py >= 1 && py < a.H - 1 && px >= 1 && px < a.W - 1) {
-#pragma unroll
-                    for (int c = 0; c < 3; ++c) {
-#pragma unroll
-                        for (int ky = 0; ky < 3; ++ky) {
-                            const TIn* q = p + c * HW + (ky - 1) * a.W;
-                            v[(ky * 3 + 0) * 3 + c] = stem_ld(q - 1);
-                            v[(ky * 3 + 1) * 3 + c] = stem_ld(q);
-                            v[(ky * 3 + 2) * 3 + c] = stem_ld(q + 1);
-                        }
-                    }
-                } else {
-#pragma unroll
-                    for (int ky = 0; ky < 3; ++ky) {
-                        const int iy = py + ky - 1;
-                        const bool oky = iy >= 0 && iy < a.H;
-#pragma unroll
-                        for (int kx = 0; kx < 3; ++kx) {
-                            const int ix = px + kx - 1;
-                            const bool ok = oky && ix >= 0 && ix < a.W;
-#pragma unroll
-                            for (int c = 0; c < 3; ++c)
-                                v[(ky * 3 + kx) * 3 + c] = ok ? stem_ld(p + c * HW + (ky - 1) * a.W + (kx - 1)) : 0.f;
-                        }
+                        const TIn* q = p + c * HW + (ky - 1) * a.W;
+                        v[(ky * 3 + 0) * 3 + c] = stem_ld(q - 1);
+                        v[(ky * 3 + 1) * 3 + c] = stem_ld(q);
+                        v[(ky * 3 + 2) * 3 + c] = stem_ld(q + 1);
                     }
                 }
             } else {
 #pragma unroll
-                for (int k = 0; k < 27; ++k) v[k] = 0.f;
+                for (int ky = 0; ky < 3; ++ky) {
+                    const int iy = py + ky - 1;
+                    const bool oky = inside && iy >= 0 && iy < a.H;
+#pragma unroll
+                    for (int kx = 0; kx < 3; ++kx) {
+                        const int ix = px + kx - 1;
+                        const bool ok = oky && ix >= 0 && ix < a.W;
+#pragma unroll
+                        for (int c = 0; c < 3; ++c)
+                            v[(ky * 3 + kx) * 3 + c] = ok ? stem_ld(p + c * HW + (ky - 1) * a.W + (kx - 1)) : 0.f;
+                    }
+                }
             }
         };
-        // L2 prefetch of this thread's pixel pf_dist rounds ahead (its three channel values of the centre row; the rows
-        // above / below are the centre rows of tiles that other CTAs gather at about the same time).  With one tile of
-        // loads in flight per producer group the gather waits out a DRAM round trip per tile (~2 300 cycles: 142 MB in
-        // 0.25 ms is what 148 SMs x 3 groups x 1.5 KB per ~1.2 us amounts to); prefetched, it waits for L2.
-        long m2 = m;
-        int pb2 = pb, py2 = py, px2 = px;
-        auto advance2 = [&]() {
-            m2 += dm;
-            px2 += dx; if (px2 >= a.W) { px2 -= a.W; ++py2; }
-            py2 += dy; if (py2 >= a.H) { py2 -= a.H; ++pb2; }
-            pb2 += db;
-        };
-        for (int k = 0; k < a.pf_dist; ++k) advance2();
         float v[27];
         if (tile < a.tiles) gather(v);
         while (tile < a.tiles) {
@@ -1058,15 +980,6 @@ stem_tc_kernel(const __grid_constant__ CUtensorMap tmOut, const StemArgs a_in) {
             h[14] = __floats2half2_rn(0.f, 0.f);
             h[15] = h[14];
             advance();
-            if (a.pf_dist) {
-                advance2();
-                if (m2 < a.M) {
-                    const TIn* p2 = static_cast<const TIn*>(a.x) + (long)pb2 * img_stride + py2 * a.W + px2;
-                    asm volatile("prefetch.global.L2 [%0];" ::"l"(p2));
-                    asm volatile("prefetch.global.L2 [%0];" ::"l"(p2 + HW));
-                    asm volatile("prefetch.global.L2 [%0];" ::"l"(p2 + 2 * HW));
-                }
-            }
             gather(v);                                     // next tile's loads in flight (zeros past the end)
             const int stage = i % kStemStages;
             const uint32_t phase = (uint32_t)(i / kStemStages) & 1u;
@@ -1149,24 +1062,16 @@ stem_tc_kernel(const __grid_constant__ CUtensorMap tmOut, const StemArgs a_in) {
                 const float4 s0 = sc4[2 * c], s1 = sc4[2 * c + 1], b0 = bi4[2 * c], b1 = bi4[2 * c + 1];
                 uint4 pk;
                 __half2* ph2 = reinterpret_cast<__half2*>(&pk);
-                if constexpr (V2) {
-                    const float2 tenth = make_float2(kLeaky, kLeaky);
-                    const float2 sc[4] = {make_float2(s0.x, s0.y), make_float2(s0.z, s0.w), make_float2(s1.x, s1.y), make_float2(s1.z, s1.w)};
-                    const float2 bi[4] = {make_float2(b0.x, b0.y), make_float2(b0.z, b0.w), make_float2(b1.x, b1.y), make_float2(b1.z, b1.w)};
+                const float2 tenth = make_float2(kLeaky, kLeaky);
+                const float2 sc[4] = {make_float2(s0.x, s0.y), make_float2(s0.z, s0.w), make_float2(s1.x, s1.y), make_float2(s1.z, s1.w)};
+                const float2 bi[4] = {make_float2(b0.x, b0.y), make_float2(b0.z, b0.w), make_float2(b1.x, b1.y), make_float2(b1.z, b1.w)};
 #pragma unroll
-                    for (int e = 0; e < 4; ++e) {
-                        const float2 acc = make_float2(__uint_as_float(rr[j0 + 2 * e]), __uint_as_float(rr[j0 + 2 * e + 1]));
-                        const float2 y = ffma2(acc, sc[e], bi[e]);
-                        const float2 t = fmul2(y, tenth);
-                        ph2[e] = __floats2half2_rn(fmaxf(y.x, t.x), fmaxf(y.y, t.y));     // LeakyReLU(0.1) = max(v, 0.1 v)
-                    }
-                    *reinterpret_cast<uint4*>(srow + ((c ^ xr) << 4)) = pk;
-                    continue;
+                for (int e = 0; e < 4; ++e) {
+                    const float2 acc = make_float2(__uint_as_float(rr[j0 + 2 * e]), __uint_as_float(rr[j0 + 2 * e + 1]));
+                    const float2 y = ffma2(acc, sc[e], bi[e]);
+                    const float2 t = fmul2(y, tenth);
+                    ph2[e] = __floats2half2_rn(fmaxf(y.x, t.x), fmaxf(y.y, t.y));     // LeakyReLU(0.1) = max(v, 0.1 v)
                 }
-                ph2[0] = __floats2half2_rn(leaky(fmaf(__uint_as_float(rr[j0 + 0]), s0.x, b0.x)), leaky(fmaf(__uint_as_float(rr[j0 + 1]), s0.y, b0.y)));
-                ph2[1] = __floats2half2_rn(leaky(fmaf(__uint_as_float(rr[j0 + 2]), s0.z, b0.z)), leaky(fmaf(__uint_as_float(rr[j0 + 3]), s0.w, b0.w)));
-                ph2[2] = __floats2half2_rn(leaky(fmaf(__uint_as_float(rr[j0 + 4]), s1.x, b1.x)), leaky(fmaf(__uint_as_float(rr[j0 + 5]), s1.y, b1.y)));
-                ph2[3] = __floats2half2_rn(leaky(fmaf(__uint_as_float(rr[j0 + 6]), s1.z, b1.z)), leaky(fmaf(__uint_as_float(rr[j0 + 7]), s1.w, b1.w)));
                 *reinterpret_cast<uint4*>(srow + ((c ^ xr) << 4)) = pk;
             }
             fence_async_smem();
@@ -1227,7 +1132,8 @@ std::string tc_make_plan(TcPlan& p, const ConvArgs& a, const __half* w16, int co
     p.cin_blocks = a.Cin / bke;
     p.split = a.split;
     p.num_kblocks = a.ks * a.ks * p.cin_blocks * (a.split ? 3 : 1);   // split mode: three sections per tap (conv_tc_kernel)
-    if (a.split && K != 3 * a.ks * a.ks * a.Cin) return "split mode expects the [tap][wh|wl|wh][Cin] weight packing";
+    if (a.split && K != 3 * a.ks * a.ks * a.Cin) return "split mode expects the [tap][channel block][wh|wl|wh] weight packing";
+    if (a.split && a.upsample) return "split mode: the upsample layers run as a plain convolution followed by a copy kernel";
     const bool split_out = a.split && !a.out_f32;
     p.M = (long)a.B * a.Ho * a.Wo;
     p.m_tiles = (int)((p.M + kBM - 1) / kBM);
@@ -1235,7 +1141,10 @@ std::string tc_make_plan(TcPlan& p, const ConvArgs& a, const __half* w16, int co
     // the cost of a candidate is (persistent waves) x (128 + BN); measured in profiles/r01_layer_sweep_v3.txt
     int best_bn = 0;
     double best_cost = 0;
-    for (int bn = std::min(cout_pad, 256); bn >= 16; bn -= 16) {
+    // split mode: a thread of the epilogue keeps its share of the tile in registers (two-level accumulation), at most
+    // 32 values: 128 columns of fp16 pairs (four warps per 64-column sub-tile) or 64 columns of fp32 (two per 32-column one)
+    const int bn_max = a.split ? (a.out_f32 ? 64 : 128) : 256;
+    for (int bn = std::min(cout_pad, bn_max); bn >= 16; bn -= 16) {
         if (cout_pad % bn) continue;
         if (bn < 64 && bn != cout_pad) break;
         const long tiles = (long)p.m_tiles * (cout_pad / bn);
@@ -1243,11 +1152,17 @@ std::string tc_make_plan(TcPlan& p, const ConvArgs& a, const __half* w16, int co
         const double cost = (double)waves * (128 + bn);
         if (!best_bn || cost < best_cost) { best_bn = bn; best_cost = cost; }
     }
+    if (!best_bn && a.split) {
+        // a head whose padded width has no divisor in [64 columns of fp32 ..]: e.g. 20 classes, 75 channels padded to 80 ->
+        // 16-column tiles (one 64-byte fp32 sub-tile each)
+        for (int bn = std::min(cout_pad, bn_max); bn >= 16 && !best_bn; bn -= 16)
+            if (cout_pad % bn == 0 && (bn * (a.out_f32 ? 4 : 2)) % 64 == 0) best_bn = bn;
+    }
     if (!best_bn) return "no valid tile width for cout_pad=" + std::to_string(cout_pad);
     p.BN = best_bn;
-    if (const char* e = getenv("YB_TC_BN")) {
+    if (const char* e = tune_env("YB_TC_BN")) {
         const int bn = atoi(e);
-        if (bn >= 16 && bn <= 256 && bn % 16 == 0 && cout_pad % bn == 0) p.BN = bn;
+        if (bn >= 16 && bn <= bn_max && bn % 16 == 0 && cout_pad % bn == 0) p.BN = bn;
     }
     p.n_tiles = cout_pad / p.BN;
     // CTA pairs (cta_group::2): 256-row UMMA tiles, each CTA stages only half of the weight rows, which
@@ -1261,10 +1176,10 @@ std::string tc_make_plan(TcPlan& p, const ConvArgs& a, const __half* w16, int co
         const size_t slot_one = ((size_t)p.BN * p.swz + 1023) & ~(size_t)1023, slot_half = ((size_t)(p.BN / 2) * p.swz + 1023) & ~(size_t)1023;
         pair128 = p.swz == 128 && p.BN == 128 && a.ks == 3 && slot_one * p.num_kblocks > 96 * 1024 &&
                   slot_half * p.num_kblocks <= 96 * 1024 && p.m_tiles > 4 * num_sms;
-        if (const char* e = getenv("YB_TC_PAIR128")) pair128 = pair128 && atoi(e) != 0;
+        if (const char* e = tune_env("YB_TC_PAIR128")) pair128 = pair128 && atoi(e) != 0;
     }
-    p.cta2 = p.swz == 128 && (p.BN == 256 || pair128) && !a.upsample && p.m_tiles >= 4 && num_sms % 2 == 0;
-    if (const char* e = getenv("YB_TC_CTA2")) p.cta2 = p.cta2 && atoi(e) != 0;
+    p.cta2 = p.swz == 128 && (p.BN == 256 || pair128 || (a.split && p.BN == 128)) && !a.upsample && p.m_tiles >= 4 && num_sms % 2 == 0;
+    if (const char* e = tune_env("YB_TC_CTA2")) p.cta2 = p.cta2 && atoi(e) != 0;
     const int ncta = p.cta2 ? 2 : 1;
     if (p.cta2) p.m_tiles = (p.m_tiles + 1) / 2;            // 256-row units from here on
     int tc = 32;
@@ -1280,11 +1195,12 @@ std::string tc_make_plan(TcPlan& p, const ConvArgs& a, const __half* w16, int co
     p.cs = p.sub_bytes / esz;
     p.n_sub = p.epi_staged ? p.BN / p.cs : 0;
     if (p.epi_staged) p.ring = a.res && !split_out ? 4 : 2;        // split mode: a slot holds a hi and a lo sub-tile
-    if (const char* e = getenv("YB_TC_RING")) if (p.epi_staged) p.ring = std::max(2, std::min(kMaxRing, atoi(e)));
+    if (const char* e = tune_env("YB_TC_RING")) if (p.epi_staged) p.ring = std::max(2, std::min(kMaxRing, atoi(e)));
     // 32-column sub-tiles (Cout = 32 in fp16, the fp32 head maps) keep only eight of the sixteen epilogue warps busy:
     // the two halves then work on alternate sub-tiles, each with its own slot of a four-deep ring
-    p.epi_split = p.epi_staged && p.cs == 32 && (p.n_sub == 1 || p.n_sub % 2 == 0) && !split_out;
-    if (const char* e = getenv("YB_TC_EPISPLIT")) p.epi_split = p.epi_split && atoi(e) != 0;
+    p.epi_split = p.epi_staged && p.cs == 32 && (p.n_sub == 1 || p.n_sub % 2 == 0) && !a.split;
+    if (a.split && (!p.epi_staged || p.n_sub > 2)) return "split mode: tile does not fit the register accumulators";
+    if (const char* e = tune_env("YB_TC_EPISPLIT")) p.epi_split = p.epi_split && atoi(e) != 0;
     if (p.epi_split) p.ring = 4;
     const size_t stg_bytes = ((size_t)kBM * p.sub_bytes * (split_out ? 2 : 1) + 1023) & ~(size_t)1023;
     const size_t ring_bytes = p.epi_staged ? p.ring * stg_bytes : 0;
@@ -1295,17 +1211,13 @@ std::string tc_make_plan(TcPlan& p, const ConvArgs& a, const __half* w16, int co
     const size_t bres_bytes = b_slot * p.num_kblocks;
     p.b_resident = (!p.cta2 || p.BN == 128) && bres_bytes <= 96 * 1024 && (p.grid / ncta) % p.n_tiles == 0 &&
                    p.m_tiles > 2 * num_sms / ncta;
-    if (const char* e = getenv("YB_TC_BRES")) p.b_resident = p.b_resident && atoi(e) != 0;
-    // Experiments kept behind overrides (profiles/r01b_sweep_prefetch.txt): an L2 prefetch of the A operand
-    // pf_dist tiles ahead makes the memory-bound layers SLOWER (32->64 s2: 0.25 -> 0.30 ms; the TMA request
-    // path, not DRAM latency, is what limits them), touching the weights before griddepcontrol.wait and the
-    // earlier staging-buffer release change nothing measurable.  Defaults = the validated behaviour.
-    p.pf_dist = 0;
-    if (const char* e = getenv("YB_TC_PF")) p.pf_dist = std::max(0, std::min(16, atoi(e)));
+    if (const char* e = tune_env("YB_TC_BRES")) p.b_resident = p.b_resident && atoi(e) != 0;
+    // (Negative results of rounds 1-2, removed from the code and kept as measurements under profiles/: an L2 prefetch of
+    // the A operand some tiles ahead makes the memory-bound layers SLOWER -- the TMA request path, not DRAM latency,
+    // limits them; touching the weights before griddepcontrol.wait, an L2 persistence window over layer outputs and a
+    // channel-blocked activation layout change nothing or lose.)
     p.srel = 1;
-    if (const char* e = getenv("YB_TC_SREL")) p.srel = std::max(0, std::min(std::min(2, p.ring - 1), atoi(e)));
-    p.b_early = 0;
-    if (const char* e = getenv("YB_TC_BEARLY")) p.b_early = atoi(e) != 0;
+    if (const char* e = tune_env("YB_TC_SREL")) p.srel = std::max(0, std::min(std::min(2, p.ring - 1), atoi(e)));
     const size_t kb_bytes = (size_t)kBM * p.swz + (p.b_resident ? 0 : b_slot);
     p.tab_bytes = (int)(((size_t)2 * cout_pad * sizeof(float) + 1023) & ~(size_t)1023);
     const size_t fixed = kSmemHeader + 1024 + p.tab_bytes + ring_bytes + (p.b_resident ? bres_bytes : 0);
@@ -1320,7 +1232,9 @@ std::string tc_make_plan(TcPlan& p, const ConvArgs& a, const __half* w16, int co
         // trip per tile (measured on the 32->64 stride-2 layer: 0.286 -> 0.247 ms, profiles/README.md)
         if (p.b_resident && !a.res && p.num_kblocks <= 9 && fixed + 2 * p.num_kblocks * kb_bytes <= kSmemBudget)
             p.kps = p.num_kblocks;
-        if (const char* e = getenv("YB_TC_KPS")) { const int c = atoi(e); if (c >= 1 && p.num_kblocks % c == 0 && c * kb_bytes <= 96 * 1024) p.kps = c; }
+        if (const char* e = tune_env("YB_TC_KPS")) { const int c = atoi(e); if (c >= 1 && p.num_kblocks % c == 0 && c * kb_bytes <= 96 * 1024) p.kps = c; }
+        // split mode: a TMEM chunk is a whole number of (tap, channel block) triples and of pipeline stages
+        if (a.split) p.kps = 3 * kb_bytes <= 48 * 1024 ? 3 : 1;
     }
     // a resident slab next to a four-deep residual ring can leave room for fewer than two multi-k-block stages
     while (p.kps > 1 && (kSmemBudget - fixed) / (kb_bytes * p.kps) < 2) {
@@ -1328,11 +1242,20 @@ std::string tc_make_plan(TcPlan& p, const ConvArgs& a, const __half* w16, int co
         while (c > 1 && p.num_kblocks % c) --c;
         p.kps = c;
     }
+    if (a.split && p.kps != 3) p.kps = 1;
     const size_t stage_bytes = kb_bytes * p.kps;
     p.stages = (int)std::min<size_t>(kMaxStages, (kSmemBudget - fixed) / stage_bytes);
-    if (const char* e = getenv("YB_TC_STAGES")) p.stages = std::max(2, std::min(p.stages, atoi(e)));
+    if (const char* e = tune_env("YB_TC_STAGES")) p.stages = std::max(2, std::min(p.stages, atoi(e)));
     if (p.stages < 2) return "not enough shared memory for two pipeline stages";
     p.smem = fixed + p.stages * stage_bytes;
+    if (a.split) {
+        // triples per chunk: one (12 MMAs of K = 16; 6 with 32-channel k-blocks, where two keep the chunk long enough
+        // for the register pass of the previous one to hide behind it)
+        int triples = p.swz == 64 ? 2 : 1;
+        if (const char* e = tune_env("YB_SPLIT_CHUNK")) triples = std::max(1, std::min(64, atoi(e)));
+        p.chunk_iters = triples * 3 / p.kps;
+        p.n_chunks = (p.num_kblocks / p.kps + p.chunk_iters - 1) / p.chunk_iters;
+    }
 
     const CUtensorMapSwizzle swz = p.swz == 128 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B;
     // B: weights [cout_pad][K] fp16, K contiguous; box = one k-block x BN rows
@@ -1346,26 +1269,10 @@ std::string tc_make_plan(TcPlan& p, const ConvArgs& a, const __half* w16, int co
                                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
         if (r != CUDA_SUCCESS) return cu_err("cuTensorMapEncodeTiled(weights)", r);
     }
-    p.exp_tiled = !a.split && a.ks == 3 && getenv("YB_TC_EXP_TILED") && atoi(getenv("YB_TC_EXP_TILED")) != 0;
-    if (p.exp_tiled) {
-        static bool warned = false;
-        if (!warned) fprintf(stderr, "[yolo_b200] YB_TC_EXP_TILED is a TIMING experiment: 3x3 convolution results are WRONG\n");
-        warned = true;
-    }
-    p.exp_blocked = !a.split && a.ks == 1 && p.swz == 128 && a.in_ld == a.Cin && getenv("YB_TC_EXP_BLOCKED") && atoi(getenv("YB_TC_EXP_BLOCKED")) != 0;
-    if (p.exp_blocked) {
-        static bool warned = false;
-        if (!warned) fprintf(stderr, "[yolo_b200] YB_TC_EXP_BLOCKED is a TIMING experiment: 1x1 convolution results are WRONG\n");
-        warned = true;
-    }
-    if (a.ks == 1 || p.exp_tiled) {
+    if (a.ks == 1) {
         // A: [M][Cin] with pixel pitch in_ld; rows past M are zero-filled
         cuuint64_t dims[2] = {(cuuint64_t)(a.split ? a.in_lo + a.Cin : a.Cin), (cuuint64_t)p.M};
         cuuint64_t strides[1] = {(cuuint64_t)a.in_ld * sizeof(__half)};
-        if (p.exp_blocked) {        // the same bytes read as [Cin/64][M][64]: rows of 128 bytes, Cin/64 * M of them
-            dims[0] = 64; dims[1] = (cuuint64_t)p.M * (a.Cin / 64);
-            strides[0] = 128;
-        }
         cuuint32_t box[2] = {(cuuint32_t)bke, (cuuint32_t)kBM};
         cuuint32_t es[2] = {1, 1};
         CUresult r = g_encode_tiled(&p.tmA, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, const_cast<void*>(a.in), dims, strides, box, es,
@@ -1445,27 +1352,18 @@ cudaError_t stem_tc_launch(const StemTcPlan& p, const void* x, int in_f16, int B
                            const float* bias, int* dbg, cudaStream_t s) {
     StemArgs a{};
     a.x = x; a.B = B; a.H = H; a.W = W; a.M = p.M; a.tiles = p.tiles; a.w = w16;
-    {
-        static const int pf = getenv("YB_STEM_PF") ? std::max(0, std::min(64, atoi(getenv("YB_STEM_PF")))) : 0;
-        a.pf_dist = pf;
-    }
     a.epi.scale = scale; a.epi.bias = bias; a.epi.leaky = 1; a.epi.out_f32 = 0; a.epi.has_res = 0; a.epi.dbg = dbg;
     static PerDeviceOnce attr_once;
     {
         cudaError_t e = attr_once.run([] {
             cudaError_t r = cudaFuncSetAttribute(stem_tc_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, 128 * 1024);
             if (r == cudaSuccess) r = cudaFuncSetAttribute(stem_tc_kernel<__half>, cudaFuncAttributeMaxDynamicSharedMemorySize, 128 * 1024);
-            if (r == cudaSuccess) {     // opt-in instantiations: best effort, a failure here must not take the validated path down
-                cudaFuncSetAttribute(stem_tc_kernel<float, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 128 * 1024);
-                cudaFuncSetAttribute(stem_tc_kernel<__half, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 128 * 1024);
-                cudaGetLastError();
-            }
             return r;
         });
         if (e != cudaSuccess) return e;
     }
     {
-        static const bool pdl = !(getenv("YB_TC_PDL") && atoi(getenv("YB_TC_PDL")) == 0);
+        static const bool pdl = !(tune_env("YB_TC_PDL") && atoi(tune_env("YB_TC_PDL")) == 0);
         cudaLaunchConfig_t cfg{};
         cfg.gridDim = dim3(p.grid);
         cfg.blockDim = dim3(kStemThreads);
@@ -1476,12 +1374,8 @@ cudaError_t stem_tc_launch(const StemTcPlan& p, const void* x, int in_f16, int B
         attr[0].val.programmaticStreamSerializationAllowed = 1;
         cfg.attrs = attr;
         cfg.numAttrs = pdl ? 1 : 0;
-        static const bool v2 = getenv("YB_STEM_V2") && atoi(getenv("YB_STEM_V2")) != 0;
-        cudaError_t e;
-        if (v2) e = in_f16 ? cudaLaunchKernelEx(&cfg, stem_tc_kernel<__half, true>, p.tmOut, a)
-                           : cudaLaunchKernelEx(&cfg, stem_tc_kernel<float, true>, p.tmOut, a);
-        else e = in_f16 ? cudaLaunchKernelEx(&cfg, stem_tc_kernel<__half>, p.tmOut, a)
-                        : cudaLaunchKernelEx(&cfg, stem_tc_kernel<float>, p.tmOut, a);
+        const cudaError_t e = in_f16 ? cudaLaunchKernelEx(&cfg, stem_tc_kernel<__half>, p.tmOut, a)
+                                     : cudaLaunchKernelEx(&cfg, stem_tc_kernel<float>, p.tmOut, a);
         if (e != cudaSuccess) return e;
     }
     return cudaGetLastError();
@@ -1489,11 +1383,14 @@ cudaError_t stem_tc_launch(const StemTcPlan& p, const void* x, int in_f16, int B
 
 cudaError_t tc_launch(const TcPlan& p, const ConvArgs& a, int* dbg, cudaStream_t s) {
     TcArgs t;
+    t.trace = nullptr;
+#ifdef YB_EXPERIMENTS
     static long long* trace_dev = nullptr;
-    static const bool trace_on = getenv("YB_TC_TRACE") && atoi(getenv("YB_TC_TRACE")) != 0;
+    static const bool trace_on = tune_env("YB_TC_TRACE") && atoi(tune_env("YB_TC_TRACE")) != 0;
     if (trace_on && !trace_dev) cudaMalloc(&trace_dev, 6 * 64 * 4 * sizeof(long long));
     if (trace_on) cudaMemsetAsync(trace_dev, 0, 6 * 64 * 4 * sizeof(long long), s);
     t.trace = trace_on ? trace_dev : nullptr;
+#endif
     t.M = p.M;
     t.Ho = a.Ho; t.Wo = a.Wo; t.HoWo = a.Ho * a.Wo;
     t.ks = a.ks; t.stride = a.stride; t.pad = a.pad;
@@ -1509,26 +1406,11 @@ cudaError_t tc_launch(const TcPlan& p, const ConvArgs& a, int* dbg, cudaStream_t
     t.epi_staged = p.epi_staged; t.ring = p.ring; t.sub_bytes = p.sub_bytes; t.cs = p.cs; t.n_sub = p.n_sub;
     t.has_res = a.res != nullptr;
     t.b_resident = p.b_resident;
-    t.pf_dist = p.pf_dist;
-    t.b_early = p.b_early;
     t.srel = p.srel;
-    {
-        static const int epi_sleep = getenv("YB_TC_EPI_SLEEP") ? std::max(0, std::min(2000, atoi(getenv("YB_TC_EPI_SLEEP")))) : 0;
-        // only where the main loop of a tile is long enough for the back-off not to matter (>= 8 k-blocks)
-        t.epi_sleep = p.num_kblocks >= 8 ? epi_sleep : 0;
-    }
-    t.exp_tiled = p.exp_tiled;
     t.epi_split = p.epi_split;
     t.a_lo = (int)a.in_lo; t.out_lo = (int)a.out_lo; t.res_lo = (int)a.res_lo;
     t.split_out = p.split && !a.out_f32;
-    {
-        static const int nostore = [] {
-            const int v = getenv("YB_TC_EXP_NOSTORE") ? atoi(getenv("YB_TC_EXP_NOSTORE")) : 0;
-            if (v) fprintf(stderr, "[yolo_b200] YB_TC_EXP_NOSTORE is a TIMING experiment: convolution outputs are NOT written\n");
-            return v;
-        }();
-        t.exp_nostore = nostore;
-    }
+    t.chunk_iters = p.chunk_iters; t.n_chunks = p.n_chunks;
     t.dbg = dbg;
     static PerDeviceOnce attr_once;
     {
@@ -1536,31 +1418,23 @@ cudaError_t tc_launch(const TcPlan& p, const ConvArgs& a, int* dbg, cudaStream_t
             cudaError_t r = cudaFuncSetAttribute(conv_tc_kernel<128, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBudget);
             if (r == cudaSuccess) r = cudaFuncSetAttribute(conv_tc_kernel<64, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBudget);
             if (r == cudaSuccess) r = cudaFuncSetAttribute(conv_tc_kernel<128, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBudget);
-            if (r == cudaSuccess) {     // experiment / opt-in instantiations: best effort, must not take the validated path down
-                cudaFuncSetAttribute(conv_tc_kernel<128, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBudget);
-                cudaFuncSetAttribute(conv_tc_kernel<128, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBudget);
-                cudaFuncSetAttribute(conv_tc_kernel<128, false, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBudget);
-                cudaFuncSetAttribute(conv_tc_kernel<64, false, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBudget);
-                cudaFuncSetAttribute(conv_tc_kernel<128, true, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBudget);
-                cudaGetLastError();
-            }
             if (r == cudaSuccess) {     // split mode (YB_MODE_FP32_TC)
-                r = cudaFuncSetAttribute(conv_tc_kernel<128, false, false, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBudget);
-                if (r == cudaSuccess) r = cudaFuncSetAttribute(conv_tc_kernel<64, false, false, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBudget);
-                if (r == cudaSuccess) r = cudaFuncSetAttribute(conv_tc_kernel<128, true, false, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBudget);
+                r = cudaFuncSetAttribute(conv_tc_kernel<128, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBudget);
+                if (r == cudaSuccess) r = cudaFuncSetAttribute(conv_tc_kernel<64, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBudget);
+                if (r == cudaSuccess) r = cudaFuncSetAttribute(conv_tc_kernel<128, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBudget);
             }
             return r;
         });
         if (e != cudaSuccess) return e;
     }
     {
-        static const bool pdl = !(getenv("YB_TC_PDL") && atoi(getenv("YB_TC_PDL")) == 0);
+        static const bool pdl = !(tune_env("YB_TC_PDL") && atoi(tune_env("YB_TC_PDL")) == 0);
         cudaLaunchConfig_t cfg{};
         cfg.gridDim = dim3(p.grid);
-        cfg.blockDim = dim3(kThreads);
+        cfg.blockDim = dim3(p.split ? kThreadsSplit : kThreads);
         cfg.dynamicSmemBytes = p.smem;
         cfg.stream = s;
-        cudaLaunchAttribute attr[3];
+        cudaLaunchAttribute attr[2];
         int na = 0;
         if (pdl) {
             attr[na].id = cudaLaunchAttributeProgrammaticStreamSerialization;
@@ -1574,29 +1448,20 @@ cudaError_t tc_launch(const TcPlan& p, const ConvArgs& a, int* dbg, cudaStream_t
             attr[na].val.clusterDim.z = 1;
             ++na;
         }
-        // experiment (off unless YB_L2_PERSIST is set): keep this layer's output in L2 for its consumer
-        if (l2_persist_window(a.out, (size_t)p.M * (a.upsample ? 4 : 1) * (size_t)a.out_ld * (a.out_f32 ? 4 : 2), &attr[na])) ++na;
         cfg.attrs = attr;
         cfg.numAttrs = na;
         cudaError_t e;
-        static const bool uw = getenv("YB_TC_UW") && atoi(getenv("YB_TC_UW")) != 0;
         if (p.split) {
-            if (p.cta2) e = cudaLaunchKernelEx(&cfg, conv_tc_kernel<128, true, false, false, true>, p.tmA, p.tmB, p.tmOut, p.tmRes, t);
-            else if (p.swz == 128) e = cudaLaunchKernelEx(&cfg, conv_tc_kernel<128, false, false, false, true>, p.tmA, p.tmB, p.tmOut, p.tmRes, t);
-            else e = cudaLaunchKernelEx(&cfg, conv_tc_kernel<64, false, false, false, true>, p.tmA, p.tmB, p.tmOut, p.tmRes, t);
-        } else
-        if (uw && !p.exp_blocked) {
-            if (p.cta2) e = cudaLaunchKernelEx(&cfg, conv_tc_kernel<128, true, false, true>, p.tmA, p.tmB, p.tmOut, p.tmRes, t);
-            else if (p.swz == 128) e = cudaLaunchKernelEx(&cfg, conv_tc_kernel<128, false, false, true>, p.tmA, p.tmB, p.tmOut, p.tmRes, t);
-            else e = cudaLaunchKernelEx(&cfg, conv_tc_kernel<64, false, false, true>, p.tmA, p.tmB, p.tmOut, p.tmRes, t);
-        } else
-        if (p.exp_blocked && p.cta2) e = cudaLaunchKernelEx(&cfg, conv_tc_kernel<128, true, true>, p.tmA, p.tmB, p.tmOut, p.tmRes, t);
-        else if (p.exp_blocked) e = cudaLaunchKernelEx(&cfg, conv_tc_kernel<128, false, true>, p.tmA, p.tmB, p.tmOut, p.tmRes, t);
+            if (p.cta2) e = cudaLaunchKernelEx(&cfg, conv_tc_kernel<128, true, true>, p.tmA, p.tmB, p.tmOut, p.tmRes, t);
+            else if (p.swz == 128) e = cudaLaunchKernelEx(&cfg, conv_tc_kernel<128, false, true>, p.tmA, p.tmB, p.tmOut, p.tmRes, t);
+            else e = cudaLaunchKernelEx(&cfg, conv_tc_kernel<64, false, true>, p.tmA, p.tmB, p.tmOut, p.tmRes, t);
+        }
         else if (p.cta2) e = cudaLaunchKernelEx(&cfg, conv_tc_kernel<128, true>, p.tmA, p.tmB, p.tmOut, p.tmRes, t);
         else if (p.swz == 128) e = cudaLaunchKernelEx(&cfg, conv_tc_kernel<128, false>, p.tmA, p.tmB, p.tmOut, p.tmRes, t);
         else e = cudaLaunchKernelEx(&cfg, conv_tc_kernel<64, false>, p.tmA, p.tmB, p.tmOut, p.tmRes, t);
         if (e != cudaSuccess) return e;
     }
+#ifdef YB_EXPERIMENTS
     if (trace_on) {                       // debugging aid: dump CTA 0's per-tile time line (cycles)
         static int dumps = 0;
         cudaStreamSynchronize(s);
@@ -1624,6 +1489,7 @@ cudaError_t tc_launch(const TcPlan& p, const ConvArgs& a, int* dbg, cudaStream_t
                         h[(4 * 64 + i) * 4] - t0);
         }
     }
+#endif
     return cudaGetLastError();
 }
 

@@ -403,11 +403,24 @@ cudaError_t launch_decode_cells(const DecodeScale sc[3], int B, int attrs, int n
     const size_t smem = (size_t)kFusedWarps * ch_pad * sizeof(float);
     const long blocks_needed = (P.cells_before[3] + kFusedWarps - 1) / kFusedWarps;
     const unsigned grid = (unsigned)std::min<long>(blocks_needed, (long)num_sms * 4);
+    if (smem > 48 * 1024) {        // more than ~500 classes: the cells of a block no longer fit the default dynamic smem limit
+        if (smem > 128 * 1024) return cudaErrorInvalidValue;
+        static PerDeviceOnce attr_once;
+        cudaError_t e = attr_once.run([] {
+            cudaError_t r = cudaFuncSetAttribute(decode_cells_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 128 * 1024);
+            if (r == cudaSuccess) r = cudaFuncSetAttribute(decode_cells_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 128 * 1024);
+            if (r == cudaSuccess) r = cudaFuncSetAttribute(decode_cells_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 128 * 1024);
+            if (r == cudaSuccess) r = cudaFuncSetAttribute(score_cells_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 128 * 1024);
+            if (r == cudaSuccess) r = cudaFuncSetAttribute(score_list_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 128 * 1024);
+            return r;
+        });
+        if (e != cudaSuccess) return e;
+    }
     if (mode == 1) decode_cells_kernel<true, false><<<grid, kFusedWarps * 32, smem, s>>>(P, det, thr, rowcount, rowcand, ch_pad);
     else if (mode == 2) {
         // YB_SCORE_MODE: 0 one cell per warp at a time, everything decoded; 1 objectness-first in one kernel;
         // 2 (default) objectness probe -> live-cell list -> scoring kernel over the list
-        static const int score_mode = getenv("YB_SCORE_MODE") ? atoi(getenv("YB_SCORE_MODE")) : 2;
+        static const int score_mode = tune_env("YB_SCORE_MODE") ? atoi(tune_env("YB_SCORE_MODE")) : 2;
         const long cells = P.cells_before[3];
         const long groups = (cells + 31) / 32;
         const unsigned grid2 = (unsigned)std::min<long>((groups + kFusedWarps - 1) / kFusedWarps, (long)num_sms * 4);

@@ -31,8 +31,8 @@ struct Op {
     TcPlan tc;
     HaloPlan halo;
     StemTcPlan stem_tc;
-    bool stem_rows = false;
-    StemRowsPlan stem_rows_plan;
+    bool upcopy = false;              // YB_MODE_FP32_TC: nearest x2 copy of up_src into the concat slice up_dst
+    TView up_src, up_dst;
 };
 
 struct Plan {
@@ -45,34 +45,6 @@ struct Plan {
     int n_backbone_ops = 0;
     size_t bytes = 0;
 };
-
-bool l2_persist_window(const void* base, size_t bytes, cudaLaunchAttribute* attr) {
-    struct State { size_t set_aside = 0, max_window = 0; };
-    static PerDeviceOnce once;
-    static State st;                     // one configuration per process (the experiment targets one-GPU-per-process runs)
-    static const long mb = getenv("YB_L2_PERSIST") ? atol(getenv("YB_L2_PERSIST")) : 0;
-    if (mb <= 0 || !base || bytes == 0) return false;
-    const cudaError_t e = once.run([] {
-        int dev = 0, max_persist = 0, max_window = 0;
-        cudaError_t r = cudaGetDevice(&dev);
-        if (r == cudaSuccess) r = cudaDeviceGetAttribute(&max_persist, cudaDevAttrMaxPersistingL2CacheSize, dev);
-        if (r == cudaSuccess) r = cudaDeviceGetAttribute(&max_window, cudaDevAttrMaxAccessPolicyWindowSize, dev);
-        if (r != cudaSuccess) return r;
-        const size_t want = std::min<size_t>((size_t)mb << 20, (size_t)max_persist);
-        r = cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, want);
-        if (r == cudaSuccess) { st.set_aside = want; st.max_window = (size_t)max_window; }
-        return r;
-    });
-    if (e != cudaSuccess) { cudaGetLastError(); return false; }
-    if (bytes > st.set_aside || bytes > st.max_window) return false;
-    attr->id = cudaLaunchAttributeAccessPolicyWindow;
-    attr->val.accessPolicyWindow.base_ptr = const_cast<void*>(base);
-    attr->val.accessPolicyWindow.num_bytes = bytes;
-    attr->val.accessPolicyWindow.hitRatio = 1.0f;
-    attr->val.accessPolicyWindow.hitProp = cudaAccessPropertyPersisting;
-    attr->val.accessPolicyWindow.missProp = cudaAccessPropertyNormal;
-    return true;
-}
 
 }  // namespace yb
 
@@ -100,12 +72,6 @@ struct yb_ctx {
     int box_params_cap = 0;
     LbImage* lb_params = nullptr;     // [B] per-image parameters of yb_letterbox
     int lb_params_cap = 0;
-    // pinned staging ring for the small per-call parameter blocks (see stage_params)
-    unsigned char* stage_host = nullptr;
-    size_t stage_slot_bytes = 0;
-    int stage_next = 0;
-    std::vector<cudaEvent_t> stage_ev;
-    std::vector<char> stage_used;
     float* det_scratch = nullptr;     // for yb_detect
     size_t det_scratch_bytes = 0;
     int* dbg = nullptr;               // device alias of dbg_host (mapped pinned memory): watchdog words of the
@@ -149,44 +115,11 @@ int fail(const yb_ctx* c, int code, const std::string& msg) {
             return fail(c, YB_E_CUDA, std::string(#expr) + ": " + cudaGetErrorString(e_));            \
     } while (0)
 
-// Per-call parameter blocks (per-image letterbox / box-correction parameters, a few KB) go to the device with
-// cudaMemcpyAsync.  From PAGEABLE memory that call first synchronises the stream (CUDA runtime API, "API synchronization
-// behavior"), which serialises host and device for every yb_letterbox / yb_resize / yb_correct_boxes call.  With
-// YB_PINNED_PARAMS=1 the block is staged in a ring of pinned slots instead, so the copy is truly asynchronous; a slot is
-// reused only after the copy that last read it has executed (event per slot).  Opt-in until validated on the GPU box.
-constexpr int kStageSlots = 8;
-
+// Per-call parameter blocks (per-image letterbox / box-correction parameters, a few KB) go to the device with a plain
+// cudaMemcpyAsync on the caller's stream.  (A ring of pinned staging slots was measured in round 2 and lost:
+// profiles/r02a_pinned_bench.txt.)
 int stage_params(yb_ctx* c, const void* src, size_t bytes, void* dst, cudaStream_t s) {
-    static const bool pinned = getenv("YB_PINNED_PARAMS") && atoi(getenv("YB_PINNED_PARAMS")) != 0;
-    if (!pinned) {
-        YB_CUDA(c, cudaMemcpyAsync(dst, src, bytes, cudaMemcpyHostToDevice, s));
-        return YB_OK;
-    }
-    if (bytes > c->stage_slot_bytes) {
-        for (size_t i = 0; i < c->stage_ev.size(); ++i)
-            if (c->stage_used[i]) YB_CUDA(c, cudaEventSynchronize(c->stage_ev[i]));
-        cudaFreeHost(c->stage_host);
-        c->stage_host = nullptr;
-        c->stage_slot_bytes = 0;
-        const size_t slot = (std::max<size_t>(bytes, 4096) + 255) / 256 * 256;
-        YB_CUDA(c, cudaHostAlloc(reinterpret_cast<void**>(&c->stage_host), slot * kStageSlots, cudaHostAllocDefault));
-        c->stage_slot_bytes = slot;
-        while ((int)c->stage_ev.size() < kStageSlots) {
-            cudaEvent_t e;
-            YB_CUDA(c, cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
-            c->stage_ev.push_back(e);
-        }
-        c->stage_used.assign(kStageSlots, 0);
-        c->stage_next = 0;
-    }
-    const int i = c->stage_next;
-    c->stage_next = (i + 1) % kStageSlots;
-    if (c->stage_used[i]) YB_CUDA(c, cudaEventSynchronize(c->stage_ev[i]));
-    unsigned char* slot = c->stage_host + (size_t)i * c->stage_slot_bytes;
-    std::memcpy(slot, src, bytes);
-    YB_CUDA(c, cudaMemcpyAsync(dst, slot, bytes, cudaMemcpyHostToDevice, s));
-    YB_CUDA(c, cudaEventRecord(c->stage_ev[i], s));
-    c->stage_used[i] = 1;
+    YB_CUDA(c, cudaMemcpyAsync(dst, src, bytes, cudaMemcpyHostToDevice, s));
     return YB_OK;
 }
 
@@ -282,8 +215,9 @@ int ensure_post(yb_ctx* c, int B, int N, int is_eval) {
     const long want = (long)N * (is_eval ? c->num_classes : 1);
     if (want >= (1L << 22)) return fail(c, YB_E_ARG, "post-process: more than 4M candidates per image");
     if (b.B >= B && b.N == N && b.cand_cap >= want && b.C == c->num_classes) return YB_OK;
+    const long old_cap = b.N == N ? b.cand_cap : 0;      // (free_post resets the struct: read the old capacity first)
     free_post(c);
-    const int cand_cap = (int)std::max<long>(want, b.cand_cap);
+    const int cand_cap = (int)std::max<long>(want, old_cap);
     int sort_cap = 2;
     while (sort_cap < cand_cap) sort_cap <<= 1;
     const int C = c->num_classes;
@@ -403,9 +337,7 @@ int build_plan(yb_ctx* c, int B, int H, int W, Plan** out) {
         op.layer = 0; op.stem = true;
         op.a.out = buf[0];
         if (p->mode == YB_MODE_FP16) {
-            op.stem_rows = stem_rows_supported(B, H, W);
-            std::string e = op.stem_rows ? stem_rows_make_plan(op.stem_rows_plan, static_cast<__half*>(buf[0]), 32, B, H, W, c->num_sms)
-                                         : stem_tc_make_plan(op.stem_tc, static_cast<__half*>(buf[0]), 32, B, H, W, c->num_sms);
+            std::string e = stem_tc_make_plan(op.stem_tc, static_cast<__half*>(buf[0]), 32, B, H, W, c->num_sms);
             if (!e.empty()) return bail("plan: stem: " + e);
         }
         p->ops.push_back(op);
@@ -435,6 +367,7 @@ int build_plan(yb_ctx* c, int B, int H, int W, Plan** out) {
     p->backbone_out = cur;
     p->n_backbone_ops = (int)p->ops.size();
 
+    int route_buf = 0;                  // physical buffer holding the route (the other one is free once the head conv ran)
     auto predet = [&](TView x, int xb, int nout, int scale_i, TView* route) -> bool {
         // PreDetectionConvGroup.forward (darknet.py:121-126); route = mlist[4] output
         for (int i = 0; i < 6; ++i) {
@@ -443,7 +376,7 @@ int build_plan(yb_ctx* c, int B, int H, int W, Plan** out) {
             TView o = pb.view(buf[ob], B, x.H, x.W, co, co);
             if (!pb.conv(li++, x, o, nullptr, false, false)) return false;
             x = o; xb = ob;
-            if (i == 4) *route = o;
+            if (i == 4) { *route = o; route_buf = ob; }
         }
         const int cp = c->layers[li].cout_pad;
         TView lg;
@@ -452,16 +385,23 @@ int build_plan(yb_ctx* c, int B, int H, int W, Plan** out) {
     };
     TView route;
     if (!predet(cur, curb, 512, 0, &route)) return bail(pb.err);
-    {   // up1: 1x1 512->256, nearest x2 into channels [0,256) of concat1 (darknet.py:159-162)
-        TView o = pb.view(cat1, B, route.H, route.W, 256, 768, 0);
-        if (!pb.conv(li++, route, o, nullptr, true, false)) return bail(pb.err);
-    }
+    // UpsampleGroup (darknet.py:159-162): 1x1 conv, nearest x2 into channels [0, C) of the concat buffer.  The fp16 and
+    // CUDA-core modes replicate in the convolution's epilogue; the split mode writes a plain tensor into the free ping-pong
+    // buffer and replicates with a copy kernel (its epilogue keeps the tile in registers and only has the staged store).
+    auto up = [&](void* cat, int C, int Ctot) -> bool {
+        TView o = pb.view(cat, B, route.H, route.W, C, Ctot, 0);
+        if (!split) return pb.conv(li++, route, o, nullptr, true, false);
+        TView t = pb.view(buf[route_buf == 0 ? 1 : 0], B, route.H, route.W, C, C);
+        if (!pb.conv(li++, route, t, nullptr, false, false)) return false;
+        Op op;
+        op.layer = li - 1; op.upcopy = true; op.up_src = t; op.up_dst = o;
+        p->ops.push_back(op);
+        return true;
+    };
+    if (!up(cat1, 256, 768)) return bail(pb.err);
     TView c1 = pb.view(cat1, B, H / 16, W / 16, 768, 768);
     if (!predet(c1, -1, 256, 1, &route)) return bail(pb.err);
-    {
-        TView o = pb.view(cat2, B, route.H, route.W, 128, 384, 0);
-        if (!pb.conv(li++, route, o, nullptr, true, false)) return bail(pb.err);
-    }
+    if (!up(cat2, 128, 384)) return bail(pb.err);
     TView c2 = pb.view(cat2, B, H / 8, W / 8, 384, 384);
     if (!predet(c2, -1, 128, 2, &route)) return bail(pb.err);
     if (li != (int)c->layers.size()) return bail("plan: internal layer count mismatch");
@@ -497,16 +437,17 @@ int run_ops(yb_ctx* c, Plan* p, const float* x, int n_ops, cudaStream_t s) {
         const Layer& L = c->layers[op.layer];
         cudaError_t e;
         if (op.stem) {
-            if (c->input_f16 && (p->mode != YB_MODE_FP16 || op.stem_rows))
-                return fail(c, YB_E_UNSUPPORTED, "fp16 input images need YB_MODE_FP16 and the default stem kernel");
-            if (p->mode == YB_MODE_FP16 && op.stem_rows)
-                e = stem_rows_launch(op.stem_rows_plan, x, p->B, p->H, p->W, L.d_w16, L.d_scale, L.d_bias, c->dbg, s);
-            else if (p->mode == YB_MODE_FP16)
+            if (c->input_f16 && p->mode != YB_MODE_FP16)
+                return fail(c, YB_E_UNSUPPORTED, "fp16 input images need YB_MODE_FP16");
+            if (p->mode == YB_MODE_FP16)
                 e = stem_tc_launch(op.stem_tc, x, c->input_f16, p->B, p->H, p->W, L.d_w16, L.d_scale, L.d_bias, c->dbg, s);
             else if (p->mode == YB_MODE_FP32_TC)     // Cin = 3: exact fp32 FMAs on the CUDA cores, output written as hi | lo
                 e = launch_stem_split(x, static_cast<__half*>(op.a.out), L.d_w32, L.d_scale, L.d_bias, p->B, p->H, p->W, s);
             else
                 e = launch_stem<float>(x, static_cast<float*>(op.a.out), L.d_w32, L.d_scale, L.d_bias, p->B, p->H, p->W, s);
+        } else if (op.upcopy) {
+            e = launch_upsample2x_split(static_cast<const __half*>(op.up_src.p), op.up_src.ld, op.up_src.lo, static_cast<__half*>(op.up_dst.p),
+                                        op.up_dst.ld, op.up_dst.lo, op.up_src.C, p->B, op.up_src.H, op.up_src.W, s);
         } else if (op.use_halo) {
             e = halo_launch(op.halo, op.a, c->dbg, s);
         } else if (op.use_tc) {
@@ -609,8 +550,6 @@ void yb_destroy(yb_ctx* c) {
     cudaFree(c->box_params);
     cudaFree(c->lb_params);
     cudaFreeHost(c->dbg_host);
-    cudaFreeHost(c->stage_host);
-    for (cudaEvent_t e : c->stage_ev) cudaEventDestroy(e);
     for (cudaEvent_t e : c->ev) cudaEventDestroy(e);
     for (cudaEvent_t e : c->bank) cudaEventDestroy(e);
     if (c->nccl_comm) comm_destroy(c->nccl_comm);
@@ -637,8 +576,15 @@ int yb_set_tensor(yb_ctx* c, const char* key, const float* data, size_t n, int o
         return fail(c, YB_E_KEY, std::string("yb_set_tensor: '") + key + "' expects " + std::to_string(slot.numel) +
                                      " elements, got " + std::to_string(n));
     std::vector<float>* v = field_vec(c->layers[slot.layer], slot.field);
-    if (on_host) std::memcpy(v->data(), data, n * sizeof(float));
-    else YB_CUDA(c, cudaMemcpy(v->data(), data, n * sizeof(float), cudaMemcpyDeviceToHost));
+    if (on_host) {
+        std::memcpy(v->data(), data, n * sizeof(float));
+    } else {
+        // the caller's tensor may have been produced on any stream (PyTorch side streams are non-blocking: the legacy
+        // default stream this copy runs on does not order against them), so wait for the device first.  Not a hot path.
+        YB_CUDA(c, cudaSetDevice(c->device));
+        YB_CUDA(c, cudaDeviceSynchronize());
+        YB_CUDA(c, cudaMemcpy(v->data(), data, n * sizeof(float), cudaMemcpyDeviceToHost));
+    }
     c->finalized = false;
     return YB_OK;
 }
@@ -758,9 +704,11 @@ int yb_finalize(yb_ctx* c, int mode) {
                         w[((size_t)t * L.cin + ci) * L.cout_pad + n] = L.w[((size_t)n * L.cin + ci) * taps + t];
         }
         if (offs[i].w16 != (size_t)-1 && split) {
-            // [cout_pad][tap][wh | wl | wh][cin]: row n is scaled by 2^s(n) so that max|w'| lies in [2048, 4096) -- the lo part
-            // of every weight down to 2^-23 of the row maximum is then a NORMAL fp16 number -- and the epilogue scale undoes
-            // it exactly (a power of two).  wh = RN16(w'), wl = RN16(w' - wh).
+            // [cout_pad][tap][channel block][wh | wl | wh][bke] (bke = 64 channels, 32 when Cin = 32: the k-block order of
+            // conv_tc_kernel's split mode): row n is scaled by 2^s(n) so that max|w'| lies in [2048, 4096) -- the lo part of
+            // every weight down to 2^-23 of the row maximum is then a NORMAL fp16 number -- and the epilogue scale undoes it
+            // exactly (a power of two).  wh = RN16(w'), wl = RN16(w' - wh).
+            const int bke = L.cin == 32 ? 32 : 64;
             __half* w = reinterpret_cast<__half*>(host.data() + offs[i].w16);
             for (int n = 0; n < L.cout; ++n) {
                 float mx = 0.f;
@@ -777,8 +725,8 @@ int yb_finalize(yb_ctx* c, int mode) {
                         const float ws = std::ldexp(L.w[((size_t)n * L.cin + ci) * taps + t], sh);
                         const __half wh = __float2half_rn(ws);
                         const __half wl = __float2half_rn(ws - __half2float(wh));
-                        __half* row = w + (size_t)n * 3 * K + (size_t)t * 3 * L.cin + ci;
-                        row[0] = wh; row[L.cin] = wl; row[2 * L.cin] = wh;
+                        __half* row = w + (size_t)n * 3 * K + ((size_t)t * (L.cin / bke) + ci / bke) * 3 * bke + ci % bke;
+                        row[0] = wh; row[bke] = wl; row[2 * bke] = wh;
                     }
             }
         } else if (offs[i].w16 != (size_t)-1) {
@@ -794,7 +742,11 @@ int yb_finalize(yb_ctx* c, int mode) {
         L.d_w32 = offs[i].w32 != (size_t)-1 ? reinterpret_cast<float*>(c->d_blob + offs[i].w32) : nullptr;
         L.d_w16 = offs[i].w16 != (size_t)-1 ? reinterpret_cast<__half*>(c->d_blob + offs[i].w16) : nullptr;
     }
+    // a forward enqueued on a non-blocking stream may still be reading the blob (weights, scale / bias tables): drain the
+    // device before overwriting it, and after, so that no later launch on any stream can race the upload
+    YB_CUDA(c, cudaDeviceSynchronize());
     YB_CUDA(c, cudaMemcpy(c->d_blob, host.data(), off, cudaMemcpyHostToDevice));
+    YB_CUDA(c, cudaDeviceSynchronize());
     c->mode = mode;
     c->finalized = true;
     return YB_OK;
@@ -813,7 +765,7 @@ int yb_forward(yb_ctx* c, const float* x, int B, int H, int W, float* det, void*
     fill_decode(c, H, W, p->logits[0], p->logits[1], p->logits[2], c->layers.back().cout_pad, sc);
     // decode: the flat-map kernel; YB_DECODE_V2=1 selects the one-warp-per-cell kernel (coalesced row stores, but one
     // cell in flight per warp: measured 0.194 ms against 0.170 ms at 608x608 batch 32, profiles/README.md)
-    static const bool decode_v2 = getenv("YB_DECODE_V2") && atoi(getenv("YB_DECODE_V2")) != 0;
+    static const bool decode_v2 = tune_env("YB_DECODE_V2") && atoi(tune_env("YB_DECODE_V2")) != 0;
     if (decode_v2)
         YB_CUDA(c, launch_decode_cells(sc, B, c->attrs, total_rows(H, W), 1, det, 0.f, nullptr, nullptr, nullptr, nullptr, c->num_sms, s));
     else
@@ -918,7 +870,7 @@ int yb_detect(yb_ctx* c, const float* x, int B, int H, int W, float conf, float 
     // Non-eval mode never materialises the [B,N,5+C] tensor: the decode kernel scores each cell's three rows while
     // they are in shared memory and hands pp_scan / pp_scatter the per-row candidates directly.  Eval mode (one
     // candidate per passing (box, class) pair, gathered from det by pp_scatter) keeps the two-kernel path.
-    static const bool fused_ok = !(getenv("YB_FUSED_DETECT") && atoi(getenv("YB_FUSED_DETECT")) == 0);
+    static const bool fused_ok = !(tune_env("YB_FUSED_DETECT") && atoi(tune_env("YB_FUSED_DETECT")) == 0);
     const bool fused = fused_ok && !is_eval;
     if (!fused) {
         const size_t need = sizeof(float) * (size_t)B * N * c->attrs;
@@ -1231,14 +1183,9 @@ int yb_run_layer(yb_ctx* c, int li, const void* in, int B, int H, int W, const v
     }
     if (li == 0) {
         cudaError_t e;
-        if (c->input_f16 && (c->mode != YB_MODE_FP16 || stem_rows_supported(B, H, W)))
-            return fail(c, YB_E_UNSUPPORTED, "fp16 input images need YB_MODE_FP16 and the default stem kernel");
-        if (c->mode == YB_MODE_FP16 && stem_rows_supported(B, H, W)) {
-            StemRowsPlan sp;
-            std::string err = stem_rows_make_plan(sp, static_cast<__half*>(out), 32, B, H, W, c->num_sms);
-            if (!err.empty()) return fail(c, YB_E_CUDA, "yb_run_layer: " + err);
-            e = stem_rows_launch(sp, static_cast<const float*>(in), B, H, W, L.d_w16, L.d_scale, L.d_bias, c->dbg, s);
-        } else if (c->mode == YB_MODE_FP16) {
+        if (c->input_f16 && c->mode != YB_MODE_FP16)
+            return fail(c, YB_E_UNSUPPORTED, "fp16 input images need YB_MODE_FP16");
+        if (c->mode == YB_MODE_FP16) {
             StemTcPlan sp;
             std::string err = stem_tc_make_plan(sp, static_cast<__half*>(out), 32, B, H, W, c->num_sms);
             if (!err.empty()) return fail(c, YB_E_CUDA, "yb_run_layer: " + err);

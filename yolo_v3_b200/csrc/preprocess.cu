@@ -301,7 +301,7 @@ __global__ void __launch_bounds__(256) letterbox_tiled_kernel(const LbImage* __r
 
 cudaError_t launch_letterbox(const LbImage* imgs_dev, int B, int canvas_h, int canvas_w, float* out, unsigned char* canvas,
                              cudaStream_t s) {
-    static const bool direct = getenv("YB_LB_DIRECT") && atoi(getenv("YB_LB_DIRECT")) != 0;   // first version, kept for A/B timing
+    static const bool direct = tune_env("YB_LB_DIRECT") && atoi(tune_env("YB_LB_DIRECT")) != 0;   // first version, kept for A/B timing
     if (direct) {
         const dim3 grid((canvas_w + 31) / 32, (canvas_h + 7) / 8, B);
         letterbox_kernel<<<grid, 256, 0, s>>>(imgs_dev, canvas_h, canvas_w, out, canvas);

@@ -8,6 +8,7 @@
 
 #include <cstdint>
 #include <cstdio>
+#include <cstdlib>
 #include <map>
 #include <mutex>
 #include <string>
@@ -60,13 +61,16 @@ private:
     unsigned long long done_ = 0;
 };
 
-// L2 persistence experiment (YB_L2_PERSIST=<MB of L2 set aside>; unset or 0 = off, the validated behaviour): a layer whose
-// output fits writes it with the persisting access property (launch attribute cudaLaunchAttributeAccessPolicyWindow over
-// the output span), so that the next layer -- which reads it as A operand and as residual -- finds it in L2.  The 1x1
-// layers at 38x38 / 19x19 run at "cold" HBM speed inside the step although their 47 / 24 MB inputs were written by the
-// previous kernel.  Host-side only; written at the end of round 1, not yet run on a GPU.
-// Returns true and fills *attr when the window applies.
-bool l2_persist_window(const void* base, size_t bytes, cudaLaunchAttribute* attr);
+// Tuning / A-B overrides are read from the environment only in builds with -DYB_EXPERIMENTS (make EXPERIMENTS=1, what
+// tools/layer_bench.py --sweep needs); the release library never calls getenv and has one code path per layer shape.
+inline const char* tune_env(const char* name) {
+#ifdef YB_EXPERIMENTS
+    return getenv(name);
+#else
+    (void)name;
+    return nullptr;
+#endif
+}
 
 // NHWC activation view: `p` already includes the channel offset of a concat slice.
 struct TView {
@@ -109,17 +113,21 @@ cudaError_t launch_stem_split(const float* x_nchw, __half* out_nhwc64, const flo
 cudaError_t launch_split_to_nchw_f32(const __half* in, long in_ld, long lo, int C, int B, int HW, float* out, cudaStream_t s);
 cudaError_t launch_f32_to_split(const float* in, __half* out, size_t M, int C, cudaStream_t s);
 cudaError_t launch_split_to_f32(const __half* in, float* out, size_t M, int C, cudaStream_t s);
+// nearest x2 of a split tensor: in [B,H,W] pixels of C hi values (+ C lo values in_lo later) -> the 2x2 block of out [B,2H,2W]
+cudaError_t launch_upsample2x_split(const __half* in, long in_ld, long in_lo, __half* out, long out_ld, long out_lo, int C,
+                                    int B, int H, int W, cudaStream_t s);
 
 // conv_tc.cu  (tcgen05 + TMA implicit GEMM)
 struct TcPlan {
     CUtensorMap tmA, tmB, tmOut, tmRes;
-    int epi_staged = 0, ring = 0, sub_bytes = 128, cs = 0, n_sub = 0, b_resident = 0, exp_tiled = 0, exp_blocked = 0;
+    int epi_staged = 0, ring = 0, sub_bytes = 128, cs = 0, n_sub = 0, b_resident = 0;
     int swz = 128;        // 128: 64-channel k-blocks, 64: 32-channel k-blocks (Cin == 32)
     int BN = 0, n_tiles = 0, m_tiles = 0, stages = 0, tmem_cols = 0;
     int num_kblocks = 0, cin_blocks = 0, kps = 1, cta2 = 0, cout_pad = 0, tab_bytes = 0;
-    int pf_dist = 0, b_early = 0, srel = 0;
+    int srel = 0;
     int epi_split = 0;    // 32-column sub-tiles: the two halves of the epilogue warps take alternate sub-tiles
-    int split = 0;        // YB_MODE_FP32_TC: hi/lo operands, three k sections per tap (conv_tc.cu)
+    int split = 0;        // YB_MODE_FP32_TC: hi/lo operands, three k sections per (tap, channel block) (conv_tc.cu)
+    int chunk_iters = 0, n_chunks = 0;   // split mode: pipeline stages per TMEM chunk, chunks per tile
     int grid = 0;
     size_t smem = 0;
     long M = 0;
@@ -139,17 +147,6 @@ std::string stem_tc_make_plan(StemTcPlan& p, __half* out, long out_ld, int B, in
 // x: the caller's NCHW image, fp32 (in_f16 = 0) or fp16 (in_f16 = 1)
 cudaError_t stem_tc_launch(const StemTcPlan& p, const void* x, int in_f16, int B, int H, int W, const __half* w16, const float* scale,
                            const float* bias, int* dbg, cudaStream_t s);
-
-// stem_rows.cu  (Cin = 3 stem from a [pixel][8 fp16] patch, tap pairs through the leading-dimension offset; W % 38 == 0)
-struct StemRowsPlan {
-    CUtensorMap tmOut;
-    int tiles_x = 0, tiles_y = 0, total_tiles = 0, grid = 0;
-    size_t smem = 0;
-};
-bool stem_rows_supported(int B, int H, int W);
-std::string stem_rows_make_plan(StemRowsPlan& p, __half* out, long out_ld, int B, int H, int W, int num_sms);
-cudaError_t stem_rows_launch(const StemRowsPlan& p, const float* x, int B, int H, int W, const __half* w16, const float* scale,
-                             const float* bias, int* dbg, cudaStream_t s);
 
 // conv_halo.cu  (3x3 stride-1 layers with Cin = 32 / 64 from a halo tile: every input pixel staged once)
 struct HaloPlan {

@@ -306,10 +306,9 @@ class YoloNet(nn.Module):
         if x.shape[2] % 32 or x.shape[3] % 32:
             raise ValueError("H and W must be multiples of 32")
         # fp16 images are read by the stem directly (yb_set_input_dtype): same bits as the fp32 path, which rounds every
-        # pixel to fp16 itself, for half the host-to-device bytes (YB_INPUT_F16=0 switches this off; the experimental
-        # pixel-row stem has no fp16 instantiation).  Any other dtype is widened to fp32, as the reference's callers pass it.
-        direct_f16 = (x.dtype == torch.float16 and self.precision == "fp16" and os.environ.get("YB_INPUT_F16", "1") != "0"
-                      and os.environ.get("YB_STEM_ROWS", "0") == "0")
+        # pixel to fp16 itself, for half the host-to-device bytes.  Any other dtype is widened to fp32, as the reference's
+        # callers pass it.
+        direct_f16 = x.dtype == torch.float16 and self.precision == "fp16"
         if not direct_f16 and x.dtype != torch.float32:
             x = x.float()
         return x.contiguous()

@@ -17,6 +17,7 @@ candidate order ascending) where the reference's unstable CPU sort is arbitrary.
 from __future__ import annotations
 
 import ctypes
+import threading
 from typing import Dict, Sequence, Tuple
 
 import numpy as np
@@ -24,14 +25,22 @@ import torch
 
 from . import _lib
 
-_POST_CTX: Dict[Tuple[int, int], ctypes.c_void_p] = {}
+_POST_CTX: Dict[Tuple[int, int, int], ctypes.c_void_p] = {}
+_POST_CTX_LOCK = threading.Lock()
 
 
 def _ctx_for(device_index: int, num_classes: int):
-    key = (device_index, num_classes)
-    if key not in _POST_CTX:
-        _POST_CTX[key] = _lib.create_ctx(device_index, num_classes, None)
-    return _POST_CTX[key]
+    """One library context per (device, class count, HOST THREAD): a yb_ctx owns scratch buffers that every call reuses
+    (include/yolo_b200.h: one ctx per device and host thread, calls serialised by the caller), so threads -- DataLoader
+    workers, serving threads -- must not share one."""
+    key = (device_index, num_classes, threading.get_ident())
+    ctx = _POST_CTX.get(key)
+    if ctx is None:
+        with _POST_CTX_LOCK:
+            ctx = _POST_CTX.get(key)
+            if ctx is None:
+                ctx = _POST_CTX[key] = _lib.create_ctx(device_index, num_classes, None)
+    return ctx
 
 
 def rows_to_list(rows: torch.Tensor, counts_h: torch.Tensor, cand_h: torch.Tensor):

@@ -72,3 +72,35 @@ class YoloLayer(nn.Module):
                 _lib.load().yb_destroy(self._ctx)
         except Exception:
             pass
+
+
+_DECODE_CTX = {}
+
+
+def decode_heads(maps, img_dim, numClass=80, anchors=None):
+    """The three YoloLayer.forward calls of YoloNet.forward plus the callers' torch.cat((det1,det2,det3),1)
+    (yololayer.py:31-59, test.py:36) in ONE launch: `maps` = the raw head maps [B,3*(5+C),H/32,W/32], [.., H/16, W/16],
+    [.., H/8, W/8] (CUDA, NCHW fp32), img_dim = (W, H).  Returns the concatenated [B,N,5+C] tensor."""
+    from .topology import DEFAULT_ANCHORS
+    x0 = maps[0]
+    if not x0.is_cuda:
+        raise RuntimeError("yolo_v3_b200 runs on CUDA devices only (no CPU fallback)")
+    lib = _lib.load()
+    index = x0.device.index if x0.device.index is not None else torch.cuda.current_device()
+    flat = tuple(float(v) for v in (anchors if anchors is not None else DEFAULT_ANCHORS))
+    key = (index, numClass, flat)
+    if key not in _DECODE_CTX:
+        _DECODE_CTX[key] = _lib.create_ctx(index, numClass, list(flat))
+    ctx = _DECODE_CTX[key]
+    W, H = int(img_dim[0]), int(img_dim[1])
+    B = x0.shape[0]
+    ms = [m.float().contiguous() for m in maps]
+    for m, t in zip(ms, (32, 16, 8)):
+        if tuple(m.shape) != (B, 3 * (5 + numClass), H // t, W // t):
+            raise ValueError(f"head map of shape {tuple(m.shape)} does not match img_dim {img_dim} at stride {t}")
+    n = sum(3 * (H // t) * (W // t) for t in (32, 16, 8))
+    det = torch.empty(B, n, 5 + numClass, device=x0.device)
+    with torch.cuda.device(x0.device):
+        _lib.check(lib.yb_decode(ctx, *[ctypes.c_void_p(m.data_ptr()) for m in ms], B, H, W, ctypes.c_void_p(det.data_ptr()),
+                                 ctypes.c_void_p(torch.cuda.current_stream(x0.device).cuda_stream)), ctx)
+    return det
