@@ -91,6 +91,12 @@ int yb_finalize(yb_ctx* ctx, int precision_mode);
 #define YB_INPUT_F16 1
 int yb_set_input_dtype(yb_ctx* ctx, int dtype);
 
+/* CUDA-graph replay of the convolution launches that follow the stem (they read and write plan-owned buffers only): mode 0
+ * never, 1 always, 2 (default) automatically for launch-bound shapes (B*H*W <= 2^20 pixels, e.g. one 416x416 image -- 80
+ * dependent kernels of a few microseconds each).  The graph of a (B,H,W) plan is captured on its second call; capture
+ * failure falls back to stream launches silently.  No reference counterpart (PyTorch eager launches every kernel). */
+int yb_set_graph_mode(yb_ctx* ctx, int mode);
+
 /* ---- the hot path ---------------------------------------------------------------------------- */
 
 /* Replaces YoloNet.forward(x, target=None) + torch.cat((det1,det2,det3),1) (darknet.py:198-231,
@@ -191,8 +197,10 @@ int yb_allgather_dets(yb_ctx* ctx, const float* rows7, const int* counts, int B_
 
 /* ---- introspection for bench.py / tests -------------------------------------------------------- */
 
-/* Number of kernels this library launched on behalf of ctx since creation. */
+/* Number of kernels this library launched on behalf of ctx since creation (kernels replayed by a captured graph included). */
 long long yb_launch_count(const yb_ctx* ctx);
+/* Number of forward calls whose post-stem convolution launches were replayed from a captured CUDA graph (yb_set_graph_mode). */
+long long yb_graph_replays(const yb_ctx* ctx);
 /* Device time (ms) of the convolution stack / decode / post-process sections of the last
  * yb_forward/yb_detect call with profiling enabled.  yb_set_profiling level: 0 off, 1 = one CUDA event at
  * each section boundary (does not disturb the back-to-back launches inside the convolution stack),

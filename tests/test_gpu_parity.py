@@ -311,6 +311,35 @@ def test_fp32_net_608_batch(oracle, sd_calibrated):
     np.testing.assert_allclose(det[..., 4:].cpu().numpy(), ref[..., 4:].numpy(), rtol=0, atol=1e-4)
 
 
+def test_standalone_darknet_backbone(oracle, sd_calibrated, tmp_path):
+    """Darknet(blkList).forward stand-alone (darknet.py:72-88), the way the reference's notebooks use the backbone for
+    classification pre-training: its own parameters, fp32-grade mode, against the oracle's backbone; and loadWeight of a
+    backbone-only darknet stream (darknet.py:102-104)."""
+    from yolo_v3_b200.darknet import Darknet
+    d = Darknet([1, 2, 8, 8, 4])
+    d.load_state_dict({k[len("feature."):]: v for k, v in sd_calibrated.items() if k.startswith("feature.")})
+    d = d.cuda().eval()
+    x = synth.make_images(2, 96, 128, seed=8)
+    owner = d._engine_owner()
+    owner.precision = "fp32"
+    y = d(x.cuda())
+    with torch.no_grad():
+        ref = oracle.backbone(sd_calibrated, x)[0]
+    assert y.shape == ref.shape == (2, 1024, 3, 4)
+    assert float((y.cpu() - ref).abs().max()) <= 1e-4 * float(ref.abs().max())
+    blob = oracle.darknet_blob_from_state_dict(sd_calibrated, 80, backbone_only=True)
+    path = tmp_path / "darknet53.conv.74"
+    with open(path, "wb") as fp:
+        np.array([0, 2, 0, 0, 0], np.int32).tofile(fp)
+        (blob * 0.5).astype(np.float32).tofile(fp)
+    d.loadWeight(str(path))
+    assert torch.equal(d.mlist[0].conv.weight.detach().cpu(), sd_calibrated["feature.mlist.0.conv.weight"] * 0.5)
+    y2 = d(x.cuda())
+    assert not torch.equal(y, y2)
+    with pytest.raises(NotImplementedError):
+        Darknet([1, 1, 1, 1, 1]).cuda().eval()(x.cuda())
+
+
 # ---------------------------------------------------------------------------------------------
 # L4: drop-in conventions
 # ---------------------------------------------------------------------------------------------

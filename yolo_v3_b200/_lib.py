@@ -33,6 +33,7 @@ PROTOTYPES = {
     "yb_save_darknet_blob": (c_int, [c_void_p, c_void_p, c_size_t, c_int, POINTER(c_size_t)]),
     "yb_finalize": (c_int, [c_void_p, c_int]),
     "yb_set_input_dtype": (c_int, [c_void_p, c_int]),
+    "yb_set_graph_mode": (c_int, [c_void_p, c_int]),
     "yb_forward": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_void_p, c_void_p]),
     "yb_forward_logits": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p]),
     "yb_backbone": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_void_p, c_void_p]),
@@ -53,6 +54,7 @@ PROTOTYPES = {
     "yb_bcast_weights": (c_int, [c_void_p, c_int, c_void_p]),
     "yb_allgather_dets": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_void_p, c_void_p, c_void_p]),
     "yb_launch_count": (c_longlong, [c_void_p]),
+    "yb_graph_replays": (c_longlong, [c_void_p]),
     "yb_debug_words": (c_int, [c_void_p, POINTER(c_int), c_int]),
     "yb_set_profiling": (c_int, [c_void_p, c_int]),
     "yb_get_section_ms": (c_int, [c_void_p, POINTER(c_float), POINTER(c_float), POINTER(c_float)]),

@@ -250,15 +250,16 @@ __global__ void split_to_f32_kernel(const __half* __restrict__ in, float* __rest
     }
 }
 
-// nearest-neighbour x2 of a split tensor into a channel slice of the concat buffer (UpsampleGroup, darknet.py:161-162, in
-// YB_MODE_FP32_TC, where the 1x1 "up" convolution writes a plain tensor): one thread per 16-byte chunk of an input pixel
-__global__ void upsample2x_split_kernel(const __half* __restrict__ in, long in_ld, long in_lo, __half* __restrict__ out, long out_ld,
-                                        long out_lo, int C, int H, int W, long total) {
+// nearest-neighbour x2 of an fp16 tensor into a channel slice of the concat buffer (UpsampleGroup, darknet.py:161-162): the
+// 1x1 "up" convolution writes a plain tensor through its staged TMA-store epilogue and this copy replicates it -- one thread
+// per 16-byte chunk of an input pixel.  `halves` = 2 in YB_MODE_FP32_TC (C hi values, then C lo values in_lo later), else 1.
+__global__ void upsample2x_kernel(const __half* __restrict__ in, long in_ld, long in_lo, __half* __restrict__ out, long out_ld,
+                                  long out_lo, int C, int H, int W, int halves, long total) {
     const int cpp = C / 8;                                 // chunks per half of a pixel
     const long stride = (long)gridDim.x * blockDim.x;
     for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += stride) {
-        const int ch = (int)(i % (2 * cpp));
-        const long pix = i / (2 * cpp);
+        const int ch = (int)(i % (halves * cpp));
+        const long pix = i / (halves * cpp);
         const int half_i = ch / cpp, c = (ch - half_i * cpp) * 8;
         const int x = (int)(pix % W);
         const long by = pix / W;                           // b * H + y
@@ -310,11 +311,11 @@ cudaError_t launch_split_to_nchw_f32(const __half* in, long in_ld, long lo, int 
     split_to_nchw_kernel<<<grid, block, 0, s>>>(in, in_ld, lo, C, HW, out);
     return cudaGetLastError();
 }
-cudaError_t launch_upsample2x_split(const __half* in, long in_ld, long in_lo, __half* out, long out_ld, long out_lo, int C,
-                                    int B, int H, int W, cudaStream_t s) {
-    const long total = (long)B * H * W * 2 * (C / 8);
+cudaError_t launch_upsample2x(const __half* in, long in_ld, long in_lo, __half* out, long out_ld, long out_lo, int C,
+                              int B, int H, int W, int halves, cudaStream_t s) {
+    const long total = (long)B * H * W * halves * (C / 8);
     const int blocks = (int)std::min<long>((total + 255) / 256, 148 * 8);
-    upsample2x_split_kernel<<<blocks, 256, 0, s>>>(in, in_ld, in_lo, out, out_ld, out_lo, C, H, W, total);
+    upsample2x_kernel<<<blocks, 256, 0, s>>>(in, in_ld, in_lo, out, out_ld, out_lo, C, H, W, halves, total);
     return cudaGetLastError();
 }
 cudaError_t launch_f32_to_split(const float* in, __half* out, size_t M, int C, cudaStream_t s) {

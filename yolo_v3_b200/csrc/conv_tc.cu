@@ -233,23 +233,24 @@ __device__ __forceinline__ void split2(float a, float b, __half2& hi, __half2& l
 // 128B- (or 64B-) swizzled like the single sub-tile of the fp16 mode; the residual arrives the same way.
 __device__ __forceinline__ void epilogue16_staged_split(const TcArgs& a, const float (&acc)[16], int n, uint8_t* srow,
                                                         uint32_t lo_delta, int grp, int xr) {
-    float v[16];
+    // eight values (one 16-byte chunk of the hi and of the lo sub-tile) at a time: the caller holds up to 64 accumulators
     const float4* sc = reinterpret_cast<const float4*>(a.tab + n);
     const float4* bi = reinterpret_cast<const float4*>(a.tab + a.cout_pad + n);
 #pragma unroll
-    for (int q = 0; q < 4; ++q) {
-        const float4 s4 = sc[q], b4 = bi[q];
-        v[4 * q + 0] = fmaf(acc[4 * q + 0], s4.x, b4.x);
-        v[4 * q + 1] = fmaf(acc[4 * q + 1], s4.y, b4.y);
-        v[4 * q + 2] = fmaf(acc[4 * q + 2], s4.z, b4.z);
-        v[4 * q + 3] = fmaf(acc[4 * q + 3], s4.w, b4.w);
-    }
-    if (a.leaky) {
-#pragma unroll
-        for (int i = 0; i < 16; ++i) v[i] = leaky(v[i]);
-    }
-#pragma unroll
     for (int h = 0; h < 2; ++h) {
+        float v[8];
+#pragma unroll
+        for (int q = 0; q < 2; ++q) {
+            const float4 s4 = sc[2 * h + q], b4 = bi[2 * h + q];
+            v[4 * q + 0] = fmaf(acc[8 * h + 4 * q + 0], s4.x, b4.x);
+            v[4 * q + 1] = fmaf(acc[8 * h + 4 * q + 1], s4.y, b4.y);
+            v[4 * q + 2] = fmaf(acc[8 * h + 4 * q + 2], s4.z, b4.z);
+            v[4 * q + 3] = fmaf(acc[8 * h + 4 * q + 3], s4.w, b4.w);
+        }
+        if (a.leaky) {
+#pragma unroll
+            for (int i = 0; i < 8; ++i) v[i] = leaky(v[i]);
+        }
         uint4* p = reinterpret_cast<uint4*>(srow + (((grp * 2 + h) ^ xr) << 4));
         uint4* pl = reinterpret_cast<uint4*>(reinterpret_cast<uint8_t*>(p) + lo_delta);
         if (a.has_res) {
@@ -259,15 +260,15 @@ __device__ __forceinline__ void epilogue16_staged_split(const TcArgs& a, const f
 #pragma unroll
             for (int i = 0; i < 4; ++i) {
                 const float2 fh = __half22float2(hh[i]), fl = __half22float2(ll[i]);
-                v[8 * h + 2 * i] += fh.x + fl.x;
-                v[8 * h + 2 * i + 1] += fh.y + fl.y;
+                v[2 * i] += fh.x + fl.x;                  // hi + lo is exact in fp32: one rounding, like the reference's x + f(x)
+                v[2 * i + 1] += fh.y + fl.y;
             }
         }
         uint4 pk, pkl;
         __half2* ph = reinterpret_cast<__half2*>(&pk);
         __half2* pq = reinterpret_cast<__half2*>(&pkl);
 #pragma unroll
-        for (int i = 0; i < 4; ++i) split2(v[8 * h + 2 * i], v[8 * h + 2 * i + 1], ph[i], pq[i]);
+        for (int i = 0; i < 4; ++i) split2(v[2 * i], v[2 * i + 1], ph[i], pq[i]);
         *p = pk;
         *pl = pkl;
     }
@@ -310,7 +311,11 @@ __device__ __forceinline__ void load_resident_weights(const CUtensorMap* tmB, co
     }
 }
 
-template <int SWZ, bool CTA2, bool SPLIT = false>
+// SUBS (split mode): sub-tiles a thread of the epilogue accumulates in registers -- 2: tiles up to 128 columns, 32 accumulators.
+// (256-column tiles would need 64 accumulators per thread, i.e. ~110 registers for the epilogue warps: a SUBS = 4 variant
+// that has the four role warps donate registers with setmaxnreg was written in round 2, but ptxas 12.9 fails its register
+// allocation (C7600) whatever counts are requested, so it is not built.)
+template <int SWZ, bool CTA2, bool SPLIT = false, int SUBS = 2>
 __global__ void __launch_bounds__(SPLIT ? kThreadsSplit : kThreads, 1)
 conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                const __grid_constant__ CUtensorMap tmOut, const __grid_constant__ CUtensorMap tmRes, const TcArgs a_in) {
@@ -384,6 +389,94 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     __syncwarp();
     pdl_wait_prior();             // activations written by the previous layer are complete and visible
     if (threadIdx.x == 0) YB_TRACE(5, 0, 2);
+    [[maybe_unused]] auto split_epilogue = [&]() {
+        // ===== epilogue of the split mode: every finished TMEM chunk is added into fp32 register accumulators (round to
+        // nearest -- the second level of the accumulation, see the comment on split2), then the usual staged hand-over:
+        // scale/bias, LeakyReLU, residual, hi/lo split, swizzled smem sub-tile, TMA store.  Warp w owns TMEM lanes
+        // 32*(w%4).. and the 16-column group (w-4)/4 of each of the (at most SUBS) sub-tiles =====
+        const int q = warp & 3, part = (warp - 4) >> 2;
+        const int row = q * 32 + lane;
+        const int xr = a.sub_bytes == 128 ? (row & 7) : ((row >> 1) & 3);
+        const bool active = part < (a.cs >> 4);
+        uint32_t accb = 0, acc_phase = 0;
+        RingWalk rw;
+        const int n_wrap = a.n_tiles * a.BN;
+        int n0 = (tile_first % a.n_tiles) * a.BN;
+        const int dn0 = (tile_step % a.n_tiles) * a.BN;
+        for (int tile = tile_first; tile < total_tiles; tile += tile_step) {
+            float sacc[SUBS][16];
+#pragma unroll
+            for (int j = 0; j < SUBS; ++j)
+#pragma unroll
+                for (int i = 0; i < 16; ++i) sacc[j][i] = 0.f;
+            for (int ch = 0; ch < a.n_chunks; ++ch) {
+                mbar_wait(tfull0 + 8 * accb, acc_phase, a.dbg, 2, 200 + (int)accb);
+                tc_fence_after();
+                const uint32_t tcol = tmem_base + accb * acc_stride + ((uint32_t)(q * 32) << 16) + (uint32_t)(part * 16);
+                // SUBS == 2: both sub-tiles in one round trip to TMEM; SUBS == 4: one at a time (16 values in flight next to
+                // the 64 accumulators -- the chunk's MMAs take four times as long as these four round trips)
+                constexpr int STEP = SUBS == 2 ? 2 : 1;
+#pragma unroll
+                for (int j = 0; j < SUBS; j += STEP) {
+                    uint32_t r0[16];
+                    [[maybe_unused]] uint32_t r1[16];
+                    const bool h0 = active && j < a.n_sub;
+                    [[maybe_unused]] const bool h1 = STEP == 2 && active && j + 1 < a.n_sub;
+                    if (h0) tmem_ld16(tcol + (uint32_t)(j * a.cs), r0);
+                    if constexpr (STEP == 2) { if (h1) tmem_ld16(tcol + (uint32_t)((j + 1) * a.cs), r1); }
+                    tmem_ld_wait();
+                    if (j + STEP >= SUBS) {                    // last read of this chunk: the buffer goes back to the MMA warp
+                        tc_fence_before();
+                        __syncwarp();
+                        if (lane == 0) {
+                            if constexpr (CTA2) mbar_arrive_leader(tempty0 + 8 * accb); else mbar_arrive(tempty0 + 8 * accb);
+                        }
+                    }
+                    if (h0) {
+#pragma unroll
+                        for (int i = 0; i < 16; ++i) sacc[j][i] = __fadd_rn(sacc[j][i], __uint_as_float(r0[i]));
+                    }
+                    if constexpr (STEP == 2) {
+                        if (h1) {
+#pragma unroll
+                            for (int i = 0; i < 16; ++i) sacc[j + 1][i] = __fadd_rn(sacc[j + 1][i], __uint_as_float(r1[i]));
+                        }
+                    }
+                }
+                accb ^= 1;
+                if (accb == 0) acc_phase ^= 1;
+            }
+#pragma unroll
+            for (int j = 0; j < SUBS; ++j) {
+                if (j < a.n_sub) {
+                    const uint32_t buf = rw.buf, ph = rw.ph;
+                    if (a.has_res) mbar_wait(sfull0 + 8 * buf, ph, a.dbg, 2, 400 + (int)buf);
+                    else mbar_wait(sempty0 + 8 * buf, ph ^ 1, a.dbg, 2, 500 + (int)buf);
+                    uint8_t* srow = gen + (stg0 - base) + buf * stg_bytes + (uint32_t)row * (uint32_t)a.sub_bytes;
+                    const int nb = n0 + j * a.cs + part * 16;
+                    if (active) {
+                        if constexpr (SUBS == 4) {             // (the fp32 head maps keep the narrow tiles of the SUBS == 2 kernels)
+                            epilogue16_staged_split(a, sacc[j], nb, srow, stg_half, part, xr);
+                        } else if (split_out) {
+                            epilogue16_staged_split(a, sacc[j], nb, srow, stg_half, part, xr);
+                        } else {                               // fp32 head maps: the plain staged epilogue on the summed values
+                            uint32_t rr[16];
+#pragma unroll
+                            for (int i = 0; i < 16; ++i) rr[i] = __float_as_uint(sacc[j][i]);
+                            epilogue16_staged(a, rr, nb, srow, part, xr);
+                        }
+                    }
+                    fence_async_smem();
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(sready0 + 8 * buf);
+                    rw.next((uint32_t)a.ring);
+                }
+            }
+            n0 += dn0;
+            if (n0 >= n_wrap) n0 -= n_wrap;
+        }
+    };
+    {
 
     if (warp < (SPLIT ? 1 : 2)) {
         // ===== TMA producers (two warps take alternate pipeline stages -- one warp takes all of them in split mode; whole warp runs the loop, one
@@ -611,77 +704,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         }
         __syncwarp();
     } else if (SPLIT && warp >= 4 && warp < 20) {
-        // ===== epilogue of the split mode: every finished TMEM chunk is added into fp32 register accumulators (round to
-        // nearest -- the second level of the accumulation, see the comment on split2), then the usual staged hand-over:
-        // scale/bias, LeakyReLU, residual, hi/lo split, swizzled smem sub-tile, TMA store.  Warp w owns TMEM lanes
-        // 32*(w%4).. and the 16-column group (w-8)/4 of each of the (at most two) sub-tiles =====
-        const int q = warp & 3, part = (warp - 4) >> 2;
-        const int row = q * 32 + lane;
-        const int xr = a.sub_bytes == 128 ? (row & 7) : ((row >> 1) & 3);
-        const bool active = part < (a.cs >> 4);
-        const bool two = a.n_sub > 1;
-        uint32_t accb = 0, acc_phase = 0;
-        RingWalk rw;
-        const int n_wrap = a.n_tiles * a.BN;
-        int n0 = (tile_first % a.n_tiles) * a.BN;
-        const int dn0 = (tile_step % a.n_tiles) * a.BN;
-        for (int tile = tile_first; tile < total_tiles; tile += tile_step) {
-            float s0[16], s1[16];
-#pragma unroll
-            for (int i = 0; i < 16; ++i) { s0[i] = 0.f; s1[i] = 0.f; }
-            for (int ch = 0; ch < a.n_chunks; ++ch) {
-                mbar_wait(tfull0 + 8 * accb, acc_phase, a.dbg, 2, 200 + (int)accb);
-                tc_fence_after();
-                const uint32_t tcol = tmem_base + accb * acc_stride + ((uint32_t)(q * 32) << 16) + (uint32_t)(part * 16);
-                uint32_t r0[16], r1[16];
-                if (active) {
-                    tmem_ld16(tcol, r0);
-                    if (two) tmem_ld16(tcol + (uint32_t)a.cs, r1);
-                }
-                tmem_ld_wait();
-                tc_fence_before();
-                __syncwarp();
-                if (lane == 0) {                               // chunk drained into registers: the buffer goes back to the MMA warp
-                    if constexpr (CTA2) mbar_arrive_leader(tempty0 + 8 * accb); else mbar_arrive(tempty0 + 8 * accb);
-                }
-                if (active) {
-#pragma unroll
-                    for (int i = 0; i < 16; ++i) s0[i] = __fadd_rn(s0[i], __uint_as_float(r0[i]));
-                    if (two) {
-#pragma unroll
-                        for (int i = 0; i < 16; ++i) s1[i] = __fadd_rn(s1[i], __uint_as_float(r1[i]));
-                    }
-                }
-                accb ^= 1;
-                if (accb == 0) acc_phase ^= 1;
-            }
-#pragma unroll
-            for (int j = 0; j < 2; ++j) {
-                if (j < a.n_sub) {
-                    const uint32_t buf = rw.buf, ph = rw.ph;
-                    if (a.has_res) mbar_wait(sfull0 + 8 * buf, ph, a.dbg, 2, 400 + (int)buf);
-                    else mbar_wait(sempty0 + 8 * buf, ph ^ 1, a.dbg, 2, 500 + (int)buf);
-                    uint8_t* srow = gen + (stg0 - base) + buf * stg_bytes + (uint32_t)row * (uint32_t)a.sub_bytes;
-                    const int nb = n0 + j * a.cs + part * 16;
-                    if (active) {
-                        if (split_out) {
-                            epilogue16_staged_split(a, j == 0 ? s0 : s1, nb, srow, stg_half, part, xr);
-                        } else {                               // fp32 head maps: the plain staged epilogue on the summed values
-                            uint32_t rr[16];
-#pragma unroll
-                            for (int i = 0; i < 16; ++i) rr[i] = __float_as_uint(j == 0 ? s0[i] : s1[i]);
-                            epilogue16_staged(a, rr, nb, srow, part, xr);
-                        }
-                    }
-                    fence_async_smem();
-                    __syncwarp();
-                    if (lane == 0) mbar_arrive(sready0 + 8 * buf);
-                    rw.next((uint32_t)a.ring);
-                }
-            }
-            n0 += dn0;
-            if (n0 >= n_wrap) n0 -= n_wrap;
-        }
+        split_epilogue();
     } else if (warp >= 8 && a.epi_staged) {
         // ===== epilogue (staged): TMEM -> registers -> swizzled smem sub-tile -> TMA store =====
         // Sixteen warps: warp w reads TMEM lanes 32*(w%4).. (its rows); the four warps of a row quarter each
@@ -797,6 +820,8 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             acc ^= 1;
             if (acc == 0) acc_phase ^= 1;
         }
+    }
+
     }
 
     tc_fence_before();
@@ -1178,7 +1203,7 @@ std::string tc_make_plan(TcPlan& p, const ConvArgs& a, const __half* w16, int co
                   slot_half * p.num_kblocks <= 96 * 1024 && p.m_tiles > 4 * num_sms;
         if (const char* e = tune_env("YB_TC_PAIR128")) pair128 = pair128 && atoi(e) != 0;
     }
-    p.cta2 = p.swz == 128 && (p.BN == 256 || pair128 || (a.split && p.BN == 128)) && !a.upsample && p.m_tiles >= 4 && num_sms % 2 == 0;
+    p.cta2 = p.swz == 128 && (p.BN == 256 || pair128 || (a.split && p.BN == 128 && !a.out_f32)) && !a.upsample && p.m_tiles >= 4 && num_sms % 2 == 0;
     if (const char* e = tune_env("YB_TC_CTA2")) p.cta2 = p.cta2 && atoi(e) != 0;
     const int ncta = p.cta2 ? 2 : 1;
     if (p.cta2) p.m_tiles = (p.m_tiles + 1) / 2;            // 256-row units from here on

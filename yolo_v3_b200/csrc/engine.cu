@@ -44,6 +44,11 @@ struct Plan {
     TView backbone_out;
     int n_backbone_ops = 0;
     size_t bytes = 0;
+    // CUDA graphs of ops [1, n_ops) -- everything after the stem works on plan-owned buffers only, so the launches can be
+    // replayed as they are.  One executable per n_ops value in use (whole network, backbone only); captured on the
+    // second call with a shape (the first call runs eagerly and sets the kernels' function attributes).
+    struct GraphSlot { int n_ops = 0; cudaGraphExec_t exec = nullptr; int calls = 0; bool failed = false; };
+    GraphSlot graphs[2];
 };
 
 }  // namespace yb
@@ -63,6 +68,10 @@ struct yb_ctx {
     std::map<std::string, int> key_index;
     int mode = -1;
     int input_f16 = 0;                // element type of the images handed to yb_forward / yb_detect / ... (yb_set_input_dtype)
+    int graph_mode = 2;               // yb_set_graph_mode: 0 never, 1 always, 2 auto (launch-bound shapes only)
+    long long graph_replays = 0;      // calls whose convolution launches were replayed from a captured graph
+    cudaStream_t cap_stream = nullptr; // capture happens on a private stream: the caller's may be the legacy default stream,
+                                      // which cannot be captured (PyTorch's current stream usually is)
     bool finalized = false;
     unsigned char* d_blob = nullptr;
     size_t blob_bytes = 0;
@@ -198,8 +207,11 @@ std::vector<float>* field_vec(Layer& L, int field) {
 }
 
 void free_plans(yb_ctx* c) {
-    for (auto& p : c->plans)
+    for (auto& p : c->plans) {
+        for (auto& g : p->graphs)
+            if (g.exec) cudaGraphExecDestroy(g.exec);
         for (void* q : p->allocs) cudaFree(q);
+    }
     c->plans.clear();
 }
 
@@ -385,12 +397,15 @@ int build_plan(yb_ctx* c, int B, int H, int W, Plan** out) {
     };
     TView route;
     if (!predet(cur, curb, 512, 0, &route)) return bail(pb.err);
-    // UpsampleGroup (darknet.py:159-162): 1x1 conv, nearest x2 into channels [0, C) of the concat buffer.  The fp16 and
-    // CUDA-core modes replicate in the convolution's epilogue; the split mode writes a plain tensor into the free ping-pong
-    // buffer and replicates with a copy kernel (its epilogue keeps the tile in registers and only has the staged store).
+    // UpsampleGroup (darknet.py:159-162): 1x1 conv, nearest x2 into channels [0, C) of the concat buffer.  The tensor-core
+    // modes write a plain tensor into the free ping-pong buffer through the staged TMA-store epilogue and replicate it with a
+    // copy kernel: the direct 2x2-replicating stores of round 1 (32-byte stores one pixel pitch apart per lane) ran the two
+    // layers at 6-10 % tensor-pipe activity, 27 + 34 us (profiles/r02_conv_metrics.csv).  The CUDA-core mode replicates in
+    // its epilogue.
     auto up = [&](void* cat, int C, int Ctot) -> bool {
         TView o = pb.view(cat, B, route.H, route.W, C, Ctot, 0);
-        if (!split) return pb.conv(li++, route, o, nullptr, true, false);
+        static const bool up_direct = tune_env("YB_UP_DIRECT") && atoi(tune_env("YB_UP_DIRECT")) != 0;   // A/B (experiment builds)
+        if (p->mode == YB_MODE_FP32 || (up_direct && !split)) return pb.conv(li++, route, o, nullptr, true, false);
         TView t = pb.view(buf[route_buf == 0 ? 1 : 0], B, route.H, route.W, C, C);
         if (!pb.conv(li++, route, t, nullptr, false, false)) return false;
         Op op;
@@ -413,6 +428,26 @@ int build_plan(yb_ctx* c, int B, int H, int W, Plan** out) {
 
 constexpr int kProfBank = 16;
 
+cudaError_t launch_op(yb_ctx* c, Plan* p, Op& op, cudaStream_t s) {
+    const Layer& L = c->layers[op.layer];
+    if (op.upcopy)
+        return launch_upsample2x(static_cast<const __half*>(op.up_src.p), op.up_src.ld, op.up_src.lo, static_cast<__half*>(op.up_dst.p),
+                                 op.up_dst.ld, op.up_dst.lo, op.up_src.C, p->B, op.up_src.H, op.up_src.W, p->mode == YB_MODE_FP32_TC ? 2 : 1, s);
+    if (op.use_halo) return halo_launch(op.halo, op.a, c->dbg, s);
+    if (op.use_tc) return tc_launch(op.tc, op.a, c->dbg, s);
+    return launch_conv_simt<float>(op.a, L.d_w32, L.cout_pad, s);
+}
+
+// ops [1, n_ops) with plain stream launches
+int run_ops_tail(yb_ctx* c, Plan* p, int n_ops, cudaStream_t s) {
+    for (int i = 1; i < n_ops; ++i) {
+        const cudaError_t e = launch_op(c, p, p->ops[i], s);
+        if (e != cudaSuccess) return fail(c, YB_E_CUDA, "launch of layer " + c->layers[p->ops[i].layer].key + ": " + cudaGetErrorString(e));
+        ++c->launches;
+    }
+    return YB_OK;
+}
+
 int run_ops(yb_ctx* c, Plan* p, const float* x, int n_ops, cudaStream_t s) {
     const bool deferred = c->profiling && c->profile_deferred;
     const bool prof = c->profiling && !deferred;
@@ -432,10 +467,38 @@ int run_ops(yb_ctx* c, Plan* p, const float* x, int n_ops, cudaStream_t s) {
         }
         YB_CUDA(c, cudaEventRecord(c->ev[0], s));
     }
+    // Launch-bound shapes (a single 416x416 image: 80 dependent kernels of a few microseconds each) replay ops [1, n_ops)
+    // as one CUDA graph: the host then issues two launches instead of eighty.  Large batches keep the stream launches --
+    // the GPU is the bottleneck there and programmatic dependent launch already overlaps the kernels' prologues.
+    const bool want_graph = !c->profiling && n_ops > 1 &&
+                            (c->graph_mode == 1 || (c->graph_mode == 2 && (long)p->B * p->H * p->W <= (1L << 20)));
+    Plan::GraphSlot* slot = nullptr;
+    if (want_graph) {
+        for (auto& g : p->graphs)
+            if (g.n_ops == n_ops || g.n_ops == 0) { slot = &g; break; }
+        if (slot) { slot->n_ops = n_ops; ++slot->calls; }
+        if (slot && slot->failed) slot = nullptr;
+    }
+    bool capturing = false;
     for (int i = 0; i < n_ops; ++i) {
         Op& op = p->ops[i];
         const Layer& L = c->layers[op.layer];
         cudaError_t e;
+        if (i == 1 && slot) {
+            if (slot->exec) {                              // replay
+                e = cudaGraphLaunch(slot->exec, s);
+                if (e != cudaSuccess) return fail(c, YB_E_CUDA, std::string("cudaGraphLaunch: ") + cudaGetErrorString(e));
+                c->launches += n_ops - 1;                  // kernels of this library executed by the graph
+                ++c->graph_replays;
+                break;
+            }
+            if (slot->calls >= 2) {                        // capture the remaining launches of this call
+                e = c->cap_stream ? cudaSuccess : cudaStreamCreateWithFlags(&c->cap_stream, cudaStreamNonBlocking);
+                if (e == cudaSuccess) e = cudaStreamBeginCapture(c->cap_stream, cudaStreamCaptureModeThreadLocal);
+                if (e == cudaSuccess) capturing = true;
+                else { cudaGetLastError(); slot->failed = true; }
+            }
+        }
         if (op.stem) {
             if (c->input_f16 && p->mode != YB_MODE_FP16)
                 return fail(c, YB_E_UNSUPPORTED, "fp16 input images need YB_MODE_FP16");
@@ -445,20 +508,35 @@ int run_ops(yb_ctx* c, Plan* p, const float* x, int n_ops, cudaStream_t s) {
                 e = launch_stem_split(x, static_cast<__half*>(op.a.out), L.d_w32, L.d_scale, L.d_bias, p->B, p->H, p->W, s);
             else
                 e = launch_stem<float>(x, static_cast<float*>(op.a.out), L.d_w32, L.d_scale, L.d_bias, p->B, p->H, p->W, s);
-        } else if (op.upcopy) {
-            e = launch_upsample2x_split(static_cast<const __half*>(op.up_src.p), op.up_src.ld, op.up_src.lo, static_cast<__half*>(op.up_dst.p),
-                                        op.up_dst.ld, op.up_dst.lo, op.up_src.C, p->B, op.up_src.H, op.up_src.W, s);
-        } else if (op.use_halo) {
-            e = halo_launch(op.halo, op.a, c->dbg, s);
-        } else if (op.use_tc) {
-            e = tc_launch(op.tc, op.a, c->dbg, s);
         } else {
-            e = launch_conv_simt<float>(op.a, L.d_w32, L.cout_pad, s);
+            e = launch_op(c, p, op, capturing ? c->cap_stream : s);     // (nothing executes while capturing)
         }
-        if (e != cudaSuccess) return fail(c, YB_E_CUDA, "launch of layer " + L.key + ": " + cudaGetErrorString(e));
-        ++c->launches;
+        if (e != cudaSuccess) {
+            if (capturing) { cudaGraph_t g = nullptr; cudaStreamEndCapture(c->cap_stream, &g); if (g) cudaGraphDestroy(g); cudaGetLastError(); }
+            return fail(c, YB_E_CUDA, "launch of layer " + L.key + ": " + cudaGetErrorString(e));
+        }
+        if (!capturing) ++c->launches;
         if (prof && (c->profile_layers || i == n_ops - 1)) YB_CUDA(c, cudaEventRecord(c->ev[i + 1], s));
         if (deferred && i == n_ops - 1) YB_CUDA(c, cudaEventRecord(c->bank[c->bank_next * 4 + 1], s));
+    }
+    if (capturing) {
+        cudaGraph_t g = nullptr;
+        cudaError_t e = cudaStreamEndCapture(c->cap_stream, &g);
+        if (e == cudaSuccess && g) e = cudaGraphInstantiate(&slot->exec, g, 0);
+        if (g) cudaGraphDestroy(g);
+        if (e == cudaSuccess && slot->exec) e = cudaGraphLaunch(slot->exec, s);
+        if (e != cudaSuccess || !slot->exec) {
+            // capture is an optimisation: on any failure fall back to eager launches for good and run this call eagerly
+            cudaGetLastError();
+            if (slot->exec) { cudaGraphExecDestroy(slot->exec); slot->exec = nullptr; }
+            slot->failed = true;
+            const int saved = c->graph_mode;
+            c->graph_mode = 0;
+            const int rc = run_ops_tail(c, p, n_ops, s);
+            c->graph_mode = saved;
+            return rc;
+        }
+        c->launches += n_ops - 1;
     }
     return YB_OK;
 }
@@ -553,6 +631,7 @@ void yb_destroy(yb_ctx* c) {
     for (cudaEvent_t e : c->ev) cudaEventDestroy(e);
     for (cudaEvent_t e : c->bank) cudaEventDestroy(e);
     if (c->nccl_comm) comm_destroy(c->nccl_comm);
+    if (c->cap_stream) cudaStreamDestroy(c->cap_stream);
     delete c;
 }
 
@@ -1083,7 +1162,16 @@ int yb_set_input_dtype(yb_ctx* c, int dtype) {
     return YB_OK;
 }
 
+int yb_set_graph_mode(yb_ctx* c, int mode) {
+    if (!c) return fail(nullptr, YB_E_ARG, "null ctx");
+    if (mode < 0 || mode > 2) return fail(c, YB_E_ARG, "yb_set_graph_mode: 0 (never), 1 (always) or 2 (auto)");
+    c->graph_mode = mode;
+    return YB_OK;
+}
+
 long long yb_launch_count(const yb_ctx* c) { return c ? c->launches : 0; }
+
+long long yb_graph_replays(const yb_ctx* c) { return c ? c->graph_replays : 0; }
 
 int yb_debug_words(const yb_ctx* c, int* out, int n) {
     if (!c || !out || !c->dbg_host) return 0;

@@ -113,9 +113,9 @@ cudaError_t launch_stem_split(const float* x_nchw, __half* out_nhwc64, const flo
 cudaError_t launch_split_to_nchw_f32(const __half* in, long in_ld, long lo, int C, int B, int HW, float* out, cudaStream_t s);
 cudaError_t launch_f32_to_split(const float* in, __half* out, size_t M, int C, cudaStream_t s);
 cudaError_t launch_split_to_f32(const __half* in, float* out, size_t M, int C, cudaStream_t s);
-// nearest x2 of a split tensor: in [B,H,W] pixels of C hi values (+ C lo values in_lo later) -> the 2x2 block of out [B,2H,2W]
-cudaError_t launch_upsample2x_split(const __half* in, long in_ld, long in_lo, __half* out, long out_ld, long out_lo, int C,
-                                    int B, int H, int W, cudaStream_t s);
+// nearest x2 of an fp16 tensor: in [B,H,W] pixels of C values (halves = 2: + C lo values in_lo later) -> the 2x2 blocks of out [B,2H,2W]
+cudaError_t launch_upsample2x(const __half* in, long in_ld, long in_lo, __half* out, long out_ld, long out_lo, int C,
+                              int B, int H, int W, int halves, cudaStream_t s);
 
 // conv_tc.cu  (tcgen05 + TMA implicit GEMM)
 struct TcPlan {

@@ -101,24 +101,39 @@ class Darknet(nn.Module):
             mods += [res_layer(ch * 2) for _ in range(nb)]
         self.mlist = nn.ModuleList(mods)
         self._owner = None
+        self._shape = (list(blkList), nout)
 
-    def __getstate__(self):                     # the back-reference is a weakref: not picklable, rebound by YoloNet.__setstate__
+    def __getstate__(self):                     # the back-references are not picklable; rebound by YoloNet.__setstate__ / lazily
         st = self.__dict__.copy()
         st["_owner"] = None
+        st.pop("_host", None)
         return st
+
+    def _engine_owner(self):
+        """The YoloNet whose engine runs this backbone: the net this module is the `feature` of, or -- for a stand-alone
+        Darknet(blkList), as darknet.py:72-88 allows -- a hidden host net created on first use that adopts THIS module as
+        its `feature` (so the engine reads this module's own parameters; the host's head weights are never executed)."""
+        owner = self._owner() if self._owner is not None else None
+        if owner is not None:
+            return owner
+        if self._shape != (list(BLOCKS), 32):
+            raise NotImplementedError("the engine runs the Darknet-53 layout only: blkList=[1,2,8,8,4], nout=32")
+        import weakref
+        host = YoloNet(None)
+        host.feature = self
+        object.__setattr__(self, "_host", host)             # strong reference, NOT a registered sub-module (no module cycle)
+        self._owner = weakref.ref(host)
+        return host
 
     def loadWeight(self, weights_path):
         """Backbone-only darknet stream, e.g. darknet53.conv.74 (darknet.py:102-104)."""
-        owner = self._owner() if self._owner is not None else None
-        if owner is None:
-            raise RuntimeError("Darknet.loadWeight is only available on YoloNet.feature")
-        owner._load_darknet_file(weights_path, backbone_only=True)
+        self._engine_owner()._load_darknet_file(weights_path, backbone_only=True)
 
     def forward(self, x):
-        owner = self._owner() if self._owner is not None else None
-        if owner is None:
-            raise RuntimeError("a stand-alone Darknet has no engine; use YoloNet(...).feature")
-        return owner.backbone(x)
+        """darknet.py:83-88: [B,1024,H/32,W/32] fp32 (the cached route outputs stay inside the engine)."""
+        if self.training:
+            raise RuntimeError("inference path only: call .eval() first (BatchNorm uses running statistics)")
+        return self._engine_owner().backbone(x)
 
 
 class PreDetectionConvGroup(nn.Module):
@@ -165,6 +180,7 @@ class YoloNet(nn.Module):
             raise ValueError("precision must be 'fp16', 'fp32' or 'fp32_simt'")
         self.check_weights = bool(check_weights)
         self._frozen = False
+        self._graph_mode = 2                                # yb_set_graph_mode: auto
 
         self.feature = Darknet(BLOCKS)
         self.feature._owner = weakref.ref(self)
@@ -223,6 +239,14 @@ class YoloNet(nn.Module):
         self._frozen = False
         return self
 
+    def set_graph_mode(self, mode="auto"):
+        """CUDA-graph replay of the convolution launches after the stem (yb_set_graph_mode): 'never', 'always' or 'auto'
+        (default: only for launch-bound shapes such as a single 416x416 image)."""
+        self._graph_mode = {"never": 0, "always": 1, "auto": 2}[mode]
+        if self._ctx is not None:
+            _lib.check(_lib.load().yb_set_graph_mode(self._ctx, self._graph_mode), self._ctx)
+        return self
+
     def freeze_weights(self, frozen: bool = True):
         """Skip the per-forward change detection (a walk over the 438 tensors, ~0.1 ms of host time -- visible at batch 1)
         until refresh_weights() / load_state_dict() / loadWeight() is called."""
@@ -250,6 +274,7 @@ class YoloNet(nn.Module):
             self._release()
             self._ctx = _lib.create_ctx(index, self.numClass, self.anchors)
             self._ctx_device = index
+            _lib.check(lib.yb_set_graph_mode(self._ctx, self._graph_mode), self._ctx)
             self._sig = None
             self._in_dtype = _lib.YB_INPUT_F32          # a new context reads fp32 images
         if self._frozen and self._sig is not None:
