@@ -536,10 +536,13 @@ def run_ours(args):
     _lib.check(lib.yb_set_profiling(ctx, 0), ctx)
 
     if rank != 0:
-        if world > 1:
-            dist.barrier()                                  # rank 0 finishes its single-GPU extras first
-            dist.destroy_process_group()
+        # every collective of the run is behind us: the other ranks leave, rank 0 finishes its single-GPU extras alone (it
+        # keeps its engine -- and with it the library's NCCL communicator -- alive until the process exits: destroying a
+        # communicator while the peers are gone or blocked elsewhere can wait for them for ever)
+        torch.cuda.synchronize()
+        dist.destroy_process_group()
         return
+    torch.set_num_threads(os.cpu_count() or 1)             # torchrun exports OMP_NUM_THREADS=1; the oracle legs below use every core
 
     # ================= rank 0 only from here: kernels timed alone, parity, other configs, CPU baseline =================
     def timed(fn, reps=10):
@@ -626,8 +629,9 @@ def run_ours(args):
         except Exception as e:  # noqa: BLE001
             line["parity"] = {"error": f"{type(e).__name__}: {e}"}
             torch.cuda.synchronize()
-    del net, comm
-    torch.cuda.empty_cache()
+    if world == 1:
+        del net
+        torch.cuda.empty_cache()
 
     def simple_bench(n, batch_x, fn, steps):
         """W warm-up + `steps` calls of fn(i) on resident inputs, CUDA events; returns ms per step."""
@@ -725,7 +729,6 @@ def run_ours(args):
         for i, v in enumerate(layer_ms):
             print(f"# op {i:2d} {v:8.4f} ms", file=sys.stderr)
     if world > 1:
-        dist.barrier()
         dist.destroy_process_group()
 
 

@@ -22,6 +22,7 @@ struct Nccl {
     ncclResult_i (*GetUniqueId)(ncclUniqueId_t*) = nullptr;
     ncclResult_i (*CommInitRank)(ncclComm_p*, int, ncclUniqueId_t, int) = nullptr;
     ncclResult_i (*CommDestroy)(ncclComm_p) = nullptr;
+    ncclResult_i (*CommAbort)(ncclComm_p) = nullptr;          // optional
     ncclResult_i (*Broadcast)(const void*, void*, size_t, int /*dtype*/, int, ncclComm_p, cudaStream_t) = nullptr;
     ncclResult_i (*AllGather)(const void*, void*, size_t, int /*dtype*/, ncclComm_p, cudaStream_t) = nullptr;
     const char* (*GetErrorString)(ncclResult_i) = nullptr;
@@ -48,6 +49,7 @@ Nccl* nccl() {
         YB_SYM(AllGather, "ncclAllGather")
         YB_SYM(GetErrorString, "ncclGetErrorString")
 #undef YB_SYM
+        *reinterpret_cast<void**>(&n.CommAbort) = dlsym(n.h, "ncclCommAbort");
         return n;
     }();
     return &n;
@@ -95,9 +97,15 @@ int comm_allgather(void* comm, const void* send, void* recv, size_t bytes, cudaS
     return check(n, n->AllGather(send, recv, bytes, kNcclChar, static_cast<ncclComm_p>(comm), s), "ncclAllGather", err);
 }
 
+// Tear-down must never wait for the peers: ranks leave at different times (rank 0 of bench.py keeps working alone after
+// the others have gone), and ncclCommDestroy synchronises with the other ranks of the communicator -- observed in round 2
+// as a deadlock against a rank blocked in an unrelated barrier.  ncclCommAbort frees the communicator without that handshake;
+// every collective this library enqueues has completed by the time a context is destroyed (the caller synchronises its streams).
 void comm_destroy(void* comm) {
     Nccl* n = nccl();
-    if (n->h && comm) n->CommDestroy(static_cast<ncclComm_p>(comm));
+    if (!n->h || !comm) return;
+    if (n->CommAbort) n->CommAbort(static_cast<ncclComm_p>(comm));
+    else n->CommDestroy(static_cast<ncclComm_p>(comm));
 }
 
 }  // namespace yb
