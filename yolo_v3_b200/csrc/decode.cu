@@ -32,7 +32,7 @@ __device__ __forceinline__ float sigmoidf_rn(float t) { return __fdiv_rn(1.0f, _
 __device__ __forceinline__ float decode_one(const DecodeScale& s, int a, int attr, int x, int y, float t) {
     const bool wh = attr == 2 || attr == 3;
     const float e = expf(wh ? t : -t);
-    const float sig = __fdiv_rn(1.0f, __fadd_rn(1.0f, e));
+    const float sig = __frcp_rn(__fadd_rn(1.0f, e));     // 1 / (1 + e), correctly rounded = __fdiv_rn(1, 1 + e) bit for bit
     const float off = attr == 0 ? (float)x : (attr == 1 ? (float)y : 0.f);
     const float mul = attr < 2 ? s.stride : 1.0f;
     const float r_sig = __fmul_rn(__fadd_rn(sig, off), mul);
@@ -47,7 +47,10 @@ __device__ __forceinline__ float decode_one(const DecodeScale& s, int a, int att
 // four consecutive channels each (the head maps are padded to a multiple of 16 channels, so the loads are
 // aligned); the four 64-thread groups of a block take every fourth cell, with four such loads in flight
 // per thread -- the kernel is latency-bound otherwise.  Stores are scalar (the 3*(5+C)-float output rows
-// are only 4-byte aligned) but consecutive threads still write consecutive addresses.
+// are only 4-byte aligned) but consecutive threads still write consecutive addresses.  (Round 2 tried staging the block's
+// output in shared memory and writing it with aligned 16-byte stores: 0.208 ms against 0.175 ms for 608x608 batch 32 -- the
+// kernel is bound by its ~40 instructions per element (full-precision expf + a correctly rounded reciprocal), not by the
+// store pattern; profiles/README.md.)
 constexpr int kCellsPerBlock = 32;
 
 __global__ void __launch_bounds__(256) decode_nhwc_kernel(const __grid_constant__ DecodeParams P, float* __restrict__ det,
