@@ -102,6 +102,13 @@ CASES = [
     # halo kernel in pair mode (Cout = 128: two spatial tiles per cta_group::2 UMMA)
     (6, 1, 9, 38, True),       # three tiles: rank 1 of the second pair gets the zero-filled / clipped tile past the batch
     (6, 3, 5, 76, False),      # no residual: the four-slot ring recycled by the stores alone; partial last row strip
+    # halo kernel at widths that are not multiples of 38: the last column tile is partial (zero-filled patch, clipped store)
+    (3, 2, 10, 104, True),     # 32->64 at the 416 network's stage-0 width / 2: 2.74 column tiles, residual
+    (3, 1, 7, 208, False),     # 416 network, 5.47 column tiles
+    (6, 2, 7, 64, True),       # pair mode at the 256 network's width: 1.68 column tiles, residual
+    (6, 1, 5, 128, False),     # pair mode, 3.37 column tiles
+    (1, 2, 20, 208, False),    # 32->64 stride 2 (four parity planes), output 10 x 104
+    (1, 1, 14, 256, False),    # stride 2 at the 256 network's input width, output 7 x 128
     # the benched batch: 608x608 batch 32 shapes of the last stage (2.49 waves of pair tiles: the tail wave is partial)
     (45, 32, 19, 19, True),    # 512->1024 3x3 + residual, M = 11 552
     (27, 32, 38, 38, False),   # 512->256 1x1 at 38^2, M = 46 208

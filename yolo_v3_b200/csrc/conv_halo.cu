@@ -407,7 +407,12 @@ bool halo_supported(const ConvArgs& a) {
     } else {
         return false;
     }
-    if (a.Wo % kHC != 0 || a.Cout % kHBN != 0 || a.Cout > 128) return false;
+    if (a.Cout % kHBN != 0 || a.Cout > 128) return false;
+    // any output width: the last column tile may be partial -- its patch load zero-fills and its store box is clipped by the
+    // tensor map, exactly like the last row strip -- as long as at least 80 % of the tile columns are real outputs
+    // (208 -> 6 tiles, 91 %; 128 -> 4, 84 %; 104 -> 3, 91 %; 64 -> 2, 84 %; multiples of 38: 100 %)
+    const int tx = (a.Wo + kHC - 1) / kHC;
+    if (a.Wo * 5 < tx * kHC * 4) return false;
     // (the scheme trades 11 % of the tensor work -- 114 useful rows of 128 -- for ~5x less L2->SM traffic; with these
     // channel counts the im2col kernel is traffic-bound, so every eligible shape takes it)
     return !(a.in_ld % 8 || a.out_ld % 8 || (a.res && a.res_ld % 8));
@@ -424,7 +429,7 @@ std::string halo_make_plan(HaloPlan& p, const ConvArgs& a, const __half* w16, in
     p.swz = a.Cin == 32 ? 64 : 128;
     p.cout_pad = cout_pad;
     p.stride = a.stride;
-    p.tiles_x = a.Wo / kHC;
+    p.tiles_x = (a.Wo + kHC - 1) / kHC;
     p.tiles_y = (a.Ho + kHR - 1) / kHR;
     // Cout = 128 with 128-byte pixels: CTA pairs, all 128 channels in one UMMA (see the kernel's header comment)
     p.pair = p.swz == 128 && a.stride == 1 && a.Cout == 2 * kHBN && num_sms % 2 == 0;
