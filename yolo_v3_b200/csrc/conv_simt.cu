@@ -131,7 +131,7 @@ __global__ void __launch_bounds__(128) stem_kernel(const float* __restrict__ x, 
                                                    const float* __restrict__ w, const float* __restrict__ scale,
                                                    const float* __restrict__ bias, int B, int H, int W) {
     constexpr int CH = SPLIT ? 64 : 32;             // values stored per pixel
-    __shared__ float ws[27 * 32];
+    __shared__ __align__(16) float ws[27 * 32];
     __shared__ float ss[32], sb[32];
     __shared__ __align__(16) T stage[4][32][CH + 8];
     for (int i = threadIdx.x; i < 27 * 32; i += blockDim.x) ws[i] = w[i];
@@ -157,9 +157,17 @@ __global__ void __launch_bounds__(128) stem_kernel(const float* __restrict__ x, 
 #pragma unroll
                 for (int c = 0; c < 3; ++c) {
                     const float v = ok ? __ldg(x + (((long)b * 3 + c) * H + iy) * W + ix) : 0.f;
-                    const float* wr = ws + ((ky * 3 + kx) * 3 + c) * 32;
+                    // the 32 weights of this tap as eight 16-byte broadcast loads (scalar loads made the kernel LDS-bound:
+                    // one shared-memory instruction per FMA)
+                    const float4* wr = reinterpret_cast<const float4*>(ws + ((ky * 3 + kx) * 3 + c) * 32);
 #pragma unroll
-                    for (int n = 0; n < 32; ++n) acc[n] = fmaf(v, wr[n], acc[n]);
+                    for (int n = 0; n < 8; ++n) {
+                        const float4 w4 = wr[n];
+                        acc[4 * n + 0] = fmaf(v, w4.x, acc[4 * n + 0]);
+                        acc[4 * n + 1] = fmaf(v, w4.y, acc[4 * n + 1]);
+                        acc[4 * n + 2] = fmaf(v, w4.z, acc[4 * n + 2]);
+                        acc[4 * n + 3] = fmaf(v, w4.w, acc[4 * n + 3]);
+                    }
                 }
             }
         }

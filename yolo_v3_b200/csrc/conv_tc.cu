@@ -311,15 +311,16 @@ __device__ __forceinline__ void load_resident_weights(const CUtensorMap* tmB, co
     }
 }
 
-// SUBS (split mode): sub-tiles a thread of the epilogue accumulates in registers -- 2: tiles up to 128 columns, 32 accumulators.
-// (256-column tiles would need 64 accumulators per thread, i.e. ~110 registers for the epilogue warps: a SUBS = 4 variant
-// that has the four role warps donate registers with setmaxnreg was written in round 2, but ptxas 12.9 fails its register
-// allocation (C7600) whatever counts are requested, so it is not built.)
+// SUBS (split mode): sub-tiles a thread of the epilogue accumulates in registers -- 2: tiles up to 128 columns, 32
+// accumulators; 4: 256-column tiles, 64 accumulators, for which the four role warps donate registers to the epilogue
+// warpgroups with setmaxnreg (96 -> 56 / 104).  Such a kernel must not call out-of-line functions from the re-partitioned
+// regions -- ptxas fails its register allocation (C7600) -- hence mbar_wait<kDonate>.
 template <int SWZ, bool CTA2, bool SPLIT = false, int SUBS = 2>
 __global__ void __launch_bounds__(SPLIT ? kThreadsSplit : kThreads, 1)
 conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                const __grid_constant__ CUtensorMap tmOut, const __grid_constant__ CUtensorMap tmRes, const TcArgs a_in) {
     constexpr int BKE = SWZ / 2;                  // fp16 elements per k-block row
+    constexpr bool kDonate = SPLIT && SUBS == 4;  // register donation (setmaxnreg): no out-of-line calls in this kernel
     TcArgs a = a_in;
     constexpr uint32_t A_BYTES = kBM * SWZ;
     extern __shared__ uint8_t smem_raw[];
@@ -410,7 +411,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 #pragma unroll
                 for (int i = 0; i < 16; ++i) sacc[j][i] = 0.f;
             for (int ch = 0; ch < a.n_chunks; ++ch) {
-                mbar_wait(tfull0 + 8 * accb, acc_phase, a.dbg, 2, 200 + (int)accb);
+                mbar_wait<kDonate>(tfull0 + 8 * accb, acc_phase, a.dbg, 2, 200 + (int)accb);
                 tc_fence_after();
                 const uint32_t tcol = tmem_base + accb * acc_stride + ((uint32_t)(q * 32) << 16) + (uint32_t)(part * 16);
                 // SUBS == 2: both sub-tiles in one round trip to TMEM; SUBS == 4: one at a time (16 values in flight next to
@@ -450,8 +451,8 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             for (int j = 0; j < SUBS; ++j) {
                 if (j < a.n_sub) {
                     const uint32_t buf = rw.buf, ph = rw.ph;
-                    if (a.has_res) mbar_wait(sfull0 + 8 * buf, ph, a.dbg, 2, 400 + (int)buf);
-                    else mbar_wait(sempty0 + 8 * buf, ph ^ 1, a.dbg, 2, 500 + (int)buf);
+                    if (a.has_res) mbar_wait<kDonate>(sfull0 + 8 * buf, ph, a.dbg, 2, 400 + (int)buf);
+                    else mbar_wait<kDonate>(sempty0 + 8 * buf, ph ^ 1, a.dbg, 2, 500 + (int)buf);
                     uint8_t* srow = gen + (stg0 - base) + buf * stg_bytes + (uint32_t)row * (uint32_t)a.sub_bytes;
                     const int nb = n0 + j * a.cs + part * 16;
                     if (active) {
@@ -476,8 +477,14 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             if (n0 >= n_wrap) n0 -= n_wrap;
         }
     };
-    {
-
+    // SUBS == 4: 640 threads x 96 registers at launch.  Warpgroup 0 (the four role warps: single-thread loops) keeps 56, each
+    // of the four epilogue warpgroups grows to 104: 64 fp32 accumulators + a 16-value TMEM load + addressing.  The two
+    // setmaxnreg instructions sit at the heads of the two branches, so that each dominates the code it governs.
+    if (kDonate && warp >= 4) {
+        asm volatile("setmaxnreg.inc.sync.aligned.u32 104;");
+        split_epilogue();
+    } else {
+    if constexpr (kDonate) asm volatile("setmaxnreg.dec.sync.aligned.u32 56;");
     if (warp < (SPLIT ? 1 : 2)) {
         // ===== TMA producers (two warps take alternate pipeline stages -- one warp takes all of them in split mode; whole warp runs the loop, one
         // elected lane issues).  Both walk the same stage/coordinate sequence and act on their own parity. =====
@@ -506,7 +513,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                     [[maybe_unused]] int cc = 0, sec = 0;      // SPLIT: channel of the A box inside its half, section 0..2
                     for (int it = 0; it < a.num_iters; ++it, ++itg) {
                         const bool mine = SPLIT || (itg & 1u) == pw;
-                        if (mine) mbar_wait(eb, phase ^ 1, a.dbg, 0, stage);
+                        if (mine) mbar_wait<kDonate>(eb, phase ^ 1, a.dbg, 0, stage);
                         const bool el = mine && elect_one();
                         if (leader && el) mbar_arrive_expect_tx(fb, tx_bytes);
                         uint32_t dst = sA;
@@ -541,7 +548,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                     const int cend = a.cin_blocks * BKE;
                     for (int it = 0; it < a.num_iters; ++it, ++itg) {
                         const bool mine = SPLIT || (itg & 1u) == pw;
-                        if (mine) mbar_wait(eb, phase ^ 1, a.dbg, 0, stage);
+                        if (mine) mbar_wait<kDonate>(eb, phase ^ 1, a.dbg, 0, stage);
                         const bool el = mine && elect_one();
                         if (leader && el) mbar_arrive_expect_tx(fb, tx_bytes);
                         uint32_t dst = sA;
@@ -586,11 +593,11 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             uint64_t adesc = adesc0;
             uint32_t fbar = full0, ebar = empty0;
             bool ready = false;
-            if (a.b_resident && tile_first < total_tiles) mbar_wait(bres_bar, 0, a.dbg, 1, 600);
+            if (a.b_resident && tile_first < total_tiles) mbar_wait<kDonate>(bres_bar, 0, a.dbg, 1, 600);
             int ti = 0;
             for (int tile = tile_first; tile < total_tiles; tile += tile_step, ++ti) {
                 YB_TRACE(1, ti, 0);
-                mbar_wait(tempty0 + 8 * acc, acc_phase ^ 1, a.dbg, 1, 100 + (int)acc);
+                mbar_wait<kDonate>(tempty0 + 8 * acc, acc_phase ^ 1, a.dbg, 1, 100 + (int)acc);
                 tc_fence_after();
                 YB_TRACE(1, ti, 1);
                 uint32_t d_tmem = tmem_base + acc * acc_stride;
@@ -605,14 +612,14 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                             }
                             acc ^= 1;
                             if (acc == 0) acc_phase ^= 1;
-                            mbar_wait(tempty0 + 8 * acc, acc_phase ^ 1, a.dbg, 1, 100 + (int)acc);
+                            mbar_wait<kDonate>(tempty0 + 8 * acc, acc_phase ^ 1, a.dbg, 1, 100 + (int)acc);
                             tc_fence_after();
                             d_tmem = tmem_base + acc * acc_stride;
                             kbc = 0; it_chunk = 0;
                         }
                         ++it_chunk;
                     }
-                    if (!ready) mbar_wait(fbar, phase, a.dbg, 1, stage);
+                    if (!ready) mbar_wait<kDonate>(fbar, phase, a.dbg, 1, stage);
                     tc_fence_after();
                     // probe the NEXT stage's barrier now: its latency overlaps the MMA issue below
                     const bool wrap = stage + 1 == a.stages;
@@ -661,7 +668,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                 const int m0 = (m_unit * NCTA + (int)rank) * kBM, n0 = n_tile * a.BN;
                 for (int j = 0; j < a.n_sub; ++j, rw.next((uint32_t)a.ring)) {
                     const uint32_t buf = rw.buf, ph = rw.ph;
-                    mbar_wait(sempty0 + 8 * buf, ph ^ 1, a.dbg, 3, 300 + (int)buf);
+                    mbar_wait<kDonate>(sempty0 + 8 * buf, ph ^ 1, a.dbg, 3, 300 + (int)buf);
                     mbar_arrive_expect_tx(sfull0 + 8 * buf, stg_bytes);
                     tma_load_2d(&tmRes, stg0 + buf * stg_bytes, sfull0 + 8 * buf, n0 + j * a.cs, m0);
                     if (split_out) tma_load_2d(&tmRes, stg0 + buf * stg_bytes + stg_half, sfull0 + 8 * buf, a.res_lo + n0 + j * a.cs, m0);
@@ -681,7 +688,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                 const int m0 = (m_unit * NCTA + (int)rank) * kBM, n0 = n_tile * a.BN;
                 for (int j = 0; j < a.n_sub; ++j, ++g, rw.next((uint32_t)a.ring)) {
                     const uint32_t buf = rw.buf, ph = rw.ph;
-                    mbar_wait(sready0 + 8 * buf, ph, a.dbg, 4, 700 + (int)buf);
+                    mbar_wait<kDonate>(sready0 + 8 * buf, ph, a.dbg, 4, 700 + (int)buf);
                     tma_store_2d(&tmOut, stg0 + buf * stg_bytes, n0 + j * a.cs, m0);
                     if (split_out) tma_store_2d(&tmOut, stg0 + buf * stg_bytes + stg_half, a.out_lo + n0 + j * a.cs, m0);
                     tma_store_commit();
@@ -703,7 +710,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             tma_store_wait_all();
         }
         __syncwarp();
-    } else if (SPLIT && warp >= 4 && warp < 20) {
+    } else if (SPLIT && !kDonate && warp >= 4 && warp < 20) {
         split_epilogue();
     } else if (warp >= 8 && a.epi_staged) {
         // ===== epilogue (staged): TMEM -> registers -> swizzled smem sub-tile -> TMA store =====
@@ -737,7 +744,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         const int dn0 = ((tmul * tile_step) % a.n_tiles) * a.BN;
         for (int tile = tile_begin; tile < total_tiles; tile += tmul * tile_step, ti += tmul) {
             if (issuer) YB_TRACE(2, ti, 0);
-            mbar_wait(tfull0 + 8 * acc, acc_phase, a.dbg, 2, 200 + (int)acc);
+            mbar_wait<kDonate>(tfull0 + 8 * acc, acc_phase, a.dbg, 2, 200 + (int)acc);
             tc_fence_after();
             if (issuer) YB_TRACE(2, ti, 1);
             const uint32_t taddr = tmem_base + acc * acc_stride + ((uint32_t)(q * 32) << 16);
@@ -747,8 +754,8 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                 const uint32_t tcol = taddr + (uint32_t)(j * a.cs + part * 16);
                 if (active) tmem_ld16(tcol, r0);
                 // the buffer is ours once the residual landed (res layers) or its previous store drained
-                if (a.has_res) mbar_wait(sfull0 + 8 * buf, ph, a.dbg, 2, 400 + (int)buf);
-                else mbar_wait(sempty0 + 8 * buf, ph ^ 1, a.dbg, 2, 500 + (int)buf);
+                if (a.has_res) mbar_wait<kDonate>(sfull0 + 8 * buf, ph, a.dbg, 2, 400 + (int)buf);
+                else mbar_wait<kDonate>(sempty0 + 8 * buf, ph ^ 1, a.dbg, 2, 500 + (int)buf);
                 if (issuer && j == 0) YB_TRACE(3, ti, 0);
                 tmem_ld_wait();
                 if (issuer && j == 0) YB_TRACE(3, ti, 1);
@@ -802,7 +809,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                 W2ld = 2L * a.Wo * a.out_ld;
                 o00 = (((long)img * 2 * a.Ho + 2 * y) * 2 * a.Wo + 2 * x) * a.out_ld;
             }
-            mbar_wait(tfull0 + 8 * acc, acc_phase, a.dbg, 2, 200 + (int)acc);
+            mbar_wait<kDonate>(tfull0 + 8 * acc, acc_phase, a.dbg, 2, 200 + (int)acc);
             tc_fence_after();
             const uint32_t taddr = tmem_base + acc * acc_stride + ((uint32_t)(q * 32) << 16);
             for (int c0 = 0; c0 < a.BN; c0 += 32) {
@@ -1168,7 +1175,9 @@ std::string tc_make_plan(TcPlan& p, const ConvArgs& a, const __half* w16, int co
     double best_cost = 0;
     // split mode: a thread of the epilogue keeps its share of the tile in registers (two-level accumulation), at most
     // 32 values: 128 columns of fp16 pairs (four warps per 64-column sub-tile) or 64 columns of fp32 (two per 32-column one)
-    const int bn_max = a.split ? (a.out_f32 ? 64 : 128) : 256;
+    // (the fp32 head maps keep the SUBS = 2 kernels: 64 columns)
+    static const bool split_wide = !(tune_env("YB_SPLIT_WIDE") && atoi(tune_env("YB_SPLIT_WIDE")) == 0);
+    const int bn_max = a.split ? (a.out_f32 ? 64 : (split_wide ? 256 : 128)) : 256;
     for (int bn = std::min(cout_pad, bn_max); bn >= 16; bn -= 16) {
         if (cout_pad % bn) continue;
         if (bn < 64 && bn != cout_pad) break;
@@ -1224,7 +1233,7 @@ std::string tc_make_plan(TcPlan& p, const ConvArgs& a, const __half* w16, int co
     // 32-column sub-tiles (Cout = 32 in fp16, the fp32 head maps) keep only eight of the sixteen epilogue warps busy:
     // the two halves then work on alternate sub-tiles, each with its own slot of a four-deep ring
     p.epi_split = p.epi_staged && p.cs == 32 && (p.n_sub == 1 || p.n_sub % 2 == 0) && !a.split;
-    if (a.split && (!p.epi_staged || p.n_sub > 2)) return "split mode: tile does not fit the register accumulators";
+    if (a.split && (!p.epi_staged || p.n_sub > (a.out_f32 ? 2 : 4))) return "split mode: tile does not fit the register accumulators";
     if (const char* e = tune_env("YB_TC_EPISPLIT")) p.epi_split = p.epi_split && atoi(e) != 0;
     if (p.epi_split) p.ring = 4;
     const size_t stg_bytes = ((size_t)kBM * p.sub_bytes * (split_out ? 2 : 1) + 1023) & ~(size_t)1023;
@@ -1447,6 +1456,8 @@ cudaError_t tc_launch(const TcPlan& p, const ConvArgs& a, int* dbg, cudaStream_t
                 r = cudaFuncSetAttribute(conv_tc_kernel<128, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBudget);
                 if (r == cudaSuccess) r = cudaFuncSetAttribute(conv_tc_kernel<64, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBudget);
                 if (r == cudaSuccess) r = cudaFuncSetAttribute(conv_tc_kernel<128, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBudget);
+                if (r == cudaSuccess) r = cudaFuncSetAttribute(conv_tc_kernel<128, false, true, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBudget);
+                if (r == cudaSuccess) r = cudaFuncSetAttribute(conv_tc_kernel<128, true, true, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBudget);
             }
             return r;
         });
@@ -1476,7 +1487,10 @@ cudaError_t tc_launch(const TcPlan& p, const ConvArgs& a, int* dbg, cudaStream_t
         cfg.attrs = attr;
         cfg.numAttrs = na;
         cudaError_t e;
-        if (p.split) {
+        if (p.split && p.n_sub > 2) {
+            if (p.cta2) e = cudaLaunchKernelEx(&cfg, conv_tc_kernel<128, true, true, 4>, p.tmA, p.tmB, p.tmOut, p.tmRes, t);
+            else e = cudaLaunchKernelEx(&cfg, conv_tc_kernel<128, false, true, 4>, p.tmA, p.tmB, p.tmOut, p.tmRes, t);
+        } else if (p.split) {
             if (p.cta2) e = cudaLaunchKernelEx(&cfg, conv_tc_kernel<128, true, true>, p.tmA, p.tmB, p.tmOut, p.tmRes, t);
             else if (p.swz == 128) e = cudaLaunchKernelEx(&cfg, conv_tc_kernel<128, false, true>, p.tmA, p.tmB, p.tmOut, p.tmRes, t);
             else e = cudaLaunchKernelEx(&cfg, conv_tc_kernel<64, false, true>, p.tmA, p.tmB, p.tmOut, p.tmRes, t);

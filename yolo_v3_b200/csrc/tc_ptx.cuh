@@ -75,8 +75,27 @@ __device__ __noinline__ void mbar_wait_slow(uint32_t bar, uint32_t parity, int* 
         }
     }
 }
+// INL: the polling loop is inlined.  Kernels that re-partition the register file with setmaxnreg must not call out-of-line
+// functions from the re-partitioned regions (ptxas fails the register allocation of such a kernel, C7600).
+template <bool INL = false>
 __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity, int* dbg, int role, int which) {
-    if (!mbar_try_wait(bar, parity)) mbar_wait_slow(bar, parity, dbg, role, which);
+    if (mbar_try_wait(bar, parity)) return;
+    if constexpr (INL) {
+        const long long t0 = clock64();
+        while (!mbar_try_wait(bar, parity)) {
+            if (clock64() - t0 > kWatchdogCycles) {
+                if (dbg) {
+                    dbg[1] = (int)blockIdx.x; dbg[2] = role; dbg[3] = which; dbg[4] = (int)parity;
+                    __threadfence_system();
+                    dbg[0] = 1;
+                    __threadfence_system();
+                }
+                __trap();
+            }
+        }
+    } else {
+        mbar_wait_slow(bar, parity, dbg, role, which);
+    }
 }
 // Same, for waits that are long by construction (the sixteen epilogue warps waiting for the next accumulator while the
 // main loop runs): back off between probes instead of spinning -- the step runs at the board's power cap, and warps
