@@ -47,10 +47,8 @@ __device__ __forceinline__ float decode_one(const DecodeScale& s, int a, int att
 // four consecutive channels each (the head maps are padded to a multiple of 16 channels, so the loads are
 // aligned); the four 64-thread groups of a block take every fourth cell, with four such loads in flight
 // per thread -- the kernel is latency-bound otherwise.  Stores are scalar (the 3*(5+C)-float output rows
-// are only 4-byte aligned) but consecutive threads still write consecutive addresses.  (Round 2 tried staging the block's
-// output in shared memory and writing it with aligned 16-byte stores: 0.208 ms against 0.175 ms for 608x608 batch 32 -- the
-// kernel is bound by its ~40 instructions per element (full-precision expf + a correctly rounded reciprocal), not by the
-// store pattern; profiles/README.md.)
+// are only 4-byte aligned) but consecutive threads still write consecutive addresses.  (Staging the block's output in
+// shared memory for aligned 16-byte stores is slower, see decode_nhwc_staged_kernel below.)
 constexpr int kCellsPerBlock = 32;
 
 __global__ void __launch_bounds__(256) decode_nhwc_kernel(const __grid_constant__ DecodeParams P, float* __restrict__ det,
@@ -93,6 +91,59 @@ __global__ void __launch_bounds__(256) decode_nhwc_kernel(const __grid_constant_
         }
     }
 }
+
+#ifdef YB_EXPERIMENTS
+// Variant with staged output (YB_DECODE_STAGED=1, experiment builds only; same-box A/B in profiles/r02t_decode_staged_ab.txt:
+// 0.181 ms against 0.167 ms for the direct kernel at 608x608 batch 32 -- the kernel is bound by its instructions per
+// element, full-precision expf and a correctly rounded reciprocal, not by the 4-byte store pattern): phase 1
+// parks the decoded values in shared memory in output order (thread q of a 64-thread group owns channels q, q+64, ...), phase
+// 2 copies the block's contiguous output run with 16-byte stores, the shared-memory image shifted by the run's misalignment.
+__global__ void __launch_bounds__(256) decode_nhwc_staged_kernel(const __grid_constant__ DecodeParams P, float* __restrict__ det,
+                                                                 int blocks_s0, int blocks_s1, int cpb) {
+    extern __shared__ __align__(16) float out_s[];                 // [mis + cpb * ch]
+    const int ch = 3 * P.attrs;
+    int blk = blockIdx.x;
+    const int si = blk >= blocks_s0 + blocks_s1 ? 2 : (blk >= blocks_s0 ? 1 : 0);
+    blk -= si == 2 ? blocks_s0 + blocks_s1 : (si == 1 ? blocks_s0 : 0);
+    const DecodeScale& s = P.sc[si];
+    const int hw = s.h * s.w;
+    const int per_img = (hw + cpb - 1) / cpb;
+    const int b = blk / per_img, p0 = (blk - b * per_img) * cpb;
+    const int np = min(cpb, hw - p0);
+    const float* in = s.logits + ((long)b * hw + p0) * s.ld;
+    float* out = det + ((long)b * P.n_total + s.row_off) * P.attrs + (long)p0 * ch;
+    const int n = np * ch;
+    const int mis = (int)((reinterpret_cast<uintptr_t>(out) >> 2) & 3);   // floats past a 16-byte boundary
+    const int grp = threadIdx.x >> 6, q = threadIdx.x & 63;
+    for (int cb = 0; cb < ch; cb += 256) {
+        int a[4], attr[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) { const int c = cb + q + 64 * u; a[u] = c / P.attrs; attr[u] = c - a[u] * P.attrs; }
+        int p = p0 + grp;
+        int y = p / s.w, x = p - y * s.w;
+        for (int i = grp; i < np; i += 4) {
+            const float* ci = in + (long)i * s.ld + cb + q;
+            float t[4];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) t[u] = cb + q + 64 * u < ch ? __ldg(ci + 64 * u) : 0.f;
+            float* o = out_s + mis + i * ch + cb + q;
+#pragma unroll
+            for (int u = 0; u < 4; ++u)
+                if (cb + q + 64 * u < ch) o[64 * u] = decode_one(s, a[u], attr[u], x, y, t[u]);
+            x += 4;
+            while (x >= s.w) { x -= s.w; ++y; }
+        }
+    }
+    __syncthreads();
+    const int head = min(n, (4 - mis) & 3);
+    if ((int)threadIdx.x < head) out[threadIdx.x] = out_s[mis + threadIdx.x];
+    const int nv = (n - head) >> 2;
+    const float4* sv = reinterpret_cast<const float4*>(out_s + mis + head);     // mis + head is a multiple of 4
+    float4* gv = reinterpret_cast<float4*>(out + head);
+    for (int v = threadIdx.x; v < nv; v += 256) gv[v] = sv[v];
+    for (int j = head + 4 * nv + (int)threadIdx.x; j < n; j += 256) out[j] = out_s[mis + j];
+}
+#endif
 
 // NCHW (reference layout, API boundary) input: a block owns 32 consecutive cells of one image and
 // scale; reads each channel row coalesced along the cells, transposes through shared memory, and
@@ -452,6 +503,16 @@ cudaError_t launch_decode(const DecodeScale sc[3], int nchw, int B, int attrs, i
     }
     if (!nchw) {
         int nb[3];
+#ifdef YB_EXPERIMENTS
+        static const bool staged = tune_env("YB_DECODE_STAGED") && atoi(tune_env("YB_DECODE_STAGED")) != 0;
+        const int ch = 3 * attrs;
+        if (staged && ch * 4 <= 40 * 1024) {
+            const int cpb = std::max(1, std::min(kCellsPerBlock, (40 * 1024) / (ch * 4)));
+            for (int i = 0; i < 3; ++i) nb[i] = B * ((sc[i].h * sc[i].w + cpb - 1) / cpb);
+            decode_nhwc_staged_kernel<<<nb[0] + nb[1] + nb[2], 256, ((size_t)cpb * ch + 4) * sizeof(float), s>>>(P, det, nb[0], nb[1], cpb);
+            return cudaGetLastError();
+        }
+#endif
         for (int i = 0; i < 3; ++i) nb[i] = B * ((sc[i].h * sc[i].w + kCellsPerBlock - 1) / kCellsPerBlock);
         decode_nhwc_kernel<<<nb[0] + nb[1] + nb[2], 256, 0, s>>>(P, det, nb[0], nb[1]);
     } else {
