@@ -17,6 +17,8 @@
 //
 // HBM-bound part is pp_score (reads the whole [B,N,5+C] tensor once: 7.73 MB / image at 608);
 // everything after touches 32 B per candidate.
+#include <type_traits>
+
 #include "yb_internal.h"
 
 namespace yb {
@@ -26,7 +28,9 @@ constexpr int kSlotBits = 22;     // candidates per image < 4M
 constexpr int kClsShift = 54;     // classes < 1024
 constexpr unsigned long long kSlotMask = (1ull << kSlotBits) - 1;
 constexpr int kSortSmemKeys = 16384;   // 128 KB of shared memory
-constexpr int kNmsSmemBoxes = 4096;    // 64 KB + flags
+constexpr int kNmsSmemBoxes = 1024;    // 16 KB + flags: eight CTAs per SM (round 1 staged up to 4096 boxes, 68 KB, three CTAs per SM:
+                                       // the stress configuration -- 5120 segments of ~120 boxes -- ran 11 latency-bound waves,
+                                       // 495 us per 64 images); longer segments work on global memory
 
 __device__ __forceinline__ float iou_rn(const float4 a, const float4 b) {
     const float ltx = fmaxf(a.x, b.x), lty = fmaxf(a.y, b.y);
@@ -298,6 +302,51 @@ __global__ void __launch_bounds__(256) pp_scatter_kernel(const float* __restrict
 }
 
 // ---- K4 ----------------------------------------------------------------------------------------
+// Bitonic sort of 1024 << LOGK keys held in REGISTERS by the 1024 threads of a CTA: element k of thread t is index
+// i = t + 1024 k.  A compare-exchange distance j >= 1024 pairs two registers of one thread, j < 32 two lanes of one warp
+// (shuffles); only the five distances 32 .. 512 of every merge go through shared memory -- 35 of the 105 stages of a
+// 16 384-key sort (round 1 ran all of them in shared memory, 256 KB of traffic each: 224 us for the stress configuration).
+// Loops are fully unrolled: register arrays, compile-time distances.  Keys beyond the data are ~0 (sort last).
+template <int LOGK>
+__device__ __forceinline__ void bitonic_sort_regs(unsigned long long (&key)[1 << LOGK], unsigned long long* sk, int tid) {
+    constexpr int K = 1 << LOGK;
+#pragma unroll
+    for (int lk = 1; lk <= 10 + LOGK; ++lk) {              // merge length 2^lk
+#pragma unroll
+        for (int lj = lk - 1; lj >= 0; --lj) {             // distance 2^lj
+            const int j = 1 << lj;
+            if (lj >= 10) {
+                const int dk = 1 << (lj - 10);
+#pragma unroll
+                for (int k = 0; k < K; ++k) {
+                    const int pk = k ^ dk;
+                    if (pk > k) {
+                        const bool asc = ((k >> (lk - 10)) & 1) == 0;     // bit lk of i = t + 1024 k
+                        const unsigned long long a = key[k], c = key[pk];
+                        if ((a > c) == asc) { key[k] = c; key[pk] = a; }
+                    }
+                }
+            } else {
+                const bool lower = (tid & j) == 0;
+                if (lj >= 5) {
+#pragma unroll
+                    for (int k = 0; k < K; ++k) sk[tid + 1024 * k] = key[k];
+                    __syncthreads();
+                }
+#pragma unroll
+                for (int k = 0; k < K; ++k) {
+                    const bool asc = lk >= 10 ? ((k >> (lk >= 10 ? lk - 10 : 0)) & 1) == 0 : ((tid >> lk) & 1) == 0;
+                    const unsigned long long a = key[k];
+                    const unsigned long long b = lj >= 5 ? sk[(tid ^ j) + 1024 * k] : __shfl_xor_sync(0xffffffffu, a, j);
+                    const bool keep_min = lower == asc;
+                    key[k] = keep_min ? (a < b ? a : b) : (a > b ? a : b);
+                }
+                if (lj >= 5) __syncthreads();
+            }
+        }
+    }
+}
+
 __global__ void __launch_bounds__(1024) pp_sort_kernel(unsigned long long* __restrict__ keys_g, const float* __restrict__ cand,
                                                        const int* __restrict__ cand_total, int cand_cap, int sort_cap, int C,
                                                        float4* __restrict__ sbox, int* __restrict__ seg) {
@@ -312,6 +361,22 @@ __global__ void __launch_bounds__(1024) pp_sort_kernel(unsigned long long* __res
     unsigned long long* kg = keys_g + (long)b * sort_cap;
     const bool in_smem = P <= kSortSmemKeys;
     unsigned long long* k = in_smem ? skeys : kg;
+    if (in_smem && nt == 1024) {
+        // register sort of 1024 / 4096 / 16384 keys (the data padded with ~0), result left in skeys
+        auto run = [&](auto logk) {
+            constexpr int LOGK = decltype(logk)::value;
+            unsigned long long key[1 << LOGK];
+#pragma unroll
+            for (int q = 0; q < (1 << LOGK); ++q) { const int i = tid + 1024 * q; key[q] = i < n ? kg[i] : ~0ull; }
+            bitonic_sort_regs<LOGK>(key, skeys, tid);
+#pragma unroll
+            for (int q = 0; q < (1 << LOGK); ++q) skeys[tid + 1024 * q] = key[q];
+        };
+        if (P <= 1024) run(std::integral_constant<int, 0>{});
+        else if (P <= 4096) run(std::integral_constant<int, 2>{});
+        else run(std::integral_constant<int, 4>{});
+        __syncthreads();
+    } else {
     for (int i = tid; i < P; i += nt) {
         const unsigned long long v = i < n ? kg[i] : ~0ull;
         if (in_smem) skeys[i] = v; else if (i >= n) kg[i] = v;
@@ -329,6 +394,7 @@ __global__ void __launch_bounds__(1024) pp_sort_kernel(unsigned long long* __res
             }
             __syncthreads();
         }
+    }
     }
     const float* cb = cand + (long)b * cand_cap * 8;
     for (int pos = tid; pos < n; pos += nt) {
@@ -397,10 +463,15 @@ __global__ void __launch_bounds__(256) pp_nms_kernel(const float4* __restrict__ 
         const unsigned long long kept = kept_s;
         if (tid < cn) al[s + tid] = (unsigned char)((kept >> tid) & 1ull);
         if (kept) {
-            for (int j = s + 64 + tid; j < m; j += blockDim.x) {
+            // suppression of the tail by the chunk's survivors: four threads share one tail box and take every fourth survivor
+            // (a chain of up to 64 dependent IOU tests per thread was what the stress configuration waited for); any hit clears
+            // the flag -- the writers all store 0
+            const int sub = tid & 3;
+            const unsigned long long mine = kept & (0x1111111111111111ull << sub);
+            for (int j = s + 64 + (tid >> 2); j < m; j += blockDim.x >> 2) {
                 if (!al[j]) continue;
                 const float4 bj = bx[j];
-                unsigned long long kk = kept;
+                unsigned long long kk = mine;
                 while (kk) {
                     const int i = __ffsll((long long)kk) - 1;
                     kk &= kk - 1;
