@@ -309,6 +309,26 @@ def test_reference_in_oracle_ref_is_what_the_oracle_restates():
     assert len(res) == len(mine) and all(torch.equal(a, b) for a, b in zip(res, mine))
 
 
+def test_bench_detection_matching():
+    """bench.py's parity block matches two detection lists one to one (same class, IOU > 0.5): identical lists match
+    completely, a shifted box still matches with its IOU, a class change or a far box does not."""
+    import importlib.util
+    spec = importlib.util.spec_from_file_location("bench_mod", os.path.join(ROOT, "bench.py"))
+    b = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(b)
+    ref = torch.tensor([[10., 10., 50., 50., .9, .8, 3.], [100., 100., 180., 160., .7, .6, 3.], [30., 200., 90., 260., .8, .7, 17.]])
+    m, ng, nr, miou, ds = b.match_detections(ref.clone(), ref)
+    assert (m, ng, nr) == (3, 3, 3) and abs(miou - 1.0) < 1e-6 and ds == 0.0
+    got = ref.clone()
+    got[0, :4] += torch.tensor([2., 0., 2., 0.])          # shifted by 2 px: IOU 38*40 / (2*1600 - 1520)
+    got[1, 6] = 4.                                        # other class: no match
+    got[2, 5] = 0.65
+    m, ng, nr, miou, ds = b.match_detections(got, ref)
+    assert (m, ng, nr) == (2, 3, 3) and abs(ds - 0.05) < 1e-6
+    assert abs(miou - (1520. / 1680. + 1.0) / 2) < 1e-6
+    assert b.match_detections(torch.zeros(0, 7), ref)[:3] == (0, 0, 3)
+
+
 def test_bench_reads_measured_peaks_whatever_the_key_names():
     """MEASURED_PEAKS.json is written by the driver; bench.py must find the sustained and burst bf16 figures and the HBM
     copy figure under any reasonable naming, and must never crash on the file."""
