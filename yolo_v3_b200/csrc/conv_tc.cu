@@ -79,7 +79,7 @@ struct TcArgs {
     // pixel pitch; a_lo / out_lo / res_lo = channel offset of the lo half relative to the hi pointer; split_out = the
     // output is written as such a pair (everything but the fp32 head maps)
     int a_lo, out_lo, res_lo, split_out;
-    int chunk_iters, n_chunks;   // two-level accumulation: pipeline stages per TMEM chunk, chunks per tile
+    int chunk_pairs, n_chunks;   // two-level accumulation: unit pairs (12 MMAs each) per TMEM chunk, chunks per tile
     int* dbg;
     long long* trace;        // optional [6 roles][64 tiles][4] clock64 stamps of CTA 0 (YB_TC_TRACE=1)
 };
@@ -209,9 +209,10 @@ __device__ __forceinline__ void epilogue16_staged(const TcArgs& a, const uint32_
 // hi + lo carries 22 bits of x), and every weight w -- pre-scaled per output channel by a power of two so that its lo part
 // stays a normal fp16 number, the scale is undone in the fp32 epilogue -- as wh + wl.  The GEMM accumulates the three
 // significant partial products xh*wh + xh*wl + xl*wh (exact in the fp32 accumulator's product stage; the dropped xl*wl
-// term is 2^-22 relative) by running the main loop over a K axis three times as long: k-blocks are ordered (tap, channel
-// block, section); section 0 = xl*wh, 1 = xh*wl (the two corrections first, while the accumulator is small), 2 = xh*wh;
-// the weight rows are packed [tap][channel block][wh | wl | wh][64] to match.  tools/split_numerics.py
+// term is 2^-22 relative).  Per (tap, channel block) the producer loads TWO k-block units -- unit 0 = (A lo, B wh), unit 1 =
+// (A hi, B wl); the weight rows are packed [tap][channel block][wh | wl][64] to match -- and the MMA warp issues THREE groups
+// on them: xl*wh and xh*wl (the two corrections first, while the accumulator is small), then xh*wh from unit 1's A tile and
+// unit 0's B tile, so that every operand tile crosses L2 -> shared memory once (four tiles per three MMA groups).  tools/split_numerics.py
 // (profiles/r02_split_numerics_cpu.txt): the operand representation error of this scheme through all 75 layers is 3e-6 of
 // max|logit| -- below the fp32 oracle's own 5e-6.
 //
@@ -219,7 +220,7 @@ __device__ __forceinline__ void epilogue16_staged(const TcArgs& a, const uint32_
 // (profiles/r02a_tc_accum_probe.txt, r02c_split_error_vs_chain_length.txt: the result shrinks toward zero by 1.7e-8 per
 // MMA in the chain -- 1.4e-5 for the 864 MMAs of a 512->1024 3x3 layer, against 1e-6 for an fp32 GEMM on the CPU), so
 // a long K loop into one TMEM accumulator cannot be fp32-grade.  The SPLIT kernels therefore accumulate in TMEM only over
-// a CHUNK of one (tap, channel block) triple -- 12 MMAs, of which only the last four carry the main term -- and the
+// a CHUNK of one (tap, channel block) pair of units -- 12 MMAs, of which only the last four carry the main term -- and the
 // epilogue warps add every finished chunk into fp32 REGISTER accumulators with round-to-nearest adds while the tensor
 // core works on the next chunk in the other TMEM buffer.  A thread owns at most 32 accumulators (two 16-column groups),
 // which caps the tile width at 128 columns (64 for the fp32 head maps).
@@ -510,7 +511,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                 if (pw == 0) YB_TRACE(0, ti, 0);
                 if (a.ks == 1) {
                     int kc = 0;
-                    [[maybe_unused]] int cc = 0, sec = 0;      // SPLIT: channel of the A box inside its half, section 0..2
+                    [[maybe_unused]] int cc = 0, sec = 0;      // SPLIT: channel of the A box inside its half, unit 0 (lo) / 1 (hi)
                     for (int it = 0; it < a.num_iters; ++it, ++itg) {
                         const bool mine = SPLIT || (itg & 1u) == pw;
                         if (mine) mbar_wait<kDonate>(eb, phase ^ 1, a.dbg, 0, stage);
@@ -529,7 +530,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                                 }
                             }
                             if constexpr (SPLIT) {
-                                if (++sec == 3) { sec = 0; cc += BKE; }
+                                if (++sec == 2) { sec = 0; cc += BKE; }
                             }
                             kc += BKE;
                             dst += kb_bytes;
@@ -543,7 +544,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                     const int p = r / a.Wo, q = r - p * a.Wo;
                     const int cw = q * a.stride - a.pad, chh = p * a.stride - a.pad;
                     int kc = 0, cc = 0;                      // k coordinate of the weights, channel coordinate of A
-                    [[maybe_unused]] int sec = 0;            // SPLIT: section 0..2 of the current tap
+                    [[maybe_unused]] int sec = 0;            // SPLIT: unit 0 (lo) / 1 (hi) of the current (tap, channel block)
                     uint16_t kw = 0, kh = 0;
                     const int cend = a.cin_blocks * BKE;
                     for (int it = 0; it < a.num_iters; ++it, ++itg) {
@@ -565,7 +566,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                             }
                             kc += BKE;
                             bool next_cb = true;
-                            if constexpr (SPLIT) { if (++sec < 3) next_cb = false; else sec = 0; }
+                            if constexpr (SPLIT) { if (++sec < 2) next_cb = false; else sec = 0; }
                             if (next_cb) {
                                 cc += BKE;
                                 if (cc == cend) { cc = 0; if (++kw == 3) { kw = 0; ++kh; } }
@@ -595,18 +596,24 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             bool ready = false;
             if (a.b_resident && tile_first < total_tiles) mbar_wait<kDonate>(bres_bar, 0, a.dbg, 1, 600);
             int ti = 0;
-            for (int tile = tile_first; tile < total_tiles; tile += tile_step, ++ti) {
-                YB_TRACE(1, ti, 0);
-                mbar_wait<kDonate>(tempty0 + 8 * acc, acc_phase ^ 1, a.dbg, 1, 100 + (int)acc);
-                tc_fence_after();
-                YB_TRACE(1, ti, 1);
-                uint32_t d_tmem = tmem_base + acc * acc_stride;
-                int kb = 0;
-                [[maybe_unused]] int kbc = 0, it_chunk = 0;   // SPLIT: k-block / stage index inside the current TMEM chunk
-                for (int it = 0; it < a.num_iters; ++it) {
-                    if constexpr (SPLIT) {
-                        if (it_chunk == a.chunk_iters) {
-                            // chunk complete: publish it to the epilogue warps and continue in the other TMEM buffer
+            if constexpr (SPLIT) {
+                // Split mode: the pipeline carries k-block UNITS in pairs -- unit 0 = (A lo, B wh), unit 1 = (A hi, B wl), in one
+                // stage (kps == 2) or in two consecutive stages (kps == 1; the stage count is even) -- and every pair gets three
+                // MMA groups: lo*wh, hi*wl, then hi*wh from unit 1's A tile and unit 0's B tile.  A TMEM chunk is chunk_pairs
+                // pairs; the finished chunk goes to the epilogue warps, the next one starts in the other TMEM buffer.
+                const int pairs = a.num_kblocks >> 1;
+                const uint32_t upair = a.kps == 2 ? 1u : 2u;                    // stages per pair
+                const uint32_t u1_off = a.kps == 2 ? kb_bytes : stage_bytes;      // byte distance of unit 1 from unit 0
+                for (int tile = tile_first; tile < total_tiles; tile += tile_step, ++ti) {
+                    YB_TRACE(1, ti, 0);
+                    mbar_wait<kDonate>(tempty0 + 8 * acc, acc_phase ^ 1, a.dbg, 1, 100 + (int)acc);
+                    tc_fence_after();
+                    YB_TRACE(1, ti, 1);
+                    uint32_t d_tmem = tmem_base + acc * acc_stride;
+                    int pc = 0;
+                    uint32_t fresh = 0;                                           // 0: the chunk's first MMA overwrites the accumulator
+                    for (int p = 0; p < pairs; ++p) {
+                        if (pc == a.chunk_pairs) {
                             if (elect_one()) {
                                 if constexpr (CTA2) umma_commit_pair(tfull0 + 8 * acc); else umma_commit(tfull0 + 8 * acc);
                             }
@@ -615,10 +622,57 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                             mbar_wait<kDonate>(tempty0 + 8 * acc, acc_phase ^ 1, a.dbg, 1, 100 + (int)acc);
                             tc_fence_after();
                             d_tmem = tmem_base + acc * acc_stride;
-                            kbc = 0; it_chunk = 0;
+                            pc = 0; fresh = 0;
                         }
-                        ++it_chunk;
+                        ++pc;
+                        mbar_wait<kDonate>(full0 + 8 * stage, phase, a.dbg, 1, stage);
+                        if (upair == 2) mbar_wait<kDonate>(full0 + 8 * (stage + 1), phase, a.dbg, 1, stage + 1);
+                        tc_fence_after();
+                        const uint32_t s0 = stage0 + (uint32_t)stage * stage_bytes;
+                        const uint64_t a0 = make_smem_desc<SWZ>(s0), a1 = make_smem_desc<SWZ>(s0 + u1_off);
+                        const uint64_t b0 = a.b_resident ? bres_desc + (uint64_t)(2 * p) * bres_inc : a0 + b_off;
+                        const uint64_t b1 = a.b_resident ? b0 + bres_inc : a1 + b_off;
+                        if (elect_one()) {
+                            if constexpr (CTA2) {
+#pragma unroll
+                                for (int k = 0; k < BKE / 16; ++k) umma_f16_pair(d_tmem, a0 + 2 * k, b0 + 2 * k, idesc, fresh | (uint32_t)k);
+#pragma unroll
+                                for (int k = 0; k < BKE / 16; ++k) umma_f16_pair(d_tmem, a1 + 2 * k, b1 + 2 * k, idesc, 1);
+#pragma unroll
+                                for (int k = 0; k < BKE / 16; ++k) umma_f16_pair(d_tmem, a1 + 2 * k, b0 + 2 * k, idesc, 1);
+                                umma_commit_pair(empty0 + 8 * stage);
+                                if (upair == 2) umma_commit_pair(empty0 + 8 * (stage + 1));
+                            } else {
+#pragma unroll
+                                for (int k = 0; k < BKE / 16; ++k) umma_f16(d_tmem, a0 + 2 * k, b0 + 2 * k, idesc, fresh | (uint32_t)k);
+#pragma unroll
+                                for (int k = 0; k < BKE / 16; ++k) umma_f16(d_tmem, a1 + 2 * k, b1 + 2 * k, idesc, 1);
+#pragma unroll
+                                for (int k = 0; k < BKE / 16; ++k) umma_f16(d_tmem, a1 + 2 * k, b0 + 2 * k, idesc, 1);
+                                umma_commit(empty0 + 8 * stage);
+                                if (upair == 2) umma_commit(empty0 + 8 * (stage + 1));
+                            }
+                        }
+                        fresh = 1;
+                        stage += (int)upair;
+                        if (stage >= a.stages) { stage = 0; phase ^= 1; }
                     }
+                    if (elect_one()) {
+                        if constexpr (CTA2) umma_commit_pair(tfull0 + 8 * acc); else umma_commit(tfull0 + 8 * acc);   // last chunk complete
+                    }
+                    YB_TRACE(1, ti, 2);
+                    acc ^= 1;
+                    if (acc == 0) acc_phase ^= 1;
+                }
+            } else {
+            for (int tile = tile_first; tile < total_tiles; tile += tile_step, ++ti) {
+                YB_TRACE(1, ti, 0);
+                mbar_wait<kDonate>(tempty0 + 8 * acc, acc_phase ^ 1, a.dbg, 1, 100 + (int)acc);
+                tc_fence_after();
+                YB_TRACE(1, ti, 1);
+                const uint32_t d_tmem = tmem_base + acc * acc_stride;
+                int kb = 0;
+                for (int it = 0; it < a.num_iters; ++it) {
                     if (!ready) mbar_wait<kDonate>(fbar, phase, a.dbg, 1, stage);
                     tc_fence_after();
                     // probe the NEXT stage's barrier now: its latency overlaps the MMA issue below
@@ -629,19 +683,17 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                     for (int j = 0; j < a.kps; ++j, ++kb) {
                         const uint64_t bd = a.b_resident ? bres_desc + (uint64_t)kb * bres_inc : ad + b_off;
                         if (el) {
-                            const int first = SPLIT ? kbc : kb;       // 0: the MMA overwrites the accumulator
                             if constexpr (CTA2) {
 #pragma unroll
-                                for (int k = 0; k < BKE / 16; ++k) umma_f16_pair(d_tmem, ad + 2 * k, bd + 2 * k, idesc, (first | k) != 0);
+                                for (int k = 0; k < BKE / 16; ++k) umma_f16_pair(d_tmem, ad + 2 * k, bd + 2 * k, idesc, (kb | k) != 0);
                             } else {
-                                umma_f16(d_tmem, ad, bd, idesc, first != 0);
+                                umma_f16(d_tmem, ad, bd, idesc, kb != 0);
 #pragma unroll
                                 for (int k = 1; k < BKE / 16; ++k)   // 16 fp16 = 32 bytes per MMA: descriptor address += 2
                                     umma_f16_imm<1>(d_tmem, ad + 2 * k, bd + 2 * k, idesc);
                             }
                         }
                         ad += kb_inc;
-                        if constexpr (SPLIT) ++kbc;
                     }
                     if (el) {
                         if constexpr (CTA2) umma_commit_pair(ebar); else umma_commit(ebar);   // frees the stage (in both CTAs)
@@ -655,6 +707,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                 YB_TRACE(1, ti, 2);
                 acc ^= 1;
                 if (acc == 0) acc_phase ^= 1;
+            }
             }
         }
         __syncwarp();
@@ -1163,8 +1216,8 @@ std::string tc_make_plan(TcPlan& p, const ConvArgs& a, const __half* w16, int co
     const int bke = p.swz / 2;
     p.cin_blocks = a.Cin / bke;
     p.split = a.split;
-    p.num_kblocks = a.ks * a.ks * p.cin_blocks * (a.split ? 3 : 1);   // split mode: three sections per tap (conv_tc_kernel)
-    if (a.split && K != 3 * a.ks * a.ks * a.Cin) return "split mode expects the [tap][channel block][wh|wl|wh] weight packing";
+    p.num_kblocks = a.ks * a.ks * p.cin_blocks * (a.split ? 2 : 1);   // split mode: two units per (tap, channel block)
+    if (a.split && K != 2 * a.ks * a.ks * a.Cin) return "split mode expects the [tap][channel block][wh|wl] weight packing";
     if (a.split && a.upsample) return "split mode: the upsample layers run as a plain convolution followed by a copy kernel";
     const bool split_out = a.split && !a.out_f32;
     p.M = (long)a.B * a.Ho * a.Wo;
@@ -1267,8 +1320,8 @@ std::string tc_make_plan(TcPlan& p, const ConvArgs& a, const __half* w16, int co
         if (p.b_resident && !a.res && p.num_kblocks <= 9 && fixed + 2 * p.num_kblocks * kb_bytes <= kSmemBudget)
             p.kps = p.num_kblocks;
         if (const char* e = tune_env("YB_TC_KPS")) { const int c = atoi(e); if (c >= 1 && p.num_kblocks % c == 0 && c * kb_bytes <= 96 * 1024) p.kps = c; }
-        // split mode: a TMEM chunk is a whole number of (tap, channel block) triples and of pipeline stages
-        if (a.split) p.kps = 3 * kb_bytes <= 48 * 1024 ? 3 : 1;
+        // split mode: a pair of units (one (tap, channel block)) per stage, or one unit per stage
+        if (a.split) p.kps = 2 * kb_bytes <= 48 * 1024 ? 2 : 1;
     }
     // a resident slab next to a four-deep residual ring can leave room for fewer than two multi-k-block stages
     while (p.kps > 1 && (kSmemBudget - fixed) / (kb_bytes * p.kps) < 2) {
@@ -1276,19 +1329,19 @@ std::string tc_make_plan(TcPlan& p, const ConvArgs& a, const __half* w16, int co
         while (c > 1 && p.num_kblocks % c) --c;
         p.kps = c;
     }
-    if (a.split && p.kps != 3) p.kps = 1;
+    if (a.split && p.kps != 2) p.kps = 1;
     const size_t stage_bytes = kb_bytes * p.kps;
     p.stages = (int)std::min<size_t>(kMaxStages, (kSmemBudget - fixed) / stage_bytes);
     if (const char* e = tune_env("YB_TC_STAGES")) p.stages = std::max(2, std::min(p.stages, atoi(e)));
+    if (a.split && p.kps == 1) p.stages &= ~1;            // unit pairs must not straddle the end of the stage ring
     if (p.stages < 2) return "not enough shared memory for two pipeline stages";
     p.smem = fixed + p.stages * stage_bytes;
     if (a.split) {
-        // triples per chunk: one (12 MMAs of K = 16; 6 with 32-channel k-blocks, where two keep the chunk long enough
+        // unit pairs per chunk: one (12 MMAs of K = 16; 6 with 32-channel k-blocks, where two keep the chunk long enough
         // for the register pass of the previous one to hide behind it)
-        int triples = p.swz == 64 ? 2 : 1;
-        if (const char* e = tune_env("YB_SPLIT_CHUNK")) triples = std::max(1, std::min(64, atoi(e)));
-        p.chunk_iters = triples * 3 / p.kps;
-        p.n_chunks = (p.num_kblocks / p.kps + p.chunk_iters - 1) / p.chunk_iters;
+        p.chunk_pairs = p.swz == 64 ? 2 : 1;
+        if (const char* e = tune_env("YB_SPLIT_CHUNK")) p.chunk_pairs = std::max(1, std::min(64, atoi(e)));
+        p.n_chunks = (p.num_kblocks / 2 + p.chunk_pairs - 1) / p.chunk_pairs;
     }
 
     const CUtensorMapSwizzle swz = p.swz == 128 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B;
@@ -1444,7 +1497,7 @@ cudaError_t tc_launch(const TcPlan& p, const ConvArgs& a, int* dbg, cudaStream_t
     t.epi_split = p.epi_split;
     t.a_lo = (int)a.in_lo; t.out_lo = (int)a.out_lo; t.res_lo = (int)a.res_lo;
     t.split_out = p.split && !a.out_f32;
-    t.chunk_iters = p.chunk_iters; t.n_chunks = p.n_chunks;
+    t.chunk_pairs = p.chunk_pairs; t.n_chunks = p.n_chunks;
     t.dbg = dbg;
     static PerDeviceOnce attr_once;
     {

@@ -296,7 +296,7 @@ struct PlanBuilder {
         if (p->mode == YB_MODE_FP32_TC) {
             if (!tc_supported(a)) { err = "plan: layer " + L.key + " not supported by the tensor-core kernel"; return false; }
             op.use_tc = true;
-            std::string e = tc_make_plan(op.tc, a, L.d_w16, L.cout_pad, 3 * L.ks * L.ks * L.cin, c->num_sms);
+            std::string e = tc_make_plan(op.tc, a, L.d_w16, L.cout_pad, 2 * L.ks * L.ks * L.cin, c->num_sms);
             if (!e.empty()) { err = "plan: layer " + L.key + ": " + e; return false; }
         } else if (p->mode == YB_MODE_FP16) {
             if (!tc_supported(a)) { err = "plan: layer " + L.key + " not supported by the tensor-core kernel"; return false; }
@@ -748,7 +748,7 @@ int yb_finalize(yb_ctx* c, int mode) {
         offs[i].w32 = need32 ? place(sizeof(float) * K * L.cout_pad) : (size_t)-1;
         // the stem's fp16 weights are [32][K padded to 32] for the tensor-core stem kernel
         offs[i].w16 = mode == YB_MODE_FP16 ? place(sizeof(__half) * (i == 0 ? 32 : K) * L.cout_pad)
-                      : (split && i != 0) ? place(sizeof(__half) * 3 * K * L.cout_pad) : (size_t)-1;
+                      : (split && i != 0) ? place(sizeof(__half) * 2 * K * L.cout_pad) : (size_t)-1;
     }
     if (off != c->blob_bytes || !c->d_blob) {
         cudaFree(c->d_blob);
@@ -783,7 +783,7 @@ int yb_finalize(yb_ctx* c, int mode) {
                         w[((size_t)t * L.cin + ci) * L.cout_pad + n] = L.w[((size_t)n * L.cin + ci) * taps + t];
         }
         if (offs[i].w16 != (size_t)-1 && split) {
-            // [cout_pad][tap][channel block][wh | wl | wh][bke] (bke = 64 channels, 32 when Cin = 32: the k-block order of
+            // [cout_pad][tap][channel block][wh | wl][bke] (bke = 64 channels, 32 when Cin = 32: the k-block unit order of
             // conv_tc_kernel's split mode): row n is scaled by 2^s(n) so that max|w'| lies in [2048, 4096) -- the lo part of
             // every weight down to 2^-23 of the row maximum is then a NORMAL fp16 number -- and the epilogue scale undoes it
             // exactly (a power of two).  wh = RN16(w'), wl = RN16(w' - wh).
@@ -804,8 +804,8 @@ int yb_finalize(yb_ctx* c, int mode) {
                         const float ws = std::ldexp(L.w[((size_t)n * L.cin + ci) * taps + t], sh);
                         const __half wh = __float2half_rn(ws);
                         const __half wl = __float2half_rn(ws - __half2float(wh));
-                        __half* row = w + (size_t)n * 3 * K + ((size_t)t * (L.cin / bke) + ci / bke) * 3 * bke + ci % bke;
-                        row[0] = wh; row[bke] = wl; row[2 * bke] = wh;
+                        __half* row = w + (size_t)n * 2 * K + ((size_t)t * (L.cin / bke) + ci / bke) * 2 * bke + ci % bke;
+                        row[0] = wh; row[bke] = wl;
                     }
             }
         } else if (offs[i].w16 != (size_t)-1) {
@@ -1257,7 +1257,7 @@ int yb_run_layer(yb_ctx* c, int li, const void* in, int B, int H, int W, const v
             if (e == cudaSuccess) {
                 if (!tc_supported(a)) { cleanup(); return fail(c, YB_E_UNSUPPORTED, "yb_run_layer: layer not supported by the tensor-core kernel"); }
                 TcPlan tp;
-                std::string err = tc_make_plan(tp, a, L.d_w16, L.cout_pad, 3 * L.ks * L.ks * L.cin, c->num_sms);
+                std::string err = tc_make_plan(tp, a, L.d_w16, L.cout_pad, 2 * L.ks * L.ks * L.cin, c->num_sms);
                 if (!err.empty()) { cleanup(); return fail(c, YB_E_CUDA, "yb_run_layer: " + err); }
                 e = tc_launch(tp, a, c->dbg, s);
             }

@@ -36,7 +36,7 @@ struct Layer {
     float* d_bias = nullptr;                  // [cout_pad]  beta-mean*scale      (conv bias for heads)
     float* d_w32 = nullptr;                   // [ks*ks][cin][cout_pad] fp32      (YB_MODE_FP32)
     __half* d_w16 = nullptr;                  // [cout_pad][ks*ks*cin] fp16, K-major (YB_MODE_FP16);
-                                              // YB_MODE_FP32_TC: [cout_pad][ks*ks][wh | wl | wh][cin], rows pre-scaled by 2^s
+                                              // YB_MODE_FP32_TC: [cout_pad][ks*ks][cin block][wh | wl][bke], rows pre-scaled by 2^s
 };
 
 // cudaFuncSetAttribute applies to the CURRENT device only, and a process may hold contexts on several devices
@@ -127,7 +127,7 @@ struct TcPlan {
     int srel = 0;
     int epi_split = 0;    // 32-column sub-tiles: the two halves of the epilogue warps take alternate sub-tiles
     int split = 0;        // YB_MODE_FP32_TC: hi/lo operands, three k sections per (tap, channel block) (conv_tc.cu)
-    int chunk_iters = 0, n_chunks = 0;   // split mode: pipeline stages per TMEM chunk, chunks per tile
+    int chunk_pairs = 0, n_chunks = 0;   // split mode: unit pairs per TMEM chunk, chunks per tile
     int grid = 0;
     size_t smem = 0;
     long M = 0;
