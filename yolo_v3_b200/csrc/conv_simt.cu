@@ -22,6 +22,15 @@ template <> __device__ __forceinline__ __half from_f32<__half>(float v) { return
 
 constexpr int TM = 64, TN = 64, TK = 16;
 
+// packed fp32 FMA (two independent IEEE fmas per instruction on sm_100: same results as two fmaf calls)
+__device__ __forceinline__ float2 ffma2(float2 a, float2 b, float2 c) {
+    unsigned long long r;
+    asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r)
+        : "l"(*reinterpret_cast<unsigned long long*>(&a)), "l"(*reinterpret_cast<unsigned long long*>(&b)),
+          "l"(*reinterpret_cast<unsigned long long*>(&c)));
+    return *reinterpret_cast<float2*>(&r);
+}
+
 template <typename T>
 __global__ void __launch_bounds__(256) conv_simt_kernel(ConvArgs a, const float* __restrict__ w, int cout_pad) {
     __shared__ float As[TK][TM + 4];
@@ -140,9 +149,9 @@ __global__ void __launch_bounds__(128) stem_kernel(const float* __restrict__ x, 
     const long total = (long)B * H * W;
     const long pix = (long)blockIdx.x * blockDim.x + threadIdx.x;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    float acc[32];
+    float2 acc2[16];                                  // 32 fp32 accumulators, updated two at a time (fma.rn.f32x2)
 #pragma unroll
-    for (int n = 0; n < 32; ++n) acc[n] = 0.f;
+    for (int n = 0; n < 16; ++n) acc2[n] = make_float2(0.f, 0.f);
     if (pix < total) {
         const int b = (int)(pix / ((long)H * W));
         const int r = (int)(pix % ((long)H * W));
@@ -160,13 +169,12 @@ __global__ void __launch_bounds__(128) stem_kernel(const float* __restrict__ x, 
                     // the 32 weights of this tap as eight 16-byte broadcast loads (scalar loads made the kernel LDS-bound:
                     // one shared-memory instruction per FMA)
                     const float4* wr = reinterpret_cast<const float4*>(ws + ((ky * 3 + kx) * 3 + c) * 32);
+                    const float2 vv = make_float2(v, v);
 #pragma unroll
                     for (int n = 0; n < 8; ++n) {
                         const float4 w4 = wr[n];
-                        acc[4 * n + 0] = fmaf(v, w4.x, acc[4 * n + 0]);
-                        acc[4 * n + 1] = fmaf(v, w4.y, acc[4 * n + 1]);
-                        acc[4 * n + 2] = fmaf(v, w4.z, acc[4 * n + 2]);
-                        acc[4 * n + 3] = fmaf(v, w4.w, acc[4 * n + 3]);
+                        acc2[2 * n] = ffma2(vv, make_float2(w4.x, w4.y), acc2[2 * n]);
+                        acc2[2 * n + 1] = ffma2(vv, make_float2(w4.z, w4.w), acc2[2 * n + 1]);
                     }
                 }
             }
@@ -174,7 +182,7 @@ __global__ void __launch_bounds__(128) stem_kernel(const float* __restrict__ x, 
     }
 #pragma unroll
     for (int n = 0; n < 32; ++n) {
-        float v = fmaf(acc[n], ss[n], sb[n]);
+        float v = fmaf((n & 1) ? acc2[n >> 1].y : acc2[n >> 1].x, ss[n], sb[n]);
         v = v > 0.f ? v : v * kLeaky;
         const T hi = from_f32<T>(v);
         stage[warp][lane][n] = hi;
