@@ -385,6 +385,18 @@ def test_c_abi_error_codes():
     assert lib.yb_finalize(ctx, 7) == -1
     assert lib.yb_forward(ctx, vp(x), 1, 64, 64, vp(det), stream()) == 0
     assert lib.yb_launch_count(ctx) == 76
+    # round-2 entry points: the graph-mode switch validates its argument; the fp32-grade tensor-core mode finalises, runs
+    # (77 launches: 75 layers + the two upsample copies, + the decode), and rejects fp16 input images like the other fp32 mode
+    assert lib.yb_set_graph_mode(ctx, 3) == -1 and lib.yb_set_graph_mode(ctx, 0) == 0
+    assert lib.yb_graph_replays(ctx) == 0
+    _lib.check(lib.yb_finalize(ctx, _lib.YB_MODE_FP32_TC), ctx)
+    n0 = lib.yb_launch_count(ctx)
+    assert lib.yb_forward(ctx, vp(x), 1, 64, 64, vp(det), stream()) == 0
+    assert lib.yb_launch_count(ctx) - n0 == 78
+    _lib.check(lib.yb_set_input_dtype(ctx, _lib.YB_INPUT_F16), ctx)
+    assert lib.yb_forward(ctx, vp(x), 1, 64, 64, vp(det), stream()) == -8          # YB_E_UNSUPPORTED
+    _lib.check(lib.yb_set_input_dtype(ctx, _lib.YB_INPUT_F32), ctx)
+    torch.cuda.synchronize()
     lib.yb_destroy(ctx)
 
 
