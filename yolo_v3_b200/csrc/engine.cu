@@ -31,6 +31,7 @@ struct Op {
     TcPlan tc;
     HaloPlan halo;
     StemTcPlan stem_tc;
+    StemHaloPlan stem_halo;
     bool upcopy = false;              // YB_MODE_FP32_TC: nearest x2 copy of up_src into the concat slice up_dst
     TView up_src, up_dst;
 };
@@ -75,6 +76,8 @@ struct yb_ctx {
     bool finalized = false;
     unsigned char* d_blob = nullptr;
     size_t blob_bytes = 0;
+    float stem_sb[64] = {};           // host mirror of the stem's scale[32] | bias[32] (kernel parameters of the halo stem):
+                                      // written by yb_finalize, re-read from the blob after yb_bcast_weights
     std::vector<std::unique_ptr<Plan>> plans;
     PostBuffers post;
     float* box_params = nullptr;      // [B][6] per-image parameters of yb_correct_boxes
@@ -350,6 +353,7 @@ int build_plan(yb_ctx* c, int B, int H, int W, Plan** out) {
         op.a.out = buf[0];
         if (p->mode == YB_MODE_FP16) {
             std::string e = stem_tc_make_plan(op.stem_tc, static_cast<__half*>(buf[0]), 32, B, H, W, c->num_sms);
+            if (e.empty()) e = stem_halo_make_plan(op.stem_halo, static_cast<__half*>(buf[0]), 32, B, H, W, c->num_sms);
             if (!e.empty()) return bail("plan: stem: " + e);
         }
         p->ops.push_back(op);
@@ -428,6 +432,12 @@ int build_plan(yb_ctx* c, int B, int H, int W, Plan** out) {
 
 constexpr int kProfBank = 16;
 
+// TEMPORARY A/B switch while the halo stem is validated (removed once it is the only stem)
+bool stem_old() {
+    static const bool v = getenv("YB_STEM_OLD") && atoi(getenv("YB_STEM_OLD")) != 0;
+    return v;
+}
+
 cudaError_t launch_op(yb_ctx* c, Plan* p, Op& op, cudaStream_t s) {
     const Layer& L = c->layers[op.layer];
     if (op.upcopy)
@@ -502,8 +512,10 @@ int run_ops(yb_ctx* c, Plan* p, const float* x, int n_ops, cudaStream_t s) {
         if (op.stem) {
             if (c->input_f16 && p->mode != YB_MODE_FP16)
                 return fail(c, YB_E_UNSUPPORTED, "fp16 input images need YB_MODE_FP16");
-            if (p->mode == YB_MODE_FP16)
+            if (p->mode == YB_MODE_FP16 && stem_old())
                 e = stem_tc_launch(op.stem_tc, x, c->input_f16, p->B, p->H, p->W, L.d_w16, L.d_scale, L.d_bias, c->dbg, s);
+            else if (p->mode == YB_MODE_FP16)
+                e = stem_halo_launch(op.stem_halo, x, c->input_f16, p->B, p->H, p->W, L.d_w16, c->stem_sb, c->dbg, s);
             else if (p->mode == YB_MODE_FP32_TC)     // Cin = 3: exact fp32 FMAs on the CUDA cores, output written as hi | lo
                 e = launch_stem_split(x, static_cast<__half*>(op.a.out), L.d_w32, L.d_scale, L.d_bias, p->B, p->H, p->W, s);
             else
@@ -826,6 +838,8 @@ int yb_finalize(yb_ctx* c, int mode) {
     YB_CUDA(c, cudaDeviceSynchronize());
     YB_CUDA(c, cudaMemcpy(c->d_blob, host.data(), off, cudaMemcpyHostToDevice));
     YB_CUDA(c, cudaDeviceSynchronize());
+    std::memcpy(c->stem_sb, host.data() + offs[0].scale, 32 * sizeof(float));
+    std::memcpy(c->stem_sb + 32, host.data() + offs[0].bias, 32 * sizeof(float));
     c->mode = mode;
     c->finalized = true;
     return YB_OK;
@@ -1141,7 +1155,12 @@ int yb_bcast_weights(yb_ctx* c, int root, void* stream) {
     if (!c->finalized) return fail(c, YB_E_STATE, "yb_bcast_weights: yb_finalize first (all ranks, same mode)");
     std::string err;
     int rc = comm_bcast(c->nccl_comm, c->d_blob, c->blob_bytes, root, static_cast<cudaStream_t>(stream), err);
-    return rc ? fail(c, rc, err) : YB_OK;
+    if (rc) return fail(c, rc, err);
+    // the halo stem takes its scale / bias as kernel parameters: refresh the host mirror from the received blob
+    YB_CUDA(c, cudaStreamSynchronize(static_cast<cudaStream_t>(stream)));
+    YB_CUDA(c, cudaMemcpy(c->stem_sb, c->layers[0].d_scale, 32 * sizeof(float), cudaMemcpyDeviceToHost));
+    YB_CUDA(c, cudaMemcpy(c->stem_sb + 32, c->layers[0].d_bias, 32 * sizeof(float), cudaMemcpyDeviceToHost));
+    return YB_OK;
 }
 
 int yb_allgather_dets(yb_ctx* c, const float* rows7, const int* counts, int B_local, int cap, float* all_rows,
@@ -1273,7 +1292,12 @@ int yb_run_layer(yb_ctx* c, int li, const void* in, int B, int H, int W, const v
         cudaError_t e;
         if (c->input_f16 && c->mode != YB_MODE_FP16)
             return fail(c, YB_E_UNSUPPORTED, "fp16 input images need YB_MODE_FP16");
-        if (c->mode == YB_MODE_FP16) {
+        if (c->mode == YB_MODE_FP16 && !stem_old() && stem_halo_supported(W, c->input_f16)) {
+            StemHaloPlan sp;
+            std::string err = stem_halo_make_plan(sp, static_cast<__half*>(out), 32, B, H, W, c->num_sms);
+            if (!err.empty()) return fail(c, YB_E_CUDA, "yb_run_layer: " + err);
+            e = stem_halo_launch(sp, in, c->input_f16, B, H, W, L.d_w16, c->stem_sb, c->dbg, s);
+        } else if (c->mode == YB_MODE_FP16) {
             StemTcPlan sp;
             std::string err = stem_tc_make_plan(sp, static_cast<__half*>(out), 32, B, H, W, c->num_sms);
             if (!err.empty()) return fail(c, YB_E_CUDA, "yb_run_layer: " + err);

@@ -148,6 +148,19 @@ std::string stem_tc_make_plan(StemTcPlan& p, __half* out, long out_ld, int B, in
 cudaError_t stem_tc_launch(const StemTcPlan& p, const void* x, int in_f16, int B, int H, int W, const __half* w16, const float* scale,
                            const float* bias, int* dbg, cudaStream_t s);
 
+// stem_halo.cu  (the Cin = 3 stem from a halo patch: planar TMA load, pixel-major fp16 conversion, two taps per tcgen05.mma
+// through the leading-dimension offset of a non-swizzled descriptor).  Needs W % 4 == 0 (fp32 images) / W % 8 == 0 (fp16).
+struct StemHaloPlan {
+    CUtensorMap tmOut;
+    int tiles_x = 0, tiles_y = 0, total_tiles = 0, grid = 0;
+    size_t smem = 0;
+};
+bool stem_halo_supported(int W, int in_f16);
+std::string stem_halo_make_plan(StemHaloPlan& p, __half* out, long out_ld, int B, int H, int W, int num_sms);
+// sb_host: the stem's scale[32] | bias[32] on the HOST -- they travel as kernel parameters (constant-bank operands)
+cudaError_t stem_halo_launch(const StemHaloPlan& p, const void* x, int in_f16, int B, int H, int W, const __half* w16,
+                             const float* sb_host, int* dbg, cudaStream_t s);
+
 // conv_halo.cu  (3x3 stride-1 layers with Cin = 32 / 64 from a halo tile: every input pixel staged once)
 struct HaloPlan {
     CUtensorMap tmIn, tmB, tmOut, tmRes;
