@@ -36,7 +36,7 @@ constexpr int kSU = 4;                         // M-tiles per UNIT: 12 output ro
 constexpr int kSUR = kSU * kSR;                // output rows per unit
 constexpr int kSPatchRows = kSUR + 2;
 constexpr int kSPatchPix = kSPatchRows * kSP;  // 560 pixels per plane
-constexpr int kSCvtPix = 576;                  // pixel-major rows per stage: M-tile 3's last K half reads up to 360 + 83 + 127 = 570
+constexpr int kSCvtPix = 576;                  // pixel-major rows per stage: M-tile 3's last K half reads up to 360 + 82 + 127 = 569
 constexpr int kSTileValid = kSR * kSC;         // 114 staged rows per M-tile
 constexpr int kSRawStages = 4, kSCvtStages = 4, kSAccStages = 4, kSRing = 3;
 constexpr int kSThreads = 896;                 // warp 0 TMA, 1 + 3 MMA (1: TMEM alloc), 2 store issuer, 4-11 converters, 12-27 epilogue
@@ -61,8 +61,7 @@ static_assert(kSSmem <= 227 * 1024, "shared memory budget");
 
 // tap pairs of the five instructions: first tap's patch offset (pixels), distance to the second tap (pixels), tap indices
 // (-1: no tap, zero weights)
-__constant__ int c_pair_off[5] = {0, 2, kSP + 1, 2 * kSP, 2 * kSP + 2};
-__constant__ int c_pair_lbo[5] = {1, kSP - 2, 1, 1, 1};
+constexpr int kSMma = 3;                       // instructions per M-tile: one per filter row
 
 struct StemHaloArgs {
     int tiles_x, tiles_y, total_tiles;
@@ -166,17 +165,21 @@ stem_halo_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant_
     __syncwarp();
     if (warp == 1) tmem_alloc(smem_u32(const_cast<uint32_t*>(tmem_ptr)), 32 * kSU * kSAccStages);
     if (threadIdx.x >= 128 && threadIdx.x < 128 + 320) {
-        // weight table: instruction j, K half h, output channel n -> 8 fp16 = the 3 channels of tap 2j+h (+ 5 zeros)
+        // weight table: instruction ky, K half h, output channel n -> 8 fp16: h = 0: taps (ky,0) and (ky,1), 3 channels each,
+        // + 2 zeros; h = 1: tap (ky,2) + 5 zeros (the 16-byte row of a pixel also holds its right neighbour's channels)
         const int idx = threadIdx.x - 128;
-        const int j = idx >> 6, h = (idx >> 5) & 1, n = idx & 31;
-        const int t = 2 * j + h;
+        const int ky = idx >> 6, h = (idx >> 5) & 1, n = idx & 31;
         uint4 v = make_uint4(0u, 0u, 0u, 0u);
-        if (t < 9) {
-            const unsigned short* wr = reinterpret_cast<const unsigned short*>(a.w) + n * 32 + t * 3;
+        if (ky < 3) {
+            const unsigned short* wr = reinterpret_cast<const unsigned short*>(a.w) + n * 32 + (ky * 3 + 2 * h) * 3;   // k = (ky*3+kx)*3 + c
             v.x = (uint32_t)__ldg(wr) | ((uint32_t)__ldg(wr + 1) << 16);
             v.y = (uint32_t)__ldg(wr + 2);
+            if (h == 0) {
+                v.y |= (uint32_t)__ldg(wr + 3) << 16;
+                v.z = (uint32_t)__ldg(wr + 4) | ((uint32_t)__ldg(wr + 5) << 16);
+            }
         }
-        *reinterpret_cast<uint4*>(gen + kSOffW + j * 1024 + h * 512 + n * 16) = v;
+        if (ky < 3) *reinterpret_cast<uint4*>(gen + kSOffW + ky * 1024 + h * 512 + n * 16) = v;
     }
     // the converted stages start as zeros: rows 560..575 are never written and only feed by-product GEMM rows
     for (uint32_t i = threadIdx.x; i < kSCvtStages * kSCvtSlot / 16; i += kSThreads)
@@ -206,10 +209,11 @@ stem_halo_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant_
         // reads the patch from pixel t*120 on and accumulates into its own 32 TMEM columns; one commit pair per unit =====
         const int k = warp >> 1;
         const uint32_t idesc = make_idesc(32);
-        uint64_t ad[5], bd[5];
+        // instruction ky: K half 0 = pixel m + ky*40 (taps kx = 0, 1), K half 1 = two pixels on (LBO = 32 B: tap kx = 2)
+        uint64_t ad[kSMma], bd[kSMma];
 #pragma unroll
-        for (int j = 0; j < 5; ++j) {
-            ad[j] = make_desc_plain(cvt0, (uint32_t)c_pair_lbo[j], 8) + (uint64_t)c_pair_off[j];
+        for (int j = 0; j < kSMma; ++j) {
+            ad[j] = make_desc_plain(cvt0, 2, 8) + (uint64_t)(j * kSP);
             bd[j] = make_desc_plain(wsm + j * 1024, 32, 8);
         }
         Slot<kSCvtStages> cs((uint32_t)k);
@@ -224,7 +228,7 @@ stem_halo_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant_
 #pragma unroll
                 for (int t = 0; t < kSU; ++t) {
 #pragma unroll
-                    for (int j = 0; j < 5; ++j)
+                    for (int j = 0; j < kSMma; ++j)
                         umma_f16(d_tmem + t * 32, ad[j] + a_off + (uint64_t)(t * kSR * kSP), bd[j], idesc, j != 0);
                 }
                 umma_commit(cempty0 + 8 * cs.i);
@@ -259,10 +263,12 @@ stem_halo_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant_
         const int grp = (warp - 4) >> 2;
         const int tid = threadIdx.x & 127;
         int q[kSCvtPer];
+        bool edge[kSCvtPer];
 #pragma unroll
         for (int i = 0; i < kSCvtPer; ++i) {
             const int p = tid + 128 * i;
             q[i] = (p / kSP) * RP + p % kSP;                  // raw index of patch pixel p (+ the unit's column shift)
+            edge[i] = p % kSP == kSP - 1;
         }
         const bool last_ok = tid + 128 * (kSCvtPer - 1) < kSPatchPix;
         Slot<kSRawStages> rs((uint32_t)grp);
@@ -275,13 +281,19 @@ stem_halo_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant_
             tx += dtx; if (tx >= a.tiles_x) tx -= a.tiles_x;
             mbar_wait(rfull0 + 8 * rs.i, rs.ph, a.dbg, 5, (int)rs.i);
             const TIn* rp = reinterpret_cast<const TIn*>(gen + kSOffRaw + rs.i * kSRawSlot) + d;
-            uint2 pk[kSCvtPer];
+            // 16-byte row of patch pixel p: its three channels, the three channels of pixel p + 1 (same patch row; zeros for the
+            // last column, whose right neighbour only ever meets zero weights or by-product rows), two zeros
+            uint32_t pk[kSCvtPer][3];
 #pragma unroll
             for (int i = 0; i < kSCvtPer; ++i) {
-                float v0 = 0.f, v1 = 0.f, v2 = 0.f;
-                if (i < kSCvtPer - 1 || last_ok) { v0 = raw_ld(rp + q[i]); v1 = raw_ld(rp + RPLANE + q[i]); v2 = raw_ld(rp + 2 * RPLANE + q[i]); }
-                const __half2 h01 = __floats2half2_rn(v0, v1), h2 = __floats2half2_rn(v2, 0.f);
-                pk[i].x = *reinterpret_cast<const uint32_t*>(&h01); pk[i].y = *reinterpret_cast<const uint32_t*>(&h2);
+                float v0 = 0.f, v1 = 0.f, v2 = 0.f, n0 = 0.f, n1 = 0.f, n2 = 0.f;
+                if (i < kSCvtPer - 1 || last_ok) {
+                    v0 = raw_ld(rp + q[i]); v1 = raw_ld(rp + RPLANE + q[i]); v2 = raw_ld(rp + 2 * RPLANE + q[i]);
+                    if (!edge[i]) { n0 = raw_ld(rp + q[i] + 1); n1 = raw_ld(rp + RPLANE + q[i] + 1); n2 = raw_ld(rp + 2 * RPLANE + q[i] + 1); }
+                }
+                const __half2 h0 = __floats2half2_rn(v0, v1), h1 = __floats2half2_rn(v2, n0), h2 = __floats2half2_rn(n1, n2);
+                pk[i][0] = *reinterpret_cast<const uint32_t*>(&h0); pk[i][1] = *reinterpret_cast<const uint32_t*>(&h1);
+                pk[i][2] = *reinterpret_cast<const uint32_t*>(&h2);
             }
             __syncwarp();
             if (lane == 0) mbar_arrive(rempty0 + 8 * rs.i);  // the raw patch is in registers
@@ -289,7 +301,7 @@ stem_halo_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant_
             uint8_t* dst = gen + kSOffCvt + cs.i * kSCvtSlot + tid * 16;
 #pragma unroll
             for (int i = 0; i < kSCvtPer; ++i)
-                if (i < kSCvtPer - 1 || last_ok) *reinterpret_cast<uint4*>(dst + i * 2048) = make_uint4(pk[i].x, pk[i].y, 0u, 0u);
+                if (i < kSCvtPer - 1 || last_ok) *reinterpret_cast<uint4*>(dst + i * 2048) = make_uint4(pk[i][0], pk[i][1], pk[i][2], 0u);
             fence_async_smem();
             __syncwarp();
             if (lane == 0) mbar_arrive(cfull0 + 8 * cs.i);
