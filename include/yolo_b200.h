@@ -220,6 +220,11 @@ int yb_debug_words(const yb_ctx* ctx, int* out, int n);
  * (fp32 or fp16), in [B,H,W,Cin] -> out [B,Ho,Wo,Cout(+pad)], with optional residual (same shape as out). */
 int yb_run_layer(yb_ctx* ctx, int layer_index, const void* in_nhwc, int B, int H, int W,
                  const void* residual_nhwc, void* out_nhwc, void* stream);
+/* Unit-test entry of the fused first kernel (YB_MODE_FP16): stem + the first stride-2 convolution (reference
+ * darknet.py:66-69) on a dev NCHW image of the current input element type -> out [B, H/2, W/2, 64] fp16 NHWC.
+ * H even, W a multiple of 4 (fp32 images) / 8 (fp16); YB_E_UNSUPPORTED for widths whose last column tile would be
+ * less than 80 % full (the network path then runs the two layers as separate kernels). */
+int yb_run_stem_block(yb_ctx* ctx, const void* x_nchw, int B, int H, int W, void* out_nhwc, void* stream);
 
 #ifdef __cplusplus
 }

@@ -160,6 +160,47 @@ def test_tc_stem_vs_torch(fp16_ctx, sd, B, H, W):
     assert not bad.any(), f"stem: {int(bad.sum())} of {bad.numel()} outside tolerance, max err {float(err.max()):.4g}"
 
 
+@pytest.mark.parametrize("B,H,W", [(2, 40, 64), (1, 64, 76), (3, 18, 128), (1, 64, 608), (2, 10, 152), (1, 2, 64), (2, 6, 304),
+                                   (1, 96, 416), (5, 14, 208)])
+def test_fused_stem_block_vs_torch(fp16_ctx, sd, B, H, W):
+    """Stem + first stride-2 convolution in one kernel (stem_block.cu; reference darknet.py:66-69): NCHW fp32 image in, layer
+    1's NHWC fp16 output out, against torch fp32 convolutions of the same fp16-rounded operands with the stem output rounded
+    to fp16 in between (what the two separate kernels produce).  Shapes cover partial row / column tiles, images smaller
+    than one tile and every image border."""
+    lib, ctx = fp16_ctx
+    rs = np.random.RandomState(11)
+    x = torch.from_numpy(rs.rand(B, 3, H, W).astype(np.float32))
+    out = torch.full((B, H // 2, W // 2, 64), float("nan"), device="cuda", dtype=torch.float16)
+    xd = x.cuda()
+    _lib.check(lib.yb_run_stem_block(ctx, vp(xd), B, H, W, vp(out), stream()), ctx)
+    torch.cuda.synchronize()
+    specs = topology.layer_specs(80)
+    y0 = ref_layer(sd, specs[0], x.half().permute(0, 2, 3, 1).contiguous(), None).half()
+    ref = ref_layer(sd, specs[1], y0, None)
+    y = out.float().cpu()
+    err = (y - ref).abs()
+    tol = 6e-3 * ref.abs().max() + 4e-3 * ref.abs()
+    bad = (err > tol) | torch.isnan(y)
+    assert not bad.any(), f"fused stem block: {int(bad.sum())} of {bad.numel()} outside tolerance, max err {float(err.max()):.4g}"
+
+
+def test_fused_stem_block_equals_separate_kernels(fp16_ctx, sd):
+    """The fused kernel against the two separate kernels (halo stem, then the stride-2 halo convolution) on the same image:
+    same fp16 operands and the same fp16 hand-over, so the results agree to the accumulation order of the tensor core."""
+    lib, ctx = fp16_ctx
+    B, H, W = 2, 96, 160
+    x = torch.rand(B, 3, H, W, device="cuda")
+    fused = torch.empty((B, H // 2, W // 2, 64), device="cuda", dtype=torch.float16)
+    _lib.check(lib.yb_run_stem_block(ctx, vp(x), B, H, W, vp(fused), stream()), ctx)
+    y0 = torch.empty((B, H, W, 32), device="cuda", dtype=torch.float16)
+    _lib.check(lib.yb_run_layer(ctx, 0, vp(x), B, H, W, None, vp(y0), stream()), ctx)
+    sep = torch.empty_like(fused)
+    _lib.check(lib.yb_run_layer(ctx, 1, vp(y0), B, H, W, None, vp(sep), stream()), ctx)
+    torch.cuda.synchronize()
+    d = (fused.float() - sep.float()).abs()
+    assert float(d.max()) <= 4e-3 * float(sep.float().abs().max()), f"max diff {float(d.max()):.4g}"
+
+
 def test_fp16_net_deviation_report(oracle, sd):
     """End to end at 416 (one image) and 608 (two images): the deviation of the fp16 tensor-core path from the fp32 CPU
     oracle is reported and bounded at about twice what is measured (rounds 1-2: logits max 0.07-0.15, xy 0.26-0.47 px,

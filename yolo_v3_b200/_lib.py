@@ -60,6 +60,7 @@ PROTOTYPES = {
     "yb_get_section_ms": (c_int, [c_void_p, POINTER(c_float), POINTER(c_float), POINTER(c_float)]),
     "yb_get_layer_ms": (c_int, [c_void_p, POINTER(c_float), c_int]),
     "yb_run_layer": (c_int, [c_void_p, c_int, c_void_p, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p]),
+    "yb_run_stem_block": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_void_p, c_void_p]),
 }
 
 _lib = None

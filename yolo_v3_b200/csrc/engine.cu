@@ -32,6 +32,8 @@ struct Op {
     HaloPlan halo;
     StemTcPlan stem_tc;
     StemHaloPlan stem_halo;
+    bool fused01 = false;             // the stem op also runs layer 1 (stem_block.cu) and writes layer 1's output
+    StemBlockPlan stem_block;
     bool upcopy = false;              // YB_MODE_FP32_TC: nearest x2 copy of up_src into the concat slice up_dst
     TView up_src, up_dst;
 };
@@ -318,6 +320,16 @@ struct PlanBuilder {
     }
 };
 
+// TEMPORARY A/B switches while the new first-layer kernels are validated
+bool stem_old() {
+    static const bool v = getenv("YB_STEM_OLD") && atoi(getenv("YB_STEM_OLD")) != 0;
+    return v;
+}
+bool stem_unfused() {
+    static const bool v = getenv("YB_STEM_UNFUSED") && atoi(getenv("YB_STEM_UNFUSED")) != 0;
+    return v;
+}
+
 int build_plan(yb_ctx* c, int B, int H, int W, Plan** out) {
     for (auto& q : c->plans)
         if (q->B == B && q->H == H && q->W == W && q->mode == c->mode) { *out = q.get(); return YB_OK; }
@@ -347,13 +359,24 @@ int build_plan(yb_ctx* c, int B, int H, int W, Plan** out) {
     if (!pb.err.empty()) return bail(pb.err);
 
     // stem
+    bool fused01 = false;
     {
         Op op;
         op.layer = 0; op.stem = true;
         op.a.out = buf[0];
         if (p->mode == YB_MODE_FP16) {
-            std::string e = stem_tc_make_plan(op.stem_tc, static_cast<__half*>(buf[0]), 32, B, H, W, c->num_sms);
-            if (e.empty()) e = stem_halo_make_plan(op.stem_halo, static_cast<__half*>(buf[0]), 32, B, H, W, c->num_sms);
+            std::string e;
+            // stem + first stride-2 convolution in one kernel (the 32-channel tensor never reaches HBM); W % 8 covers both
+            // image element types
+            fused01 = stem_block_supported(H, W, 1) && !stem_unfused();
+            if (fused01) {
+                op.fused01 = true;
+                op.a.out = buf[1];
+                e = stem_block_make_plan(op.stem_block, c->layers[1].d_w16, static_cast<__half*>(buf[1]), 64, B, H, W, c->num_sms);
+            } else {
+                e = stem_tc_make_plan(op.stem_tc, static_cast<__half*>(buf[0]), 32, B, H, W, c->num_sms);
+                if (e.empty()) e = stem_halo_make_plan(op.stem_halo, static_cast<__half*>(buf[0]), 32, B, H, W, c->num_sms);
+            }
             if (!e.empty()) return bail("plan: stem: " + e);
         }
         p->ops.push_back(op);
@@ -365,7 +388,8 @@ int build_plan(yb_ctx* c, int B, int H, int W, Plan** out) {
         // down-sampling conv (darknet.py:69)
         const int ob = curb == 0 ? 1 : 0;
         TView o = pb.view(buf[ob], B, h / 2, w / 2, ch * 2, ch * 2);
-        if (!pb.conv(li++, cur, o, nullptr, false, false)) return bail(pb.err);
+        if (s == 0 && fused01) ++li;    // layer 1 ran inside the stem kernel
+        else if (!pb.conv(li++, cur, o, nullptr, false, false)) return bail(pb.err);
         cur = o; curb = ob; h /= 2; w /= 2; ch *= 2;
         for (int j = 0; j < kBlocks[s]; ++j) {
             const int tb = curb == 0 ? 1 : 0;
@@ -432,11 +456,7 @@ int build_plan(yb_ctx* c, int B, int H, int W, Plan** out) {
 
 constexpr int kProfBank = 16;
 
-// TEMPORARY A/B switch while the halo stem is validated (removed once it is the only stem)
-bool stem_old() {
-    static const bool v = getenv("YB_STEM_OLD") && atoi(getenv("YB_STEM_OLD")) != 0;
-    return v;
-}
+
 
 cudaError_t launch_op(yb_ctx* c, Plan* p, Op& op, cudaStream_t s) {
     const Layer& L = c->layers[op.layer];
@@ -512,7 +532,10 @@ int run_ops(yb_ctx* c, Plan* p, const float* x, int n_ops, cudaStream_t s) {
         if (op.stem) {
             if (c->input_f16 && p->mode != YB_MODE_FP16)
                 return fail(c, YB_E_UNSUPPORTED, "fp16 input images need YB_MODE_FP16");
-            if (p->mode == YB_MODE_FP16 && stem_old())
+            if (p->mode == YB_MODE_FP16 && op.fused01)
+                e = stem_block_launch(op.stem_block, x, c->input_f16, p->B, p->H, p->W, L.d_w16, c->stem_sb, c->layers[1].d_scale,
+                                      c->layers[1].d_bias, c->dbg, s);
+            else if (p->mode == YB_MODE_FP16 && stem_old())
                 e = stem_tc_launch(op.stem_tc, x, c->input_f16, p->B, p->H, p->W, L.d_w16, L.d_scale, L.d_bias, c->dbg, s);
             else if (p->mode == YB_MODE_FP16)
                 e = stem_halo_launch(op.stem_halo, x, c->input_f16, p->B, p->H, p->W, L.d_w16, c->stem_sb, c->dbg, s);
@@ -1337,6 +1360,21 @@ int yb_run_layer(yb_ctx* c, int li, const void* in, int B, int H, int W, const v
     } else {
         YB_CUDA(c, launch_conv_simt<float>(a, L.d_w32, L.cout_pad, s));
     }
+    ++c->launches;
+    return YB_OK;
+}
+
+int yb_run_stem_block(yb_ctx* c, const void* x, int B, int H, int W, void* out, void* stream) {
+    if (!c) return fail(nullptr, YB_E_ARG, "null ctx");
+    if (!c->finalized || c->mode != YB_MODE_FP16) return fail(c, YB_E_STATE, "yb_run_stem_block: yb_finalize(YB_MODE_FP16) first");
+    if (!x || !out || B <= 0 || H <= 0 || W <= 0) return fail(c, YB_E_ARG, "yb_run_stem_block: bad arguments");
+    if (!stem_block_supported(H, W, c->input_f16)) return fail(c, YB_E_UNSUPPORTED, "yb_run_stem_block: shape not supported by the fused kernel");
+    YB_CUDA(c, cudaSetDevice(c->device));
+    StemBlockPlan sp;
+    std::string err = stem_block_make_plan(sp, c->layers[1].d_w16, static_cast<__half*>(out), 64, B, H, W, c->num_sms);
+    if (!err.empty()) return fail(c, YB_E_CUDA, "yb_run_stem_block: " + err);
+    YB_CUDA(c, stem_block_launch(sp, x, c->input_f16, B, H, W, c->layers[0].d_w16, c->stem_sb, c->layers[1].d_scale, c->layers[1].d_bias,
+                                 c->dbg, static_cast<cudaStream_t>(stream)));
     ++c->launches;
     return YB_OK;
 }

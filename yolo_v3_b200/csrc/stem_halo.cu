@@ -70,20 +70,7 @@ struct StemHaloArgs {
     int* dbg;
 };
 
-__device__ __forceinline__ void tma_load_4d(const CUtensorMap* tm, uint32_t dst, uint32_t bar, int c0, int c1, int c2, int c3) {
-    asm volatile(
-        "cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
-        ::"r"(dst), "l"(tm), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "r"(c3) : "memory");
-}
-__device__ __forceinline__ void tma_store_4d(const CUtensorMap* tm, uint32_t src, int c0, int c1, int c2, int c3) {
-    asm volatile("cp.async.bulk.tensor.4d.global.shared::cta.bulk_group [%0, {%2, %3, %4, %5}], [%1];"
-                 ::"l"(tm), "r"(src), "r"(c0), "r"(c1), "r"(c2), "r"(c3) : "memory");
-}
 
-// non-swizzled K-major operand: start address, LBO (between the two K halves) and SBO (between 8-row groups), all >> 4
-__device__ __forceinline__ uint64_t make_desc_plain(uint32_t saddr, uint32_t lbo16, uint32_t sbo16) {
-    return (uint64_t)((saddr >> 4) & 0x3FFF) | ((uint64_t)lbo16 << 16) | ((uint64_t)sbo16 << 32) | (1ull << 46);
-}
 
 // tile = (img * tiles_y + ty) * tiles_x + tx, walked with a constant step without divisions
 struct StemWalk {
@@ -107,8 +94,6 @@ struct StemWalk {
     __device__ __forceinline__ int y0() const { return ty * kSUR; }
 };
 
-__device__ __forceinline__ float raw_ld(const float* p) { return *p; }
-__device__ __forceinline__ float raw_ld(const __half* p) { return __half2float(*p); }
 
 __device__ __forceinline__ float2 ffma2(float2 a, float2 b, float2 c) {
     unsigned long long ra;
@@ -124,13 +109,6 @@ __device__ __forceinline__ float2 fmul2(float2 a, float2 b) {
     return *reinterpret_cast<float2*>(&ra);
 }
 
-// A round-robin slot counter: index g % N and parity (g / N) & 1 of the g-th use, advanced by a constant step < 2N
-template <int N>
-struct Slot {
-    uint32_t i, ph;
-    __device__ __forceinline__ explicit Slot(uint32_t first) : i(first % N), ph((first / N) & 1u) {}
-    __device__ __forceinline__ void advance(uint32_t step) { i += step; if (i >= (uint32_t)N) { i -= N; ph ^= 1u; } }
-};
 
 template <typename TIn>
 __global__ void __launch_bounds__(kSThreads, 1)

@@ -144,6 +144,15 @@ __device__ __forceinline__ void tma_store_2d(const CUtensorMap* tm, uint32_t src
     asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];"
                  ::"l"(tm), "r"(src), "r"(c0), "r"(c1) : "memory");
 }
+__device__ __forceinline__ void tma_load_4d(const CUtensorMap* tm, uint32_t dst, uint32_t bar, int c0, int c1, int c2, int c3) {
+    asm volatile(
+        "cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
+        ::"r"(dst), "l"(tm), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "r"(c3) : "memory");
+}
+__device__ __forceinline__ void tma_store_4d(const CUtensorMap* tm, uint32_t src, int c0, int c1, int c2, int c3) {
+    asm volatile("cp.async.bulk.tensor.4d.global.shared::cta.bulk_group [%0, {%2, %3, %4, %5}], [%1];"
+                 ::"l"(tm), "r"(src), "r"(c0), "r"(c1), "r"(c2), "r"(c3) : "memory");
+}
 __device__ __forceinline__ void tma_store_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
 template <int N>
 __device__ __forceinline__ void tma_store_wait_read() { asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(N) : "memory"); }
@@ -261,11 +270,27 @@ __device__ __forceinline__ uint64_t make_smem_desc(uint32_t saddr) {
     constexpr uint64_t layout = SWZ == 128 ? 2 : 4;
     return (uint64_t)((saddr >> 4) & 0x3FFF) | (1ull << 16) | (sbo << 32) | (1ull << 46) | (layout << 61);
 }
+// non-swizzled K-major operand: start address, LBO (between the two K halves) and SBO (between 8-row groups), all >> 4
+__device__ __forceinline__ uint64_t make_desc_plain(uint32_t saddr, uint32_t lbo16, uint32_t sbo16) {
+    return (uint64_t)((saddr >> 4) & 0x3FFF) | ((uint64_t)lbo16 << 16) | ((uint64_t)sbo16 << 32) | (1ull << 46);
+}
 // kind::f16 instruction descriptor (cute::UMMA::InstrDescriptor): D fp32 (bits [4,6) = 1), A/B fp16
 // (0), both K-major, N >> 3 in [17,23), M >> 4 in [24,29).
 __device__ __forceinline__ uint32_t make_idesc(int n, int m = 128) { return (1u << 4) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(m >> 4) << 24); }
 
 __device__ __forceinline__ float leaky(float v) { return v > 0.f ? v : v * kLeaky; }
+
+// A round-robin slot counter: index g % N and parity (g / N) & 1 of the g-th use, advanced by a constant step < 2N
+template <int N>
+struct Slot {
+    uint32_t i, ph;
+    __device__ __forceinline__ explicit Slot(uint32_t first) : i(first % N), ph((first / N) & 1u) {}
+    __device__ __forceinline__ void advance(uint32_t step) { i += step; if (i >= (uint32_t)N) { i -= N; ph ^= 1u; } }
+};
+
+// element of a planar image patch staged in shared memory (fp32 or fp16 images)
+__device__ __forceinline__ float raw_ld(const float* p) { return *p; }
+__device__ __forceinline__ float raw_ld(const __half* p) { return __half2float(*p); }
 
 }  // namespace
 }  // namespace yb

@@ -161,6 +161,18 @@ std::string stem_halo_make_plan(StemHaloPlan& p, __half* out, long out_ld, int B
 cudaError_t stem_halo_launch(const StemHaloPlan& p, const void* x, int in_f16, int B, int H, int W, const __half* w16,
                              const float* sb_host, int* dbg, cudaStream_t s);
 
+// stem_block.cu  (stem + the first stride-2 convolution in one kernel: the 32-channel stem output never leaves the SM)
+struct StemBlockPlan {
+    CUtensorMap tmW1, tmOut;
+    int tiles_x = 0, tiles_y = 0, total_tiles = 0, grid = 0;
+    size_t smem = 0;
+};
+bool stem_block_supported(int H, int W, int in_f16);
+// w1: layer 1's fp16 weights [64][9*32] (k = tap*32 + c); out: layer 1's output [B, H/2, W/2, out_ld >= 64]
+std::string stem_block_make_plan(StemBlockPlan& p, const __half* w1, __half* out, long out_ld, int B, int H, int W, int num_sms);
+cudaError_t stem_block_launch(const StemBlockPlan& p, const void* x, int in_f16, int B, int H, int W, const __half* w0,
+                              const float* sb0_host, const float* scale1, const float* bias1, int* dbg, cudaStream_t s);
+
 // conv_halo.cu  (3x3 stride-1 layers with Cin = 32 / 64 from a halo tile: every input pixel staged once)
 struct HaloPlan {
     CUtensorMap tmIn, tmB, tmOut, tmRes;
