@@ -64,6 +64,20 @@ static_assert(kFSmem <= 227 * 1024, "shared memory budget");
 constexpr uint32_t kFAcc1Cols = 32 * kFMT;        // 160 TMEM columns per stem accumulator set
 constexpr uint32_t kFAcc2Base = 2 * kFAcc1Cols;   // layer-1 accumulators: 2 x 64 columns from column 320
 
+__device__ __forceinline__ float2 ffma2x(float2 a, float2 b, float2 c) {
+    unsigned long long ra;
+    asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(ra)
+        : "l"(*reinterpret_cast<unsigned long long*>(&a)), "l"(*reinterpret_cast<unsigned long long*>(&b)),
+          "l"(*reinterpret_cast<unsigned long long*>(&c)));
+    return *reinterpret_cast<float2*>(&ra);
+}
+__device__ __forceinline__ float2 fmul2x(float2 a, float2 b) {
+    unsigned long long ra;
+    asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(ra)
+        : "l"(*reinterpret_cast<unsigned long long*>(&a)), "l"(*reinterpret_cast<unsigned long long*>(&b)));
+    return *reinterpret_cast<float2*>(&ra);
+}
+
 template <typename TIn> struct FRaw;
 template <> struct FRaw<float> { static constexpr int kPitch = 84, kMask = 3; };
 template <> struct FRaw<__half> { static constexpr int kPitch = 88, kMask = 7; };
@@ -202,10 +216,11 @@ stem_block_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant
             if (elect_one()) {
                 const uint64_t a_off = (uint64_t)(s * (kFCvtSlot >> 4));
                 const uint32_t d_tmem = tmem_base + s * kFAcc1Cols;
+                // filter-row-major order: consecutive instructions accumulate into different M-tiles
 #pragma unroll
-                for (int t = 0; t < kFMT; ++t) {
+                for (int j = 0; j < 3; ++j) {
 #pragma unroll
-                    for (int j = 0; j < 3; ++j) umma_f16(d_tmem + t * 32, ad0[j] + a_off + (uint64_t)(t * 128), bd0[j], idesc0, j != 0);
+                    for (int t = 0; t < kFMT; ++t) umma_f16(d_tmem + t * 32, ad0[j] + a_off + (uint64_t)(t * 128), bd0[j], idesc0, j != 0);
                 }
                 umma_commit(cempty0 + 8 * s);
                 umma_commit(t1full0 + 8 * s);
@@ -333,17 +348,19 @@ stem_block_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant
         const bool valid1 = r1 < kFR && c1 < kFC;
         const int mp = r1 * kFC + c1;
         const int xr = mp & 7;
-        float4 sc4[4], bi4[4];
-        {
-            const float4* sc = reinterpret_cast<const float4*>(gen + kFOffTab) + part * 4;
-            const float4* bi = reinterpret_cast<const float4*>(gen + kFOffTab + 256) + part * 4;
+        const float4* sc1 = reinterpret_cast<const float4*>(gen + kFOffTab) + part * 4;          // layer-1 scale / bias of this thread's
+        const float4* bi1 = reinterpret_cast<const float4*>(gen + kFOffTab + 256) + part * 4;    // sixteen channels (shared-memory table)
+        float2 sc0[4], bi0[4];                           // stem scale / bias of this thread's eight channels
 #pragma unroll
-            for (int i = 0; i < 4; ++i) { sc4[i] = sc[i]; bi4[i] = bi[i]; }
+        for (int e = 0; e < 4; ++e) {
+            sc0[e] = make_float2(a.sb0[part * 8 + 2 * e], a.sb0[part * 8 + 2 * e + 1]);
+            bi0[e] = make_float2(a.sb0[32 + part * 8 + 2 * e], a.sb0[32 + part * 8 + 2 * e + 1]);
         }
         BlockWalk tw(a, unit_first, unit_step);          // position of the unit being handed over
         auto handover = [&](uint32_t s, uint32_t ph) {
             // stem output (gy, gx) = (2*y0 - 1 + Y, 2*x0 - 1 + X); outside the image -> zero (layer 1's padding)
             const int gy0 = 2 * tw.y0() - 1, gx0 = 2 * tw.x0() - 1;
+            const bool interior = gy0 >= 0 && gy0 + kFSY <= a.H && gx0 >= 0 && gx0 + kFSX <= a.W;   // only border units can hold padding pixels
             mbar_wait(t1full0 + 8 * s, ph, a.dbg, 2, 200 + (int)s);
             tc_fence_after();
             mbar_wait(pempty0 + 8 * s, ph ^ 1, a.dbg, 2, 300 + (int)s);
@@ -354,20 +371,21 @@ stem_block_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant
                 tmem_ld8(tmem_base + s * kFAcc1Cols + (uint32_t)(t * 32 + part * 8) + ((uint32_t)(q * 32) << 16), v);
                 tmem_ld_wait();
                 if (hoff[t] >= 0) {
-                    const int L = 128 * t + ml, Y = L / kFIP;
-                    const int gy = gy0 + Y, gx = gx0 + (L - Y * kFIP);
-                    const bool in_img = gy >= 0 && gy < a.H && gx >= 0 && gx < a.W;
+                    bool in_img = true;
+                    if (!interior) {
+                        const int L = 128 * t + ml, Y = L / kFIP;
+                        const int gy = gy0 + Y, gx = gx0 + (L - Y * kFIP);
+                        in_img = gy >= 0 && gy < a.H && gx >= 0 && gx < a.W;
+                    }
                     uint4 pk;
                     __half2* ph2 = reinterpret_cast<__half2*>(&pk);
 #pragma unroll
                     for (int e = 0; e < 4; ++e) {
-                        const int ch = part * 8 + 2 * e;
-                        float y0 = fmaf(__uint_as_float(v[2 * e]), a.sb0[ch], a.sb0[32 + ch]);
-                        float y1 = fmaf(__uint_as_float(v[2 * e + 1]), a.sb0[ch + 1], a.sb0[32 + ch + 1]);
-                        y0 = in_img ? fmaxf(y0, y0 * kLeaky) : 0.f;
-                        y1 = in_img ? fmaxf(y1, y1 * kLeaky) : 0.f;
-                        ph2[e] = __floats2half2_rn(y0, y1);
+                        const float2 y = ffma2x(make_float2(__uint_as_float(v[2 * e]), __uint_as_float(v[2 * e + 1])), sc0[e], bi0[e]);
+                        const float2 z = fmul2x(y, make_float2(kLeaky, kLeaky));
+                        ph2[e] = __floats2half2_rn(fmaxf(y.x, z.x), fmaxf(y.y, z.y));      // LeakyReLU(0.1) = max(v, 0.1 v)
                     }
+                    if (!in_img) pk = make_uint4(0u, 0u, 0u, 0u);
                     *reinterpret_cast<uint4*>(pbase + hoff[t]) = pk;
                 }
             }
@@ -397,7 +415,7 @@ stem_block_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant
                 float v[16];
 #pragma unroll
                 for (int i = 0; i < 4; ++i) {
-                    const float4 s4 = sc4[i], b4 = bi4[i];
+                    const float4 s4 = sc1[i], b4 = bi1[i];
                     v[4 * i + 0] = leaky(fmaf(__uint_as_float(r0[4 * i + 0]), s4.x, b4.x));
                     v[4 * i + 1] = leaky(fmaf(__uint_as_float(r0[4 * i + 1]), s4.y, b4.y));
                     v[4 * i + 2] = leaky(fmaf(__uint_as_float(r0[4 * i + 2]), s4.z, b4.z));

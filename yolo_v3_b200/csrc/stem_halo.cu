@@ -49,7 +49,7 @@ constexpr uint32_t kSRawSlot = 7424;           // 3 x 14 x 44 fp32 = 7392 B, pad
 template <typename TIn> struct RawGeom;
 template <> struct RawGeom<float> { static constexpr int kPitch = 44, kMask = 3; };
 template <> struct RawGeom<__half> { static constexpr int kPitch = 48, kMask = 7; };
-constexpr uint32_t kSCvtSlot = kSCvtPix * 16;  // 9216
+constexpr uint32_t kSCvtSlot = kSCvtPix * 32;  // 18432: 32 bytes per pixel (one K = 16 row), 32B swizzle
 constexpr uint32_t kSStgSlot = 58 * 512;       // 4 x 114 compact rows x 32 fp16 = 29184 B, padded to the 512-byte swizzle period
 constexpr uint32_t kSOffW = 2048, kSOffStg = 8192;
 constexpr uint32_t kSOffCvt = kSOffStg + kSRing * kSStgSlot;
@@ -62,6 +62,11 @@ static_assert(kSSmem <= 227 * 1024, "shared memory budget");
 // tap pairs of the five instructions: first tap's patch offset (pixels), distance to the second tap (pixels), tap indices
 // (-1: no tap, zero weights)
 constexpr int kSMma = 3;                       // instructions per M-tile: one per filter row
+
+// K-major operand with 32-byte rows and the 32B swizzle (layout type 6): SBO = 8 rows = 256 bytes
+__device__ __forceinline__ uint64_t make_desc_sw32(uint32_t saddr) {
+    return (uint64_t)((saddr >> 4) & 0x3FFF) | (1ull << 16) | (16ull << 32) | (1ull << 46) | (6ull << 61);
+}
 
 struct StemHaloArgs {
     int tiles_x, tiles_y, total_tiles;
@@ -143,21 +148,23 @@ stem_halo_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant_
     __syncwarp();
     if (warp == 1) tmem_alloc(smem_u32(const_cast<uint32_t*>(tmem_ptr)), 32 * kSU * kSAccStages);
     if (threadIdx.x >= 128 && threadIdx.x < 128 + 320) {
-        // weight table: instruction ky, K half h, output channel n -> 8 fp16: h = 0: taps (ky,0) and (ky,1), 3 channels each,
-        // + 2 zeros; h = 1: tap (ky,2) + 5 zeros (the 16-byte row of a pixel also holds its right neighbour's channels)
+        // weight table: filter row ky, output channel n -> one 32-byte K-major row (32B swizzle) = the nine weights of taps
+        // (ky,0), (ky,1), (ky,2) x 3 channels, + 7 zeros; idx also enumerates the 16-byte chunk h of the row
         const int idx = threadIdx.x - 128;
         const int ky = idx >> 6, h = (idx >> 5) & 1, n = idx & 31;
-        uint4 v = make_uint4(0u, 0u, 0u, 0u);
         if (ky < 3) {
-            const unsigned short* wr = reinterpret_cast<const unsigned short*>(a.w) + n * 32 + (ky * 3 + 2 * h) * 3;   // k = (ky*3+kx)*3 + c
-            v.x = (uint32_t)__ldg(wr) | ((uint32_t)__ldg(wr + 1) << 16);
-            v.y = (uint32_t)__ldg(wr + 2);
+            const unsigned short* wr = reinterpret_cast<const unsigned short*>(a.w) + n * 32 + ky * 9;   // k = (ky*3+kx)*3 + c
+            uint4 v = make_uint4(0u, 0u, 0u, 0u);
             if (h == 0) {
-                v.y |= (uint32_t)__ldg(wr + 3) << 16;
+                v.x = (uint32_t)__ldg(wr) | ((uint32_t)__ldg(wr + 1) << 16);
+                v.y = (uint32_t)__ldg(wr + 2) | ((uint32_t)__ldg(wr + 3) << 16);
                 v.z = (uint32_t)__ldg(wr + 4) | ((uint32_t)__ldg(wr + 5) << 16);
+                v.w = (uint32_t)__ldg(wr + 6) | ((uint32_t)__ldg(wr + 7) << 16);
+            } else {
+                v.x = (uint32_t)__ldg(wr + 8);
             }
+            *reinterpret_cast<uint4*>(gen + kSOffW + ky * 1024 + n * 32 + ((h ^ ((n >> 2) & 1)) << 4)) = v;
         }
-        if (ky < 3) *reinterpret_cast<uint4*>(gen + kSOffW + ky * 1024 + h * 512 + n * 16) = v;
     }
     // the converted stages start as zeros: rows 560..575 are never written and only feed by-product GEMM rows
     for (uint32_t i = threadIdx.x; i < kSCvtStages * kSCvtSlot / 16; i += kSThreads)
@@ -187,12 +194,12 @@ stem_halo_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant_
         // reads the patch from pixel t*120 on and accumulates into its own 32 TMEM columns; one commit pair per unit =====
         const int k = warp >> 1;
         const uint32_t idesc = make_idesc(32);
-        // instruction ky: K half 0 = pixel m + ky*40 (taps kx = 0, 1), K half 1 = two pixels on (LBO = 32 B: tap kx = 2)
+        // instruction ky: the 32-byte rows of pixels m + ky*40 .. (each holds the pixel and its two right neighbours = taps kx = 0, 1, 2)
         uint64_t ad[kSMma], bd[kSMma];
 #pragma unroll
         for (int j = 0; j < kSMma; ++j) {
-            ad[j] = make_desc_plain(cvt0, 2, 8) + (uint64_t)(j * kSP);
-            bd[j] = make_desc_plain(wsm + j * 1024, 32, 8);
+            ad[j] = make_desc_sw32(cvt0) + (uint64_t)(2 * j * kSP);
+            bd[j] = make_desc_sw32(wsm + j * 1024);
         }
         Slot<kSCvtStages> cs((uint32_t)k);
         Slot<kSAccStages> as((uint32_t)k);
@@ -203,11 +210,13 @@ stem_halo_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant_
             if (elect_one()) {
                 const uint64_t a_off = (uint64_t)(cs.i * (kSCvtSlot >> 4));
                 const uint32_t d_tmem = tmem_base + as.i * (32 * kSU);
+                // filter-row-major order: consecutive instructions accumulate into different M-tiles (back-to-back instructions on
+                // one accumulator serialise on its read-modify-write, ~150 cycles each for these short N = 32 instructions)
 #pragma unroll
-                for (int t = 0; t < kSU; ++t) {
+                for (int j = 0; j < kSMma; ++j) {
 #pragma unroll
-                    for (int j = 0; j < kSMma; ++j)
-                        umma_f16(d_tmem + t * 32, ad[j] + a_off + (uint64_t)(t * kSR * kSP), bd[j], idesc, j != 0);
+                    for (int t = 0; t < kSU; ++t)
+                        umma_f16(d_tmem + t * 32, ad[j] + a_off + (uint64_t)(2 * t * kSR * kSP), bd[j], idesc, j != 0);
                 }
                 umma_commit(cempty0 + 8 * cs.i);
                 umma_commit(tfull0 + 8 * as.i);
@@ -241,12 +250,12 @@ stem_halo_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant_
         const int grp = (warp - 4) >> 2;
         const int tid = threadIdx.x & 127;
         int q[kSCvtPer];
-        bool edge[kSCvtPer];
+        int room[kSCvtPer];                                   // right neighbours inside the patch row (0..2)
 #pragma unroll
         for (int i = 0; i < kSCvtPer; ++i) {
             const int p = tid + 128 * i;
             q[i] = (p / kSP) * RP + p % kSP;                  // raw index of patch pixel p (+ the unit's column shift)
-            edge[i] = p % kSP == kSP - 1;
+            room[i] = min(2, kSP - 1 - p % kSP);
         }
         const bool last_ok = tid + 128 * (kSCvtPer - 1) < kSPatchPix;
         Slot<kSRawStages> rs((uint32_t)grp);
@@ -259,27 +268,42 @@ stem_halo_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant_
             tx += dtx; if (tx >= a.tiles_x) tx -= a.tiles_x;
             mbar_wait(rfull0 + 8 * rs.i, rs.ph, a.dbg, 5, (int)rs.i);
             const TIn* rp = reinterpret_cast<const TIn*>(gen + kSOffRaw + rs.i * kSRawSlot) + d;
-            // 16-byte row of patch pixel p: its three channels, the three channels of pixel p + 1 (same patch row; zeros for the
-            // last column, whose right neighbour only ever meets zero weights or by-product rows), two zeros
-            uint32_t pk[kSCvtPer][3];
+            // 32-byte row of patch pixel p: its three channels, those of its two right neighbours in the patch row (zeros past
+            // the row end: they only meet by-product GEMM rows), seven zeros (never written: the stages start zeroed)
+            uint32_t pk[kSCvtPer][5];
 #pragma unroll
             for (int i = 0; i < kSCvtPer; ++i) {
-                float v0 = 0.f, v1 = 0.f, v2 = 0.f, n0 = 0.f, n1 = 0.f, n2 = 0.f;
+                float v[9];
+#pragma unroll
+                for (int k = 0; k < 9; ++k) v[k] = 0.f;
                 if (i < kSCvtPer - 1 || last_ok) {
-                    v0 = raw_ld(rp + q[i]); v1 = raw_ld(rp + RPLANE + q[i]); v2 = raw_ld(rp + 2 * RPLANE + q[i]);
-                    if (!edge[i]) { n0 = raw_ld(rp + q[i] + 1); n1 = raw_ld(rp + RPLANE + q[i] + 1); n2 = raw_ld(rp + 2 * RPLANE + q[i] + 1); }
+#pragma unroll
+                    for (int k = 0; k < 3; ++k) {
+                        if (k <= room[i]) {
+                            v[3 * k] = raw_ld(rp + q[i] + k); v[3 * k + 1] = raw_ld(rp + RPLANE + q[i] + k); v[3 * k + 2] = raw_ld(rp + 2 * RPLANE + q[i] + k);
+                        }
+                    }
                 }
-                const __half2 h0 = __floats2half2_rn(v0, v1), h1 = __floats2half2_rn(v2, n0), h2 = __floats2half2_rn(n1, n2);
-                pk[i][0] = *reinterpret_cast<const uint32_t*>(&h0); pk[i][1] = *reinterpret_cast<const uint32_t*>(&h1);
-                pk[i][2] = *reinterpret_cast<const uint32_t*>(&h2);
+#pragma unroll
+                for (int k = 0; k < 4; ++k) {
+                    const __half2 h = __floats2half2_rn(v[2 * k], v[2 * k + 1]);
+                    pk[i][k] = *reinterpret_cast<const uint32_t*>(&h);
+                }
+                const __half2 h8 = __floats2half2_rn(v[8], 0.f);
+                pk[i][4] = *reinterpret_cast<const uint32_t*>(&h8);
             }
             __syncwarp();
             if (lane == 0) mbar_arrive(rempty0 + 8 * rs.i);  // the raw patch is in registers
             mbar_wait(cempty0 + 8 * cs.i, cs.ph ^ 1, a.dbg, 5, 100 + (int)cs.i);
-            uint8_t* dst = gen + kSOffCvt + cs.i * kSCvtSlot + tid * 16;
+            // row p = tid + 128 i at p*32; 16-byte chunk j at ((j ^ (p >> 2)) & 1) << 4 (32B swizzle; p >> 2 has the parity of tid >> 2)
+            uint8_t* dst = gen + kSOffCvt + cs.i * kSCvtSlot + tid * 32;
+            const uint32_t c0 = ((tid >> 2) & 1) << 4;
 #pragma unroll
             for (int i = 0; i < kSCvtPer; ++i)
-                if (i < kSCvtPer - 1 || last_ok) *reinterpret_cast<uint4*>(dst + i * 2048) = make_uint4(pk[i][0], pk[i][1], pk[i][2], 0u);
+                if (i < kSCvtPer - 1 || last_ok) {
+                    *reinterpret_cast<uint4*>(dst + i * 4096 + c0) = make_uint4(pk[i][0], pk[i][1], pk[i][2], pk[i][3]);
+                    *reinterpret_cast<uint32_t*>(dst + i * 4096 + (c0 ^ 16u)) = pk[i][4];
+                }
             fence_async_smem();
             __syncwarp();
             if (lane == 0) mbar_arrive(cfull0 + 8 * cs.i);
