@@ -22,7 +22,7 @@
 //   * persistent CTAs (one per SM), static round-robin over the (m-tile, n-tile) grid.
 //
 // Layers with Cin == 32 use 32-channel k-blocks with the 64B swizzle; everything else 64-channel
-// k-blocks with the 128B swizzle.  The Cin == 3 stem is stem_tc_kernel below (producer warps build the im2col rows).
+// k-blocks with the 128B swizzle.  The Cin == 3 stem lives in stem_halo.cu / stem_block.cu.
 //
 // Every role reads its warp index through a shuffle broadcast, which the compiler knows to be warp-uniform (what
 // cutlass::canonical_warp_idx_sync does): the role dispatch is then a uniform branch and the single-thread issue loops and
@@ -894,284 +894,6 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     if (threadIdx.x == 0) YB_TRACE(5, 0, 3);
 }
 
-// ---- stem: 3 -> 32, 3x3, stride 1, straight from the caller's NCHW fp32 image ---------------------------
-// Cin = 3 is too narrow for TMA (6-byte pixels), so four producer warps build the im2col rows
-// themselves: thread r of a tile gathers the 27 taps of output pixel r (coalesced along x, L1-resident
-// neighbourhood), converts to fp16, pads K to 32 and writes the 64-byte row in the 64B-swizzled
-// K-major layout the tensor core expects; a proxy fence + mbarrier hands the stage to the MMA warp
-// (one tcgen05.mma pair per tile: M=128, N=32, K=32).  Four TMEM accumulators of 32 columns keep the
-// producers, the tensor core and the epilogue warps (same staged TMA-store epilogue) overlapped.
-constexpr int kStemGroups = 3;            // producer groups of 128 threads
-constexpr int kStemThreads = 704;          // warps 0-11 producers (three groups), 12-19 epilogue (two groups), 20 MMA + TMEM alloc, 21 store issuer
-                                           // (22 warps)
-constexpr int kStemStages = 8;
-constexpr int kStemAcc = 4;
-constexpr int kStemRing = 4;              // epilogue staging buffers (a two-deep ring chained the tiles one after another)
-
-struct StemArgs {
-    const void* x;                          // NCHW image, fp32 or fp16 (kernel template parameter)
-    int B, H, W;
-    long M;
-    int tiles;
-    TcArgs epi;                             // scale, bias, leaky; staged-epilogue fields
-    const __half* w;                        // [32][32] fp16, k = (ky*3+kx)*3 + c, zero padded
-};
-
-// TIn: element type of the caller's image.  fp32 is what the reference's callers hold; the fp16 instantiation reads half
-// the bytes and produces the same bits, because the fp32 path rounds every pixel to fp16 (round to nearest even, what
-// Tensor.half() does on the host) before it reaches the tensor core anyway.
-__device__ __forceinline__ float stem_ld(const float* p) { return __ldg(p); }
-__device__ __forceinline__ float stem_ld(const __half* p) { return __half2float(__ldg(p)); }
-
-// The kernel is instruction-issue-bound, so the loops are written for instruction count: the interior / border decision of
-// the gather is taken per WARP (a vote), so the fast path is a uniform branch and the compiler keeps the memory descriptor
-// in uniform registers instead of re-copying it for every load; the epilogue uses packed fp32 arithmetic (fma.rn.f32x2,
-// mul.f32x2) and LeakyReLU as max(v, 0.1 v).  (Round 1's per-thread version: 0.266 ms at 608x608 batch 32; this one 0.231.)
-__device__ __forceinline__ float2 ffma2(float2 a, float2 b, float2 c) {
-    unsigned long long ra;
-    asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(ra)
-        : "l"(*reinterpret_cast<unsigned long long*>(&a)), "l"(*reinterpret_cast<unsigned long long*>(&b)),
-          "l"(*reinterpret_cast<unsigned long long*>(&c)));
-    return *reinterpret_cast<float2*>(&ra);
-}
-__device__ __forceinline__ float2 fmul2(float2 a, float2 b) {
-    unsigned long long ra;
-    asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(ra)
-        : "l"(*reinterpret_cast<unsigned long long*>(&a)), "l"(*reinterpret_cast<unsigned long long*>(&b)));
-    return *reinterpret_cast<float2*>(&ra);
-}
-
-template <typename TIn>
-__global__ void __launch_bounds__(kStemThreads, 1)
-stem_tc_kernel(const __grid_constant__ CUtensorMap tmOut, const StemArgs a_in) {
-    StemArgs a = a_in;
-    extern __shared__ uint8_t smem_raw[];
-    const uint32_t raw = smem_u32(smem_raw);
-    const uint32_t base = (raw + 1023u) & ~1023u;
-    uint8_t* gen = smem_raw + (base - raw);
-    // header: full[8] | empty[8] | tfull[4] | tempty[4] | sempty[4] | sready[4] | tmem_ptr
-    const uint32_t full0 = base, empty0 = base + 64, tfull0 = base + 128, tempty0 = base + 160, sempty0 = base + 192, sready0 = base + 224;
-    volatile uint32_t* tmem_ptr = reinterpret_cast<volatile uint32_t*>(gen + 256);
-    constexpr uint32_t A_BYTES = kBM * 64, STG_BYTES = kBM * 64;
-    const uint32_t wsm = base + 1024;                      // weights 32 x 64 B (2 KB), swizzled
-    const uint32_t stg0 = base + 4096;                     // kStemRing staging buffers
-    const uint32_t stage0 = stg0 + kStemRing * STG_BYTES;
-    // the warp index read through a shuffle is warp-uniform for the compiler (what cutlass::canonical_warp_idx_sync does),
-    // so the role dispatch below is a uniform branch and uniform registers stay usable inside the roles
-    const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0);
-    const int lane = threadIdx.x & 31;
-
-    if (warp == 0 && lane == 0) prefetch_tmap(&tmOut);
-    if (warp == 20 && lane == 0) {
-        for (int s = 0; s < kStemStages; ++s) { mbar_init(full0 + 8 * s, 128); mbar_init(empty0 + 8 * s, 1); }
-        for (int i = 0; i < kStemAcc; ++i) { mbar_init(tfull0 + 8 * i, 1); mbar_init(tempty0 + 8 * i, 4); }     // four epilogue
-        for (int i = 0; i < kStemRing; ++i) { mbar_init(sempty0 + 8 * i, 1); mbar_init(sready0 + 8 * i, 4); }   // warps per tile
-        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-    }
-    if (warp == 20) tmem_alloc(smem_u32(const_cast<uint32_t*>(tmem_ptr)), 32 * kStemAcc);
-    a.epi.tab = reinterpret_cast<const float*>(gen + 3072);   // scale[32] | bias[32]
-    a.epi.cout_pad = 32;
-    if (threadIdx.x >= 64 && threadIdx.x < 128) {
-        float* tab = reinterpret_cast<float*>(gen + 3072);
-        const int i = threadIdx.x - 64;
-        tab[i] = i < 32 ? __ldg(a.epi.scale + i) : __ldg(a.epi.bias + i - 32);
-    }
-    if (threadIdx.x < 32) {                                // weight rows -> swizzled smem
-        const int r = threadIdx.x;
-        const uint4* src = reinterpret_cast<const uint4*>(a.w + r * 32);
-#pragma unroll
-        for (int c = 0; c < 4; ++c)
-            *reinterpret_cast<uint4*>(gen + 1024 + r * 64 + ((c ^ ((r >> 1) & 3)) << 4)) = __ldg(src + c);
-        fence_async_smem();
-    }
-    tc_fence_before();
-    __syncthreads();
-    tc_fence_after();
-    const uint32_t tmem_base = *tmem_ptr;
-    pdl_launch_dependents();
-    pdl_wait_prior();             // the output buffer may still be read by the previous step's kernels
-
-    if (warp < 4 * kStemGroups) {
-        // ===== producers: one output pixel (im2col row) per thread; kStemGroups groups of 128 threads take
-        // tiles round-robin, and each thread keeps the 27 loads of its next tile in flight while it converts
-        // and stores the current one.  The kernel is instruction-issue-bound (ncu: 71 % issue-active, 840
-        // warp instructions per 32 pixels in the first version), so the loop is kept lean: the pixel's
-        // (image, y, x) is carried incrementally instead of divided out per tile, interior pixels take an
-        // unpredicated path (nine row pointers, immediate +-1 offsets), and the taps are packed to fp16
-        // before the next tile's loads are issued into the same registers (one set instead of two + a copy) =====
-        const int grp = warp >> 2;
-        const int r = threadIdx.x & 127;
-        const int xr = (r >> 1) & 3;
-        const int HW = a.H * a.W;
-        const long img_stride = 3L * HW;
-        const int tstep = kStemGroups * (int)gridDim.x;
-        int i = grp;                                       // index of this CTA's i-th tile
-        int tile = (int)blockIdx.x + i * (int)gridDim.x;
-        long m = (long)tile * kBM + r;                     // this thread's pixel in the tile being gathered
-        const long dm = (long)tstep * kBM;
-        int pb = (int)(m / HW), py, px;
-        {
-            const int rem = (int)(m - (long)pb * HW);
-            py = rem / a.W; px = rem - py * a.W;
-        }
-        const int db = (int)(dm / HW);
-        const int drem = (int)(dm - (long)db * HW);
-        const int dy = drem / a.W, dx = drem - dy * a.W;
-        auto advance = [&]() {
-            m += dm;
-            px += dx; if (px >= a.W) { px -= a.W; ++py; }
-            py += dy; if (py >= a.H) { py -= a.H; ++pb; }
-            pb += db;
-        };
-        auto gather = [&](float (&v)[27]) {
-            const bool inside = m < a.M;
-            const bool interior = inside && py >= 1 && py < a.H - 1 && px >= 1 && px < a.W - 1;
-            const TIn* p = static_cast<const TIn*>(a.x) + (long)pb * img_stride + py * a.W + px;
-            if (__all_sync(0xffffffffu, interior)) {       // warp-uniform: 32 consecutive pixels of one image row
-#pragma unroll
-                for (int c = 0; c < 3; ++c) {
-#pragma unroll
-                    for (int ky = 0; ky < 3; ++ky) {
-                        const TIn* q = p + c * HW + (ky - 1) * a.W;
-                        v[(ky * 3 + 0) * 3 + c] = stem_ld(q - 1);
-                        v[(ky * 3 + 1) * 3 + c] = stem_ld(q);
-                        v[(ky * 3 + 2) * 3 + c] = stem_ld(q + 1);
-                    }
-                }
-            } else {
-#pragma unroll
-                for (int ky = 0; ky < 3; ++ky) {
-                    const int iy = py + ky - 1;
-                    const bool oky = inside && iy >= 0 && iy < a.H;
-#pragma unroll
-                    for (int kx = 0; kx < 3; ++kx) {
-                        const int ix = px + kx - 1;
-                        const bool ok = oky && ix >= 0 && ix < a.W;
-#pragma unroll
-                        for (int c = 0; c < 3; ++c)
-                            v[(ky * 3 + kx) * 3 + c] = ok ? stem_ld(p + c * HW + (ky - 1) * a.W + (kx - 1)) : 0.f;
-                    }
-                }
-            }
-        };
-        float v[27];
-        if (tile < a.tiles) gather(v);
-        while (tile < a.tiles) {
-            uint4 pk[4];                                   // waits for the loads issued one iteration ago
-            __half2* h = reinterpret_cast<__half2*>(pk);
-#pragma unroll
-            for (int j = 0; j < 13; ++j) h[j] = __floats2half2_rn(v[2 * j], v[2 * j + 1]);
-            h[13] = __floats2half2_rn(v[26], 0.f);
-            h[14] = __floats2half2_rn(0.f, 0.f);
-            h[15] = h[14];
-            advance();
-            gather(v);                                     // next tile's loads in flight (zeros past the end)
-            const int stage = i % kStemStages;
-            const uint32_t phase = (uint32_t)(i / kStemStages) & 1u;
-            mbar_wait(empty0 + 8 * stage, phase ^ 1, a.epi.dbg, 0, stage);
-            uint8_t* row = gen + (stage0 - base) + stage * A_BYTES + r * 64;
-#pragma unroll
-            for (int c = 0; c < 4; ++c) *reinterpret_cast<uint4*>(row + ((c ^ xr) << 4)) = pk[c];
-            fence_async_smem();
-            mbar_arrive(full0 + 8 * stage);
-            i += kStemGroups; tile += tstep;
-        }
-    } else if (warp == 20) {
-        // ===== MMA issuer =====
-        if (lane == 0) {
-            const uint32_t idesc = make_idesc(32);
-            const uint64_t bdesc = make_smem_desc<64>(wsm);
-            int stage = 0;
-            uint32_t phase = 0, acc = 0, acc_phase = 0;
-            for (int tile = blockIdx.x; tile < a.tiles; tile += gridDim.x) {
-                mbar_wait(tempty0 + 8 * acc, acc_phase ^ 1, a.epi.dbg, 1, 100 + (int)acc);
-                mbar_wait(full0 + 8 * stage, phase, a.epi.dbg, 1, stage);
-                tc_fence_after();
-                const uint64_t adesc = make_smem_desc<64>(stage0 + stage * A_BYTES);
-                umma_f16(tmem_base + acc * 32, adesc, bdesc, idesc, 0);
-                umma_f16(tmem_base + acc * 32, adesc + 2, bdesc + 2, idesc, 1);
-                umma_commit(empty0 + 8 * stage);
-                umma_commit(tfull0 + 8 * acc);
-                if (++stage == kStemStages) { stage = 0; phase ^= 1; }
-                if (++acc == kStemAcc) { acc = 0; acc_phase ^= 1; }
-            }
-        }
-        __syncwarp();
-    } else if (warp == 21) {
-        // ===== store issuer =====
-        if (lane == 0) {
-            uint32_t g = 0;
-            for (int tile = blockIdx.x; tile < a.tiles; tile += gridDim.x, ++g) {
-                const uint32_t buf = g % kStemRing, ph = (g / kStemRing) & 1u;
-                mbar_wait(sready0 + 8 * buf, ph, a.epi.dbg, 4, 700 + (int)buf);
-                tma_store_2d(&tmOut, stg0 + buf * STG_BYTES, 0, tile * kBM);
-                tma_store_commit();
-                if (g >= 2) {                              // two stores may stay unread; buffer g-2 goes back to the epilogue
-                    tma_store_wait_read<2>();
-                    mbar_arrive(sempty0 + 8 * ((g - 2) % kStemRing));
-                }
-            }
-            tma_store_wait_all();
-        }
-        __syncwarp();
-    } else if (warp >= 12 && warp < 20) {
-        // ===== epilogue: TMEM -> scale/bias/LeakyReLU -> fp16 -> swizzled smem.  Two groups of four warps take ALTERNATE
-        // tiles (a warp owns the 32 rows of TMEM lane quarter warp % 4 and all 32 channels): the per-tile chain
-        // accumulator-ready -> tcgen05.ld -> math -> staged write -> hand-over is ~800 cycles of dependent latency however
-        // many warps share a tile, and with one group it paced the kernel (624 tiles per CTA x 822 cycles = the 0.27 ms). =====
-        const int q = warp & 3, grp = (warp - 12) >> 2;
-        const int row = q * 32 + lane;
-        const int xr = (row >> 1) & 3;
-        const float4* sc4 = reinterpret_cast<const float4*>(a.epi.tab);     // scale[32] | bias[32] (shared memory, broadcast reads)
-        const float4* bi4 = sc4 + 8;
-        uint32_t g = (uint32_t)grp;                                          // index of the tile among this CTA's tiles
-        for (int tile = (int)blockIdx.x + grp * (int)gridDim.x; tile < a.tiles; tile += 2 * (int)gridDim.x, g += 2) {
-            const uint32_t acc = g % kStemAcc, acc_phase = (g / kStemAcc) & 1u;
-            const uint32_t buf = g % kStemRing, ph = (g / kStemRing) & 1u;
-            mbar_wait(tfull0 + 8 * acc, acc_phase, a.epi.dbg, 2, 200 + (int)acc);
-            tc_fence_after();
-            uint32_t r0[16], r1[16];
-            const uint32_t taddr = tmem_base + acc * 32 + ((uint32_t)(q * 32) << 16);
-            tmem_ld16(taddr, r0);
-            tmem_ld16(taddr + 16, r1);
-            mbar_wait(sempty0 + 8 * buf, ph ^ 1, a.epi.dbg, 2, 500 + (int)buf);
-            tmem_ld_wait();
-            tc_fence_before();
-            __syncwarp();
-            if (lane == 0) mbar_arrive(tempty0 + 8 * acc);   // accumulator drained into registers
-            uint8_t* srow = gen + (stg0 - base) + buf * STG_BYTES + row * 64;
-#pragma unroll
-            for (int c = 0; c < 4; ++c) {                     // 16-byte chunk c = channels 8c .. 8c+7
-                const uint32_t* rr = c < 2 ? r0 : r1;
-                const int j0 = 8 * (c & 1);
-                const float4 s0 = sc4[2 * c], s1 = sc4[2 * c + 1], b0 = bi4[2 * c], b1 = bi4[2 * c + 1];
-                uint4 pk;
-                __half2* ph2 = reinterpret_cast<__half2*>(&pk);
-                const float2 tenth = make_float2(kLeaky, kLeaky);
-                const float2 sc[4] = {make_float2(s0.x, s0.y), make_float2(s0.z, s0.w), make_float2(s1.x, s1.y), make_float2(s1.z, s1.w)};
-                const float2 bi[4] = {make_float2(b0.x, b0.y), make_float2(b0.z, b0.w), make_float2(b1.x, b1.y), make_float2(b1.z, b1.w)};
-#pragma unroll
-                for (int e = 0; e < 4; ++e) {
-                    const float2 acc = make_float2(__uint_as_float(rr[j0 + 2 * e]), __uint_as_float(rr[j0 + 2 * e + 1]));
-                    const float2 y = ffma2(acc, sc[e], bi[e]);
-                    const float2 t = fmul2(y, tenth);
-                    ph2[e] = __floats2half2_rn(fmaxf(y.x, t.x), fmaxf(y.y, t.y));     // LeakyReLU(0.1) = max(v, 0.1 v)
-                }
-                *reinterpret_cast<uint4*>(srow + ((c ^ xr) << 4)) = pk;
-            }
-            fence_async_smem();
-            __syncwarp();
-            if (lane == 0) mbar_arrive(sready0 + 8 * buf);
-        }
-    }
-    tc_fence_before();
-    __syncthreads();
-    if (warp == 20) {
-        tc_fence_after();
-        tmem_dealloc(tmem_base, 32 * kStemAcc);
-    }
-}
-
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
                                   const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
                                   CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
@@ -1417,56 +1139,6 @@ std::string tc_make_plan(TcPlan& p, const ConvArgs& a, const __half* w16, int co
     return "";
 }
 
-std::string stem_tc_make_plan(StemTcPlan& p, __half* out, long out_ld, int B, int H, int W, int num_sms) {
-    std::string e = load_driver_entry_points();
-    if (!e.empty()) return e;
-    p.M = (long)B * H * W;
-    p.tiles = (int)((p.M + kBM - 1) / kBM);
-    p.grid = std::min(p.tiles, num_sms);
-    p.smem = 1024 + 4096 + kStemRing * (size_t)kBM * 64 + (size_t)kStemStages * kBM * 64;
-    cuuint64_t dims[2] = {32, (cuuint64_t)p.M};
-    cuuint64_t strides[1] = {(cuuint64_t)out_ld * sizeof(__half)};
-    cuuint32_t box[2] = {32, (cuuint32_t)kBM};
-    cuuint32_t es[2] = {1, 1};
-    CUresult r = g_encode_tiled(&p.tmOut, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, out, dims, strides, box, es,
-                                CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_NONE,
-                                CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-    if (r != CUDA_SUCCESS) return cu_err("cuTensorMapEncodeTiled(stem output)", r);
-    return "";
-}
-
-cudaError_t stem_tc_launch(const StemTcPlan& p, const void* x, int in_f16, int B, int H, int W, const __half* w16, const float* scale,
-                           const float* bias, int* dbg, cudaStream_t s) {
-    StemArgs a{};
-    a.x = x; a.B = B; a.H = H; a.W = W; a.M = p.M; a.tiles = p.tiles; a.w = w16;
-    a.epi.scale = scale; a.epi.bias = bias; a.epi.leaky = 1; a.epi.out_f32 = 0; a.epi.has_res = 0; a.epi.dbg = dbg;
-    static PerDeviceOnce attr_once;
-    {
-        cudaError_t e = attr_once.run([] {
-            cudaError_t r = cudaFuncSetAttribute(stem_tc_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, 128 * 1024);
-            if (r == cudaSuccess) r = cudaFuncSetAttribute(stem_tc_kernel<__half>, cudaFuncAttributeMaxDynamicSharedMemorySize, 128 * 1024);
-            return r;
-        });
-        if (e != cudaSuccess) return e;
-    }
-    {
-        static const bool pdl = !(tune_env("YB_TC_PDL") && atoi(tune_env("YB_TC_PDL")) == 0);
-        cudaLaunchConfig_t cfg{};
-        cfg.gridDim = dim3(p.grid);
-        cfg.blockDim = dim3(kStemThreads);
-        cfg.dynamicSmemBytes = p.smem;
-        cfg.stream = s;
-        cudaLaunchAttribute attr[1];
-        attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
-        attr[0].val.programmaticStreamSerializationAllowed = 1;
-        cfg.attrs = attr;
-        cfg.numAttrs = pdl ? 1 : 0;
-        const cudaError_t e = in_f16 ? cudaLaunchKernelEx(&cfg, stem_tc_kernel<__half>, p.tmOut, a)
-                                     : cudaLaunchKernelEx(&cfg, stem_tc_kernel<float>, p.tmOut, a);
-        if (e != cudaSuccess) return e;
-    }
-    return cudaGetLastError();
-}
 
 cudaError_t tc_launch(const TcPlan& p, const ConvArgs& a, int* dbg, cudaStream_t s) {
     TcArgs t;

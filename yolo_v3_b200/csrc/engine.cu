@@ -30,7 +30,6 @@ struct Op {
     bool use_tc = false, use_halo = false;
     TcPlan tc;
     HaloPlan halo;
-    StemTcPlan stem_tc;
     StemHaloPlan stem_halo;
     bool fused01 = false;             // the stem op also runs layer 1 (stem_block.cu) and writes layer 1's output
     StemBlockPlan stem_block;
@@ -320,13 +319,9 @@ struct PlanBuilder {
     }
 };
 
-// TEMPORARY A/B switches while the new first-layer kernels are validated
-bool stem_old() {
-    static const bool v = getenv("YB_STEM_OLD") && atoi(getenv("YB_STEM_OLD")) != 0;
-    return v;
-}
+// A/B switch of experiment builds: the first two layers as separate kernels even where the fused kernel applies
 bool stem_unfused() {
-    static const bool v = getenv("YB_STEM_UNFUSED") && atoi(getenv("YB_STEM_UNFUSED")) != 0;
+    static const bool v = tune_env("YB_STEM_UNFUSED") && atoi(tune_env("YB_STEM_UNFUSED")) != 0;
     return v;
 }
 
@@ -374,8 +369,7 @@ int build_plan(yb_ctx* c, int B, int H, int W, Plan** out) {
                 op.a.out = buf[1];
                 e = stem_block_make_plan(op.stem_block, c->layers[1].d_w16, static_cast<__half*>(buf[1]), 64, B, H, W, c->num_sms);
             } else {
-                e = stem_tc_make_plan(op.stem_tc, static_cast<__half*>(buf[0]), 32, B, H, W, c->num_sms);
-                if (e.empty()) e = stem_halo_make_plan(op.stem_halo, static_cast<__half*>(buf[0]), 32, B, H, W, c->num_sms);
+                e = stem_halo_make_plan(op.stem_halo, static_cast<__half*>(buf[0]), 32, B, H, W, c->num_sms);
             }
             if (!e.empty()) return bail("plan: stem: " + e);
         }
@@ -535,8 +529,6 @@ int run_ops(yb_ctx* c, Plan* p, const float* x, int n_ops, cudaStream_t s) {
             if (p->mode == YB_MODE_FP16 && op.fused01)
                 e = stem_block_launch(op.stem_block, x, c->input_f16, p->B, p->H, p->W, L.d_w16, c->stem_sb, c->layers[1].d_scale,
                                       c->layers[1].d_bias, c->dbg, s);
-            else if (p->mode == YB_MODE_FP16 && stem_old())
-                e = stem_tc_launch(op.stem_tc, x, c->input_f16, p->B, p->H, p->W, L.d_w16, L.d_scale, L.d_bias, c->dbg, s);
             else if (p->mode == YB_MODE_FP16)
                 e = stem_halo_launch(op.stem_halo, x, c->input_f16, p->B, p->H, p->W, L.d_w16, c->stem_sb, c->dbg, s);
             else if (p->mode == YB_MODE_FP32_TC)     // Cin = 3: exact fp32 FMAs on the CUDA cores, output written as hi | lo
@@ -1315,16 +1307,13 @@ int yb_run_layer(yb_ctx* c, int li, const void* in, int B, int H, int W, const v
         cudaError_t e;
         if (c->input_f16 && c->mode != YB_MODE_FP16)
             return fail(c, YB_E_UNSUPPORTED, "fp16 input images need YB_MODE_FP16");
-        if (c->mode == YB_MODE_FP16 && !stem_old() && stem_halo_supported(W, c->input_f16)) {
+        if (c->mode == YB_MODE_FP16) {
+            // the image is read by TMA: its row pitch must be a multiple of 16 bytes (the network path has W % 32 == 0)
+            if (!stem_halo_supported(W, c->input_f16)) return fail(c, YB_E_ARG, "yb_run_layer: the stem needs W % 4 == 0 (fp32 images) / W % 8 == 0 (fp16)");
             StemHaloPlan sp;
             std::string err = stem_halo_make_plan(sp, static_cast<__half*>(out), 32, B, H, W, c->num_sms);
             if (!err.empty()) return fail(c, YB_E_CUDA, "yb_run_layer: " + err);
             e = stem_halo_launch(sp, in, c->input_f16, B, H, W, L.d_w16, c->stem_sb, c->dbg, s);
-        } else if (c->mode == YB_MODE_FP16) {
-            StemTcPlan sp;
-            std::string err = stem_tc_make_plan(sp, static_cast<__half*>(out), 32, B, H, W, c->num_sms);
-            if (!err.empty()) return fail(c, YB_E_CUDA, "yb_run_layer: " + err);
-            e = stem_tc_launch(sp, in, c->input_f16, B, H, W, L.d_w16, L.d_scale, L.d_bias, c->dbg, s);
         } else {
             e = launch_stem<float>(static_cast<const float*>(in), static_cast<float*>(out), L.d_w32, L.d_scale, L.d_bias, B, H, W, s);
         }

@@ -136,18 +136,6 @@ struct TcPlan {
 std::string tc_make_plan(TcPlan& p, const ConvArgs& a, const __half* w16, int cout_pad, int K, int num_sms);
 cudaError_t tc_launch(const TcPlan& p, const ConvArgs& a, int* dbg, cudaStream_t s);
 bool tc_supported(const ConvArgs& a);
-// Cin=3 stem on the tensor cores (producer warps build the im2col rows): NCHW fp32 image -> NHWC fp16 [B,H,W,32]
-struct StemTcPlan {
-    CUtensorMap tmOut;
-    long M = 0;
-    int tiles = 0, grid = 0;
-    size_t smem = 0;
-};
-std::string stem_tc_make_plan(StemTcPlan& p, __half* out, long out_ld, int B, int H, int W, int num_sms);
-// x: the caller's NCHW image, fp32 (in_f16 = 0) or fp16 (in_f16 = 1)
-cudaError_t stem_tc_launch(const StemTcPlan& p, const void* x, int in_f16, int B, int H, int W, const __half* w16, const float* scale,
-                           const float* bias, int* dbg, cudaStream_t s);
-
 // stem_halo.cu  (the Cin = 3 stem from a halo patch: planar TMA load, pixel-major fp16 conversion, two taps per tcgen05.mma
 // through the leading-dimension offset of a non-swizzled descriptor).  Needs W % 4 == 0 (fp32 images) / W % 8 == 0 (fp16).
 struct StemHaloPlan {
