@@ -9,18 +9,20 @@
 #   <tag>_sanitizer.txt      compute-sanitizer memcheck / racecheck / synccheck on small shapes of both tensor-core modes
 T=${1:-prof}
 mkdir -p gpurun_out
-ncu --metrics gpu__time_duration.sum --clock-control none -s 252 -c 84 --csv --log-file gpurun_out/${T}_launches.csv \
+ncu --metrics gpu__time_duration.sum --clock-control none -s 249 -c 83 --csv --log-file gpurun_out/${T}_launches.csv \
     python tools/one_step.py --steps 1 --warmup 3 --recipe calibrated > gpurun_out/${T}_launches.log 2>&1
 M=gpu__time_duration.sum,dram__bytes_read.sum,dram__bytes_write.sum,sm__pipe_tc_cycles_active.avg.pct_of_peak_sustained_active,lts__throughput.avg.pct_of_peak_sustained_elapsed,gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed,l1tex__m_xbar2l1tex_read_bytes.sum,sm__throughput.avg.pct_of_peak_sustained_elapsed,launch__grid_size,launch__registers_per_thread
-ncu --metrics $M --clock-control none -k regex:"conv_tc|stem_tc|conv_halo" -s 225 -c 75 --csv --log-file gpurun_out/${T}_conv_metrics.csv \
+ncu --metrics $M --clock-control none -k regex:"conv_tc|stem_block|stem_halo|conv_halo" -s 222 -c 74 --csv --log-file gpurun_out/${T}_conv_metrics.csv \
     python tools/one_step.py --steps 1 --warmup 3 --recipe calibrated > gpurun_out/${T}_conv_metrics.log 2>&1
 ncu --metrics $M --clock-control none -k regex:"probe_cells|score_list|decode|pp_" -s 21 -c 7 --csv --log-file gpurun_out/${T}_post_metrics.csv \
     python tools/one_step.py --steps 1 --warmup 3 --recipe calibrated > gpurun_out/${T}_post_metrics.log 2>&1
 ncu --metrics gpu__time_duration.sum,sm__pipe_tc_cycles_active.avg.pct_of_peak_sustained_active,dram__bytes_read.sum,dram__bytes_write.sum --clock-control none -s 252 -c 84 --csv \
     --log-file gpurun_out/${T}_split_launches.csv python tools/one_step.py --steps 1 --warmup 3 --recipe calibrated --precision fp32 > gpurun_out/${T}_split_launches.log 2>&1
-# launch index = layer index: stem, 32->64 s2 (halo), 64->128 (halo pairs), 128->256 3x3 @76, a 1x1 at 38^2, 512->1024 @19, head at 76^2
-for L in 0 1 6 11 27 45 74; do
-  timeout 300 ncu --set full --clock-control none --import-source on -k regex:"conv_tc|stem_tc|conv_halo" -s $((225 + L)) -c 1 -f -o /tmp/${T}_full_$L \
+# conv launch k of a step: 0 = the fused stem + layer 1, k >= 1 = layer k + 1.  Captured: fused first kernel, 64->128 (halo pairs),
+# 128->256 3x3 @76, a 1x1 at 38^2, 512->1024 @19, head at 76^2 -- file names keep the LAYER index
+for L in 0 6 11 27 45 74; do
+  K=$((L == 0 ? 0 : L - 1))
+  timeout 300 ncu --set full --clock-control none --import-source on -k regex:"conv_tc|stem_block|stem_halo|conv_halo" -s $((222 + K)) -c 1 -f -o /tmp/${T}_full_$L \
       python tools/one_step.py --steps 1 --warmup 3 --recipe calibrated > /dev/null 2>&1
   ncu -i /tmp/${T}_full_$L.ncu-rep --page raw --csv > gpurun_out/${T}_full_raw_layer$L.csv 2>/dev/null
 done

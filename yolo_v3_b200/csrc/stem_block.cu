@@ -2,8 +2,9 @@
 // (32 -> 64, 3x3, stride 2) -- with the 608 x 608 x 32 stem output kept ON CHIP.
 //
 // As separate kernels the pair moves 142 MB (image) + 757 MB (stem output written) + 757 MB (read back) + 378 MB (layer-1
-// output) per 32-image batch: both run at their HBM bound, 0.164 + 0.175 ms.  Fused, only the image is read and the
-// 304 x 304 x 64 tensor written (520 MB = 0.08 ms of HBM time) and the tensor pipe becomes the bound.
+// output) per 32-image batch: both run at their HBM bound, 0.157 + 0.175 ms.  Fused, only the image is read and the
+// 304 x 304 x 64 tensor written (520 MB = 0.08 ms of HBM time); the bound moves on chip (the per-unit chains of the epilogue
+// warps and the short N = 32 / 64 tensor-core instructions: 0.293 ms).
 //
 //   unit      = one layer-1 output tile of conv_halo.cu's stride-2 geometry: 3 rows x 38 columns (GEMM row m = r*40 + c).
 //   needs     = stem outputs rows 2*y0-1 .. 2*y0+5, columns 2*x0-1 .. 2*x0+75 (7 x 77), i.e. the image patch rows
@@ -20,8 +21,10 @@
 //               instructions each, M = 128 x N = 64; resident weights (36 KB); epilogue -> 128B-swizzled staging -> TMA store
 //               of a {64 ch, 38, 3, 1} box.
 //
-// The MMA issuer runs the stem of unit u+1 BEFORE layer 1 of unit u and the epilogue warps drain stem u+1 before layer 1 of
-// unit u, so the tensor pipe works on the next stem while the planes of the current unit are being written.
+// Two units are in flight: the epilogue warps form two groups of eight that take alternate units (group g works in stage g
+// of everything: stem accumulator set, parity planes, layer-1 accumulator, staging slot), and the MMA issuer runs layer 1 of
+// unit u as soon as its planes are written and the stem of unit u+2 as soon as the hand-over of u has drained that
+// accumulator set.
 //
 // reference: darknet.py:37-44 (conv_bn_relu), :66-69 (Darknet.__init__: conv 3->32, then the stride-2 conv of stage 0).
 #include <algorithm>
@@ -142,10 +145,10 @@ stem_block_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant
         for (int s = 0; s < kFRawStages; ++s) { mbar_init(rfull0 + 8 * s, 1); mbar_init(rempty0 + 8 * s, 4); }
         for (int s = 0; s < 2; ++s) {
             mbar_init(cfull0 + 8 * s, 4); mbar_init(cempty0 + 8 * s, 1);
-            mbar_init(t1full0 + 8 * s, 1); mbar_init(t1empty0 + 8 * s, 16);
-            mbar_init(pfull0 + 8 * s, 16); mbar_init(pempty0 + 8 * s, 1);
-            mbar_init(t2full0 + 8 * s, 1); mbar_init(t2empty0 + 8 * s, 16);
-            mbar_init(sready0 + 8 * s, 16); mbar_init(sempty0 + 8 * s, 1);
+            mbar_init(t1full0 + 8 * s, 1); mbar_init(t1empty0 + 8 * s, 8);      // eight epilogue warps per unit (see below)
+            mbar_init(pfull0 + 8 * s, 8); mbar_init(pempty0 + 8 * s, 1);
+            mbar_init(t2full0 + 8 * s, 1); mbar_init(t2empty0 + 8 * s, 8);
+            mbar_init(sready0 + 8 * s, 8); mbar_init(sempty0 + 8 * s, 1);
         }
         mbar_init(wbar, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -228,21 +231,21 @@ stem_block_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant
             __syncwarp();
         };
         const int n_units = unit_first < a.total_tiles ? (a.total_tiles - unit_first + unit_step - 1) / unit_step : 0;
+        // stem(0), stem(1); then per unit u: layer1(u) as soon as its planes are written, stem(u+2) as soon as the hand-over
+        // of u has drained that accumulator set (the two halves of the epilogue warps work on alternate units)
         if (n_units > 0) {
             mbar_wait(cfull0, 0, a.dbg, 1, 0);
             tc_fence_after();
             stem(0);
             mbar_wait(wbar, 0, a.dbg, 1, 600);
         }
+        if (n_units > 1) {
+            mbar_wait(cfull0 + 8, 0, a.dbg, 1, 1);
+            tc_fence_after();
+            stem(1);
+        }
         for (int u = 0; u < n_units; ++u) {
             const uint32_t s = (uint32_t)u & 1u, ph = ((uint32_t)u >> 1) & 1u;
-            if (u + 1 < n_units) {
-                const uint32_t s1 = s ^ 1u, ph1 = ((uint32_t)(u + 1) >> 1) & 1u;
-                mbar_wait(t1empty0 + 8 * s1, ph1 ^ 1, a.dbg, 1, 100 + (int)s1);
-                mbar_wait(cfull0 + 8 * s1, ph1, a.dbg, 1, (int)s1);
-                tc_fence_after();
-                stem(s1);
-            }
             mbar_wait(t2empty0 + 8 * s, ph ^ 1, a.dbg, 1, 200 + (int)s);
             mbar_wait(pfull0 + 8 * s, ph, a.dbg, 1, 300 + (int)s);
             tc_fence_after();
@@ -263,6 +266,13 @@ stem_block_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant
                 umma_commit(t2full0 + 8 * s);
             }
             __syncwarp();
+            if (u + 2 < n_units) {
+                const uint32_t ph2 = ((uint32_t)(u + 2) >> 1) & 1u;
+                mbar_wait(t1empty0 + 8 * s, ph2 ^ 1, a.dbg, 1, 100 + (int)s);
+                mbar_wait(cfull0 + 8 * s, ph2, a.dbg, 1, (int)s);
+                tc_fence_after();
+                stem(s);
+            }
         }
     } else if (warp == 1) {
         // ===== store issuer =====
@@ -330,45 +340,55 @@ stem_block_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant
             if (lane == 0) mbar_arrive(cfull0 + 8 * cs.i);
         }
     } else if (warp >= 8) {
-        // ===== epilogue warps (q = TMEM lane quarter, part = column group): hand-over(0); per unit u: hand-over(u+1), then
-        // layer-1 epilogue(u) =====
-        const int q = warp & 3, part = (warp - 8) >> 2;
+        // ===== epilogue warps.  TWO independent groups of eight warps (q = TMEM lane quarter, half = column half) take
+        // alternate units: group g always works in stage g of everything (stem accumulator set, parity planes, layer-1
+        // accumulator, staging slot).  Per unit: hand-over (stem accumulators -> parity planes), then -- once the MMA issuer
+        // has run layer 1 from those planes -- the layer-1 epilogue.  With one group of sixteen warps the dependent chain of a
+        // unit (five tcgen05.ld round trips, proxy fences, waiting for the layer-1 MMAs) paced the kernel at ~3 800 cycles per
+        // unit while the tensor pipe idled (profiles/r04e_stem_block_timeline.txt); two chains overlap each other's waits =====
+        const int q = warp & 3, idx = (warp - 8) >> 2;
+        const int half = idx & 1;
+        const uint32_t g = (uint32_t)(idx >> 1);
         const int ml = q * 32 + lane;
-        // hand-over: this thread's stem pixel of M-tile t is L = 128 t + ml = (Y, X); channels 8*part .. 8*part+7 = 16-byte
-        // chunk `part` of the pixel's 64-byte plane row
-        int hoff[kFMT];            // byte offset inside a plane slot, or -1: not a stem output the unit needs
+        // hand-over: this thread's stem pixel of M-tile t is L = 128 t + ml = (Y, X); channels 16*half .. 16*half+15 = 16-byte
+        // chunks 2*half, 2*half+1 of the pixel's 64-byte plane row (64B swizzle: chunk c at (c ^ (pix >> 1 & 3)) << 4)
+        int hoff[kFMT];            // byte offset of the pixel's row inside a plane slot | swizzle phase in bits 0-1, or -1
 #pragma unroll
         for (int t = 0; t < kFMT; ++t) {
             const int L = 128 * t + ml, Y = L / kFIP, X = L - Y * kFIP;
             const int pl = ((Y & 1) << 1) | (X & 1), pix = (Y >> 1) * kFP + (X >> 1);
-            hoff[t] = (Y < kFSY && X < kFSX) ? (int)(pl * kFPlaneBytes + pix * 64 + ((part ^ ((pix >> 1) & 3)) << 4)) : -1;
+            hoff[t] = (Y < kFSY && X < kFSX) ? (int)(pl * kFPlaneBytes + pix * 64 + ((pix >> 1) & 3)) : -1;
         }
-        // layer-1 epilogue: GEMM row ml = (r, c), staging row r*38 + c, channels 16*part .. 16*part+15
+        // layer-1 epilogue: GEMM row ml = (r, c), staging row r*38 + c, channels 32*half .. 32*half+31
         const int r1 = ml / kFP, c1 = ml - r1 * kFP;
         const bool valid1 = r1 < kFR && c1 < kFC;
         const int mp = r1 * kFC + c1;
         const int xr = mp & 7;
-        const float4* sc1 = reinterpret_cast<const float4*>(gen + kFOffTab) + part * 4;          // layer-1 scale / bias of this thread's
-        const float4* bi1 = reinterpret_cast<const float4*>(gen + kFOffTab + 256) + part * 4;    // sixteen channels (shared-memory table)
-        float2 sc0[4], bi0[4];                           // stem scale / bias of this thread's eight channels
+        const float4* sc1 = reinterpret_cast<const float4*>(gen + kFOffTab) + half * 8;          // layer-1 scale / bias of this thread's
+        const float4* bi1 = reinterpret_cast<const float4*>(gen + kFOffTab + 256) + half * 8;    // 32 channels (shared-memory table)
+        float2 sc0[8], bi0[8];                                                                   // stem scale / bias of its 16 channels
 #pragma unroll
-        for (int e = 0; e < 4; ++e) {
-            sc0[e] = make_float2(a.sb0[part * 8 + 2 * e], a.sb0[part * 8 + 2 * e + 1]);
-            bi0[e] = make_float2(a.sb0[32 + part * 8 + 2 * e], a.sb0[32 + part * 8 + 2 * e + 1]);
+        for (int e = 0; e < 8; ++e) {
+            sc0[e] = make_float2(a.sb0[half * 16 + 2 * e], a.sb0[half * 16 + 2 * e + 1]);
+            bi0[e] = make_float2(a.sb0[32 + half * 16 + 2 * e], a.sb0[32 + half * 16 + 2 * e + 1]);
         }
-        BlockWalk tw(a, unit_first, unit_step);          // position of the unit being handed over
-        auto handover = [&](uint32_t s, uint32_t ph) {
-            // stem output (gy, gx) = (2*y0 - 1 + Y, 2*x0 - 1 + X); outside the image -> zero (layer 1's padding)
+        const int n_units = unit_first < a.total_tiles ? (a.total_tiles - unit_first + unit_step - 1) / unit_step : 0;
+        BlockWalk tw(a, unit_first + (int)g * unit_step, 2 * unit_step);      // position of this group's current unit
+        uint8_t* pbase = gen + kFOffPlane + g * kFPlaneSlot;
+        uint8_t* sbase = gen + kFOffStg + g * kFStgSlot;
+        uint32_t ph = 0;
+        for (int u = (int)g; u < n_units; u += 2, ph ^= 1u, tw.next()) {
+            // ---- hand-over of unit u: stem output (gy, gx) = (2*y0 - 1 + Y, 2*x0 - 1 + X); outside the image -> zero (layer
+            // 1's padding).  Only units on the image border can hold such pixels.
             const int gy0 = 2 * tw.y0() - 1, gx0 = 2 * tw.x0() - 1;
-            const bool interior = gy0 >= 0 && gy0 + kFSY <= a.H && gx0 >= 0 && gx0 + kFSX <= a.W;   // only border units can hold padding pixels
-            mbar_wait(t1full0 + 8 * s, ph, a.dbg, 2, 200 + (int)s);
+            const bool interior = gy0 >= 0 && gy0 + kFSY <= a.H && gx0 >= 0 && gx0 + kFSX <= a.W;
+            mbar_wait(t1full0 + 8 * g, ph, a.dbg, 2, 200 + (int)g);
             tc_fence_after();
-            mbar_wait(pempty0 + 8 * s, ph ^ 1, a.dbg, 2, 300 + (int)s);
-            uint8_t* pbase = gen + kFOffPlane + s * kFPlaneSlot;
+            mbar_wait(pempty0 + 8 * g, ph ^ 1, a.dbg, 2, 300 + (int)g);
 #pragma unroll
             for (int t = 0; t < kFMT; ++t) {
-                uint32_t v[8];
-                tmem_ld8(tmem_base + s * kFAcc1Cols + (uint32_t)(t * 32 + part * 8) + ((uint32_t)(q * 32) << 16), v);
+                uint32_t v[16];
+                tmem_ld16(tmem_base + g * kFAcc1Cols + (uint32_t)(t * 32 + half * 16) + ((uint32_t)(q * 32) << 16), v);
                 tmem_ld_wait();
                 if (hoff[t] >= 0) {
                     bool in_img = true;
@@ -377,62 +397,59 @@ stem_block_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant
                         const int gy = gy0 + Y, gx = gx0 + (L - Y * kFIP);
                         in_img = gy >= 0 && gy < a.H && gx >= 0 && gx < a.W;
                     }
-                    uint4 pk;
-                    __half2* ph2 = reinterpret_cast<__half2*>(&pk);
+                    uint8_t* prow = pbase + (hoff[t] & ~3);
+                    const int sw = hoff[t] & 3;
 #pragma unroll
-                    for (int e = 0; e < 4; ++e) {
-                        const float2 y = ffma2x(make_float2(__uint_as_float(v[2 * e]), __uint_as_float(v[2 * e + 1])), sc0[e], bi0[e]);
-                        const float2 z = fmul2x(y, make_float2(kLeaky, kLeaky));
-                        ph2[e] = __floats2half2_rn(fmaxf(y.x, z.x), fmaxf(y.y, z.y));      // LeakyReLU(0.1) = max(v, 0.1 v)
+                    for (int h = 0; h < 2; ++h) {
+                        uint4 pk;
+                        __half2* ph2 = reinterpret_cast<__half2*>(&pk);
+#pragma unroll
+                        for (int e = 0; e < 4; ++e) {
+                            const float2 y = ffma2x(make_float2(__uint_as_float(v[8 * h + 2 * e]), __uint_as_float(v[8 * h + 2 * e + 1])),
+                                                    sc0[4 * h + e], bi0[4 * h + e]);
+                            const float2 z = fmul2x(y, make_float2(kLeaky, kLeaky));
+                            ph2[e] = __floats2half2_rn(fmaxf(y.x, z.x), fmaxf(y.y, z.y));      // LeakyReLU(0.1) = max(v, 0.1 v)
+                        }
+                        if (!in_img) pk = make_uint4(0u, 0u, 0u, 0u);
+                        *reinterpret_cast<uint4*>(prow + (((2 * half + h) ^ sw) << 4)) = pk;
                     }
-                    if (!in_img) pk = make_uint4(0u, 0u, 0u, 0u);
-                    *reinterpret_cast<uint4*>(pbase + hoff[t]) = pk;
                 }
             }
             tc_fence_before();
             fence_async_smem();
             __syncwarp();
-            if (lane == 0) { mbar_arrive(t1empty0 + 8 * s); mbar_arrive(pfull0 + 8 * s); }
-            tw.next();
-        };
-        const int n_units = unit_first < a.total_tiles ? (a.total_tiles - unit_first + unit_step - 1) / unit_step : 0;
-        if (n_units > 0) handover(0, 0);
-        Slot<kFRing> ss(0);
-        for (int u = 0; u < n_units; ++u, ss.advance(1)) {
-            const uint32_t s = (uint32_t)u & 1u, ph = ((uint32_t)u >> 1) & 1u;
-            if (u + 1 < n_units) handover(s ^ 1u, ((uint32_t)(u + 1) >> 1) & 1u);
-            mbar_wait(t2full0 + 8 * s, ph, a.dbg, 2, 400 + (int)s);
+            if (lane == 0) { mbar_arrive(t1empty0 + 8 * g); mbar_arrive(pfull0 + 8 * g); }
+            // ---- layer-1 epilogue of unit u
+            mbar_wait(t2full0 + 8 * g, ph, a.dbg, 2, 400 + (int)g);
             tc_fence_after();
-            uint32_t r0[16];
-            tmem_ld16(tmem_base + kFAcc2Base + s * 64 + (uint32_t)(part * 16) + ((uint32_t)(q * 32) << 16), r0);
-            mbar_wait(sempty0 + 8 * ss.i, ss.ph ^ 1, a.dbg, 2, 500 + (int)ss.i);
+            uint32_t r0[16], r1v[16];
+            const uint32_t tcol = tmem_base + kFAcc2Base + g * 64 + (uint32_t)(half * 32) + ((uint32_t)(q * 32) << 16);
+            tmem_ld16(tcol, r0);
+            tmem_ld16(tcol + 16, r1v);
+            mbar_wait(sempty0 + 8 * g, ph ^ 1, a.dbg, 2, 500 + (int)g);
             tmem_ld_wait();
             tc_fence_before();
             __syncwarp();
-            if (lane == 0) mbar_arrive(t2empty0 + 8 * s);    // accumulator drained into registers
+            if (lane == 0) mbar_arrive(t2empty0 + 8 * g);    // accumulator drained into registers
             if (valid1) {
-                uint8_t* srow = gen + kFOffStg + ss.i * kFStgSlot + (uint32_t)mp * 128u;
-                float v[16];
+                uint8_t* srow = sbase + (uint32_t)mp * 128u;
 #pragma unroll
-                for (int i = 0; i < 4; ++i) {
-                    const float4 s4 = sc1[i], b4 = bi1[i];
-                    v[4 * i + 0] = leaky(fmaf(__uint_as_float(r0[4 * i + 0]), s4.x, b4.x));
-                    v[4 * i + 1] = leaky(fmaf(__uint_as_float(r0[4 * i + 1]), s4.y, b4.y));
-                    v[4 * i + 2] = leaky(fmaf(__uint_as_float(r0[4 * i + 2]), s4.z, b4.z));
-                    v[4 * i + 3] = leaky(fmaf(__uint_as_float(r0[4 * i + 3]), s4.w, b4.w));
-                }
-#pragma unroll
-                for (int h = 0; h < 2; ++h) {
+                for (int c = 0; c < 4; ++c) {                 // 16-byte chunk 4*half + c = channels 32*half + 8c .. + 7
+                    const uint32_t* rr = c < 2 ? r0 : r1v;
+                    const int j0 = 8 * (c & 1);
+                    const float4 s0 = sc1[2 * c], s1 = sc1[2 * c + 1], b0 = bi1[2 * c], b1 = bi1[2 * c + 1];
                     uint4 pk;
                     __half2* ph2 = reinterpret_cast<__half2*>(&pk);
-#pragma unroll
-                    for (int i = 0; i < 4; ++i) ph2[i] = __floats2half2_rn(v[8 * h + 2 * i], v[8 * h + 2 * i + 1]);
-                    *reinterpret_cast<uint4*>(srow + (((part * 2 + h) ^ xr) << 4)) = pk;
+                    ph2[0] = __floats2half2_rn(leaky(fmaf(__uint_as_float(rr[j0 + 0]), s0.x, b0.x)), leaky(fmaf(__uint_as_float(rr[j0 + 1]), s0.y, b0.y)));
+                    ph2[1] = __floats2half2_rn(leaky(fmaf(__uint_as_float(rr[j0 + 2]), s0.z, b0.z)), leaky(fmaf(__uint_as_float(rr[j0 + 3]), s0.w, b0.w)));
+                    ph2[2] = __floats2half2_rn(leaky(fmaf(__uint_as_float(rr[j0 + 4]), s1.x, b1.x)), leaky(fmaf(__uint_as_float(rr[j0 + 5]), s1.y, b1.y)));
+                    ph2[3] = __floats2half2_rn(leaky(fmaf(__uint_as_float(rr[j0 + 6]), s1.z, b1.z)), leaky(fmaf(__uint_as_float(rr[j0 + 7]), s1.w, b1.w)));
+                    *reinterpret_cast<uint4*>(srow + (((4 * half + c) ^ xr) << 4)) = pk;
                 }
             }
             fence_async_smem();
             __syncwarp();
-            if (lane == 0) mbar_arrive(sready0 + 8 * ss.i);
+            if (lane == 0) mbar_arrive(sready0 + 8 * g);
         }
     }
     tc_fence_before();
