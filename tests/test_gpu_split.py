@@ -118,7 +118,7 @@ def test_split_layer_vs_float64(split_ctx, sd, li, B, H, W, with_res):
                            f"{tuple(int(v) for v in bad.nonzero()[0])}")
 
 
-@pytest.mark.parametrize("B,H,W", [(2, 40, 56), (3, 17, 23), (1, 64, 608)])
+@pytest.mark.parametrize("B,H,W", [(2, 40, 56), (3, 17, 23), (3, 17, 24), (1, 64, 608), (2, 13, 152), (1, 3, 40)])
 def test_split_stem_vs_float64(split_ctx, sd, B, H, W):
     lib, ctx = split_ctx
     spec = topology.layer_specs(80)[0]

@@ -31,6 +31,7 @@ struct Op {
     TcPlan tc;
     HaloPlan halo;
     StemHaloPlan stem_halo;
+    bool stem_split_tc = false;       // YB_MODE_FP32_TC: the split halo stem (stem_halo_split.cu) instead of the CUDA-core kernel
     bool fused01 = false;             // the stem op also runs layer 1 (stem_block.cu) and writes layer 1's output
     StemBlockPlan stem_block;
     bool upcopy = false;              // YB_MODE_FP32_TC: nearest x2 copy of up_src into the concat slice up_dst
@@ -78,7 +79,9 @@ struct yb_ctx {
     unsigned char* d_blob = nullptr;
     size_t blob_bytes = 0;
     float stem_sb[64] = {};           // host mirror of the stem's scale[32] | bias[32] (kernel parameters of the halo stem):
-                                      // written by yb_finalize, re-read from the blob after yb_bcast_weights
+                                      // re-read from the blob by yb_finalize and after yb_bcast_weights
+    float stem_sc_eff[32] = {};       // fp32-grade mode: scale * 2^-(shift + 8) and the per-channel weight shift of the split
+    int stem_shift[32] = {};          // halo stem (stem_halo_split.cu), derived from the blob's fp32 stem weights
     std::vector<std::unique_ptr<Plan>> plans;
     PostBuffers post;
     float* box_params = nullptr;      // [B][6] per-image parameters of yb_correct_boxes
@@ -319,6 +322,21 @@ struct PlanBuilder {
     }
 };
 
+// The stem kernels take the stem's scale / bias (and, in the fp32-grade mode, the per-channel weight shift) as kernel
+// parameters: the host mirror is read back from the device blob, which is what the kernels' other operands come from and
+// what yb_bcast_weights overwrites.
+int refresh_stem_mirror(yb_ctx* c) {
+    const Layer& L = c->layers[0];
+    YB_CUDA(c, cudaMemcpy(c->stem_sb, L.d_scale, 32 * sizeof(float), cudaMemcpyDeviceToHost));
+    YB_CUDA(c, cudaMemcpy(c->stem_sb + 32, L.d_bias, 32 * sizeof(float), cudaMemcpyDeviceToHost));
+    if (L.d_w32) {
+        float w[27 * 32], bi[32];
+        YB_CUDA(c, cudaMemcpy(w, L.d_w32, sizeof(w), cudaMemcpyDeviceToHost));
+        stem_split_host_params(w, c->stem_sb, c->stem_sb + 32, c->stem_sc_eff, bi, c->stem_shift);
+    }
+    return YB_OK;
+}
+
 // A/B switch of experiment builds: the first two layers as separate kernels even where the fused kernel applies
 bool stem_unfused() {
     static const bool v = tune_env("YB_STEM_UNFUSED") && atoi(tune_env("YB_STEM_UNFUSED")) != 0;
@@ -371,6 +389,10 @@ int build_plan(yb_ctx* c, int B, int H, int W, Plan** out) {
             } else {
                 e = stem_halo_make_plan(op.stem_halo, static_cast<__half*>(buf[0]), 32, B, H, W, c->num_sms);
             }
+            if (!e.empty()) return bail("plan: stem: " + e);
+        } else if (p->mode == YB_MODE_FP32_TC && stem_split_supported(W)) {
+            op.stem_split_tc = true;
+            std::string e = stem_split_make_plan(op.stem_halo, static_cast<__half*>(buf[0]), 64, B, H, W, c->num_sms);
             if (!e.empty()) return bail("plan: stem: " + e);
         }
         p->ops.push_back(op);
@@ -531,7 +553,9 @@ int run_ops(yb_ctx* c, Plan* p, const float* x, int n_ops, cudaStream_t s) {
                                       c->layers[1].d_bias, c->dbg, s);
             else if (p->mode == YB_MODE_FP16)
                 e = stem_halo_launch(op.stem_halo, x, c->input_f16, p->B, p->H, p->W, L.d_w16, c->stem_sb, c->dbg, s);
-            else if (p->mode == YB_MODE_FP32_TC)     // Cin = 3: exact fp32 FMAs on the CUDA cores, output written as hi | lo
+            else if (p->mode == YB_MODE_FP32_TC && op.stem_split_tc)
+                e = stem_split_launch(op.stem_halo, x, p->B, p->H, p->W, L.d_w32, c->stem_sc_eff, c->stem_sb + 32, c->stem_shift, c->dbg, s);
+            else if (p->mode == YB_MODE_FP32_TC)     // widths TMA cannot read: exact fp32 FMAs on the CUDA cores, output written as hi | lo
                 e = launch_stem_split(x, static_cast<__half*>(op.a.out), L.d_w32, L.d_scale, L.d_bias, p->B, p->H, p->W, s);
             else
                 e = launch_stem<float>(x, static_cast<float*>(op.a.out), L.d_w32, L.d_scale, L.d_bias, p->B, p->H, p->W, s);
@@ -853,8 +877,9 @@ int yb_finalize(yb_ctx* c, int mode) {
     YB_CUDA(c, cudaDeviceSynchronize());
     YB_CUDA(c, cudaMemcpy(c->d_blob, host.data(), off, cudaMemcpyHostToDevice));
     YB_CUDA(c, cudaDeviceSynchronize());
-    std::memcpy(c->stem_sb, host.data() + offs[0].scale, 32 * sizeof(float));
-    std::memcpy(c->stem_sb + 32, host.data() + offs[0].bias, 32 * sizeof(float));
+    int rc_mirror = YB_OK;
+    rc_mirror = refresh_stem_mirror(c);
+    if (rc_mirror) return rc_mirror;
     c->mode = mode;
     c->finalized = true;
     return YB_OK;
@@ -1173,9 +1198,7 @@ int yb_bcast_weights(yb_ctx* c, int root, void* stream) {
     if (rc) return fail(c, rc, err);
     // the halo stem takes its scale / bias as kernel parameters: refresh the host mirror from the received blob
     YB_CUDA(c, cudaStreamSynchronize(static_cast<cudaStream_t>(stream)));
-    YB_CUDA(c, cudaMemcpy(c->stem_sb, c->layers[0].d_scale, 32 * sizeof(float), cudaMemcpyDeviceToHost));
-    YB_CUDA(c, cudaMemcpy(c->stem_sb + 32, c->layers[0].d_bias, 32 * sizeof(float), cudaMemcpyDeviceToHost));
-    return YB_OK;
+    return refresh_stem_mirror(c);
 }
 
 int yb_allgather_dets(yb_ctx* c, const float* rows7, const int* counts, int B_local, int cap, float* all_rows,
@@ -1274,7 +1297,12 @@ int yb_run_layer(yb_ctx* c, int li, const void* in, int B, int H, int W, const v
         if (!head && cudaMalloc(&xout, Mout * 2 * L.cout * sizeof(__half)) != cudaSuccess) { cleanup(); return fail(c, YB_E_NOMEM, "yb_run_layer: scratch"); }
         if (res && cudaMalloc(&xres, Mout * 2 * L.cout * sizeof(__half)) != cudaSuccess) { cleanup(); return fail(c, YB_E_NOMEM, "yb_run_layer: scratch"); }
         cudaError_t e = cudaSuccess;
-        if (li == 0) {
+        if (li == 0 && stem_split_supported(W)) {
+            StemHaloPlan sp;
+            std::string err = stem_split_make_plan(sp, xout, 64, B, H, W, c->num_sms);
+            if (!err.empty()) { cleanup(); return fail(c, YB_E_CUDA, "yb_run_layer: " + err); }
+            e = stem_split_launch(sp, static_cast<const float*>(in), B, H, W, L.d_w32, c->stem_sc_eff, c->stem_sb + 32, c->stem_shift, c->dbg, s);
+        } else if (li == 0) {
             e = launch_stem_split(static_cast<const float*>(in), xout, L.d_w32, L.d_scale, L.d_bias, B, H, W, s);
         } else {
             e = launch_f32_to_split(static_cast<const float*>(in), xin, Min, L.cin, s);

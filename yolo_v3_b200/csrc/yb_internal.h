@@ -149,6 +149,13 @@ std::string stem_halo_make_plan(StemHaloPlan& p, __half* out, long out_ld, int B
 cudaError_t stem_halo_launch(const StemHaloPlan& p, const void* x, int in_f16, int B, int H, int W, const __half* w16,
                              const float* sb_host, int* dbg, cudaStream_t s);
 
+// stem_halo_split.cu  (the halo stem of YB_MODE_FP32_TC: hi/lo operand pairs, output [B,H,W,32 hi | 32 lo]; fp32 images, W % 4 == 0)
+bool stem_split_supported(int W);
+void stem_split_host_params(const float* w27x32, const float* scale, const float* bias, float* sc_eff, float* bi_out, int* shift);
+std::string stem_split_make_plan(StemHaloPlan& p, __half* out, long out_ld, int B, int H, int W, int num_sms);
+cudaError_t stem_split_launch(const StemHaloPlan& p, const float* x, int B, int H, int W, const float* w32, const float* sc_eff_host,
+                              const float* bias_host, const int* shift_host, int* dbg, cudaStream_t s);
+
 // stem_block.cu  (stem + the first stride-2 convolution in one kernel: the 32-channel stem output never leaves the SM)
 struct StemBlockPlan {
     CUtensorMap tmW1, tmOut;
