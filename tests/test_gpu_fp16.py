@@ -294,6 +294,33 @@ def test_fp16_other_shapes_and_class_counts(oracle):
             assert np.array_equal(i, ei) and torch.equal(r, e)
 
 
+def test_fp16_net_where_the_first_two_layers_are_not_fused(oracle, sd):
+    """Widths whose last 38-column tile of layer 1 would be less than 80 % full (W = 160 -> 80 output columns = 2.1 tiles)
+    run the stem (stem_halo.cu) and the first stride-2 convolution as separate kernels: same deviation bounds against the
+    fp32 oracle as the fused path, and the post-process stays bit-exact on the same candidates."""
+    from yolo_v3_b200 import YoloNet, postprocessing
+    lib = _lib.load()
+    for (h, w) in ((160, 160), (128, 96)):
+        x = synth.make_images(2, h, w, seed=21)
+        net = YoloNet((w, h), precision="fp16")
+        net.load_state_dict(sd)
+        net = net.cuda().eval()
+        n0 = None
+        det = torch.cat(net(x.cuda(), None), 1)
+        n0 = lib.yb_launch_count(net._ctx)
+        det = torch.cat(net(x.cuda(), None), 1)
+        launches = lib.yb_launch_count(net._ctx) - n0
+        assert launches == 78, launches                        # 75 convolution kernels (nothing fused) + 2 upsample copies + decode
+        ref = torch.cat(oracle.forward(sd, x), 1)
+        d = (det.cpu() - ref).abs()
+        print(f"[fp16 deviation] unfused first layers {h}x{w}: max|d xy|={float(d[..., :2].max()):.3f}px max|d conf/cls|={float(d[..., 4:].max()):.4f}")
+        assert float(d[..., :2].max()) < 0.75 and float(d[..., 4:].max()) < 0.06
+        res, idx = postprocessing(det, 80, 0.05, 0.4, return_index=True)
+        ref_res, ref_idx = oracle.postprocessing_c(det.cpu(), 80, 0.05, 0.4)
+        for r, e, i, ei in zip(res, ref_res, idx, ref_idx):
+            assert np.array_equal(i, ei) and torch.equal(r, e)
+
+
 def test_fp16_plan_cache_two_shapes(sd):
     """Alternating shapes reuses cached plans and keeps results identical."""
     from yolo_v3_b200 import YoloNet
