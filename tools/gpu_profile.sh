@@ -37,5 +37,10 @@ for tool in memcheck racecheck synccheck; do
     timeout 420 compute-sanitizer --tool $tool --print-limit 5 python tools/one_step.py --steps 1 --warmup 0 --batch 2 --size 160 --recipe analytic --precision $prec 2>&1 | grep -E "ERROR SUMMARY|RACECHECK SUMMARY|done|Error|hazard" | head -8
   done
 done
+# the fused first kernel is not on the 160 x 160 path (its last column tile would be < 80 % full): cover it separately
+for tool in memcheck racecheck synccheck; do
+  echo "### compute-sanitizer --tool $tool: fused stem + layer 1 kernel, 2 x 40 x 64"
+  timeout 250 compute-sanitizer --tool $tool --print-limit 5 python tools/stem_block_debug.py 2 40 64 2>&1 | grep -E "ERROR SUMMARY|RACECHECK SUMMARY|bad |Error|hazard" | head -6
+done
 } | tee gpurun_out/${T}_sanitizer.txt
 du -sh gpurun_out
