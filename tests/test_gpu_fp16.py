@@ -358,6 +358,32 @@ def test_stem_fp16_input_same_bits_as_fp32(fp16_ctx, B, H, W):
     assert torch.equal(out32.view(torch.int16), out16.view(torch.int16))
 
 
+def test_detect_right_after_an_async_h2d_copy_sees_the_new_batch(sd):
+    """The first kernel is launched with the programmatic-stream-serialisation attribute (its prologue overlaps the previous
+    KERNEL's tail).  A host->device copy enqueued on the same stream right before the call is not a kernel: the launch must
+    stay fully ordered behind it.  Alternating batches are copied into ONE device buffer and detected immediately; every
+    result must equal the one computed from a synchronised copy of that batch."""
+    from yolo_v3_b200 import YoloNet
+    net = YoloNet((608, 608), precision="fp16")
+    net.load_state_dict(sd)
+    net = net.cuda().eval()
+    hx = [synth.make_images(8, 608, 608, seed=31 + i).pin_memory() for i in range(2)]
+    ref = []
+    for h in hx:
+        d = h.cuda()
+        torch.cuda.synchronize()
+        ref.append([r.clone() for r in net.detect(d, 0.1, 0.4)])
+        torch.cuda.synchronize()
+    assert not all(torch.equal(a, b) for a, b in zip(ref[0], ref[1]) if a.shape == b.shape) or any(a.shape != b.shape for a, b in zip(ref[0], ref[1]))
+    dev = torch.empty_like(hx[0], device="cuda")
+    for i in range(8):
+        dev.copy_(hx[i & 1], non_blocking=True)              # same stream, no synchronisation before the detect call
+        out = net.detect(dev, 0.1, 0.4)
+        assert len(out) == len(ref[i & 1])
+        for a, b in zip(out, ref[i & 1]):
+            assert torch.equal(a, b), f"iteration {i}: the detect call did not see the batch copied right before it"
+
+
 def test_detect_fp16_input_same_detections(sd):
     from yolo_v3_b200 import YoloNet
     net = YoloNet((224, 160), precision="fp16")
