@@ -184,6 +184,21 @@ def test_fused_stem_block_vs_torch(fp16_ctx, sd, B, H, W):
     assert not bad.any(), f"fused stem block: {int(bad.sum())} of {bad.numel()} outside tolerance, max err {float(err.max()):.4g}"
 
 
+def test_fused_stem_block_error_codes(fp16_ctx):
+    """yb_run_stem_block: YB_E_UNSUPPORTED (-8) for shapes the fused kernel does not take (odd H, widths TMA cannot read, widths
+    whose last column tile would be < 80 % full), YB_E_ARG (-1) for null tensors / empty shapes."""
+    lib, ctx = fp16_ctx
+    x = torch.zeros(1, 3, 64, 160, device="cuda")
+    out = torch.zeros(1, 32, 80, 64, device="cuda", dtype=torch.float16)
+    assert lib.yb_run_stem_block(ctx, vp(x), 1, 64, 160, vp(out), stream()) == -8      # 80 output columns = 2.1 tiles
+    assert lib.yb_run_stem_block(ctx, vp(x), 1, 63, 64, vp(out), stream()) == -8       # odd height
+    assert lib.yb_run_stem_block(ctx, vp(x), 1, 64, 70, vp(out), stream()) == -8       # row pitch not a multiple of 16 bytes
+    assert lib.yb_run_stem_block(ctx, None, 1, 64, 64, vp(out), stream()) == -1
+    assert lib.yb_run_stem_block(ctx, vp(x), 0, 64, 64, vp(out), stream()) == -1
+    assert lib.yb_run_stem_block(ctx, vp(x), 1, 64, 64, vp(out), stream()) == 0
+    torch.cuda.synchronize()
+
+
 def test_fused_stem_block_equals_separate_kernels(fp16_ctx, sd):
     """The fused kernel against the two separate kernels (halo stem, then the stride-2 halo convolution) on the same image:
     same fp16 operands and the same fp16 hand-over, so the results agree to the accumulation order of the tensor core."""
